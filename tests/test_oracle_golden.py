@@ -1,0 +1,120 @@
+"""CPU: the oracle restatement (oracle/restatement.py) against golden vectors that were
+produced by the unmodified reference (oracle/make_golden.py).  Bit-exact where the
+restatement uses the same torch operators in the same order."""
+import json
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import swag_stats
+from bnn_chaos_model_b200 import synth
+from oracle import restatement as R
+
+torch.set_num_threads(1)
+SEEDS = (0, 3, 17)
+
+
+def spec_for(seed):
+    return R.ModelSpec.from_hparams(swag_stats(seed)["hparams"])
+
+
+def test_layout_matches_survey_offsets():
+    spec = spec_for(0)
+    off = spec.offsets()
+    assert spec.d == 7583
+    assert off["feature_nn.0.weight"] == (81, (40, 41))
+    assert off["feature_nn.4.bias"] == (4201, (20,))
+    assert off["regress_nn.0.weight"] == (4221, (40, 40))
+    assert off["regress_nn.4.bias"] == (7581, (2,))
+    assert spec.zero_cols == (1, 2, 3, 4, 5, 6, 7, 38, 39, 40)
+
+
+def test_synth_inputs_reproduce(gold_predict):
+    X = synth.make_systems(int(gold_predict["n_sys"]), seed=int(gold_predict["x_seed"]))
+    assert X.shape == (256, 100, 41) and X.dtype == np.float32
+    assert zlib.crc32(X.tobytes()) == int(gold_predict["x_crc32"])
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_sample_weights_bit_exact(gold_predict, seed):
+    st = swag_stats(seed)
+    w_avg, w2_avg, pre_D = (torch.from_numpy(st[k]) for k in ("w_avg", "w2_avg", "pre_D"))
+    z1 = torch.from_numpy(gold_predict[f"z1_s{seed}"])
+    z2 = torch.from_numpy(gold_predict[f"z2_s{seed}"])
+    ref = torch.from_numpy(gold_predict[f"theta_ref_s{seed}"])
+    for i in range(z1.shape[0]):
+        th = R.sample_weights(w_avg, w2_avg, pre_D, 30, 0.5, z1[i], z2[i])
+        assert torch.equal(th, ref[i])
+    # the dense d x d form of the reference (230 MB) once: identical bits
+    th = R.sample_weights(w_avg, w2_avg, pre_D, 30, 0.5, z1[0], z2[0], dense_diag=True)
+    assert torch.equal(th, ref[0])
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_forward_swag_fast_bit_exact(gold_predict, seed):
+    spec = spec_for(seed)
+    X = torch.from_numpy(synth.make_systems(256, seed=123))
+    theta = torch.from_numpy(gold_predict[f"theta_ref_s{seed}"])
+    eps = torch.from_numpy(gold_predict[f"eps_s{seed}"])
+    ref = torch.from_numpy(gold_predict[f"out_ref_s{seed}"])
+    for i in range(theta.shape[0]):
+        out = R.forward_swag_fast(spec, theta[i], X, eps[i, :, :20], eps[i, :, 20:])
+        assert torch.equal(out, ref[i])
+    # the goldens are in-distribution (not pinned at the soft clamps)
+    mu = ref[..., 0]
+    assert 5.0 < float(mu.median()) < 6.5 and float((mu < 4.001).float().mean()) < 0.05
+
+
+def test_loss_and_grad(gold_loss):
+    testy = torch.from_numpy(gold_loss["testy"]).requires_grad_(True)
+    y = torch.from_numpy(gold_loss["y"])
+    per = R.lossfnc_per_system(testy, y)
+    assert torch.equal(per.detach(), torch.from_numpy(gold_loss["loss_ref"]))
+    (g,) = torch.autograd.grad(per.sum(), testy)
+    assert torch.equal(g, torch.from_numpy(gold_loss["grad_ref"]))
+    sle = R.safe_log_erf(torch.from_numpy(gold_loss["sle_x"]))
+    assert torch.equal(sle, torch.from_numpy(gold_loss["sle_ref"]))
+    # the x >= -1 branch carries f_under(0) (2.7512632e-5 in exact arithmetic,
+    # 2.7477741e-5 once the two 0.6432... constants are rounded to fp32)
+    assert float(R.safe_log_erf(torch.tensor([0.0]))) == 2.7477741241455078e-05
+
+
+def test_aggregate_trajectory(gold_aggregate):
+    g = gold_aggregate
+    ws = torch.from_numpy(g["ws"])
+    st = R.SwagState(K=int(g["K"]), c=int(g["c"]))
+    for epoch in range(int(g["n_epochs"])):
+        st = R.aggregate_model(st, ws[epoch], epoch)
+        assert torch.equal(st.w_avg, torch.from_numpy(g[f"w_avg_{epoch}"]))
+        assert torch.equal(st.w2_avg, torch.from_numpy(g[f"w2_avg_{epoch}"]))
+        assert torch.equal(st.pre_D, torch.from_numpy(g[f"pre_D_{epoch}"]))
+    assert st.pre_D.shape[1] == int(g["K"])  # FIFO rolled over
+
+
+def test_training_steps(gold_train):
+    g = gold_train
+    spec = spec_for(0)
+    B = int(g["B"])
+    X = torch.from_numpy(synth.make_systems(B, seed=int(g["x_seed"])))
+    y = torch.from_numpy(g["y"])
+    theta = torch.from_numpy(g["theta0"]).clone()
+    eps12 = torch.from_numpy(g["eps12"])
+    out, _ = R.forward(spec, theta, X, False, None, eps12[0, :, :20], eps12[0, :, 20:], None)
+    assert float(R.lossfnc_per_system(out, y).sum()) == float(g["val_loss_ref"])
+    buf = torch.zeros_like(theta)
+    for s in range(3):
+        th = theta.clone().requires_grad_(True)
+        eps_in = torch.from_numpy(g["eps_in"][s].astype(np.float32))
+        total, logs = R.training_loss(spec, th, X, y, eps_in, eps12[s, :, :20], eps12[s, :, 20:],
+                                      torch.from_numpy(g["eps_sum"][s]))
+        (grad,) = torch.autograd.grad(total, th)
+        assert float(total) == pytest.approx(float(g[f"loss_ref_{s}"]), rel=1e-6)
+        np.testing.assert_allclose(np.array([float(v) for v in logs.values()]), g[f"logs_ref_{s}"], rtol=1e-6)
+        np.testing.assert_allclose(grad.numpy(), g[f"grad_ref_{s}"], rtol=2e-4, atol=2e-5)
+        theta, buf, gn = R.clip_and_sgd_step(theta, grad, buf, float(g["lr"]), float(g["momentum"]),
+                                             float(g["weight_decay"]), float(g["clip"]), s == 0)
+        assert float(gn) == pytest.approx(float(g[f"gradnorm_ref_{s}"]), rel=1e-5)
+        np.testing.assert_allclose(theta.numpy(), g[f"theta_ref_{s}"], rtol=1e-6, atol=1e-7)
+        theta = torch.from_numpy(g[f"theta_ref_{s}"]).clone()
