@@ -1,0 +1,179 @@
+// Shared device/host helpers for libbnnchaos (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bnnchaos.h"
+
+namespace bnn {
+
+// ---------------------------------------------------------------------------------------
+// Error plumbing (C ABI: no exceptions).
+// ---------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_device();  // BNN_OK or BNN_E_ARCH
+
+#define BNN_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            bnn::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (int)_e;                                                                 \
+        }                                                                                   \
+    } while (0)
+
+#define BNN_REQUIRE(cond, code, ...)      \
+    do {                                  \
+        if (!(cond)) {                    \
+            bnn::set_error(__VA_ARGS__);  \
+            return (code);                \
+        }                                 \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------
+// Compiled model shape.  The kernels are specialised for the reference's only shipped
+// architecture (hidden=40, latent=20, in=out=1; find_minima.py:36-41); n_features, the
+// zero mask and T stay runtime parameters.
+// ---------------------------------------------------------------------------------------
+constexpr int H = 40;        // hidden
+constexpr int L = 20;        // latent
+constexpr int S2 = 2 * L;    // summary width
+constexpr int GC = 12;       // padded columns per lane group (10 real + 2 pad)
+constexpr int HP = 4 * GC;   // padded hidden row: 4 lane groups x 12
+constexpr int MAXF = 64;     // zero_mask is 64 bits wide
+constexpr int SYS_TILE = 8;  // systems per CTA tile
+
+// Flat (SWAGModel.flatten, spock_reg_model.py:734-746) offsets for in=out=1.
+struct FlatLayout {
+    int F, d;
+    int lv_in, lv_sum, W0, b0, W1, b1, W2, b2, V0, c0, V1, c1, V2, c2;
+    __host__ __device__ explicit FlatLayout(int F_) : F(F_) {
+        int o = 0;
+        lv_in = o;  o += F;
+        lv_sum = o; o += S2;
+        W0 = o; o += H * F;
+        b0 = o; o += H;
+        W1 = o; o += H * H;
+        b1 = o; o += H;
+        W2 = o; o += L * H;
+        b2 = o; o += L;
+        V0 = o; o += H * S2;
+        c0 = o; o += H;
+        V1 = o; o += H * H;
+        c1 = o; o += H;
+        V2 = o; o += 2 * H;
+        c2 = o; o += 2;
+        d = o;
+    }
+};
+
+// Kernel-side ("packed") layout of one unit's weights.  All matrices are stored k-major
+// (input index first) so that a lane group's output columns are contiguous:
+//   W0p[kin][48]  kin = live input columns only;  [k][q*12+i] = W0[q*10+i][col(k)], i<10
+//   W1p[40][48], V0p[40][48], V1p[40][48] likewise
+//   W2p[40][48]   [k][q*12+2i+{0,1}] = W2[q*5+i][k], i<5   (duplicated: f32x2 row pairs)
+//   biases b0p/b1p/c0p/c1p[48] ([q*12+i]), b2p[48] (duplicated like W2p), V2[2][40], c2[4],
+//   then the two logvar vectors verbatim: lv_sum[40], lv_in[F rounded up to 4]
+// The feature part (first feat_floats) is what the MLP warps stage in shared memory.
+struct PackedLayout {
+    int kin;  // live input columns
+    int W0p, b0p, W1p, b1p, W2p, b2p, feat_floats;
+    int V0p, c0p, V1p, c1p, V2, c2, lv_sum, lv_in, P;
+    __host__ __device__ explicit PackedLayout(int kin_, int F_ = MAXF) : kin(kin_) {
+        int o = 0;
+        W0p = o; o += kin * HP;
+        b0p = o; o += HP;
+        W1p = o; o += H * HP;
+        b1p = o; o += HP;
+        W2p = o; o += H * HP;
+        b2p = o; o += HP;
+        feat_floats = o;
+        V0p = o; o += S2 * HP;
+        c0p = o; o += HP;
+        V1p = o; o += H * HP;
+        c1p = o; o += HP;
+        V2 = o; o += 2 * H;
+        c2 = o; o += 4;
+        lv_sum = o; o += S2;                 // summary_noise_logvar (noisy forward only)
+        lv_in = o; o += (F_ + 3) & ~3;       // input_noise_logvar, all F columns
+        P = o;
+    }
+};
+
+struct LiveCols {
+    int n;
+    int8_t col[MAXF];
+};
+
+static inline LiveCols live_columns(const bnn_model_config* cfg) {
+    LiveCols lc;
+    lc.n = 0;
+    for (int c = 0; c < cfg->n_features; ++c)
+        if (!((cfg->zero_mask >> c) & 1ull)) lc.col[lc.n++] = (int8_t)c;
+    for (int i = lc.n; i < MAXF; ++i) lc.col[i] = -1;
+    return lc;
+}
+
+int validate_config(const bnn_model_config* cfg);
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) + Box-Muller; mirrors oracle/restatement.py.
+// counter = (blk, a, b, stream), key = (seed lo, seed hi).
+// ---------------------------------------------------------------------------------------
+enum : uint32_t { STREAM_Z1 = 1, STREAM_Z2 = 2, STREAM_EPS = 3, STREAM_EPS_IN = 4, STREAM_EPS_SUM = 5 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+
+__device__ __forceinline__ float u01(uint32_t u) {
+    return (__uint2float_rn(u >> 8) + 1.0f) * 5.9604644775390625e-08f;  // 2^-24, in (0,1]
+}
+
+__device__ __forceinline__ float4 box_muller(uint4 u) {
+    float a0 = u01(u.x), b0 = u01(u.y), a1 = u01(u.z), b1 = u01(u.w);
+    float r0 = sqrtf(-2.0f * logf(a0)), r1 = sqrtf(-2.0f * logf(a1));
+    float s0, c0, s1, c1;
+    sincosf(6.283185307179586f * b0, &s0, &c0);
+    sincosf(6.283185307179586f * b1, &s1, &c1);
+    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b,
+                                                 uint32_t blk) {
+    uint4 r = philox4x32_10(make_uint4(blk, a, b, stream), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    return box_muller(r);
+}
+
+// ---------------------------------------------------------------------------------------
+// Packed fp32x2 FMA (Blackwell FFMA2): one issue slot, two IEEE fp32 FMAs.
+// ---------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+}  // namespace bnn

@@ -1,0 +1,243 @@
+// K2: fused MultiSWAG posterior predictive.  See predict_device.cuh for the decomposition.
+//
+// Replaces, for every (unit, system) pair in one launch, the reference's per-sample Python
+// loop body SWAGModel.forward_swag_fast (/root/reference/spock_reg_model.py:878-908; callers
+// figures/main_figures.py:127-156, figures/spock/regression.py:74-92,
+// figures/multiswag_5_planet.py:295-298).
+#include "predict_device.cuh"
+
+namespace bnn {
+
+struct PredictParams {
+    const float* X;       // [N,T,F]
+    const float* thp;     // [U,P]
+    const float* eps;     // [U,N,2L] or null
+    const float* eps_sum; // [U,N,2L] or null (noisy forward)
+    float* summary;       // [U,N,2L] or null
+    float* out;           // [U,N,2] or [N,U,2]
+    int64_t N, U;
+    int64_t unit_offset, system_offset;
+    int64_t out_unit_stride, out_sys_stride;  // in floats
+    uint64_t seed;
+    int F, kin;
+    int units_per_cta;
+    HeadConsts hc;
+    ColMap cm;
+};
+
+// ---------------------------------------------------------------------------------------
+// v1: synchronous variant.  grid = (tiles, unit chunks).  Per unit: stage the feature
+// weights in shared memory, warps take tasks round-robin, warp 0 runs the tail of the
+// previous unit's records while the others already work on the next unit.
+// ---------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) predict_v1_kernel(const PredictParams prm, const int T) {
+    extern __shared__ __align__(16) float smem[];
+    const TileGeom g(T);
+    const PackedLayout pl(prm.kin, prm.F);
+    float* xT = smem;
+    float* wbuf = xT + prm.kin * g.RP;
+    float* hbuf = wbuf + pl.feat_floats;
+    float* rec = hbuf + NW * HT_FLOATS;
+    float* scratch = rec + 2 * rec_floats(g);
+
+    const int warp = threadIdx.x >> 5;
+    const int64_t n0 = (int64_t)blockIdx.x * SYS_TILE;
+    const int n_valid = (int)min((int64_t)SYS_TILE, prm.N - n0);
+    const int64_t u_begin = (int64_t)blockIdx.y * prm.units_per_cta;
+    const int64_t u_end = min(prm.U, u_begin + prm.units_per_cta);
+
+    load_x_tile(prm.X, n0, n_valid, prm.F, g, prm.kin, prm.cm, xT, reinterpret_cast<int*>(hbuf));
+
+    for (int64_t u = u_begin; u < u_end; ++u) {
+        const float* thp = prm.thp + u * pl.P;
+        // stage feature weights (all threads), previous unit's tasks are complete (barrier below)
+        for (int i = threadIdx.x; i < pl.feat_floats / 4; i += NW * 32)
+            reinterpret_cast<float4*>(wbuf)[i] = __ldg(reinterpret_cast<const float4*>(thp) + i);
+        __syncthreads();
+        float* rec_u = rec + (int)((u - u_begin) & 1) * rec_floats(g);
+        for (int t = warp; t < g.n_tasks; t += NW)
+            mlp_task(xT, g, prm.kin, wbuf, pl, hbuf + warp * HT_FLOATS, t, rec_u);
+        __syncthreads();
+        // tail by the last warp (it had the fewest tasks when n_tasks % NW != 0)
+        if (warp == NW - 1) {
+            const float* eps_u = prm.eps ? prm.eps + u * prm.N * S2 : nullptr;
+            const float* eps_sum_u = prm.eps_sum ? prm.eps_sum + u * prm.N * S2 : nullptr;
+            float* summary_u = prm.summary ? prm.summary + u * prm.N * S2 : nullptr;
+            tail_unit(rec_u, g, thp, pl, eps_u, eps_sum_u, summary_u, prm.seed, (uint32_t)(prm.unit_offset + u),
+                      prm.system_offset + n0, n0, n_valid, prm.hc, scratch, prm.out + u * prm.out_unit_stride,
+                      prm.out_sys_stride);
+        }
+        // the other warps run ahead to the next unit: they touch wbuf (safe: all tasks done) and the
+        // other rec slot; the barrier after the next staging orders the tail before slot reuse.
+    }
+}
+
+static size_t v1_smem_bytes(int kin, int T, int NW) {
+    TileGeom g(T);
+    PackedLayout pl(kin);
+    size_t fl = (size_t)kin * g.RP + pl.feat_floats + (size_t)NW * HT_FLOATS + 2 * rec_floats(g) + 1024;
+    return fl * sizeof(float);
+}
+
+template <int NW>
+static int launch_v1(const PredictParams& prm, int T, cudaStream_t st) {
+    const size_t smem = v1_smem_bytes(prm.kin, T, NW);
+    BNN_REQUIRE(smem <= 227 * 1024, BNN_E_CONFIG, "predict tile needs %zu bytes of shared memory (> 227 KB)", smem);
+    static bool attr_done = false;
+    if (!attr_done) {
+        BNN_CUDA(cudaFuncSetAttribute(predict_v1_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    const int64_t tiles = (prm.N + SYS_TILE - 1) / SYS_TILE;
+    const int64_t chunks = (prm.U + prm.units_per_cta - 1) / prm.units_per_cta;
+    BNN_REQUIRE(tiles < (1ll << 31) && chunks < 65536, BNN_E_ARG, "grid too large (%lld tiles, %lld chunks)",
+                (long long)tiles, (long long)chunks);
+    dim3 grid((unsigned)tiles, (unsigned)chunks);
+    predict_v1_kernel<NW><<<grid, NW * 32, smem, st>>>(prm, T);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+}  // namespace bnn
+
+extern "C" {
+
+size_t bnn_predict_workspace_bytes(const bnn_model_config*, int64_t, int64_t) { return 0; }
+
+int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems, const float* d_theta_packed,
+                int64_t n_units, const float* d_eps, const float* d_eps_sum, uint64_t seed, int64_t unit_offset,
+                int64_t system_offset, int32_t out_system_major, float* d_out, float* d_summary_out,
+                void* d_workspace, void* stream) {
+    using namespace bnn;
+    (void)d_workspace;
+    int rc = validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    if ((rc = check_device()) != BNN_OK) return rc;
+    BNN_REQUIRE(d_x && d_theta_packed && d_out, BNN_E_ARG, "bnn_predict: null pointer");
+    BNN_REQUIRE(n_systems > 0 && n_units > 0, BNN_E_ARG, "bnn_predict: empty problem (N=%lld, U=%lld)",
+                (long long)n_systems, (long long)n_units);
+    BNN_REQUIRE(aligned16(d_theta_packed) && aligned16(d_out) && aligned16(d_x), BNN_E_ALIGN,
+                "bnn_predict: pointers must be 16-byte aligned");
+    PredictParams prm;
+    prm.X = d_x;
+    prm.thp = d_theta_packed;
+    prm.eps = d_eps;
+    prm.eps_sum = d_eps_sum;
+    prm.summary = d_summary_out;
+    prm.out = d_out;
+    prm.N = n_systems;
+    prm.U = n_units;
+    prm.unit_offset = unit_offset;
+    prm.system_offset = system_offset;
+    prm.out_unit_stride = out_system_major ? 2 : n_systems * 2;
+    prm.out_sys_stride = out_system_major ? n_units * 2 : 2;
+    prm.seed = seed;
+    prm.F = cfg->n_features;
+    LiveCols lc = live_columns(cfg);
+    prm.kin = lc.n;
+    for (int c = 0; c < MAXF; ++c) prm.cm.inv[c] = -1;
+    for (int k = 0; k < lc.n; ++k) prm.cm.inv[(int)lc.col[k]] = (int8_t)k;
+    prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
+    // split units over CTAs only when the tiles alone cannot fill the GPU twice
+    const int64_t tiles = (n_systems + SYS_TILE - 1) / SYS_TILE;
+    int64_t chunks = 1;
+    if (tiles < 2 * 148) chunks = (2 * 148 + tiles - 1) / tiles;
+    if (chunks > n_units) chunks = n_units;
+    prm.units_per_cta = (int)((n_units + chunks - 1) / chunks);
+    return launch_v1<8>(prm, cfg->n_times, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Small companions of the noisy / split forward.
+// ---------------------------------------------------------------------------------------
+namespace bnn {
+
+__global__ void add_input_noise_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                       const float* __restrict__ lv_in, int F, uint64_t zero_mask, int64_t total,
+                                       float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % F);
+    // x - mask keeps NaN/Inf as NaN in a zeroed column (:452-478)
+    const float xv = ((zero_mask >> c) & 1ull) ? __fsub_rn(x[i], x[i]) : x[i];
+    out[i] = __fadd_rn(xv, __fmul_rn(eps[i], expf(__fdiv_rn(__ldg(lv_in + c), 2.0f))));
+}
+
+// one warp per group of 8 systems: regress_nn + soft_clamp from given summary statistics
+__global__ void __launch_bounds__(32) head_only_kernel(const float* __restrict__ summary, int64_t B,
+                                                       const float* __restrict__ thp, PackedLayout pl, HeadConsts hc,
+                                                       float* __restrict__ out) {
+    __shared__ float sA[SYS_TILE * 41], sB[SYS_TILE * 41];
+    const int lane = threadIdx.x, p = lane >> 2, q = lane & 3;
+    const int64_t n0 = (int64_t)blockIdx.x * SYS_TILE;
+    const int n_valid = (int)min((int64_t)SYS_TILE, B - n0);
+    for (int idx = lane; idx < SYS_TILE * S2; idx += 32) {
+        const int s = idx / S2, j = idx % S2;
+        sA[s * 41 + j] = (s < n_valid) ? summary[(n0 + s) * S2 + j] : 0.f;
+    }
+    __syncwarp();
+    head_layer(sA, thp + pl.V0p, thp + pl.c0p, S2, p, q, sB);
+    __syncwarp();
+    head_layer(sB, thp + pl.V1p, thp + pl.c1p, H, p, q, sA);
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int k = q * 10 + i;
+        const float r = sA[p * 41 + k];
+        o0 = fmaf(r, __ldg(thp + pl.V2 + k), o0);
+        o1 = fmaf(r, __ldg(thp + pl.V2 + H + k), o1);
+    }
+    o0 += __shfl_xor_sync(0xffffffffu, o0, 1);
+    o1 += __shfl_xor_sync(0xffffffffu, o1, 1);
+    o0 += __shfl_xor_sync(0xffffffffu, o0, 2);
+    o1 += __shfl_xor_sync(0xffffffffu, o1, 2);
+    if (q == 0 && p < n_valid) {
+        o0 += __ldg(thp + pl.c2);
+        o1 += __ldg(thp + pl.c2 + 1);
+        out[(n0 + p) * 2] = soft_clamp_dev(o0, hc.lo_mu, hc.hi_mu);
+        out[(n0 + p) * 2 + 1] = soft_clamp_dev(o1, hc.lo_sd, hc.hi_sd);
+    }
+}
+
+}  // namespace bnn
+
+extern "C" {
+
+int bnn_add_input_noise(const bnn_model_config* cfg, const float* d_x, const float* d_eps_in, const float* d_lv_in,
+                        int64_t n_rows, float* d_x_noisy, void* stream) {
+    using namespace bnn;
+    int rc = validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    if ((rc = check_device()) != BNN_OK) return rc;
+    BNN_REQUIRE(d_x && d_eps_in && d_lv_in && d_x_noisy && n_rows > 0, BNN_E_ARG, "bnn_add_input_noise: null pointer");
+    const int64_t total = n_rows * cfg->n_features;
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_add_input_noise: too many rows");
+    add_input_noise_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        d_x, d_eps_in, d_lv_in, cfg->n_features, cfg->zero_mask, total, d_x_noisy);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+int bnn_predict_instability(const bnn_model_config* cfg, const float* d_summary, int64_t B,
+                            const float* d_theta_packed, float* d_out, void* stream) {
+    using namespace bnn;
+    int rc = validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    if ((rc = check_device()) != BNN_OK) return rc;
+    BNN_REQUIRE(d_summary && d_theta_packed && d_out && B > 0, BNN_E_ARG, "bnn_predict_instability: null pointer");
+    PackedLayout pl(live_columns(cfg).n, cfg->n_features);
+    HeadConsts hc{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
+    const int64_t blocks = (B + SYS_TILE - 1) / SYS_TILE;
+    BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_predict_instability: B too large");
+    head_only_kernel<<<(unsigned)blocks, 32, 0, (cudaStream_t)stream>>>(d_summary, B, d_theta_packed, pl, hc, d_out);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+}  // extern "C"

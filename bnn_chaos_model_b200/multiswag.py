@@ -1,0 +1,171 @@
+"""MultiSWAG ensemble: one batched launch instead of the reference's per-sample Python loops.
+
+Reference loops replaced (all call SWAGModel.forward_swag(_fast) once per weight sample):
+  * figures/main_figures.py:127-156        2000 samples x val batches of 3000, random model
+  * figures/spock/regression.py:74-92,149  FeatureRegressor.sample_full_swag / .sample
+  * figures/multiswag_5_planet.py:280-298  5-planet: every adjacent trio, 10 chunks x samples
+
+``MultiSWAG.predict`` evaluates every (model, weight sample, system) triple in one sampler
+launch + one fused predictive launch with counter-based Philox draws keyed on GLOBAL
+(unit, system) indices, so a run sharded over ranks equals the single-GPU run bit for bit.
+``sample_full_swag`` keeps the reference's per-call semantics (uniformly random model from
+numpy's global RNG, torch draws) for drop-in use.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BnnChaosError
+from .spock_reg_model import SWAGModel
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block partition of range(n): first n % world ranks get one extra item."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_system_shards(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """The path's only collective: all_gather of the system-major block [N_local, ...] of every
+    rank into [n_total, ...] (ranks own ``shard_range`` blocks, so the result needs no permute)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    assert local.shape[0] == sizes[rank][1] - sizes[rank][0]
+    tail = tuple(local.shape[1:])
+    full = torch.empty((n_total,) + tail, device=local.device, dtype=local.dtype)
+    if all(b - a == sizes[0][1] - sizes[0][0] for a, b in sizes):
+        dist.all_gather_into_tensor(full, local.contiguous(), group=group)
+        return full
+    # ragged split (n_total % world != 0): pad every shard to the largest, still ONE all_gather
+    nmax = max(b - a for a, b in sizes)
+    send = torch.zeros((nmax,) + tail, device=local.device, dtype=local.dtype)
+    send[: local.shape[0]] = local
+    recv = torch.empty((world, nmax) + tail, device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(recv.view((world * nmax,) + tail), send, group=group)
+    for r, (a, b) in enumerate(sizes):
+        full[a:b] = recv[r, : b - a]
+    return full
+
+
+class MultiSWAG:
+    """An ensemble of SWAG posteriors (the reference's ``swag_ensemble`` list) resident on one GPU."""
+
+    def __init__(self, models: Sequence[SWAGModel], device=None):
+        if len(models) == 0:
+            raise ValueError("empty SWAG ensemble")  # main_figures.py:102-103
+        self.models: List[SWAGModel] = list(models)
+        m0 = self.models[0]
+        for m in self.models:
+            if m.K != m0.K or m.n_features != m0.n_features or m.zero_columns() != m0.zero_columns() \
+                    or m.lowest != m0.lowest or m.pre_D.shape[1] != m.K:
+                raise ValueError("ensemble members must share the architecture, flags, K and have K deviations")
+        self.K = m0.K
+        self.ssX = m0.ssX
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise BnnChaosError("MultiSWAG needs a CUDA device: there is no CPU fallback")
+        dev = self.device
+        self.w_avg = torch.stack([m.w_avg.float() for m in self.models]).to(dev).contiguous()      # [M,d]
+        self.w2_avg = torch.stack([m.w2_avg.float() for m in self.models]).to(dev).contiguous()    # [M,d]
+        self.pre_D = torch.stack([m.pre_D.float().contiguous() for m in self.models]).to(dev).contiguous()  # [M,d,K]
+        self._m0 = m0
+
+    @property
+    def n_models(self):
+        return len(self.models)
+
+    def config(self, n_times=100):
+        return self._m0.config(n_times)
+
+    # ------------------------------------------------------------------ batched path
+    def sample_thetas(self, samples_per_model: int, seed: int, scale: float = 0.5, unit_model=None,
+                      unit_offset: int = 0, n_units: Optional[int] = None, z1=None, z2=None, want_flat=True):
+        """(theta[U,d], theta_packed[U,P]).  Unit u = model*S + sample unless unit_model is given."""
+        lib = _lib.load()
+        cfg = self.config()
+        M, d = self.w_avg.shape
+        U = n_units if n_units is not None else M * samples_per_model
+        P = lib.bnn_packed_param_count(cfg)
+        with torch.cuda.device(self.device):
+            theta = torch.empty((U, d), device=self.device)
+            thp = torch.empty((U, P), device=self.device)
+            um = None
+            if unit_model is not None:
+                um = torch.as_tensor(unit_model, dtype=torch.int32, device=self.device).contiguous()
+            _lib.check(
+                lib.bnn_swag_sample(cfg, _lib.ptr(self.w_avg), _lib.ptr(self.w2_avg), _lib.ptr(self.pre_D), M, self.K,
+                                    _lib.ptr(um), U, unit_offset, max(int(samples_per_model), 1), float(scale),
+                                    int(seed), _lib.ptr(z1), _lib.ptr(z2), _lib.ptr(theta), _lib.ptr(thp),
+                                    _lib.current_stream_ptr()),
+                "bnn_swag_sample",
+            )
+        return theta, thp
+
+    def predict(self, x: torch.Tensor, samples_per_model: int, seed: int = 0, scale: float = 0.5,
+                system_offset: int = 0, system_major: bool = False, thp: Optional[torch.Tensor] = None):
+        """All models x samples x systems: returns [M*S, N, 2] (or [N, M*S, 2]) of (mu, std)."""
+        lib = _lib.load()
+        _lib.require_cuda(x, "x")
+        x = x.contiguous().float()
+        cfg = self.config(x.shape[1])
+        if thp is None:
+            _, thp = self.sample_thetas(samples_per_model, seed, scale)
+        U, N = thp.shape[0], x.shape[0]
+        with torch.cuda.device(self.device):
+            out = torch.empty((N, U, 2) if system_major else (U, N, 2), device=self.device)
+            _lib.check(
+                lib.bnn_predict(cfg, _lib.ptr(x), N, _lib.ptr(thp), U, None, None, int(seed), 0, int(system_offset),
+                                int(system_major), _lib.ptr(out), None, None, _lib.current_stream_ptr()),
+                "bnn_predict",
+            )
+        return out
+
+    def predict_sharded(self, x_local: torch.Tensor, n_total: int, samples_per_model: int, seed: int = 0,
+                        scale: float = 0.5, group=None, gather: bool = True):
+        """Systems are block-partitioned over ranks (``shard_range``); every rank evaluates all
+        units on its shard (system-major output, one contiguous send buffer) and ONE all_gather
+        over NCCL assembles [N_total, M*S, 2].  No other collective: the path is embarrassingly
+        parallel."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lo, hi = shard_range(n_total, rank, world)
+        assert x_local.shape[0] == hi - lo, (x_local.shape, lo, hi)
+        local = self.predict(x_local, samples_per_model, seed, scale, system_offset=lo, system_major=True)
+        if not gather or world == 1:
+            return local
+        return gather_system_shards(local, n_total, group)
+
+    # ------------------------------------------------------------------ drop-in per-call path
+    def sample_full_swag(self, X_sample):
+        """figures/spock/regression.py:74-92: pick a model with numpy's global RNG, sample its
+        weights, forward_swag_fast.  (The statistics stay resident on the GPU; the reference moves
+        model and statistics host<->device on every call.)"""
+        swag_i = np.random.randint(0, len(self.models))
+        model = self.models[swag_i]
+        if model.device != self.device:
+            model.to(self.device)
+        return model.forward_swag_fast(X_sample, scale=0.5)
+
+    def predict_trios(self, X: torch.Tensor, samples: int, seed: int = 0, scale: float = 0.5):
+        """5-planet style input (figures/multiswag_5_planet.py:280-298): X [N, n_trios, T, F]
+        (already normalised) -> [samples*M?]..."""
+        N, R = X.shape[0], X.shape[1]
+        flat = X.reshape(N * R, X.shape[2], X.shape[3])
+        out = self.predict(flat, samples, seed, scale)  # [U, N*R, 2]
+        return out.reshape(out.shape[0], N, R, 2)
+
+
+def load_ensemble(paths: Sequence[str], device=None) -> MultiSWAG:
+    """[load_swag(f) for f in glob(...)] (main_figures.py:39-42) -> MultiSWAG."""
+    from .spock_reg_model import load_swag
+
+    return MultiSWAG([load_swag(p) for p in paths], device=device)

@@ -1,0 +1,482 @@
+"""Drop-in host mirror of the reference's ``spock_reg_model`` hot path, backed by libbnnchaos.
+
+Same names, argument meaning and error behaviour as the reference classes
+(/root/reference/spock_reg_model.py): ``VarModel`` (:339-687), ``SWAGModel`` (:690-908),
+``save_swag`` / ``load_swag`` (:911-967).  The arithmetic is done by the sm_100a kernels of
+``csrc/`` through the C ABI in ``include/bnnchaos.h``; PyTorch is used for device memory,
+streams and -- on the single-call paths -- for drawing the normals with ``torch.randn`` /
+``torch.randn_like`` in exactly the reference's order, so that the same torch generator
+state yields the same draws as the reference on the same device (SURVEY.md section 0,
+fact 5).  There is no CPU fallback: tensors on the CPU raise ``BnnChaosError``.
+
+Not mirrored (outside the hot path): the Lightning trainer hooks, the
+dataloaders / ``get_data``, ``CustomOneCycleLR``, ``VarModel.sample``, ``augment`` and the
+megno side channel (``fix_megno=True``).
+"""
+from __future__ import annotations
+
+import io
+import pickle
+import random
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import BnnChaosError, ModelConfig, TrainHParams
+
+EPSILON = 1e-5  # spock_reg_model.py:337
+
+MEGNO_LOCATION = 7  # :370-373
+MMR_LOCATION = (3, 6)
+NAN_LOCATION = (38, 39, 40)
+EPLUSMINUS_LOCATION = (1, 2, 4, 5)
+
+
+class AttributeDict(dict):
+    """Plain stand-in for pytorch_lightning.utilities.parsing.AttributeDict (the class the
+    reference's checkpoints pickle their hparams as)."""
+
+    def __getattr__(self, key):
+        try:
+            return self[key]
+        except KeyError as e:
+            raise AttributeError(key) from e
+
+    def __setattr__(self, key, val):
+        self[key] = val
+
+
+def _param_stack(in_n, out_n, hidden, layers):
+    """Parameter container with the reference's ``mlp()`` structure (:301-321) so that
+    ``state_dict()`` keys and order are identical; it is never called for compute."""
+    if layers < 1:
+        raise NotImplementedError("layers=0 (a bare Linear, :309-310) is not on the compiled path")
+    mods = [nn.Linear(in_n, hidden), nn.ReLU()]
+    for _ in range(layers):
+        mods += [nn.Linear(hidden, hidden), nn.ReLU()]
+    mods += [nn.Linear(hidden, out_n)]
+    return nn.Sequential(*mods)
+
+
+class VarModel(nn.Module):
+    """Bayesian neural network predicting instability time (reference :339-687)."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        hparams = AttributeDict(hparams) if not isinstance(hparams, AttributeDict) else hparams
+        hparams.setdefault("seed", 0)
+        seed = hparams["seed"]
+        random.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)  # pl.seed_everything (:344)
+        hparams.setdefault("include_derivatives", False)
+        hparams.setdefault("time_series_features", 38 + 3)
+        if hparams["time_series_features"] == 82:
+            hparams["time_series_features"] = 41
+        self.fix_megno = bool(hparams.get("fix_megno", False))
+        self.fix_megno2 = bool(hparams.get("fix_megno2", False))
+        self.include_angles = bool(hparams.get("include_angles", False))
+        if self.fix_megno:
+            raise NotImplementedError("fix_megno=True (megno mean/std side channel) is outside the hot path")
+
+        self.n_features = hparams["time_series_features"] * (1 + int(hparams["include_derivatives"]))
+        self.feature_nn = _param_stack(self.n_features, hparams["latent"], hparams["hidden"], hparams["in"])
+        self.regress_nn = _param_stack(hparams["latent"] * 2, 2, hparams["hidden"], hparams["out"])
+        self.input_noise_logvar = nn.Parameter(torch.zeros(self.n_features) - 2)
+        self.summary_noise_logvar = nn.Parameter(torch.zeros(hparams["latent"] * 2) - 2)
+        self.lowest = 0.1 if hparams.get("lower_std", False) else 0.5
+
+        self.latents = None
+        self.beta_in = hparams.get("beta_in", 1)
+        self.beta_out = hparams.get("beta_out", 1)
+        self.megno_location = MEGNO_LOCATION
+        self.mmr_location = list(MMR_LOCATION)
+        self.nan_location = list(NAN_LOCATION)
+        self.eplusminus_location = list(EPLUSMINUS_LOCATION)
+
+        hparams["scheduler_choice"] = "swa"
+        hparams.setdefault("save_freq", 25)
+        hparams.setdefault("eval_freq", 5)
+        hparams.setdefault("momentum", 0.9)
+        hparams.setdefault("weight_decay", 1e-4)
+        hparams.setdefault("noisy_val", True)
+
+        self.hparams = hparams
+        self.steps = hparams["steps"]
+        self.batch_size = hparams["batch_size"]
+        self.lr = hparams["lr"]
+        self.random_sample = bool(hparams.get("random_sample", False))
+        if self.random_sample:
+            raise NotImplementedError("random_sample (augment, :404-408) is outside the hot path")
+        self.train_len = 78660
+        self.test_len = 8740
+        self._summary_kl = 0.0
+        self.include_mmr = hparams["include_mmr"]
+        self.include_nan = hparams["include_nan"]
+        self.include_eplusminus = hparams.get("include_eplusminus", True)
+        self.train_all = hparams.get("train_all", False)
+        self._cur_summary = None
+        self.ssX = None
+        self.ssy = None
+        self.current_epoch = 0
+        self.global_step = 0
+        for p in self.parameters():
+            p.requires_grad_(False)  # gradients come from the fused training kernels, not autograd
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def device(self):
+        return self.input_noise_logvar.device
+
+    def zero_columns(self):
+        """Columns the zero_* methods (:452-478) clear under this model's flags (:487-500)."""
+        cols = []
+        if self.fix_megno or self.fix_megno2:
+            cols.append(self.megno_location)
+        if not self.include_mmr:
+            cols += self.mmr_location
+        if not self.include_nan:
+            cols += self.nan_location
+        if not self.include_eplusminus:
+            cols += self.eplusminus_location
+        return sorted(set(cols))
+
+    def config(self, n_times: int = 100, zero: bool = True) -> ModelConfig:
+        hp = self.hparams
+        mask = 0
+        if zero:
+            for c in self.zero_columns():
+                mask |= 1 << c
+        return ModelConfig(
+            n_features=self.n_features, hidden=hp["hidden"], latent=hp["latent"], n_in_layers=hp["in"],
+            n_out_layers=hp["out"], n_times=n_times, zero_mask=mask, lo_mu=4.0, hi_mu=12.0, lo_sd=self.lowest,
+            hi_sd=6.0,
+        )
+
+    def _flat(self) -> torch.Tensor:
+        return torch.cat([p.detach().reshape(-1) for p in self.state_dict().values()])
+
+    def _packed(self, cfg: ModelConfig, theta: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lib = _lib.load()
+        theta = (self._flat() if theta is None else theta).contiguous().float()
+        _lib.require_cuda(theta, "model parameters")
+        n_units = 1 if theta.dim() == 1 else theta.shape[0]
+        P = lib.bnn_packed_param_count(cfg)
+        if P < 0:
+            _lib.check(int(P), "bnn_packed_param_count")
+        out = torch.empty((n_units, P), device=theta.device, dtype=torch.float32)
+        _lib.check(lib.bnn_pack_theta(cfg, _lib.ptr(theta), n_units, _lib.ptr(out), _lib.current_stream_ptr()),
+                   "bnn_pack_theta")
+        return out
+
+    def _check_x(self, x):
+        _lib.require_cuda(x, "x")
+        if x.dim() != 3 or x.shape[-1] != self.n_features:
+            raise ValueError(f"x must be [batch, time, {self.n_features}], got {tuple(x.shape)}")
+        return x.contiguous().float()
+
+    def _predict(self, x, thp, eps, eps_sum=None, cfg=None, want_summary=False, system_major=False):
+        """[U,B,2] predictions (and [U,B,2L] summary statistics) for packed weights thp[U,P]."""
+        lib = _lib.load()
+        cfg = cfg or self.config(x.shape[1])
+        U, B = thp.shape[0], x.shape[0]
+        out = torch.empty((B, U, 2) if system_major else (U, B, 2), device=x.device, dtype=torch.float32)
+        summ = torch.empty((U, B, 2 * self.hparams["latent"]), device=x.device) if want_summary else None
+        _lib.check(
+            lib.bnn_predict(cfg, _lib.ptr(x), B, _lib.ptr(thp), U, _lib.ptr(eps), _lib.ptr(eps_sum), 0, 0, 0,
+                            int(system_major), _lib.ptr(out), _lib.ptr(summ), None, _lib.current_stream_ptr()),
+            "bnn_predict",
+        )
+        return out, summ
+
+    # ------------------------------------------------------------------ reference API
+    def compute_summary_stats(self, x):
+        """:416-435.  x is used as given (no zero_* masks, like the reference method)."""
+        x = self._check_x(x)
+        L = self.hparams["latent"]
+        with torch.cuda.device(x.device):
+            cfg = self.config(x.shape[1], zero=False)
+            eps1 = torch.randn((x.shape[0], L), device=x.device)
+            eps2 = torch.randn((x.shape[0], L), device=x.device)
+            eps = torch.cat((eps1, eps2), dim=1)[None].contiguous()
+            _, summ = self._predict(x, self._packed(cfg), eps, cfg=cfg, want_summary=True)
+        return summ[0]
+
+    def predict_instability(self, summary_stats):
+        """:437-442 -> (mu[B,1], std[B,1])."""
+        lib = _lib.load()
+        _lib.require_cuda(summary_stats, "summary_stats")
+        s = summary_stats.contiguous().float()
+        with torch.cuda.device(s.device):
+            cfg = self.config()
+            out = torch.empty((s.shape[0], 2), device=s.device, dtype=torch.float32)
+            _lib.check(lib.bnn_predict_instability(cfg, _lib.ptr(s), s.shape[0], _lib.ptr(self._packed(cfg)),
+                                                   _lib.ptr(out), _lib.current_stream_ptr()),
+                       "bnn_predict_instability")
+        return out[:, [0]], out[:, [1]]
+
+    def forward(self, x, noisy_val=True):
+        """:486-528.  RNG draw order as the reference: (input noise [B,T,F] if noisy), eps1,
+        eps2 [B,L], (summary noise [B,2L] if noisy)."""
+        lib = _lib.load()
+        x = self._check_x(x)
+        B, T, _ = x.shape
+        L = self.hparams["latent"]
+        with torch.cuda.device(x.device):
+            eps_sum = None
+            if noisy_val:
+                eps_in = torch.randn_like(x)
+                cfg_mask = self.config(T)
+                xn = torch.empty_like(x)
+                _lib.check(lib.bnn_add_input_noise(cfg_mask, _lib.ptr(x), _lib.ptr(eps_in),
+                                                   _lib.ptr(self.input_noise_logvar.detach().contiguous()), B * T,
+                                                   _lib.ptr(xn), _lib.current_stream_ptr()), "bnn_add_input_noise")
+                x, cfg = xn, self.config(T, zero=False)
+            else:
+                cfg = self.config(T)
+            eps1 = torch.randn((B, L), device=x.device)
+            eps2 = torch.randn((B, L), device=x.device)
+            eps = torch.cat((eps1, eps2), dim=1)[None].contiguous()
+            if noisy_val:
+                eps_sum = torch.randn((B, 2 * L), device=x.device)[None].contiguous()
+            out, summ = self._predict(x, self._packed(cfg), eps, eps_sum, cfg=cfg, want_summary=True)
+        self._cur_summary = summ[0]
+        lv = self.summary_noise_logvar.detach()
+        self._summary_kl = 0.5 * (summ[0] ** 2 + torch.exp(lv)[None, :] - lv[None, :] - 1)  # :515-520
+        return out[0]
+
+
+    def _lossfnc(self, testy, y):
+        """:547-577 -> per-system loss [B]."""
+        lib = _lib.load()
+        _lib.require_cuda(testy, "testy")
+        testy, y = testy.contiguous().float(), y.contiguous().float()
+        loss = torch.empty(testy.shape[0], device=testy.device, dtype=torch.float32)
+        with torch.cuda.device(testy.device):
+            _lib.check(lib.bnn_nll_fwd_bwd(_lib.ptr(testy), _lib.ptr(y), testy.shape[0], _lib.ptr(loss), None, None,
+                                           _lib.current_stream_ptr()), "bnn_nll_fwd_bwd")
+        return loss
+
+    def lossfnc(self, x, y, samples=1, noisy_val=True):
+        """:579-583."""
+        testy = self.forward(x, noisy_val=noisy_val)
+        return self._lossfnc(testy, y).sum()
+
+    def input_kl(self):
+        """:585-590 (41 elements: plain tensor arithmetic)."""
+        lv = self.input_noise_logvar.detach()
+        return 0.5 * (torch.exp(lv) - lv - 1).sum()
+
+    def summary_kl(self):
+        """:592-593."""
+        return self._summary_kl.sum()
+
+
+class SWAGModel(VarModel):
+    """SWAG moment collection and weight sampling (reference :690-908)."""
+
+    def init_params(self, swa_params):
+        self.swa_params = swa_params
+        self.swa_params.setdefault("swa_lr", 0.001)
+        self.swa_params.setdefault("swa_start", 1000)
+        self.swa_params.setdefault("swa_recording_lr_factor", 0.5)
+        self.n_models = 0
+        self.w_avg = None
+        self.w2_avg = None
+        self.pre_D = None
+        self.K = self.swa_params.get("K", 20)
+        self.c = self.swa_params.get("c", 2)
+        self.swa_params["c"] = self.c
+        self.swa_params["K"] = self.K
+        self._momentum = None
+        self._first_step = True
+        return self
+
+    # flatten / load (:734-761)
+    def flatten(self):
+        return self._flat()
+
+    def load(self, p_vec):
+        i = 0
+        with torch.no_grad():
+            for p in self.state_dict().values():
+                n = p.numel()
+                p.copy_(p_vec[i:i + n].reshape(p.shape))
+                i += n
+
+    # aggregate_model (:763-785)
+    def aggregate_model(self):
+        lib = _lib.load()
+        cur_w = self.flatten().contiguous()
+        _lib.require_cuda(cur_w, "model parameters")
+        d = cur_w.numel()
+        dev = cur_w.device
+        if self.w_avg is None:
+            self.w_avg = torch.zeros(d, device=dev)
+            self.w2_avg = torch.zeros(d, device=dev)
+            self._pre_D_buf = torch.zeros((d, self.K), device=dev)
+            self._n_models_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._n_cols_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._n_cols = 0
+        elif not hasattr(self, "_pre_D_buf") or self._pre_D_buf is None:
+            self._adopt_stats(dev)
+        with torch.cuda.device(dev):
+            _lib.check(
+                lib.bnn_swag_collect(_lib.ptr(cur_w), d, 1, self.K, _lib.ptr(self.w_avg), _lib.ptr(self.w2_avg),
+                                     _lib.ptr(self._pre_D_buf), _lib.ptr(self._n_models_dev),
+                                     _lib.ptr(self._n_cols_dev), int(self.current_epoch), int(self.c),
+                                     _lib.current_stream_ptr()),
+                "bnn_swag_collect",
+            )
+        if self._n_cols == 0 or self.current_epoch % self.c == 0:
+            self._n_cols = min(self._n_cols + 1, self.K)
+        self.pre_D = self._pre_D_buf[:, : self._n_cols]
+        self.n_models += 1
+
+    def _adopt_stats(self, dev):
+        """Statistics assigned from outside (load_swag): build the fixed [d,K] buffer."""
+        self.w_avg = self.w_avg.to(dev).contiguous().float()
+        self.w2_avg = self.w2_avg.to(dev).contiguous().float()
+        ncol = self.pre_D.shape[1]
+        self._pre_D_buf = torch.zeros((self.w_avg.numel(), self.K), device=dev)
+        self._pre_D_buf[:, :ncol] = self.pre_D.to(dev)
+        self._n_cols = ncol
+        self._n_models_dev = torch.tensor([self.n_models], dtype=torch.int32, device=dev)
+        self._n_cols_dev = torch.tensor([ncol], dtype=torch.int32, device=dev)
+        self.pre_D = self._pre_D_buf[:, :ncol]
+
+    def _stats_on(self, dev):
+        if self.w_avg is None:
+            raise BnnChaosError("no SWAG statistics: call aggregate_model() or load_swag() first")
+        if self.w_avg.device != dev or self.pre_D.device != dev or not self.pre_D.is_contiguous():
+            self.w_avg = self.w_avg.to(dev).contiguous().float()
+            self.w2_avg = self.w2_avg.to(dev).contiguous().float()
+            self.pre_D = self.pre_D.to(dev).contiguous().float()
+        if self.pre_D.shape[1] != self.K:
+            # the reference fails in D @ z_2 when fewer than K deviations were recorded (:835)
+            raise RuntimeError(
+                f"mat1 and mat2 shapes cannot be multiplied ({self.pre_D.shape[0]}x{self.pre_D.shape[1]} and {self.K}x1)"
+            )
+        return self.w_avg, self.w2_avg, self.pre_D.contiguous()
+
+    # sample_weights (:815-838)
+    def sample_weights(self, scale=1):
+        lib = _lib.load()
+        dev = self.device
+        _lib.require_cuda(self.input_noise_logvar, "model parameters")
+        w_avg, w2_avg, pre_D = self._stats_on(dev)
+        d = w_avg.shape[0]
+        with torch.cuda.device(dev):
+            z_1 = torch.randn((1, d), device=dev)        # :830
+            z_2 = torch.randn((self.K, 1), device=dev)   # :831
+            theta = torch.empty((1, d), device=dev)
+            cfg = self.config()
+            _lib.check(
+                lib.bnn_swag_sample(cfg, _lib.ptr(w_avg), _lib.ptr(w2_avg), _lib.ptr(pre_D), 1, self.K, None, 1, 0, 1,
+                                    float(scale), 0, _lib.ptr(z_1), _lib.ptr(z_2.reshape(1, self.K).contiguous()),
+                                    _lib.ptr(theta), None, _lib.current_stream_ptr()),
+                "bnn_swag_sample",
+            )
+        self.load(theta[0])
+
+    def forward_swag(self, x, scale=0.5):
+        """:840-876 -- sample weights (they stay loaded in the module, like the reference),
+        masks, summary statistics, head; also records _summary_kl."""
+        x = self._check_x(x)
+        self.sample_weights(scale=scale)
+        out = self.forward(x, noisy_val=False)
+        return out
+
+    def forward_swag_fast(self, x, scale=0.5):
+        """:878-908."""
+        x = self._check_x(x)
+        self.sample_weights(scale=scale)
+        B, T, _ = x.shape
+        L = self.hparams["latent"]
+        with torch.cuda.device(x.device):
+            cfg = self.config(T)
+            eps1 = torch.randn((B, L), device=x.device)
+            eps2 = torch.randn((B, L), device=x.device)
+            eps = torch.cat((eps1, eps2), dim=1)[None].contiguous()
+            out, _ = self._predict(x, self._packed(cfg), eps, cfg=cfg)
+        return out[0]
+
+
+# ----------------------------------------------------------------------------------------
+# save_swag / load_swag (:911-967): same dict, same keys.
+# ----------------------------------------------------------------------------------------
+def save_swag(swag_model, path):
+    save_items = {
+        "hparams": swag_model.hparams,
+        "swa_params": swag_model.swa_params,
+        "w_avg": swag_model.w_avg.cpu(),
+        "w2_avg": swag_model.w2_avg.cpu(),
+        "pre_D": swag_model.pre_D.cpu().contiguous(),
+    }
+    torch.save(save_items, path)
+
+
+class _SafeUnpickler(pickle.Unpickler):
+    """Only the four globals the reference's SWAG pickles contain,
+    plus what torch.save of this module's own dicts adds."""
+
+    _ALLOWED = {
+        ("collections", "OrderedDict"): OrderedDict,
+        ("pytorch_lightning.utilities.parsing", "AttributeDict"): AttributeDict,
+        ("bnn_chaos_model_b200.spock_reg_model", "AttributeDict"): AttributeDict,
+    }
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            return self._ALLOWED[(module, name)]
+        if module == "torch._utils" and name in ("_rebuild_tensor_v2", "_rebuild_tensor"):
+            return getattr(torch._utils, name)
+        if module == "torch" and name in ("FloatStorage", "LongStorage", "IntStorage", "DoubleStorage"):
+            return getattr(torch, name)
+        raise pickle.UnpicklingError(f"global {module}.{name} is not allowed in a SWAG checkpoint")
+
+
+class _SafePickleModule:
+    __name__ = "bnn_safe_pickle"
+    Unpickler = _SafeUnpickler
+    load = staticmethod(pickle.load)
+    loads = staticmethod(pickle.loads)
+    dump = staticmethod(pickle.dump)
+    dumps = staticmethod(pickle.dumps)
+    HIGHEST_PROTOCOL = pickle.HIGHEST_PROTOCOL
+    UnpicklingError = pickle.UnpicklingError
+
+
+def fixed_v50_scaler():
+    """The StandardScaler constants hard-coded in load_swag for 'v50' checkpoints (:931-957)."""
+    from sklearn.preprocessing import StandardScaler
+
+    from .synth import SSX_MEAN, SSX_SCALE
+
+    ssX = StandardScaler()
+    ssX.scale_ = SSX_SCALE.copy()
+    ssX.mean_ = SSX_MEAN.copy()
+    ssX.var_ = ssX.scale_ ** 2
+    return ssX
+
+
+def load_swag(path):
+    save_items = torch.load(path, map_location="cpu", pickle_module=_SafePickleModule, weights_only=False)
+    swag_model = SWAGModel(save_items["hparams"]).init_params(save_items["swa_params"])
+    swag_model.w_avg = save_items["w_avg"]
+    swag_model.w2_avg = save_items["w2_avg"]
+    swag_model.pre_D = save_items["pre_D"]
+    if "v50" in str(path):
+        swag_model.ssX = fixed_v50_scaler()
+    else:
+        ssX_file = str(path)[:-4] + "_ssX.pkl"
+        try:
+            with open(ssX_file, "rb") as f:
+                swag_model.ssX = pickle.load(f)
+        except FileNotFoundError:
+            print(f"ssX file not found! {ssX_file}")
+    return swag_model

@@ -1,0 +1,187 @@
+/*
+ * bnnchaos.h -- C ABI of libbnnchaos.so: the B200 (sm_100a) kernels behind the drop-in
+ * replacement of bnn_chaos_model's MultiSWAG posterior-predictive and SWAG-training path.
+ *
+ * The reference has no FFI: the path sits behind a Python class API
+ * (/root/reference/spock_reg_model.py:339-967, VarModel / SWAGModel / save_swag /
+ * load_swag).  Each entry point below names the reference method(s) it replaces; the
+ * Python host mirror (bnn_chaos_model_b200/spock_reg_model.py) binds them with ctypes --
+ * see INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer to contiguous fp32 (or int32 where said),
+ *     16-byte aligned, owned by the caller; h_* are HOST pointers;
+ *   - `stream` is a cudaStream_t passed as void*; the library only enqueues work on it and
+ *     never synchronises (except the h_* convenience entry points, which say so);
+ *   - return value: 0 ok; >0 a cudaError_t; <0 an argument error (BNN_E_*);
+ *     bnn_last_error_string() describes the last failure on the calling thread;
+ *   - no allocation, no global mutable state except one-time cudaFuncSetAttribute;
+ *   - sm_100a only: every entry point returns BNN_E_ARCH on another device.  There is no
+ *     CPU fallback.
+ */
+#ifndef BNNCHAOS_H_
+#define BNNCHAOS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNN_ABI_VERSION 1
+
+enum {
+    BNN_OK = 0,
+    BNN_E_ARG = -1,     /* null pointer / bad size */
+    BNN_E_CONFIG = -2,  /* model shape not supported by the compiled kernels */
+    BNN_E_ARCH = -3,    /* device is not sm_100 */
+    BNN_E_ALIGN = -4    /* pointer not 16-byte aligned */
+};
+
+/* Model description: VarModel.__init__ (spock_reg_model.py:341-402). */
+typedef struct bnn_model_config {
+    int32_t n_features;   /* F: hparams['time_series_features'] (41)              :348-358 */
+    int32_t hidden;       /* H: hparams['hidden'] (40)                            :359-360 */
+    int32_t latent;       /* L: hparams['latent'] (20)                            :359-362 */
+    int32_t n_in_layers;  /* hparams['in']  (1): hidden->hidden layers, feature_nn :359   */
+    int32_t n_out_layers; /* hparams['out'] (1): hidden->hidden layers, regress_nn :360   */
+    int32_t n_times;      /* T: time steps per system (100); runtime, 4 <= T, T % 4 == 0   */
+    uint64_t zero_mask;   /* bit c set <=> column c is zeroed by zero_megno/mmr/nan/
+                             eplusminus (:452-478) under this model's include_* flags      */
+    float lo_mu, hi_mu;   /* soft_clamp bounds of mu  (4, 12)                     :440     */
+    float lo_sd, hi_sd;   /* soft_clamp bounds of std (self.lowest = 0.5|0.1, 6)  :441     */
+} bnn_model_config;
+
+int bnn_abi_version(void);
+const char* bnn_last_error_string(void);
+
+/* d: length of SWAGModel.flatten() (:734-746) for this config, or <0. */
+int64_t bnn_param_count(const bnn_model_config* cfg);
+/* P: floats per unit of the kernel-side ("packed") weight layout, or <0. */
+int64_t bnn_packed_param_count(const bnn_model_config* cfg);
+
+/* ---------------------------------------------------------------------------------------
+ * SWAGModel.sample_weights (:815-838) for U = n_units (model, weight-sample) units at once:
+ *   theta = w_avg + (scale/sqrt2 * z1) * sqrt|w2_avg - w_avg^2| + scale * (D z2) / sqrt(2(K-1)),
+ *   D = pre_D - w_avg[:,None].
+ * Unit u uses model d_unit_model[u] (NULL: model = (unit_offset+u) / samples_per_model).
+ * d_z1 [U,d] / d_z2 [U,K] explicit normal draws (the reference's randn((1,d)), randn((K,1))),
+ * or both NULL: drawn in-kernel from Philox4x32-10 keyed on (seed; unit_offset+u, element).
+ * Outputs (either may be NULL): d_theta [U,d] in flatten() order (what SWAGModel.load()
+ * would install, :748-761) and d_theta_packed [U,P] in the layout bnn_predict consumes.
+ * pre_D is [M,d,K] row-major, exactly the saved tensor (:917).
+ */
+int bnn_swag_sample(const bnn_model_config* cfg, const float* d_w_avg, const float* d_w2_avg,
+                    const float* d_pre_D, int32_t n_models, int32_t K, const int32_t* d_unit_model,
+                    int64_t n_units, int64_t unit_offset, int32_t samples_per_model, float scale,
+                    uint64_t seed, const float* d_z1, const float* d_z2, float* d_theta,
+                    float* d_theta_packed, void* stream);
+
+/* SWAGModel.load (:748-761) for the kernels: flatten()-order theta [U,d] -> packed [U,P]. */
+int bnn_pack_theta(const bnn_model_config* cfg, const float* d_theta, int64_t n_units,
+                   float* d_theta_packed, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * SWAGModel.forward_swag_fast / forward_swag (:840-908) and VarModel.forward(noisy_val=False)
+ * (:486-528) for every (unit, system) pair in one launch:
+ *   zero_* masks -> feature_nn per time step -> mean / unbiased variance over time ->
+ *   sampled summary statistics (eps1, eps2) -> regress_nn -> soft_clamp.
+ * d_x [N,T,F] already StandardScaler-normalised (as every reference caller passes it).
+ * d_eps [U,N,2L] explicit draws (eps1 = [..., :L], eps2 = [..., L:], the two randn_like of
+ * :426-427), or NULL: Philox keyed on (seed; unit_offset+u, system_offset+n, element).
+ * d_eps_sum [U,N,2L] or NULL: add_summary_noise (:448-450, VarModel.forward(noisy_val=True));
+ * the input noise of that path (:444-446) is applied beforehand by bnn_add_input_noise.
+ * d_out [U,N,2] (mu, std) when out_system_major == 0, else [N,U,2].
+ * d_summary_out [U,N,2L] or NULL: the summary statistics compute_summary_stats returns
+ * (:416-435), before any summary noise -- what _summary_kl is computed from (:515-520).
+ * d_workspace: bnn_predict_workspace_bytes() bytes (may be NULL when that returns 0).
+ */
+size_t bnn_predict_workspace_bytes(const bnn_model_config* cfg, int64_t n_systems, int64_t n_units);
+int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems,
+                const float* d_theta_packed, int64_t n_units, const float* d_eps,
+                const float* d_eps_sum, uint64_t seed, int64_t unit_offset, int64_t system_offset,
+                int32_t out_system_major, float* d_out, float* d_summary_out, void* d_workspace,
+                void* stream);
+
+/* VarModel.add_input_noise (:444-446) after the zero_* masks (:487-500):
+ * x_noisy = x (zeroed columns set to 0) + eps_in * exp(input_noise_logvar/2).
+ * d_x, d_eps_in, d_x_noisy [n_rows = B*T, F]; d_lv_in [F].  The result is then passed to
+ * bnn_predict with a config whose zero_mask is 0 (every column carries noise). */
+int bnn_add_input_noise(const bnn_model_config* cfg, const float* d_x, const float* d_eps_in,
+                        const float* d_lv_in, int64_t n_rows, float* d_x_noisy, void* stream);
+
+/* VarModel.predict_instability (:437-442): regress_nn + soft_clamp on given summary
+ * statistics d_summary [B,2L] with ONE unit of packed weights -> d_out [B,2]. */
+int bnn_predict_instability(const bnn_model_config* cfg, const float* d_summary, int64_t B,
+                            const float* d_theta_packed, float* d_out, void* stream);
+
+/* Host-buffer convenience entry (what a non-torch caller binds): h_x [N,T,F] and h_out
+ * are HOST buffers; SWAG statistics are device-resident.  Copies x in, samples U =
+ * n_models*samples_per_model units with Philox, predicts, copies out back, synchronises.
+ * d_scratch must hold bnn_multiswag_host_scratch_bytes() bytes of device memory. */
+size_t bnn_multiswag_host_scratch_bytes(const bnn_model_config* cfg, int64_t n_systems, int64_t n_units);
+int bnn_multiswag_predict_host(const bnn_model_config* cfg, const float* h_x, int64_t n_systems,
+                               const float* d_w_avg, const float* d_w2_avg, const float* d_pre_D,
+                               int32_t n_models, int32_t K, int32_t samples_per_model, float scale,
+                               uint64_t seed, float* h_out, void* d_scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * VarModel._lossfnc (:547-577) + safe_log_erf (:323-335), forward and analytic backward:
+ * d_mu_sd [B,2], d_y [B,2] -> d_loss_per_system [B] (may be NULL), d_loss_sum [1] (may be
+ * NULL; accumulated deterministically), d_grad [B,2] = d(sum loss)/d(mu,sd) (may be NULL).
+ */
+int bnn_nll_fwd_bwd(const float* d_mu_sd, const float* d_y, int64_t B, float* d_loss_per_system,
+                    float* d_loss_sum, float* d_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * SWAGModel.training_step (:722-732) + backward + clip_grad_norm_ + torch.optim.SGD
+ * (:709-711; run_swag.py:61,74-79) for n_seeds independent models in one call.
+ * State per seed (device, caller-owned): theta [d], momentum buffer [d].
+ * d_x [B,T,F], d_y [B,2] shared by all seeds (d_batch_index [n_seeds,B] int32 gathers rows
+ * of d_x per seed when not NULL).  Noise: explicit d_eps_in [n_seeds,B,T,F], d_eps12
+ * [n_seeds,B,2L], d_eps_sum [n_seeds,B,2L], or all NULL: Philox keyed on (seed, step).
+ * d_metrics [n_seeds,8]: loss_no_reg, loss_with_reg, input_kl, summary_kl (each /B, as
+ * logged :731), grad_norm, clip_coef, non-finite flag, reserved.
+ */
+typedef struct bnn_train_hparams {
+    float lr, momentum, weight_decay, clip_norm; /* swa_lr, 0.9, hparams.weight_decay, 0.1*d */
+    float beta_in, beta_out;                     /* find_minima.py:50-51                     */
+    int32_t first_step;                          /* 1: momentum buffer is initialised (SGD)  */
+    int32_t apply_update;                        /* 0: gradients only (d_grad_out)           */
+} bnn_train_hparams;
+
+size_t bnn_train_workspace_bytes(const bnn_model_config* cfg, int64_t B, int32_t n_seeds);
+int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int32_t n_seeds,
+                   float* d_theta, float* d_momentum, const float* d_x, const float* d_y,
+                   const int32_t* d_batch_index, int64_t B, const float* d_eps_in,
+                   const float* d_eps12, const float* d_eps_sum, uint64_t seed, uint64_t step,
+                   float* d_grad_out, float* d_metrics, void* d_workspace, void* stream);
+
+/* lossfnc(x, y, noisy_val) (:579-583) without gradients: validation_step (:787-799).
+ * d_loss_sum [n_units]: sum over systems of _lossfnc for each unit's weights. */
+int bnn_eval_loss(const bnn_model_config* cfg, const float* d_x, const float* d_y, int64_t B,
+                  const float* d_theta_packed, int64_t n_units, const float* d_eps, uint64_t seed,
+                  float* d_out_mu_sd, float* d_loss_sum, void* d_workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * SWAGModel.aggregate_model (:763-785) for n_seeds models at once.
+ *   w_avg  <- (w_avg*n + w)/(n+1),  w2_avg <- (w2_avg*n + w*w)/(n+1)   (first call: w, w*w)
+ *   when the model has no deviation column yet, or current_epoch % c == 0 (:776-782):
+ *   append w as the newest column of pre_D[s] ([d,K] row-major, columns oldest -> newest,
+ *   d_n_cols[s] valid columns; the oldest is dropped beyond K).
+ * d_w [n_seeds,d] current flat weights; d_n_models / d_n_cols [n_seeds] int32, updated in place.
+ */
+int bnn_swag_collect(const float* d_w, int64_t d, int32_t n_seeds, int32_t K, float* d_w_avg,
+                     float* d_w2_avg, float* d_pre_D, int32_t* d_n_models, int32_t* d_n_cols,
+                     int32_t current_epoch, int32_t c, void* stream);
+
+/* Measured-FFMA-peak micro-kernel (roofline denominator check): runs `iters` dependent-free
+ * fma.rn.f32x2 (packed=1) or fma.rn.f32 (packed=0) per thread on every SM, returns via
+ * d_sink.  flops = 2 * grid*block*iters*16 ; time it with events around the call. */
+int bnn_ffma_peak(int32_t packed, int64_t iters, float* d_sink, int64_t* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNNCHAOS_H_ */

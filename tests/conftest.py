@@ -59,3 +59,21 @@ def swag_stats(seed):
         "hparams": json.loads(str(z["hparams"])),
         "swa_params": json.loads(str(z["swa_params"])),
     }
+
+
+def make_swag_model(seed, device):
+    """SWAGModel mirror with the v50 seed-`seed` statistics from tests/golden (no reference tree needed)."""
+    import torch
+
+    from bnn_chaos_model_b200 import spock_reg_model as S
+
+    st = swag_stats(seed)
+    m = S.SWAGModel(st["hparams"]).init_params(st["swa_params"]).to(device)
+    m.w_avg, m.w2_avg, m.pre_D = (torch.from_numpy(st[k]).to(device) for k in ("w_avg", "w2_avg", "pre_D"))
+    return m
+
+
+def rel_err(a, b):
+    import torch
+
+    return float(((a - b).abs() / b.abs().clamp_min(1e-30)).max())

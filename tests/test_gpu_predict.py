@@ -1,0 +1,240 @@
+"""GPU parity tests of the MultiSWAG posterior-predictive path (K1 sampler + K2 fused predict),
+all through the C ABI.  Tolerances: per-system mu / std within 1e-5 relative (fp32), theta within
+1e-6 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_swag_model, rel_err, swag_stats
+from bnn_chaos_model_b200 import _lib, synth
+from bnn_chaos_model_b200.multiswag import MultiSWAG, shard_range
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+SEEDS = (0, 3, 17)
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def cpu_stats(seed):
+    st = swag_stats(seed)
+    return tuple(torch.from_numpy(st[k]) for k in ("w_avg", "w2_avg", "pre_D"))
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_sampler_explicit_draws_vs_reference_theta(gold_predict, dev, seed):
+    ens = MultiSWAG([make_swag_model(seed, dev)], device=dev)
+    z1 = torch.from_numpy(gold_predict[f"z1_s{seed}"]).to(dev)
+    z2 = torch.from_numpy(gold_predict[f"z2_s{seed}"]).to(dev)
+    theta, thp = ens.sample_thetas(z1.shape[0], seed=0, scale=0.5, z1=z1, z2=z2)
+    ref = torch.from_numpy(gold_predict[f"theta_ref_s{seed}"])
+    # element-wise terms are computed with the reference's roundings; only the K=30 dot
+    # product of D z2 may differ in summation order
+    np.testing.assert_allclose(theta.cpu().numpy(), ref.numpy(), rtol=1e-6, atol=1e-7)
+    assert float((theta.cpu() == ref).float().mean()) > 0.5
+
+
+def test_pack_theta_layout(gold_predict, dev):
+    m = make_swag_model(0, dev)
+    cfg = m.config()
+    theta = torch.from_numpy(gold_predict["theta_ref_s0"]).to(dev)
+    thp = m._packed(cfg, theta).cpu()
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    live = [c for c in range(41) if c not in spec.zero_cols]
+    for u in range(theta.shape[0]):
+        p = R.unflatten(spec, theta[u].cpu())
+        W0 = p["feature_nn.0.weight"]
+        o = 0
+        W0p = thp[u, o:o + len(live) * 48].reshape(len(live), 4, 12); o += len(live) * 48
+        assert torch.equal(W0p[:, :, :10].reshape(len(live), 40), W0[:, live].T)
+        assert float(W0p[:, :, 10:].abs().max()) == 0.0
+        b0p = thp[u, o:o + 48].reshape(4, 12); o += 48
+        assert torch.equal(b0p[:, :10].reshape(40), p["feature_nn.0.bias"])
+        W1p = thp[u, o:o + 40 * 48].reshape(40, 4, 12); o += 40 * 48 + 48
+        assert torch.equal(W1p[:, :, :10].reshape(40, 40), p["feature_nn.2.weight"].T)
+        W2p = thp[u, o:o + 40 * 48].reshape(40, 4, 12); o += 40 * 48
+        W2 = p["feature_nn.4.weight"]  # [20,40]
+        assert torch.equal(W2p[:, :, 0:10:2].reshape(40, 20), W2.T)
+        assert torch.equal(W2p[:, :, 1:10:2].reshape(40, 20), W2.T)
+    assert thp.shape[1] == _lib.load().bnn_packed_param_count(cfg)
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_predict_vs_reference_golden(gold_predict, dev, seed):
+    """theta, eps and the 256 in-distribution systems of the reference-generated golden file."""
+    m = make_swag_model(seed, dev)
+    cfg = m.config()
+    x = torch.from_numpy(synth.make_systems(256, seed=123)).to(dev)
+    theta = torch.from_numpy(gold_predict[f"theta_ref_s{seed}"]).to(dev)
+    eps = torch.from_numpy(gold_predict[f"eps_s{seed}"]).to(dev).contiguous()
+    out, _ = m._predict(x, m._packed(cfg, theta), eps, cfg=cfg)
+    ref = torch.from_numpy(gold_predict[f"out_ref_s{seed}"])
+    assert rel_err(out.cpu(), ref) < TOL
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_forward_swag_fast_dropin_same_torch_draws(dev, seed):
+    """Same torch CUDA generator state -> same draws as the reference's call order (randn(1,d),
+    randn(K,1), randn_like x2) -> same prediction as the oracle fed those draws."""
+    m = make_swag_model(seed, dev)
+    spec = R.ModelSpec.from_hparams(swag_stats(seed)["hparams"])
+    B = 77  # ragged: not a multiple of the 8-system tile
+    x = torch.from_numpy(synth.make_systems(B, seed=5))
+    torch.manual_seed(100 + seed)
+    out = m.forward_swag_fast(x.to(dev), scale=0.5).cpu()
+    torch.manual_seed(100 + seed)
+    z1 = torch.randn((1, spec.d), device=dev).cpu()
+    z2 = torch.randn((30, 1), device=dev).cpu()
+    e1 = torch.randn((B, 20), device=dev).cpu()
+    e2 = torch.randn((B, 20), device=dev).cpu()
+    theta = R.sample_weights(*cpu_stats(seed), 30, 0.5, z1, z2)
+    np.testing.assert_allclose(m.flatten().cpu().numpy(), theta.numpy(), rtol=1e-6, atol=1e-7)  # weights stay loaded
+    ref = R.forward_swag_fast(spec, theta, x, e1, e2)
+    assert out.shape == (B, 2)
+    assert rel_err(out, ref) < TOL
+
+
+def test_forward_swag_records_summary_kl(dev):
+    m = make_swag_model(0, dev)
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    x = torch.from_numpy(synth.make_systems(40, seed=6))
+    torch.manual_seed(1)
+    out = m.forward_swag(x.to(dev), scale=0.5).cpu()
+    theta = m.flatten().cpu()
+    torch.manual_seed(1)
+    torch.randn((1, spec.d), device=dev); torch.randn((30, 1), device=dev)
+    e1 = torch.randn((40, 20), device=dev).cpu(); e2 = torch.randn((40, 20), device=dev).cpu()
+    ref, skl = R.forward(spec, theta, x, False, None, e1, e2, None)
+    assert rel_err(out, ref) < TOL
+    assert float(m.summary_kl()) == pytest.approx(float(skl.sum()), rel=1e-5)
+
+
+def test_forward_noisy_and_split_api(dev):
+    """VarModel.forward(noisy_val=True) draw order: eps_in, eps1, eps2, eps_sum; and the split
+    compute_summary_stats / predict_instability pair."""
+    m = make_swag_model(3, dev)
+    m.load(m.w_avg.clone())
+    spec = R.ModelSpec.from_hparams(swag_stats(3)["hparams"])
+    B = 24
+    x = torch.from_numpy(synth.make_systems(B, seed=8))
+    theta = m.flatten().cpu()
+    torch.manual_seed(9)
+    out = m.forward(x.to(dev), noisy_val=True).cpu()
+    skl = float(m.summary_kl())
+    torch.manual_seed(9)
+    eps_in = torch.randn_like(x.to(dev)).cpu()
+    e1 = torch.randn((B, 20), device=dev).cpu(); e2 = torch.randn((B, 20), device=dev).cpu()
+    es = torch.randn((B, 40), device=dev).cpu()
+    ref, skl_ref = R.forward(spec, theta, x, True, eps_in, e1, e2, es)
+    assert rel_err(out, ref) < TOL
+    assert skl == pytest.approx(float(skl_ref.sum()), rel=1e-5)
+    # split API: summary stats of the un-masked input, then the head
+    torch.manual_seed(10)
+    s = m.compute_summary_stats(x.to(dev))
+    torch.manual_seed(10)
+    e1 = torch.randn((B, 20), device=dev).cpu(); e2 = torch.randn((B, 20), device=dev).cpu()
+    p = R.unflatten(spec, theta)
+    s_ref = R.compute_summary_stats(spec, p, x, e1, e2)
+    np.testing.assert_allclose(s.cpu().numpy(), s_ref.numpy(), rtol=2e-5, atol=2e-6)
+    mu, sd = m.predict_instability(s)
+    mu_ref, sd_ref = R.predict_instability(spec, p, s.cpu())
+    assert mu.shape == (B, 1) and rel_err(mu.cpu(), mu_ref) < TOL and rel_err(sd.cpu(), sd_ref) < TOL
+
+
+def test_batched_philox_vs_oracle(dev):
+    """In-kernel Philox draws (sampler z1/z2, predict eps) against the oracle's restatement."""
+    models = [make_swag_model(s, dev) for s in SEEDS]
+    ens = MultiSWAG(models, device=dev)
+    S_, N, seed = 3, 41, 2024
+    x = torch.from_numpy(synth.make_systems(N, seed=12))
+    theta, thp = ens.sample_thetas(S_, seed)
+    got = ens.predict(x.to(dev), S_, seed=seed, thp=thp).cpu()
+    assert got.shape == (len(SEEDS) * S_, N, 2)
+    units = np.arange(len(SEEDS) * S_)
+    z1 = torch.from_numpy(R.draw_z1(seed, units, 7583)); z2 = torch.from_numpy(R.draw_z2(seed, units, 30))
+    eps = torch.from_numpy(R.draw_eps(seed, units, np.arange(N), 40))
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    for u in units:
+        th = R.sample_weights(*cpu_stats(SEEDS[u // S_]), 30, 0.5, z1[u], z2[u])
+        np.testing.assert_allclose(theta[u].cpu().numpy(), th.numpy(), rtol=2e-5, atol=2e-6)
+        ref = R.forward_swag_fast(spec, theta[u].cpu(), x, eps[u, :, :20], eps[u, :, 20:])
+        assert rel_err(got[u], ref) < TOL
+
+
+def test_sharded_equals_single_bitwise(dev):
+    """Counter-based draws keyed on global indices: evaluating shards with system_offset gives the
+    single-launch result bit for bit; system-major output is the transpose."""
+    ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(17, dev)], device=dev)
+    N, S_ = 61, 5
+    x = torch.from_numpy(synth.make_systems(N, seed=13)).to(dev)
+    full = ens.predict(x, S_, seed=4)
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(N, r, world)
+            parts.append(ens.predict(x[lo:hi], S_, seed=4, system_offset=lo, system_major=True))
+        got = torch.cat(parts, 0)
+        assert torch.equal(got, full.permute(1, 0, 2))
+
+
+def test_edge_cases(dev):
+    m = make_swag_model(0, dev)
+    m.load(m.w_avg.clone())
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    theta = m.flatten().cpu()
+    # (a) one system, (b) NaN / Inf in a zeroed column poisons that system only, (c) T != 100
+    for T in (100, 40, 8, 128):
+        B = 5
+        x = torch.from_numpy(synth.make_systems(B, seed=20 + T, t=T))
+        torch.manual_seed(T)
+        out = m.forward(x.to(dev), noisy_val=False).cpu()
+        torch.manual_seed(T)
+        e1 = torch.randn((B, 20), device=dev).cpu(); e2 = torch.randn((B, 20), device=dev).cpu()
+        ref, _ = R.forward(spec, theta, x, False, None, e1, e2, None)
+        assert rel_err(out, ref) < TOL, T
+    x = torch.from_numpy(synth.make_systems(3, seed=30))
+    x[1, 17, 3] = float("nan")
+    x[2, 5, 38] = float("inf")
+    out = m.forward(x.to(dev), noisy_val=False).cpu()
+    assert torch.isfinite(out[0]).all() and torch.isnan(out[1]).all() and torch.isnan(out[2]).all()
+    out1 = m.forward(x[:1].to(dev), noisy_val=False)
+    assert out1.shape == (1, 2)
+    with pytest.raises(ValueError):
+        m.forward(torch.zeros(2, 100, 40, device=dev), noisy_val=False)
+    # fewer than K recorded deviations: same failure mode as the reference's D @ z_2 (:835)
+    m.pre_D = m.pre_D[:, :10]
+    with pytest.raises(RuntimeError):
+        m.sample_weights(0.5)
+
+
+def test_full_size_properties(dev):
+    """BASELINE config-2-sized run (10k systems x 1000 samples would take the oracle hours):
+    check size-independent properties at a large size + spot checks against the oracle."""
+    ens = MultiSWAG([make_swag_model(0, dev)], device=dev)
+    N, S_ = 10000, 64
+    xh = synth.make_systems(N, seed=0)
+    x = torch.from_numpy(xh).to(dev)
+    theta, thp = ens.sample_thetas(S_, seed=77)
+    out = ens.predict(x, S_, seed=77, thp=thp)
+    assert out.shape == (S_, N, 2) and bool(torch.isfinite(out).all())
+    mu, sd = out[..., 0], out[..., 1]
+    assert float(mu.min()) >= 4.0 and float(mu.max()) <= 12.0 and float(sd.min()) >= 0.5 and float(sd.max()) <= 6.0
+    # permutation equivariance over systems with explicit eps (no index-keyed draws)
+    eps = torch.randn((S_, N, 40), device=dev)
+    m = ens.models[0]
+    cfg = m.config()
+    a, _ = m._predict(x, thp, eps, cfg=cfg)
+    perm = torch.randperm(N, device=dev)
+    b, _ = m._predict(x[perm].contiguous(), thp, eps[:, perm].contiguous(), cfg=cfg)
+    assert torch.equal(a[:, perm], b)
+    # spot check 3 units x 64 systems against the oracle
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    idx = torch.arange(0, N, N // 64)[:64]
+    for u in (0, 31, 63):
+        ref = R.forward_swag_fast(spec, theta[u].cpu(), torch.from_numpy(xh)[idx], eps[u, idx, :20].cpu(),
+                                  eps[u, idx, 20:].cpu())
+        assert rel_err(a[u, idx].cpu(), ref) < TOL

@@ -1,0 +1,170 @@
+"""CPU: host-side logic, the C-ABI surface, Philox known answers, and the N>1 gather (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, swag_stats
+from oracle import restatement as R
+
+HEADER = os.path.join(ROOT, "include", "bnnchaos.h")
+LIB = os.path.join(ROOT, "bnn_chaos_model_b200", "libbnnchaos.so")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(bnn_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+
+        g.build()
+    lib = ctypes.CDLL(LIB)
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/bnnchaos.h but not exported"
+    from bnn_chaos_model_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == syms  # the ctypes table covers the whole header
+    assert _lib.load().bnn_abi_version() == 1
+
+
+def test_layout_queries_and_config_errors():
+    from bnn_chaos_model_b200 import _lib
+
+    lib = _lib.load()
+    cfg = _lib.ModelConfig(41, 40, 20, 1, 1, 100, 0x1C0000000FE, 4.0, 12.0, 0.5, 6.0)
+    assert lib.bnn_param_count(cfg) == 7583
+    P = lib.bnn_packed_param_count(cfg)
+    assert P > 0 and P % 4 == 0
+    bad = _lib.ModelConfig(41, 64, 20, 1, 1, 100, 0, 4.0, 12.0, 0.5, 6.0)
+    assert lib.bnn_param_count(bad) == -2  # BNN_E_CONFIG
+    assert b"hidden" in lib.bnn_last_error_string()
+
+
+def test_no_cpu_fallback():
+    from bnn_chaos_model_b200 import spock_reg_model as S
+    from bnn_chaos_model_b200._lib import BnnChaosError
+
+    st = swag_stats(0)
+    m = S.SWAGModel(st["hparams"]).init_params(st["swa_params"])
+    m.w_avg, m.w2_avg, m.pre_D = (torch.from_numpy(st[k]) for k in ("w_avg", "w2_avg", "pre_D"))
+    with pytest.raises(BnnChaosError):
+        m.forward_swag_fast(torch.zeros(2, 100, 41))
+    with pytest.raises(BnnChaosError):
+        m.forward(torch.zeros(2, 100, 41), noisy_val=False)
+
+
+def test_mirror_matches_reference_surface(tmp_path):
+    from bnn_chaos_model_b200 import spock_reg_model as S
+
+    st = swag_stats(3)
+    m = S.SWAGModel(st["hparams"]).init_params(st["swa_params"])
+    spec = R.ModelSpec.from_hparams(st["hparams"])
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == spec.layout()
+    assert m.flatten().shape == (7583,)
+    assert tuple(m.zero_columns()) == spec.zero_cols
+    assert (m.K, m.c, m.lowest) == (30, 5, 0.5)
+    for name in ("forward", "compute_summary_stats", "predict_instability", "_lossfnc", "lossfnc", "input_kl",
+                 "summary_kl", "init_params", "flatten", "load", "aggregate_model", "sample_weights", "forward_swag",
+                 "forward_swag_fast"):
+        assert callable(getattr(m, name)), name
+    # load() is the inverse of flatten()
+    v = torch.randn(7583)
+    m.load(v)
+    assert torch.equal(m.flatten(), v)
+    # save_swag / load_swag round trip with the reference's dict keys
+    m.w_avg, m.w2_avg, m.pre_D = (torch.from_numpy(st[k]) for k in ("w_avg", "w2_avg", "pre_D"))
+    path = str(tmp_path / "x_v50_0_output.pkl")
+    S.save_swag(m, path)
+    raw = torch.load(path, weights_only=False)
+    assert sorted(raw) == ["hparams", "pre_D", "swa_params", "w2_avg", "w_avg"]
+    m2 = S.load_swag(path)
+    assert torch.equal(m2.pre_D, m.pre_D) and m2.K == 30 and m2.ssX is not None
+    assert abs(m2.ssX.mean_[0] - 4954.58585) < 1e-4
+    assert float(m.input_kl()) == pytest.approx(float(R.input_kl({"input_noise_logvar": m.input_noise_logvar})))
+
+
+def test_unsafe_pickle_rejected(tmp_path):
+    import pickle
+
+    from bnn_chaos_model_b200 import spock_reg_model as S
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+
+    path = str(tmp_path / "evil.pkl")
+    torch.save({"hparams": Evil()}, path)
+    with pytest.raises(pickle.UnpicklingError):
+        S.load_swag(path)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in kat:
+        got = R.philox4x32_10(np.array(ctr, np.uint32), np.array(key, np.uint32))
+        assert tuple(int(v) for v in got) == want
+    z = R.draw_z1(1234, np.arange(64), 7583)
+    assert z.shape == (64, 7583) and abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1) < 0.01
+    e = R.draw_eps(5, np.arange(3), np.arange(1000), 40)
+    assert e.shape == (3, 1000, 40) and np.isfinite(e).all()
+
+
+def test_shard_range_partitions():
+    from bnn_chaos_model_b200.multiswag import shard_range
+
+    for n in (0, 1, 7, 8, 100000, 12345):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from bnn_chaos_model_b200.multiswag import gather_system_shards, shard_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+for n_total in (10, 11):
+    lo, hi = shard_range(n_total, rank, 2)
+    full_ref = torch.arange(n_total * 3 * 2, dtype=torch.float32).reshape(n_total, 3, 2)
+    full = gather_system_shards(full_ref[lo:hi].clone(), n_total)
+    assert torch.equal(full, full_ref), (rank, n_total)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_system_shards_gloo_world2(tmp_path):
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
