@@ -4,7 +4,11 @@
 // loop body SWAGModel.forward_swag_fast (/root/reference/spock_reg_model.py:878-908; callers
 // figures/main_figures.py:127-156, figures/spock/regression.py:74-92,
 // figures/multiswag_5_planet.py:295-298).
+#include <stdlib.h>
+#include <string.h>
+
 #include "predict_device.cuh"
+#include "pipeline.cuh"
 
 namespace bnn {
 
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(NW * 32, 1) predict_v1_kernel(const PredictPar
             const float* eps_u = prm.eps ? prm.eps + u * prm.N * S2 : nullptr;
             const float* eps_sum_u = prm.eps_sum ? prm.eps_sum + u * prm.N * S2 : nullptr;
             float* summary_u = prm.summary ? prm.summary + u * prm.N * S2 : nullptr;
-            tail_unit(rec_u, g, thp, pl, eps_u, eps_sum_u, summary_u, prm.seed, (uint32_t)(prm.unit_offset + u),
+            tail_unit<true>(rec_u, g, thp, pl, eps_u, eps_sum_u, summary_u, prm.seed, (uint32_t)(prm.unit_offset + u),
                       prm.system_offset + n0, n0, n_valid, prm.hc, scratch, prm.out + u * prm.out_unit_stride,
                       prm.out_sys_stride);
         }
@@ -95,6 +99,156 @@ static int launch_v1(const PredictParams& prm, int T, cudaStream_t st) {
                 (long long)tiles, (long long)chunks);
     dim3 grid((unsigned)tiles, (unsigned)chunks);
     predict_v1_kernel<NW><<<grid, NW * 32, smem, st>>>(prm, T);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// v2: warp-specialised persistent kernel.  grid = #SMs; every CTA walks a static list of
+// work items (tile of 8 systems, contiguous range of units).  Per item:
+//   producer warp : streams each unit's packed weights (38 KB) into a 2-slot shared-memory
+//                   ring with cp.async.bulk (TMA 1-D) + mbarrier complete_tx
+//   NC consumers  : fetch (unit, 32-row task) pairs from a shared counter, run feature_nn on
+//                   FFMA2, write pooled (mean, M2) records, arrive on done[slot]
+//   tail warp     : when the 25 tasks of a unit are done: merge records, sample summary
+//                   statistics, regress_nn from the shared-memory copy of the head weights,
+//                   store (mu, std), release the slot to the producer
+// No CTA-wide barrier inside an item; x stays resident in shared memory for all units.
+// ---------------------------------------------------------------------------------------
+struct V2Smem {
+    uint64_t full[2], done[2], tail_done[2];
+    int task_ctr;
+    int pad;
+};
+
+template <int NC>
+__global__ void __launch_bounds__((NC + 2) * 32, 1)
+predict_v2_kernel(const PredictParams prm, const int T, const int n_tiles, const int chunks) {
+    extern __shared__ __align__(128) float smem_v2[];
+    float* smem = smem_v2;
+    const TileGeom g(T);
+    const PackedLayout pl(prm.kin, prm.F);
+    const int P4 = pl.P;  // floats per unit (multiple of 4)
+    float* xT = smem;
+    float* ring = xT + prm.kin * g.RP;
+    float* hq = ring + 2 * P4;
+    float* rec = hq + NC * HQ_FLOATS;
+    float* scratch = rec + 2 * rec_floats(g);
+    V2Smem* sh = reinterpret_cast<V2Smem*>(scratch + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = n_tiles * chunks;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / chunks, chunk = item % chunks;
+        const int64_t n0 = (int64_t)tile * SYS_TILE;
+        const int n_valid = (int)min((int64_t)SYS_TILE, prm.N - n0);
+        // units of this item: even split of [0,U) into `chunks` ranges
+        const int64_t u_begin = prm.U * chunk / chunks, u_end = prm.U * (chunk + 1) / chunks;
+        const int n_units = (int)(u_end - u_begin);
+
+        __syncthreads();  // previous item fully drained by every role
+        if (threadIdx.x == 0) {
+            if (item != (int)blockIdx.x) {
+                for (int s = 0; s < 2; ++s) { mbar_inval(&sh->full[s]); mbar_inval(&sh->done[s]); mbar_inval(&sh->tail_done[s]); }
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&sh->full[s], 1);
+                mbar_init(&sh->done[s], g.n_tasks);
+                mbar_init(&sh->tail_done[s], 1);
+            }
+            sh->task_ctr = 0;
+            mbar_init_fence();
+        }
+        // hq doubles as the poison scratch of the tile load (NC*640 floats >= RP ints for NC >= 2)
+        load_x_tile(prm.X, n0, n_valid, prm.F, g, prm.kin, prm.cm, xT, reinterpret_cast<int*>(hq));
+        __syncthreads();
+
+        if (warp == NC) {
+            // ---------------- producer ----------------
+            if (lane == 0) {
+                for (int i = 0; i < n_units; ++i) {
+                    const int s = i & 1;
+                    if (i >= 2) mbar_wait(&sh->tail_done[s], ((i >> 1) - 1) & 1);
+                    mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(P4 * sizeof(float)));
+                    bulk_g2s(ring + s * P4, prm.thp + (u_begin + i) * P4, (uint32_t)(P4 * sizeof(float)), &sh->full[s]);
+                }
+            }
+        } else if (warp == NC + 1) {
+            // ---------------- tail ----------------
+            for (int i = 0; i < n_units; ++i) {
+                const int s = i & 1;
+                const uint32_t par = (i >> 1) & 1;
+                mbar_wait(&sh->full[s], par);  // visibility of the bulk-copied head weights
+                mbar_wait(&sh->done[s], par);  // all tasks of the unit have written their records
+                const int64_t u = u_begin + i;
+                const float* eps_u = prm.eps ? prm.eps + u * prm.N * S2 : nullptr;
+                const float* eps_sum_u = prm.eps_sum ? prm.eps_sum + u * prm.N * S2 : nullptr;
+                float* summary_u = prm.summary ? prm.summary + u * prm.N * S2 : nullptr;
+                tail_unit<false>(rec + s * rec_floats(g), g, ring + s * P4, pl, eps_u, eps_sum_u, summary_u, prm.seed,
+                                 (uint32_t)(prm.unit_offset + u), prm.system_offset + n0, n0, n_valid, prm.hc,
+                                 scratch, prm.out + u * prm.out_unit_stride, prm.out_sys_stride);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh->tail_done[s]);
+            }
+        } else {
+            // ---------------- consumers ----------------
+            float* my_hq = hq + warp * HQ_FLOATS;
+            const int total = n_units * g.n_tasks;
+            while (true) {
+                int id = 0;
+                if (lane == 0) id = atomicAdd(&sh->task_ctr, 1);
+                id = __shfl_sync(0xffffffffu, id, 0);
+                if (id >= total) break;
+                const int i = id / g.n_tasks, t = id - i * g.n_tasks;
+                const int s = i & 1;
+                mbar_wait(&sh->full[s], (i >> 1) & 1);
+                mlp_task_v2(xT, g, prm.kin, ring + s * P4, pl, my_hq, t, rec + s * rec_floats(g));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh->done[s]);
+            }
+        }
+    }
+}
+
+static size_t v2_smem_bytes(int kin, int F, int T, int NC) {
+    TileGeom g(T);
+    PackedLayout pl(kin, F);
+    size_t fl = (size_t)kin * g.RP + 2 * (size_t)pl.P + (size_t)NC * HQ_FLOATS + 2 * rec_floats(g) + 1024;
+    return fl * sizeof(float) + sizeof(V2Smem);
+}
+
+template <int NC>
+static int launch_v2(const PredictParams& prm, int T, cudaStream_t st) {
+    const size_t smem = v2_smem_bytes(prm.kin, prm.F, T, NC);
+    static bool attr_done = false;
+    static int n_sms = 0;
+    if (!attr_done) {
+        BNN_CUDA(cudaFuncSetAttribute(predict_v2_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int dev = 0;
+        BNN_CUDA(cudaGetDevice(&dev));
+        BNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_done = true;
+    }
+    const int64_t tiles = (prm.N + SYS_TILE - 1) / SYS_TILE;
+    BNN_REQUIRE(tiles < (1ll << 24), BNN_E_ARG, "too many system tiles for one launch (%lld)", (long long)tiles);
+    // Split each tile's units into `chunks` items so that the item count is close to a multiple of the
+    // SM count (static round-robin over persistent CTAs) while items stay long enough to amortise the
+    // x-tile load and the pipeline fill (>= 32 units per item when U allows).
+    int64_t max_chunks = prm.U >= 64 ? prm.U / 32 : 1;
+    if (max_chunks > 64) max_chunks = 64;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int c = 1; c <= max_chunks; ++c) {
+        const int64_t items = tiles * c;
+        const int64_t rounds = (items + n_sms - 1) / n_sms;
+        const double eff = (double)items / (double)(rounds * n_sms);
+        if (eff > best_eff + 0.005) { best_eff = eff; best = c; }
+    }
+    const int64_t items = tiles * best;
+    const int grid = (int)(items < n_sms ? items : n_sms);
+    predict_v2_kernel<NC><<<grid, (NC + 2) * 32, smem, st>>>(prm, T, (int)tiles, best);
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }
@@ -145,7 +299,18 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     if (tiles < 2 * 148) chunks = (2 * 148 + tiles - 1) / tiles;
     if (chunks > n_units) chunks = n_units;
     prm.units_per_cta = (int)((n_units + chunks - 1) / chunks);
-    return launch_v1<8>(prm, cfg->n_times, (cudaStream_t)stream);
+    // variant selection: v2 (warp-specialised, TMA ring) when its tile fits in shared memory, else v1.
+    // BNN_PREDICT_VARIANT=v1|v2c8|v2c12|v2c16 forces one (benchmarks / cross-checks).
+    const char* force = getenv("BNN_PREDICT_VARIANT");
+    const int T = cfg->n_times;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto fits = [&](int nc) { return v2_smem_bytes(prm.kin, prm.F, T, nc) <= 227 * 1024; };
+    if (force && !strcmp(force, "v1")) return launch_v1<8>(prm, T, st);
+    if (force && !strcmp(force, "v2c8") && fits(8)) return launch_v2<8>(prm, T, st);
+    if (force && !strcmp(force, "v2c16") && fits(16)) return launch_v2<16>(prm, T, st);
+    if (fits(12)) return launch_v2<12>(prm, T, st);
+    if (fits(8)) return launch_v2<8>(prm, T, st);
+    return launch_v1<8>(prm, T, st);
 }
 
 }  // extern "C"
@@ -179,9 +344,9 @@ __global__ void __launch_bounds__(32) head_only_kernel(const float* __restrict__
         sA[s * 41 + j] = (s < n_valid) ? summary[(n0 + s) * S2 + j] : 0.f;
     }
     __syncwarp();
-    head_layer(sA, thp + pl.V0p, thp + pl.c0p, S2, p, q, sB);
+    head_layer<true>(sA, thp + pl.V0p, thp + pl.c0p, S2, p, q, sB);
     __syncwarp();
-    head_layer(sB, thp + pl.V1p, thp + pl.c1p, H, p, q, sA);
+    head_layer<true>(sB, thp + pl.V1p, thp + pl.c1p, H, p, q, sA);
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
 #pragma unroll

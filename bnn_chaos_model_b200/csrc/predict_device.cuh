@@ -77,6 +77,13 @@ __device__ __forceinline__ void dense40(const float* __restrict__ src, int src_p
     }
 }
 
+// torch.relu propagates NaN; CUDA's fmaxf returns the non-NaN operand, so use max.NaN.f32.
+__device__ __forceinline__ float relu_nan(float x) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ReLU + transposed store of a lane's 4x10 block into the warp buffer hT[col][32].
 __device__ __forceinline__ void relu_store(const u64 (&acc)[4][5], float* __restrict__ hT, int p, int q) {
 #pragma unroll
@@ -84,8 +91,8 @@ __device__ __forceinline__ void relu_store(const u64 (&acc)[4][5], float* __rest
         float lo[4], hi[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) unpack2(acc[r][jp], lo[r], hi[r]);
-        float4 v0 = make_float4(fmaxf(lo[0], 0.f), fmaxf(lo[1], 0.f), fmaxf(lo[2], 0.f), fmaxf(lo[3], 0.f));
-        float4 v1 = make_float4(fmaxf(hi[0], 0.f), fmaxf(hi[1], 0.f), fmaxf(hi[2], 0.f), fmaxf(hi[3], 0.f));
+        float4 v0 = make_float4(relu_nan(lo[0]), relu_nan(lo[1]), relu_nan(lo[2]), relu_nan(lo[3]));
+        float4 v1 = make_float4(relu_nan(hi[0]), relu_nan(hi[1]), relu_nan(hi[2]), relu_nan(hi[3]));
         const int col = q * 10 + 2 * jp;
         *reinterpret_cast<float4*>(hT + col * TASK_ROWS + p * 4) = v0;
         *reinterpret_cast<float4*>(hT + (col + 1) * TASK_ROWS + p * 4) = v1;
@@ -184,6 +191,156 @@ __device__ __forceinline__ void mlp_task(const float* __restrict__ xT, const Til
 }
 
 // ---------------------------------------------------------------------------------------
+// v2 task: same arithmetic as mlp_task, but the activations of a layer are handed to the next
+// one a QUARTER at a time (the 10 columns owned by lane group j), through two ping-pong
+// buffers hq[2][10][32] (2.5 KB per warp instead of 5 KB), so that 12+ consumer warps fit
+// next to the resident x tile.  The previous layer's accumulators stay in registers while the
+// next layer accumulates.
+// ---------------------------------------------------------------------------------------
+constexpr int HQ_FLOATS = 2 * 10 * TASK_ROWS;  // per consumer warp
+
+__device__ __forceinline__ void store_quarter(const u64 (&acc)[4][5], float* __restrict__ hq, int p) {
+#pragma unroll
+    for (int jp = 0; jp < 5; ++jp) {
+        float lo[4], hi[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) unpack2(acc[r][jp], lo[r], hi[r]);
+        *reinterpret_cast<float4*>(hq + (2 * jp) * TASK_ROWS + p * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(hq + (2 * jp + 1) * TASK_ROWS + p * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    }
+}
+
+__device__ __forceinline__ void relu_inplace(u64 (&acc)[4][5]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int jp = 0; jp < 5; ++jp) {
+            float lo, hi;
+            unpack2(acc[r][jp], lo, hi);
+            acc[r][jp] = pack2(relu_nan(lo), relu_nan(hi));
+        }
+}
+
+__device__ __forceinline__ void mlp_task_v2(const float* __restrict__ xT, const TileGeom& g, int kin,
+                                            const float* __restrict__ wsm, const PackedLayout& pl,
+                                            float* __restrict__ hq, int t, float* __restrict__ rec) {
+    const int lane = threadIdx.x & 31;
+    const int p = lane >> 2, q = lane & 3;
+    int sys, r_idx, quad;
+    const bool full = t < SYS_TILE * g.QF;
+    if (full) {
+        sys = t / g.QF;
+        r_idx = t % g.QF;
+        quad = r_idx * 8 + p;
+    } else {
+        sys = p;
+        r_idx = g.QF + (t - SYS_TILE * g.QF);
+        quad = g.QF * 8 + (t - SYS_TILE * g.QF);
+    }
+    const int roff = sys * g.T + quad * 4;
+
+    u64 a1[4][5], a2[4][5];
+    dense40(xT, g.RP, roff, kin, wsm + pl.W0p, wsm + pl.b0p, q, a1);
+    relu_inplace(a1);
+
+    // layer 2: a2 = b1 + h1 W1^T, h1 streamed through hq one lane group at a time
+    {
+        const float* bq = wsm + pl.b1p + q * GC;
+#pragma unroll
+        for (int jp = 0; jp < 5; ++jp) {
+            const u64 b = *reinterpret_cast<const u64*>(bq + 2 * jp);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a2[r][jp] = b;
+        }
+        const float* wq = wsm + pl.W1p + q * GC;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            float* hb = hq + (j & 1) * (10 * TASK_ROWS);
+            if (q == j) store_quarter(a1, hb, p);
+            __syncwarp();
+            const float* xp = hb + p * 4;
+            const float* wp = wq + (j * 10) * HP;
+#pragma unroll
+            for (int kk = 0; kk < 10; ++kk) {
+                const float4 xv = *reinterpret_cast<const float4*>(xp + kk * TASK_ROWS);
+                const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(wp + kk * HP);
+                const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(wp + kk * HP + 4);
+                const u64 w4 = *reinterpret_cast<const u64*>(wp + kk * HP + 8);
+                const u64 wv[5] = {w01.x, w01.y, w23.x, w23.y, w4};
+                const u64 xd[4] = {pack2(xv.x, xv.x), pack2(xv.y, xv.y), pack2(xv.z, xv.z), pack2(xv.w, xv.w)};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int jp = 0; jp < 5; ++jp) a2[r][jp] = fma2(xd[r], wv[jp], a2[r][jp]);
+            }
+        }
+    }
+    relu_inplace(a2);
+
+    // layer 3: 40 -> 20, row-pair accumulators, duplicated W2p
+    u64 a3[5][2];
+    {
+        const float* bq = wsm + pl.b2p + q * GC;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const u64 b = *reinterpret_cast<const u64*>(bq + 2 * i);
+            a3[i][0] = b;
+            a3[i][1] = b;
+        }
+        const float* wq = wsm + pl.W2p + q * GC;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            float* hb = hq + (j & 1) * (10 * TASK_ROWS);
+            // ping-pong: buffer (j&1) was last read in phase j-2, and every lane passed the
+            // __syncwarp of phase j-1 since; for j<2 the layer-2 reads are covered the same way
+            if (q == j) store_quarter(a2, hb, p);
+            __syncwarp();
+            const float* xp = hb + p * 4;
+            const float* wp = wq + (j * 10) * HP;
+#pragma unroll
+            for (int kk = 0; kk < 10; ++kk) {
+                const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(xp + kk * TASK_ROWS);
+                const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(wp + kk * HP);
+                const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(wp + kk * HP + 4);
+                const u64 w4 = *reinterpret_cast<const u64*>(wp + kk * HP + 8);
+                const u64 wv[5] = {w01.x, w01.y, w23.x, w23.y, w4};
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    a3[i][0] = fma2(xv.x, wv[i], a3[i][0]);
+                    a3[i][1] = fma2(xv.y, wv[i], a3[i][1]);
+                }
+            }
+        }
+    }
+    __syncwarp();  // all reads of hq done before this warp's next task writes it
+
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        float f0, f1, f2, f3;
+        unpack2(a3[i][0], f0, f1);
+        unpack2(a3[i][1], f2, f3);
+        float mean = ((f0 + f1) + (f2 + f3)) * 0.25f;
+        float d0 = f0 - mean, d1 = f1 - mean, d2 = f2 - mean, d3 = f3 - mean;
+        float m2 = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        if (full) {
+#pragma unroll
+            for (int lvl = 0; lvl < 3; ++lvl) {
+                const float om = __shfl_xor_sync(0xffffffffu, mean, 4 << lvl);
+                const float o2 = __shfl_xor_sync(0xffffffffu, m2, 4 << lvl);
+                const float delta = om - mean;
+                m2 = (m2 + o2) + delta * delta * (float)(2 << lvl);
+                mean = 0.5f * (mean + om);
+            }
+        }
+        if (!full || p == 0) {
+            float* rp = rec + ((sys * g.n_rec + r_idx) * L + (q * 5 + i)) * 2;
+            rp[0] = mean;
+            rp[1] = m2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Tail of one unit for the tile's 8 systems, executed by ONE warp: merge records, sampled
 // summary statistics (:422-432), regress_nn (:437-438), soft_clamp (:440-441).
 //   lane = p*4+q: p = system, q = group of 5 latent / 10 hidden columns.
@@ -202,20 +359,37 @@ __device__ __forceinline__ float soft_clamp_dev(float x, float lo, float hi) {
     return __fadd_rn(__fmul_rn(__fmul_rn(0.5f, __fadd_rn(tanhf(x), 1.0f)), __fsub_rn(hi, lo)), lo);
 }
 
+template <bool GLOBAL_W>
+__device__ __forceinline__ float4 ldw4(const float* p) {
+    if (GLOBAL_W) return __ldg(reinterpret_cast<const float4*>(p));
+    return *reinterpret_cast<const float4*>(p);
+}
+template <bool GLOBAL_W>
+__device__ __forceinline__ float2 ldw2(const float* p) {
+    if (GLOBAL_W) return __ldg(reinterpret_cast<const float2*>(p));
+    return *reinterpret_cast<const float2*>(p);
+}
+template <bool GLOBAL_W>
+__device__ __forceinline__ float ldw1(const float* p) {
+    if (GLOBAL_W) return __ldg(p);
+    return *p;
+}
+
+template <bool GLOBAL_W>
 __device__ __forceinline__ void head_layer(const float* __restrict__ sin_, const float* __restrict__ wg,
                                            const float* __restrict__ bg, int nk, int p, int q,
                                            float* __restrict__ sout) {
     float acc[10];
     const float* bq = bg + q * GC;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) acc[i] = __ldg(bq + i);
+    for (int i = 0; i < 10; ++i) acc[i] = ldw1<GLOBAL_W>(bq + i);
     const float* wq = wg + q * GC;
 #pragma unroll 4
     for (int k = 0; k < nk; ++k) {
         const float sv = sin_[p * 41 + k];
-        const float4 a = __ldg(reinterpret_cast<const float4*>(wq + k * HP));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(wq + k * HP + 4));
-        const float2 c = __ldg(reinterpret_cast<const float2*>(wq + k * HP + 8));
+        const float4 a = ldw4<GLOBAL_W>(wq + k * HP);
+        const float4 b = ldw4<GLOBAL_W>(wq + k * HP + 4);
+        const float2 c = ldw2<GLOBAL_W>(wq + k * HP + 8);
         acc[0] = fmaf(sv, a.x, acc[0]); acc[1] = fmaf(sv, a.y, acc[1]);
         acc[2] = fmaf(sv, a.z, acc[2]); acc[3] = fmaf(sv, a.w, acc[3]);
         acc[4] = fmaf(sv, b.x, acc[4]); acc[5] = fmaf(sv, b.y, acc[5]);
@@ -223,9 +397,10 @@ __device__ __forceinline__ void head_layer(const float* __restrict__ sin_, const
         acc[8] = fmaf(sv, c.x, acc[8]); acc[9] = fmaf(sv, c.y, acc[9]);
     }
 #pragma unroll
-    for (int i = 0; i < 10; ++i) sout[p * 41 + q * 10 + i] = fmaxf(acc[i], 0.f);
+    for (int i = 0; i < 10; ++i) sout[p * 41 + q * 10 + i] = relu_nan(acc[i]);
 }
 
+template <bool GLOBAL_W>
 __device__ __forceinline__ void tail_unit(const float* __restrict__ rec, const TileGeom& g,
                                           const float* __restrict__ thp, const PackedLayout& pl,
                                           const float* __restrict__ eps_u, const float* __restrict__ eps_sum_u,
@@ -285,33 +460,33 @@ __device__ __forceinline__ void tail_unit(const float* __restrict__ rec, const T
             if (eps_sum_u) {  // add_summary_noise (:448-450): s + eps * exp(logvar/2)
                 const float e0 = __ldg(eps_sum_u + (n0 + p) * S2 + col);
                 const float e1 = __ldg(eps_sum_u + (n0 + p) * S2 + L + col);
-                s_mu = __fadd_rn(s_mu, __fmul_rn(e0, expf(__fdiv_rn(__ldg(thp + pl.lv_sum + col), 2.0f))));
-                s_sd = __fadd_rn(s_sd, __fmul_rn(e1, expf(__fdiv_rn(__ldg(thp + pl.lv_sum + L + col), 2.0f))));
+                s_mu = __fadd_rn(s_mu, __fmul_rn(e0, expf(__fdiv_rn(ldw1<GLOBAL_W>(thp + pl.lv_sum + col), 2.0f))));
+                s_sd = __fadd_rn(s_sd, __fmul_rn(e1, expf(__fdiv_rn(ldw1<GLOBAL_W>(thp + pl.lv_sum + L + col), 2.0f))));
             }
         }
         sA[p * 41 + col] = s_mu;
         sA[p * 41 + L + col] = s_sd;
     }
     __syncwarp();
-    head_layer(sA, thp + pl.V0p, thp + pl.c0p, S2, p, q, sB);
+    head_layer<GLOBAL_W>(sA, thp + pl.V0p, thp + pl.c0p, S2, p, q, sB);
     __syncwarp();
-    head_layer(sB, thp + pl.V1p, thp + pl.c1p, H, p, q, sA);
+    head_layer<GLOBAL_W>(sB, thp + pl.V1p, thp + pl.c1p, H, p, q, sA);
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const int k = q * 10 + i;
         const float r = sA[p * 41 + k];
-        o0 = fmaf(r, __ldg(thp + pl.V2 + k), o0);
-        o1 = fmaf(r, __ldg(thp + pl.V2 + H + k), o1);
+        o0 = fmaf(r, ldw1<GLOBAL_W>(thp + pl.V2 + k), o0);
+        o1 = fmaf(r, ldw1<GLOBAL_W>(thp + pl.V2 + H + k), o1);
     }
     o0 += __shfl_xor_sync(0xffffffffu, o0, 1);
     o1 += __shfl_xor_sync(0xffffffffu, o1, 1);
     o0 += __shfl_xor_sync(0xffffffffu, o0, 2);
     o1 += __shfl_xor_sync(0xffffffffu, o1, 2);
     if (q == 0 && p < n_valid) {
-        o0 += __ldg(thp + pl.c2);
-        o1 += __ldg(thp + pl.c2 + 1);
+        o0 += ldw1<GLOBAL_W>(thp + pl.c2);
+        o1 += ldw1<GLOBAL_W>(thp + pl.c2 + 1);
         float2 o = make_float2(soft_clamp_dev(o0, hc.lo_mu, hc.hi_mu), soft_clamp_dev(o1, hc.lo_sd, hc.hi_sd));
         *reinterpret_cast<float2*>(out_unit + (n0 + p) * out_sys_stride) = o;
     }

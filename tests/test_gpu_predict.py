@@ -238,3 +238,20 @@ def test_full_size_properties(dev):
         ref = R.forward_swag_fast(spec, theta[u].cpu(), torch.from_numpy(xh)[idx], eps[u, idx, :20].cpu(),
                                   eps[u, idx, 20:].cpu())
         assert rel_err(a[u, idx].cpu(), ref) < TOL
+
+
+def test_kernel_variants_agree_bitwise(dev, monkeypatch):
+    """The synchronous kernel (v1) and the warp-specialised TMA/mbarrier kernel (v2, any consumer
+    count) share the arithmetic order: outputs must be identical, also on ragged sizes and when an
+    item's unit range is split into chunks."""
+    ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(3, dev)], device=dev)
+    for N, S_ in ((13, 3), (203, 40), (1200, 70)):
+        x = torch.from_numpy(synth.make_systems(N, seed=N)).to(dev)
+        _, thp = ens.sample_thetas(S_, seed=N)
+        outs = {}
+        for v in ("v1", "v2c8", "v2c12", "v2c16"):
+            monkeypatch.setenv("BNN_PREDICT_VARIANT", v)
+            outs[v] = ens.predict(x, S_, seed=N, thp=thp)
+        torch.cuda.synchronize()
+        for v in ("v2c8", "v2c12", "v2c16"):
+            assert torch.equal(outs[v], outs["v1"]), (v, N, S_)

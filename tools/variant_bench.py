@@ -1,0 +1,46 @@
+"""Time the predict-kernel variants on the BASELINE config-2 workload and cross-check them
+bit for bit (they share the arithmetic order).  GPU only; used while tuning."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import FLOP_PER_EVAL_V50, load_stats  # noqa: E402
+from bnn_chaos_model_b200 import spock_reg_model as S, synth  # noqa: E402
+from bnn_chaos_model_b200.multiswag import MultiSWAG  # noqa: E402
+
+variants = sys.argv[1].split(",") if len(sys.argv) > 1 else ["v1", "v2c8", "v2c12", "v2c16"]
+n_sys = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
+n_samp = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+dev = torch.device("cuda:0")
+z, hp, sp = load_stats(0)
+m = S.SWAGModel(hp).init_params(sp).to(dev)
+m.w_avg, m.w2_avg, m.pre_D = (torch.from_numpy(z[k]).to(dev) for k in ("w_avg", "w2_avg", "pre_D"))
+ens = MultiSWAG([m], device=dev)
+x = torch.from_numpy(synth.make_systems(n_sys, seed=1)).to(dev)
+_, thp = ens.sample_thetas(n_samp, seed=1)
+ref = None
+for v in variants:
+    os.environ["BNN_PREDICT_VARIANT"] = v
+    out = ens.predict(x, n_samp, seed=1, thp=thp)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = ens.predict(x, n_samp, seed=1, thp=thp)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = min(ts)
+    same = None if ref is None else bool(torch.equal(out, ref))
+    if ref is None:
+        ref = out.clone()
+    tf = FLOP_PER_EVAL_V50 * n_sys * n_samp / (ms * 1e-3) / 1e12
+    print(json.dumps({"variant": v, "ms": round(ms, 3), "all_ms": [round(t, 2) for t in ts], "evals_per_s": n_sys * n_samp / (ms * 1e-3),
+                      "tflops": round(tf, 2), "frac_fp32_peak": round(tf / 74.45, 4), "bitwise_equal_to_first": same,
+                      "finite": bool(torch.isfinite(out).all())}), flush=True)
