@@ -1,0 +1,85 @@
+// Hardware probe for the tcgen05 building blocks used by the tensor-core predictive kernel:
+// D[128,N] = A[128,K] * B[N,K]^T with kind::tf32, A in TMEM (written with tcgen05.st), B in
+// shared memory in the canonical K-major no-swizzle layout, D read back with tcgen05.ld.
+// tests/test_gpu_tc.py compares against numpy for several (N, K, descriptor) variants.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace bnn {
+
+__global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                       float* __restrict__ D, int K, int N, int variant) {
+    extern __shared__ __align__(128) float bs[];  // B canonical: chunk-major [K/4][N][4]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        tmem_alloc(&tmem_base_s, 256);
+        tmem_relinquish();
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init_fence();
+    }
+    for (int i = tid; i < N * K; i += 128) {
+        const int n = i / K, k = i % K;
+        bs[((k >> 2) * N + n) * 4 + (k & 3)] = B[i];
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t a_col = 0, d_col = 128;
+    // A row `tid` -> TMEM lane tid, columns [0,K)
+    for (int c = 0; c < K; c += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(A[tid * K + c + j]);
+        tmem_st8(tmem + lane_base + a_col + c, v);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0 && !(variant & 4)) {
+        const uint32_t idesc = idesc_tf32(128, N);
+        const uint32_t chunk_bytes = (uint32_t)N * 16u;  // distance between 16-byte K chunks
+        const uint32_t lbo = (variant & 1) ? 128u : chunk_bytes;
+        const uint32_t sbo = (variant & 1) ? chunk_bytes : 128u;
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const uint64_t bdesc = smem_desc_kmajor(smem_u32(bs) + ks * 2 * chunk_bytes, lbo, sbo);
+            mma_tf32_ts(tmem + d_col, tmem + a_col + ks * 8, bdesc, idesc, ks > 0);
+        }
+        mma_commit(&bar);
+    }
+    if (!(variant & 4)) mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t rd_col = (variant & 2) ? a_col : d_col;  // variant&2: read back the A region instead of D
+    for (int c = 0; c < N; c += 8) {
+        uint32_t v[8];
+        tmem_ld8(tmem + lane_base + rd_col + c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) D[tid * N + c + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace bnn
+
+extern "C" int bnn_tc_probe(const float* d_A, const float* d_B, float* d_D, int32_t K, int32_t N, int32_t variant,
+                            void* stream) {
+    using namespace bnn;
+    int rc = check_device();
+    if (rc != BNN_OK) return rc;
+    BNN_REQUIRE(d_A && d_B && d_D, BNN_E_ARG, "bnn_tc_probe: null pointer");
+    BNN_REQUIRE(K % 8 == 0 && K >= 8 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 128, BNN_E_ARG,
+                "bnn_tc_probe: need K%%8==0 (8..128), N%%16==0 (16..128)");
+    tc_probe_kernel<<<1, 128, (size_t)N * K * 4, (cudaStream_t)stream>>>(d_A, d_B, d_D, K, N, variant);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}

@@ -214,7 +214,8 @@ class VarModel(nn.Module):
         with torch.cuda.device(s.device):
             cfg = self.config()
             out = torch.empty((s.shape[0], 2), device=s.device, dtype=torch.float32)
-            _lib.check(lib.bnn_predict_instability(cfg, _lib.ptr(s), s.shape[0], _lib.ptr(self._packed(cfg)),
+            thp = self._packed(cfg)  # keep a reference while the kernel is enqueued
+            _lib.check(lib.bnn_predict_instability(cfg, _lib.ptr(s), s.shape[0], _lib.ptr(thp),
                                                    _lib.ptr(out), _lib.current_stream_ptr()),
                        "bnn_predict_instability")
         return out[:, [0]], out[:, [1]]

@@ -181,6 +181,12 @@ int bnn_swag_collect(const float* d_w, int64_t d, int32_t n_seeds, int32_t K, fl
  * d_sink.  flops = 2 * grid*block*iters*16 ; time it with events around the call. */
 int bnn_ffma_peak(int32_t packed, int64_t iters, float* d_sink, int64_t* flops_out, void* stream);
 
+/* Diagnostic: one tcgen05 (kind::tf32) GEMM D[128,N] = A[128,K] B[N,K]^T with A staged in TMEM and
+ * B in shared memory (canonical K-major, no swizzle); variant 0 is the descriptor convention the
+ * tensor-core predictive kernel uses.  Used by tests/test_gpu_tc.py to pin the hardware layouts. */
+int bnn_tc_probe(const float* d_A, const float* d_B, float* d_D, int32_t K, int32_t N, int32_t variant,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif
