@@ -27,6 +27,7 @@ struct PredictParams {
     int units_per_cta;
     HeadConsts hc;
     ColMap cm;
+    long long* dbg;  // optional timeline buffer (tools/tc_timeline.py), normally null
 };
 
 // ---------------------------------------------------------------------------------------
@@ -129,7 +130,7 @@ predict_v2_kernel(const PredictParams prm, const int T, const int n_tiles, const
     float* smem = smem_v2;
     const TileGeom g(T);
     const PackedLayout pl(prm.kin, prm.F);
-    const int P4 = pl.P;  // floats per unit (multiple of 4)
+    const int P4 = pl.B1h;  // floats staged per unit: feature + head (+ logvars); the tensor-core section is skipped
     float* xT = smem;
     float* ring = xT + prm.kin * g.RP;
     float* hq = ring + 2 * P4;
@@ -172,7 +173,7 @@ predict_v2_kernel(const PredictParams prm, const int T, const int n_tiles, const
                     const int s = i & 1;
                     if (i >= 2) mbar_wait(&sh->tail_done[s], ((i >> 1) - 1) & 1);
                     mbar_arrive_expect_tx(&sh->full[s], (uint32_t)(P4 * sizeof(float)));
-                    bulk_g2s(ring + s * P4, prm.thp + (u_begin + i) * P4, (uint32_t)(P4 * sizeof(float)), &sh->full[s]);
+                    bulk_g2s(ring + s * P4, prm.thp + (u_begin + i) * pl.P, (uint32_t)(P4 * sizeof(float)), &sh->full[s]);
                 }
             }
         } else if (warp == NC + 1) {
@@ -215,7 +216,7 @@ predict_v2_kernel(const PredictParams prm, const int T, const int n_tiles, const
 static size_t v2_smem_bytes(int kin, int F, int T, int NC) {
     TileGeom g(T);
     PackedLayout pl(kin, F);
-    size_t fl = (size_t)kin * g.RP + 2 * (size_t)pl.P + (size_t)NC * HQ_FLOATS + 2 * rec_floats(g) + 1024;
+    size_t fl = (size_t)kin * g.RP + 2 * (size_t)pl.B1h + (size_t)NC * HQ_FLOATS + 2 * rec_floats(g) + 1024;
     return fl * sizeof(float) + sizeof(V2Smem);
 }
 
@@ -255,6 +256,8 @@ static int launch_v2(const PredictParams& prm, int T, cudaStream_t st) {
 
 }  // namespace bnn
 
+#include "predict_tc_kernel.cuh"
+
 extern "C" {
 
 size_t bnn_predict_workspace_bytes(const bnn_model_config*, int64_t, int64_t) { return 0; }
@@ -293,18 +296,25 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     for (int c = 0; c < MAXF; ++c) prm.cm.inv[c] = -1;
     for (int k = 0; k < lc.n; ++k) prm.cm.inv[(int)lc.col[k]] = (int8_t)k;
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
+    {
+        const char* dbgp = getenv("BNN_TC_TIMELINE_PTR");  // device pointer (decimal) to 8*512 int64, debugging only
+        prm.dbg = dbgp ? reinterpret_cast<long long*>(strtoull(dbgp, nullptr, 10)) : nullptr;
+    }
     // split units over CTAs only when the tiles alone cannot fill the GPU twice
     const int64_t tiles = (n_systems + SYS_TILE - 1) / SYS_TILE;
     int64_t chunks = 1;
     if (tiles < 2 * 148) chunks = (2 * 148 + tiles - 1) / tiles;
     if (chunks > n_units) chunks = n_units;
     prm.units_per_cta = (int)((n_units + chunks - 1) / chunks);
-    // variant selection: v2 (warp-specialised, TMA ring) when its tile fits in shared memory, else v1.
-    // BNN_PREDICT_VARIANT=v1|v2c8|v2c12|v2c16 forces one (benchmarks / cross-checks).
+    // variant selection: tensor cores (tcgen05, 3xTF32) when T = 100 and at most 31 live input columns;
+    // else the FFMA2 kernels: v2 (warp-specialised, TMA ring) when its tile fits in shared memory, else v1.
+    // BNN_PREDICT_VARIANT=tc3|tc2|v1|v2c8|v2c12|v2c16 forces one (benchmarks / cross-checks).
     const char* force = getenv("BNN_PREDICT_VARIANT");
     const int T = cfg->n_times;
     cudaStream_t st = (cudaStream_t)stream;
     auto fits = [&](int nc) { return v2_smem_bytes(prm.kin, prm.F, T, nc) <= 227 * 1024; };
+    if (force && !strcmp(force, "tc2") && tc::tc_fits<2>(prm, T)) return tc::launch_tc<2>(prm, st);
+    if (force && !strcmp(force, "tc3") && tc::tc_fits<3>(prm, T)) return tc::launch_tc<3>(prm, st);
     if (force && !strcmp(force, "v1")) return launch_v1<8>(prm, T, st);
     if (force && !strcmp(force, "v2c8") && fits(8)) return launch_v2<8>(prm, T, st);
     if (force && !strcmp(force, "v2c16") && fits(16)) return launch_v2<16>(prm, T, st);

@@ -131,9 +131,32 @@ __global__ void pack_theta_kernel(const float* __restrict__ theta, int64_t n_uni
         if (r < 2) src = fl.c2 + r;
     } else if (i < pl.lv_in) {
         src = fl.lv_sum + (i - pl.lv_sum);
-    } else {
+    } else if (i < pl.B1h) {
         int r = i - pl.lv_in;
         if (r < fl.F) src = fl.lv_in + r;
+    } else {
+        // tensor-core B operands: element (n, k) of a [N][K] matrix sits at ((k/4)*N + n)*4 + k%4
+        int r, N, kbias, nreal, wsrc, bsrc, kreal, ld;
+        bool lo;
+        if (i < pl.B2h) {
+            r = i - pl.B1h; N = TC_N; lo = r >= TC_K1 * TC_N; r -= lo ? TC_K1 * TC_N : 0;
+            kbias = TC_K1 - 1; nreal = H; kreal = pl.kin; wsrc = fl.W0; bsrc = fl.b0; ld = fl.F;
+        } else if (i < pl.B3h) {
+            r = i - pl.B2h; N = TC_N; lo = r >= TC_K2 * TC_N; r -= lo ? TC_K2 * TC_N : 0;
+            kbias = H; nreal = H; kreal = H; wsrc = fl.W1; bsrc = fl.b1; ld = H;
+        } else {
+            r = i - pl.B3h; N = TC_N3; lo = r >= TC_K2 * TC_N3; r -= lo ? TC_K2 * TC_N3 : 0;
+            kbias = H; nreal = L; kreal = H; wsrc = fl.W2; bsrc = fl.b2; ld = H;
+        }
+        const int chunk = r / (N * 4), n = (r / 4) % N, k = chunk * 4 + (r & 3);
+        float w = 0.f;
+        if (n < nreal) {
+            if (k < kreal) w = th[wsrc + n * ld + ((wsrc == fl.W0) ? (int)lc.col[k] : k)];
+            else if (k == kbias) w = th[bsrc + n];
+        }
+        const float hi = tf32_rna(w);
+        packed[idx] = lo ? (w - hi) : hi;
+        return;
     }
     packed[idx] = src >= 0 ? th[src] : 0.f;
 }

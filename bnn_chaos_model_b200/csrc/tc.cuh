@@ -59,6 +59,20 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
            | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
+// One lane of a converged warp (uniform control flow around it keeps addresses/descriptors in uniform
+// registers, so that a tcgen05.mma costs a handful of issue slots instead of an R2UR/ELECT loop).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]^T, one K=8 step; issued by ONE thread.
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             bool accumulate) {

@@ -69,7 +69,79 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// Timing probe: `reps` x (K/8) dependent tcgen05.mma (same D) issued back to back by one thread;
+// out[0] = cycles from first issue to commit completion, out[1] = cycles spent issuing.
+__global__ void __launch_bounds__(128) tc_time_kernel(int K, int N, int reps, int from_smem, long long* out) {
+    extern __shared__ __align__(128) float bs[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        tmem_alloc(&tmem_base_s, 512);
+        tmem_relinquish();
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init_fence();
+    }
+    for (int i = tid; i < (N + 128) * K; i += 128) bs[i] = 0.f;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (warp == 0) {
+        const uint32_t idesc = idesc_tf32(128, N);
+        const uint32_t chunk_bytes = (uint32_t)N * 16u;
+        const uint32_t a_chunk = 128u * 16u;
+        const uint32_t a_base = smem_u32(bs) + (uint32_t)N * K * 4;
+        long long t0 = 0, t1 = 0;
+        // warp-uniform control flow and addresses, one elected lane per instruction (as in predict_tc)
+        const uint64_t bd0 = smem_desc_kmajor(smem_u32(bs), chunk_bytes, 128u);
+        const uint64_t ad0 = smem_desc_kmajor(a_base, a_chunk, 128u);
+        const uint64_t bstep = 2ull * (uint64_t)N, astep = 2ull * 128ull;
+        t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int ks = 0; ks < 6; ++ks) {
+                    if (from_smem)
+                        mma_tf32_ss(tmem + 256, ad0 + ks * astep, bd0 + ks * bstep, idesc, (r | ks) > 0);
+                    else
+                        mma_tf32_ts(tmem + 256, tmem + ks * 8, bd0 + ks * bstep, idesc, (r | ks) > 0);
+                }
+            }
+            __syncwarp();
+        }
+        t1 = clock64();
+        if (elect_one_sync()) mma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (tid == 0) {
+            out[0] = t2 - t0;
+            out[1] = t1 - t0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace bnn
+
+extern "C" int bnn_tc_time(int32_t K, int32_t N, int32_t reps, int32_t from_smem, long long* d_out, void* stream) {
+    using namespace bnn;
+    int rc = check_device();
+    if (rc != BNN_OK) return rc;
+    BNN_REQUIRE(d_out && K % 8 == 0 && K >= 8 && K <= 64 && N % 16 == 0 && N >= 16 && N <= 256, BNN_E_ARG,
+                "bnn_tc_time: bad arguments");
+    const size_t smem = (size_t)(N + 128) * K * 4;
+    cudaFuncSetAttribute(tc_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    tc_time_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(K, N, reps, from_smem, d_out);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
 
 extern "C" int bnn_tc_probe(const float* d_A, const float* d_B, float* d_D, int32_t K, int32_t N, int32_t variant,
                             void* stream) {

@@ -187,6 +187,10 @@ int bnn_ffma_peak(int32_t packed, int64_t iters, float* d_sink, int64_t* flops_o
 int bnn_tc_probe(const float* d_A, const float* d_B, float* d_D, int32_t K, int32_t N, int32_t variant,
                  void* stream);
 
+/* Diagnostic: cycles for reps x (K/8) dependent tcgen05.mma (M=128, kind::tf32) issued back to back;
+ * d_out[0] = issue-to-completion cycles, d_out[1] = cycles spent issuing.  from_smem: A from shared memory. */
+int bnn_tc_time(int32_t K, int32_t N, int32_t reps, int32_t from_smem, long long* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

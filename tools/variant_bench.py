@@ -38,9 +38,10 @@ for v in variants:
         ts.append(a.elapsed_time(b))
     ms = min(ts)
     same = None if ref is None else bool(torch.equal(out, ref))
+    relerr = None if ref is None else float(((out - ref).abs() / ref.abs()).max())
     if ref is None:
         ref = out.clone()
     tf = FLOP_PER_EVAL_V50 * n_sys * n_samp / (ms * 1e-3) / 1e12
     print(json.dumps({"variant": v, "ms": round(ms, 3), "all_ms": [round(t, 2) for t in ts], "evals_per_s": n_sys * n_samp / (ms * 1e-3),
-                      "tflops": round(tf, 2), "frac_fp32_peak": round(tf / 74.45, 4), "bitwise_equal_to_first": same,
+                      "tflops": round(tf, 2), "frac_fp32_peak": round(tf / 74.45, 4), "bitwise_equal_to_first": same, "max_rel_err_vs_first": relerr,
                       "finite": bool(torch.isfinite(out).all())}), flush=True)
