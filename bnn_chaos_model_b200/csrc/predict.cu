@@ -313,8 +313,12 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     const int T = cfg->n_times;
     cudaStream_t st = (cudaStream_t)stream;
     auto fits = [&](int nc) { return v2_smem_bytes(prm.kin, prm.F, T, nc) <= 227 * 1024; };
-    if (force && !strcmp(force, "tc2") && tc::tc_fits<2>(prm, T)) return tc::launch_tc<2>(prm, st);
-    if (force && !strcmp(force, "tc3") && tc::tc_fits<3>(prm, T)) return tc::launch_tc<3>(prm, st);
+    if (tc::tc_fits(prm, T)) {
+        if (force && !strcmp(force, "tc3n4")) return tc::launch_tc<3, 4>(prm, st);
+        if (force && !strcmp(force, "tc3n3")) return tc::launch_tc<3, 3>(prm, st);
+        if (force && !strcmp(force, "tc3n2")) return tc::launch_tc<3, 2>(prm, st);
+        if (force && !strcmp(force, "tc2n4")) return tc::launch_tc<2, 4>(prm, st);
+    }
     if (force && !strcmp(force, "v1")) return launch_v1<8>(prm, T, st);
     if (force && !strcmp(force, "v2c8") && fits(8)) return launch_v2<8>(prm, T, st);
     if (force && !strcmp(force, "v2c16") && fits(16)) return launch_v2<16>(prm, T, st);

@@ -17,9 +17,11 @@
 //       stage x: smem -> hi/lo -> tcgen05.st A          -> arrive a_ready
 //       after each layer: tcgen05.ld D -> ReLU -> hi/lo -> tcgen05.st A   -> arrive a_ready
 //       last layer: D -> per-32-row-block pooled (mean, M2) records
-//   MMA warp (one thread): waits a_ready, issues 12/17/17 tcgen05.mma per layer, tcgen05.commit -> d_ready
-//   producer warp: cp.async.bulk of each unit's weights (hi/lo B operands + fp32 head) into a 2-slot ring
-//   2 tail warps: Chan-merge the records per system, sampled summary statistics, regress_nn, store.
+//   MMA warps (one per slot, one elected lane): wait a_ready, issue 12/17/17 tcgen05.mma per layer, commit -> d_ready
+//   producer warp: cp.async.bulk of each unit's hi/lo B operands (43 KB) into a 2-slot ring
+//   NT tail warps (unit i -> warp i % NT): merge the records per system, sampled summary statistics,
+//       regress_nn with the fp32 head weights read through L2, store (mu, std); records live in an NT-deep ring
+//       (unit_done / rec_free barriers give the epilogue back-pressure when the tails fall behind).
 // Biases ride in the GEMMs: x carries a ones column (index 31), the hidden activations a constant
 // ones block in TMEM columns 40..47 of A_hi.
 #pragma once
@@ -37,14 +39,35 @@ constexpr int TM_AHI = 0, TM_ALO = 48, TM_D = 88, TM_SLOT = 136;
 constexpr int N_BLOCKS = MT * 4;  // 32-row blocks per tile
 constexpr int REC_FLOATS = N_BLOCKS * 2 * L * 2;  // [block][segment][col][mean, M2]
 constexpr int FB_FLOATS = 32 * L;                 // per epilogue warp
-constexpr int TAIL_SCRATCH = 1024;
+constexpr int TAIL_SCRATCH = 640;                // sA[5*41] + sB[5*41] + eS[5*40] floats per tail warp
+constexpr int MAX_NT = 4;
 
 struct Bars {
-    uint64_t w_full[2], w_empty[2], unit_done[2];
+    uint64_t w_full[2];                                // B operands of unit i landed in ring slot i & 1
+    uint64_t unit_done[MAX_NT], rec_free[MAX_NT];      // record ring slot i % NT: written by the epilogue / read by the tail
     uint64_t a_ready[3], d_ready[3];
     uint32_t tmem_base;
     uint32_t pad;
 };
+
+// The 4 records of system p (T = 100, 5 systems per tile, 32-row blocks): record index (block*2 + segment) and
+// row count.  System p starts at row 100p: a leading partial block (segment 1 of block (100p)/32 when 100p % 32
+// != 0), full blocks, and a trailing partial block (segment 0).
+struct SysRec { int idx[4]; float cnt[4]; };
+__device__ __forceinline__ SysRec sys_records(int p) {
+    SysRec r;
+    const int first = T_FIXED * p, last = T_FIXED * p + T_FIXED - 1;
+    const int b0 = first >> 5, b1 = last >> 5;  // 4 blocks for every p in 0..4
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = b0 + k;
+        const int lo = max(first, 32 * b), hi = min(last, 32 * b + 31);
+        const int seg = ((32 * b) / T_FIXED == p) ? 0 : 1;
+        r.idx[k] = b * 2 + seg;
+        r.cnt[k] = (b <= b1) ? (float)(hi - lo + 1) : 0.f;
+    }
+    return r;
+}
 
 // block b covers tile rows [32b, 32b+32): rows of system sysA up to `split`, then system sysA+1
 __device__ __forceinline__ void block_geom(int b, int& sysA, int& split, int& nvalid) {
@@ -128,29 +151,61 @@ __device__ __forceinline__ void issue_layer(uint32_t ts, uint32_t bh_addr, uint3
 }
 
 // ---------------------------------------------------------------------------------------
-// Tail of one unit from the per-block records (one warp; lane = p*4+q, p = system slot, q = 5 columns).
-// ring: this unit's ring slot (starts at PackedLayout::V0p); scratch: TAIL_SCRATCH floats.
+// Tail of one unit from the per-block records (one warp; lane = p*4+q, p = system slot, q = 10 hidden / 5 latent
+// columns).  thp: this unit's packed weights in GLOBAL memory (13 KB of head weights, read once through L2 with
+// 8 k-steps of loads in flight); scratch: TAIL_SCRATCH floats of warp-private shared memory.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, const float* __restrict__ ring,
+__device__ __forceinline__ void head_layer_g(const float* __restrict__ sin_, const float* __restrict__ wg,
+                                             const float* __restrict__ bg, int p, int q, float* __restrict__ sout) {
+    float acc[10];
+    const float* bq = bg + q * GC;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = __ldg(bq + i);
+    const float* wq = wg + q * GC;
+#pragma unroll 1
+    for (int k0 = 0; k0 < H; k0 += 8) {
+        float4 a[8], b[8];
+        float2 c[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            a[kk] = __ldg(reinterpret_cast<const float4*>(wq + (k0 + kk) * HP));
+            b[kk] = __ldg(reinterpret_cast<const float4*>(wq + (k0 + kk) * HP + 4));
+            c[kk] = __ldg(reinterpret_cast<const float2*>(wq + (k0 + kk) * HP + 8));
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const float sv = sin_[p * 41 + k0 + kk];
+            acc[0] = fmaf(sv, a[kk].x, acc[0]); acc[1] = fmaf(sv, a[kk].y, acc[1]);
+            acc[2] = fmaf(sv, a[kk].z, acc[2]); acc[3] = fmaf(sv, a[kk].w, acc[3]);
+            acc[4] = fmaf(sv, b[kk].x, acc[4]); acc[5] = fmaf(sv, b[kk].y, acc[5]);
+            acc[6] = fmaf(sv, b[kk].z, acc[6]); acc[7] = fmaf(sv, b[kk].w, acc[7]);
+            acc[8] = fmaf(sv, c[kk].x, acc[8]); acc[9] = fmaf(sv, c[kk].y, acc[9]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) sout[p * 41 + q * 10 + i] = relu_nan(acc[i]);
+}
+
+__device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, const float* __restrict__ thp,
                                              const PackedLayout& pl, const float* __restrict__ eps_u,
                                              const float* __restrict__ eps_sum_u, float* __restrict__ summary_u,
                                              uint64_t seed, uint32_t gunit, int64_t gsys0, int64_t n0, int n_valid,
                                              const HeadConsts& hc, float* __restrict__ scratch,
                                              float* __restrict__ out_unit, int64_t out_sys_stride) {
     const int lane = threadIdx.x & 31;
-    const int p = lane >> 2, q = lane & 3;
-    const float* thp = ring - pl.V0p;  // so that thp + pl.<head field> addresses the ring slot
+    const int p = min(lane >> 2, SYS - 1), q = lane & 3;  // lanes of p >= SYS shadow system SYS-1 (stores are masked)
+    const bool live = (lane >> 2) < SYS;
     float* sA = scratch;
-    float* sB = scratch + SYS_TILE * 41;
-    float* eS = scratch + 2 * SYS_TILE * 41;
+    float* sB = scratch + SYS * 41;
+    float* eS = scratch + ((2 * SYS * 41 + 3) & ~3);  // float4 stores of the Philox draws: 16-byte aligned
 
     if (eps_u) {
-        for (int idx = lane; idx < SYS_TILE * S2; idx += 32) {
+        for (int idx = lane; idx < SYS * S2; idx += 32) {
             const int s = idx / S2, j = idx % S2;
             eS[idx] = (s < n_valid) ? __ldg(eps_u + (n0 + s) * S2 + j) : 0.f;
         }
     } else {
-        for (int b = lane; b < SYS_TILE * (S2 / 4); b += 32) {
+        for (int b = lane; b < SYS * (S2 / 4); b += 32) {
             const int s = b / (S2 / 4), blk = b % (S2 / 4);
             const float4 n4 = philox_normal4(seed, STREAM_EPS, gunit, (uint32_t)(gsys0 + s), (uint32_t)blk);
             *reinterpret_cast<float4*>(eS + s * S2 + blk * 4) = n4;
@@ -158,40 +213,31 @@ __device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, cons
     }
     __syncwarp();
 
+    const SysRec sr = sys_records(p);
     const float Tf = (float)T_FIXED, Tm1 = (float)(T_FIXED - 1);
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const int col = q * 5 + i;
-        float n = 0.f, mean = 0.f, m2 = 0.f;
-        if (p < SYS) {
-            const int bfirst = (T_FIXED * p) / 32, blast = (T_FIXED * p + T_FIXED - 1) / 32;
-            for (int b = bfirst; b <= blast; ++b) {
-                int sysA, split, nvalid;
-                block_geom(b, sysA, split, nvalid);
-                const int seg = (sysA == p) ? 0 : 1;
-                const int cnt = (seg == 0) ? min(split, nvalid) : (nvalid - split);
-                if (cnt <= 0) continue;
-                const float2 r = *reinterpret_cast<const float2*>(rec + ((b * 2 + seg) * L + col) * 2);
-                const float nb = (float)cnt;
-                if (n == 0.f) {
-                    n = nb; mean = r.x; m2 = r.y;
-                } else {
-                    const float nn = n + nb, delta = r.x - mean;
-                    mean = mean + delta * (nb / nn);
-                    m2 = (m2 + r.y) + delta * delta * (n * nb / nn);
-                    n = nn;
-                }
-            }
+        float2 r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = *reinterpret_cast<const float2*>(rec + (sr.idx[k] * L + col) * 2);
+        // exact two-level mean / M2: mean = sum n_k m_k / T, M2 = sum M2_k + sum n_k (m_k - mean)^2
+        const float mean = ((sr.cnt[0] * r[0].x + sr.cnt[1] * r[1].x) + (sr.cnt[2] * r[2].x + sr.cnt[3] * r[3].x)) / Tf;
+        float m2 = (r[0].y + r[1].y) + (r[2].y + r[3].y);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dlt = r[k].x - mean;
+            m2 = fmaf(sr.cnt[k] * dlt, dlt, m2);
         }
         const float sd = sqrtf(__fdiv_rn(m2, Tm1));  // torch.std(x, dim=1)**2 (:419)
         const float var = __fmul_rn(sd, sd);
-        const float std_in_mu = sqrtf(__fdiv_rn(var, Tf));
-        const float std_in_var = sqrtf(__fdiv_rn(__fmul_rn(2.0f, __fmul_rn(var, var)), Tm1));
-        const float mu_s = __fadd_rn(__fmul_rn(eS[p * S2 + col], std_in_mu), mean);
-        const float var_s = __fadd_rn(__fmul_rn(eS[p * S2 + L + col], std_in_var), var);
+        const float std_in_mu = sqrtf(__fdiv_rn(var, Tf));                                    // :422
+        const float std_in_var = sqrtf(__fdiv_rn(__fmul_rn(2.0f, __fmul_rn(var, var)), Tm1));   // :423
+        const float mu_s = __fadd_rn(__fmul_rn(eS[p * S2 + col], std_in_mu), mean);            // :426
+        const float var_s = __fadd_rn(__fmul_rn(eS[p * S2 + L + col], std_in_var), var);       // :427
         float s_mu = mu_s;
-        float s_sd = sqrtf(__fadd_rn(fabsf(var_s), 1e-5f));
-        if (p < n_valid) {
+        float s_sd = sqrtf(__fadd_rn(fabsf(var_s), 1e-5f));                                    // :430
+        if (live && p < n_valid) {
             if (summary_u) {
                 summary_u[(n0 + p) * S2 + col] = s_mu;
                 summary_u[(n0 + p) * S2 + L + col] = s_sd;
@@ -199,33 +245,35 @@ __device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, cons
             if (eps_sum_u) {
                 const float e0 = __ldg(eps_sum_u + (n0 + p) * S2 + col);
                 const float e1 = __ldg(eps_sum_u + (n0 + p) * S2 + L + col);
-                s_mu = __fadd_rn(s_mu, __fmul_rn(e0, expf(__fdiv_rn(thp[pl.lv_sum + col], 2.0f))));
-                s_sd = __fadd_rn(s_sd, __fmul_rn(e1, expf(__fdiv_rn(thp[pl.lv_sum + L + col], 2.0f))));
+                s_mu = __fadd_rn(s_mu, __fmul_rn(e0, expf(__fdiv_rn(__ldg(thp + pl.lv_sum + col), 2.0f))));
+                s_sd = __fadd_rn(s_sd, __fmul_rn(e1, expf(__fdiv_rn(__ldg(thp + pl.lv_sum + L + col), 2.0f))));
             }
         }
-        sA[p * 41 + col] = s_mu;
-        sA[p * 41 + L + col] = s_sd;
+        if (live) {
+            sA[p * 41 + col] = s_mu;
+            sA[p * 41 + L + col] = s_sd;
+        }
     }
     __syncwarp();
-    head_layer<false>(sA, thp + pl.V0p, thp + pl.c0p, S2, p, q, sB);
+    if (live) head_layer_g(sA, thp + pl.V0p, thp + pl.c0p, p, q, sB);
     __syncwarp();
-    head_layer<false>(sB, thp + pl.V1p, thp + pl.c1p, H, p, q, sA);
+    if (live) head_layer_g(sB, thp + pl.V1p, thp + pl.c1p, p, q, sA);
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const int k = q * 10 + i;
         const float r = sA[p * 41 + k];
-        o0 = fmaf(r, thp[pl.V2 + k], o0);
-        o1 = fmaf(r, thp[pl.V2 + H + k], o1);
+        o0 = fmaf(r, __ldg(thp + pl.V2 + k), o0);
+        o1 = fmaf(r, __ldg(thp + pl.V2 + H + k), o1);
     }
     o0 += __shfl_xor_sync(0xffffffffu, o0, 1);
     o1 += __shfl_xor_sync(0xffffffffu, o1, 1);
     o0 += __shfl_xor_sync(0xffffffffu, o0, 2);
     o1 += __shfl_xor_sync(0xffffffffu, o1, 2);
-    if (q == 0 && p < n_valid) {
-        o0 += thp[pl.c2];
-        o1 += thp[pl.c2 + 1];
+    if (q == 0 && live && p < n_valid) {
+        o0 += __ldg(thp + pl.c2);
+        o1 += __ldg(thp + pl.c2 + 1);
         float2 o = make_float2(soft_clamp_dev(o0, hc.lo_mu, hc.hi_mu), soft_clamp_dev(o1, hc.lo_sd, hc.hi_sd));
         *reinterpret_cast<float2*>(out_unit + (n0 + p) * out_sys_stride) = o;
     }

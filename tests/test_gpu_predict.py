@@ -255,3 +255,42 @@ def test_kernel_variants_agree_bitwise(dev, monkeypatch):
         torch.cuda.synchronize()
         for v in ("v2c8", "v2c12", "v2c16"):
             assert torch.equal(outs[v], outs["v1"]), (v, N, S_)
+
+
+TC_VARIANTS = ("tc3n4", "tc3n3", "tc3n2", "tc2n4")
+
+
+@pytest.mark.parametrize("variant", TC_VARIANTS)
+def test_tensor_core_variants_vs_reference_golden(gold_predict, dev, monkeypatch, variant):
+    """tcgen05 3xTF32 kernels: same golden theta / eps / systems as the FFMA path, same 1e-5 tolerance."""
+    monkeypatch.setenv("BNN_PREDICT_VARIANT", variant)
+    for seed in SEEDS:
+        m = make_swag_model(seed, dev)
+        cfg = m.config()
+        x = torch.from_numpy(synth.make_systems(256, seed=123)).to(dev)
+        theta = torch.from_numpy(gold_predict[f"theta_ref_s{seed}"]).to(dev)
+        eps = torch.from_numpy(gold_predict[f"eps_s{seed}"]).to(dev).contiguous()
+        out, _ = m._predict(x, m._packed(cfg, theta), eps, cfg=cfg)
+        ref = torch.from_numpy(gold_predict[f"out_ref_s{seed}"])
+        assert rel_err(out.cpu(), ref) < TOL, (variant, seed)
+
+
+def test_tensor_core_variants_vs_fp32_kernel(dev, monkeypatch):
+    """Ragged sizes, unit chunking, many units per CTA (exercises the record ring back-pressure and the weight
+    ring) and a NaN-poisoned system: every tc variant against the FFMA kernel, which is pinned to the oracle."""
+    ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(3, dev)], device=dev)
+    for N, S_ in ((13, 3), (203, 40), (1200, 70), (745, 33)):
+        xh = synth.make_systems(N, seed=N)
+        xh[N // 2, 7, 3] = float("nan")  # zeroed column: poisons that system only
+        x = torch.from_numpy(xh).to(dev)
+        _, thp = ens.sample_thetas(S_, seed=N)
+        monkeypatch.setenv("BNN_PREDICT_VARIANT", "v1")
+        want = ens.predict(x, S_, seed=N, thp=thp)
+        ok = torch.isfinite(want[:, :, 0])
+        assert not bool(ok[:, N // 2].any()) and bool(ok[:, : N // 2].all())
+        for v in TC_VARIANTS:
+            monkeypatch.setenv("BNN_PREDICT_VARIANT", v)
+            for rep in range(2):  # twice: races show up as run-to-run differences
+                got = ens.predict(x, S_, seed=N, thp=thp)
+                assert bool(torch.isnan(got[:, N // 2]).all()), (v, N)
+                assert rel_err(got[ok], want[ok]) < TOL, (v, N, S_, rep)

@@ -5,7 +5,7 @@ import torch
 dev = torch.device("cuda:0")
 dbg = torch.zeros(8 * 512, dtype=torch.int64, device=dev)
 os.environ["BNN_TC_TIMELINE_PTR"] = str(dbg.data_ptr())
-os.environ["BNN_PREDICT_VARIANT"] = sys.argv[1] if len(sys.argv) > 1 else "tc2"
+os.environ["BNN_PREDICT_VARIANT"] = sys.argv[1] if len(sys.argv) > 1 else "tc3n4"
 from bench import load_stats
 from bnn_chaos_model_b200 import spock_reg_model as S, synth
 from bnn_chaos_model_b200.multiswag import MultiSWAG
@@ -27,17 +27,17 @@ for role in range(8):
 ev.sort()
 t0 = ev[0][0]
 names = {1: "x staged", 2: "pooled", 3: "d1 wake", 4: "e1 done", 5: "d2 wake", 6: "e2 done", 7: "d3 wake", 8: "e3 done"}
+tnames = {1: "wait unit", 2: "unit ready", 3: "tail done"}
 xs = [t - t0 for t, role, code in ev if role == 0 and code == 1]
 print("slot0 x-staged times:", xs)
 print("slot0 job periods:", [b - a for a, b in zip(xs, xs[1:])])
-for r in (5, 6):
-    print(f"tail{r-5}:", [(code, t - t0) for t, role, code in ev if role == r][:40])
-print("mma0 w_full wait (400+u start, 500+u end):", [(code, t - t0) for t, role, code in ev if role == 7 and code >= 400][:40])
+for r in (3, 4):
+    print(f"tail{r-3}:", [(code, t - t0) for t, role, code in ev if role == r][:40])
 for t, role, code in ev[:int(os.environ.get("TL_N", "0"))]:
     if role == 7:
         s, l = (code % 100) // 10, code % 10
         kind = {0: "issue-start", 1: "issue-end  ", 2: "committed  ", 3: "loop-top   "}[code // 100]
         print(f"{t - t0:8d}  MMA   {kind} slot{s} L{l + 1}")
     else:
-        who = f"EPI{role}   " if role < 3 else f"EPI0.q{role - 2}"
-        print(f"{t - t0:8d}  {who}  {names.get(code, code)}")
+        who = f"EPI{role}   " if role < 3 else f"TAIL{role - 3}  "
+        print(f"{t - t0:8d}  {who}  {(names if role < 3 else tnames).get(code, code)}")
