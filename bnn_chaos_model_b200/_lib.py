@@ -65,6 +65,7 @@ SIGNATURES = {
     ),
     "bnn_pack_theta": (C.c_int, [_CFG, c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     "bnn_predict_workspace_bytes": (C.c_size_t, [_CFG, C.c_int64, C.c_int64]),
+    "bnn_predict_system_granule": (C.c_int32, [_CFG]),
     "bnn_predict": (
         C.c_int,
         [_CFG, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32,

@@ -262,6 +262,19 @@ extern "C" {
 
 size_t bnn_predict_workspace_bytes(const bnn_model_config*, int64_t, int64_t) { return 0; }
 
+// true when bnn_predict runs the tensor-core kernel for this config (no BNN_PREDICT_VARIANT override)
+static bool tc_selected(const bnn_model_config* cfg, int kin) {
+    const char* force = getenv("BNN_PREDICT_VARIANT");
+    if (force && strncmp(force, "tc", 2) != 0) return false;
+    return cfg->n_times == bnn::tc::T_FIXED && kin + 1 <= bnn::TC_K1;
+}
+
+int32_t bnn_predict_system_granule(const bnn_model_config* cfg) {
+    int rc = bnn::validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    return tc_selected(cfg, bnn::live_columns(cfg).n) ? bnn::tc::SYS : 1;
+}
+
 int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems, const float* d_theta_packed,
                 int64_t n_units, const float* d_eps, const float* d_eps_sum, uint64_t seed, int64_t unit_offset,
                 int64_t system_offset, int32_t out_system_major, float* d_out, float* d_summary_out,
@@ -306,9 +319,10 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     if (tiles < 2 * 148) chunks = (2 * 148 + tiles - 1) / tiles;
     if (chunks > n_units) chunks = n_units;
     prm.units_per_cta = (int)((n_units + chunks - 1) / chunks);
-    // variant selection: tensor cores (tcgen05, 3xTF32) when T = 100 and at most 31 live input columns;
-    // else the FFMA2 kernels: v2 (warp-specialised, TMA ring) when its tile fits in shared memory, else v1.
-    // BNN_PREDICT_VARIANT=tc3|tc2|v1|v2c8|v2c12|v2c16 forces one (benchmarks / cross-checks).
+    // variant selection: tensor cores (tcgen05, 3xTF32; 3 TMEM slots, 4 tail warps) when T = 100 and at most 31
+    // live input columns; else the FFMA2 kernels: v2 (warp-specialised, TMA ring) when its tile fits in shared
+    // memory, else v1.  BNN_PREDICT_VARIANT=tc3n4|tc3n3|tc3n2|tc2n4|v1|v2c8|v2c12|v2c16 forces one (benchmarks /
+    // cross-checks).
     const char* force = getenv("BNN_PREDICT_VARIANT");
     const int T = cfg->n_times;
     cudaStream_t st = (cudaStream_t)stream;
@@ -318,6 +332,7 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
         if (force && !strcmp(force, "tc3n3")) return tc::launch_tc<3, 3>(prm, st);
         if (force && !strcmp(force, "tc3n2")) return tc::launch_tc<3, 2>(prm, st);
         if (force && !strcmp(force, "tc2n4")) return tc::launch_tc<2, 4>(prm, st);
+        if (!force) return tc::launch_tc<3, 4>(prm, st);
     }
     if (force && !strcmp(force, "v1")) return launch_v1<8>(prm, T, st);
     if (force && !strcmp(force, "v2c8") && fits(8)) return launch_v2<8>(prm, T, st);

@@ -23,20 +23,25 @@ from ._lib import BnnChaosError
 from .spock_reg_model import SWAGModel
 
 
-def shard_range(n: int, rank: int, world: int):
-    """Contiguous block partition of range(n): first n % world ranks get one extra item."""
-    base, extra = divmod(n, world)
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+def shard_range(n: int, rank: int, world: int, granule: int = 1):
+    """Contiguous block partition of range(n) into `world` shards whose boundaries are multiples of
+    `granule` (the kernel's position-independent system group, ``bnn_predict_system_granule``): groups
+    are dealt out evenly, the first ``n_groups % world`` ranks get one extra group, the last non-empty
+    shard takes the ragged remainder.  With granule=1 the first n % world ranks get one extra item."""
+    groups = -(-n // granule)
+    base, extra = divmod(groups, world)
+    glo = rank * base + min(rank, extra)
+    ghi = glo + base + (1 if rank < extra else 0)
+    return min(glo * granule, n), min(ghi * granule, n)
 
 
-def gather_system_shards(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+def gather_system_shards(local: torch.Tensor, n_total: int, group=None, granule: int = 1) -> torch.Tensor:
     """The path's only collective: all_gather of the system-major block [N_local, ...] of every
     rank into [n_total, ...] (ranks own ``shard_range`` blocks, so the result needs no permute)."""
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    sizes = [shard_range(n_total, r, world, granule) for r in range(world)]
     assert local.shape[0] == sizes[rank][1] - sizes[rank][0]
     tail = tuple(local.shape[1:])
     full = torch.empty((n_total,) + tail, device=local.device, dtype=local.dtype)
@@ -84,6 +89,13 @@ class MultiSWAG:
     def config(self, n_times=100):
         return self._m0.config(n_times)
 
+    def system_granule(self, n_times=100) -> int:
+        """Shard / chunk boundaries at multiples of this keep results bit-identical to one launch."""
+        g = _lib.load().bnn_predict_system_granule(self.config(n_times))
+        if g < 0:
+            _lib.check(int(g), "bnn_predict_system_granule")
+        return int(g)
+
     # ------------------------------------------------------------------ batched path
     def sample_thetas(self, samples_per_model: int, seed: int, scale: float = 0.5, unit_model=None,
                       unit_offset: int = 0, n_units: Optional[int] = None, z1=None, z2=None, want_flat=True):
@@ -120,6 +132,8 @@ class MultiSWAG:
         U, N = thp.shape[0], x.shape[0]
         with torch.cuda.device(self.device):
             out = torch.empty((N, U, 2) if system_major else (U, N, 2), device=self.device)
+            if N == 0:  # an empty shard (fewer system groups than ranks)
+                return out
             _lib.check(
                 lib.bnn_predict(cfg, _lib.ptr(x), N, _lib.ptr(thp), U, None, None, int(seed), 0, int(system_offset),
                                 int(system_major), _lib.ptr(out), None, None, _lib.current_stream_ptr()),
@@ -137,12 +151,13 @@ class MultiSWAG:
 
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
-        lo, hi = shard_range(n_total, rank, world)
+        granule = self.system_granule(x_local.shape[1])
+        lo, hi = shard_range(n_total, rank, world, granule)
         assert x_local.shape[0] == hi - lo, (x_local.shape, lo, hi)
         local = self.predict(x_local, samples_per_model, seed, scale, system_offset=lo, system_major=True)
         if not gather or world == 1:
             return local
-        return gather_system_shards(local, n_total, group)
+        return gather_system_shards(local, n_total, group, granule)
 
     # ------------------------------------------------------------------ drop-in per-call path
     def sample_full_swag(self, X_sample):

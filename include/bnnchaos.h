@@ -98,6 +98,10 @@ int bnn_pack_theta(const bnn_model_config* cfg, const float* d_theta, int64_t n_
  * d_workspace: bnn_predict_workspace_bytes() bytes (may be NULL when that returns 0).
  */
 size_t bnn_predict_workspace_bytes(const bnn_model_config* cfg, int64_t n_systems, int64_t n_units);
+/* Systems per position-independent group of the kernel bnn_predict selects for cfg (or <0): a batch split at
+ * multiples of it (shards, chunks) gives bit-identical per-system results to the unsplit batch.  The FFMA
+ * kernels treat every system alike (1); the tensor-core kernel pools in 32-row blocks of its 5-system tile (5). */
+int32_t bnn_predict_system_granule(const bnn_model_config* cfg);
 int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems,
                 const float* d_theta_packed, int64_t n_units, const float* d_eps,
                 const float* d_eps_sum, uint64_t seed, int64_t unit_offset, int64_t system_offset,

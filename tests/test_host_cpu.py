@@ -136,6 +136,12 @@ def test_shard_range_partitions():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+            for g in (5, 8):  # granule-aligned boundaries (tensor-core tile), still a partition
+                spans = [shard_range(n, r, w, g) for r in range(w)]
+                assert spans[0][0] == 0 and spans[-1][1] == n
+                assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+                assert all(a % g == 0 for a, _ in spans if a < n)
+                assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 2 * g
 
 
 _GLOO_WORKER = r"""
@@ -144,11 +150,11 @@ sys.path.insert(0, {root!r})
 from bnn_chaos_model_b200.multiswag import gather_system_shards, shard_range
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
-for n_total in (10, 11):
-    lo, hi = shard_range(n_total, rank, 2)
+for n_total, g in ((10, 1), (11, 1), (23, 5), (4, 5)):
+    lo, hi = shard_range(n_total, rank, 2, g)
     full_ref = torch.arange(n_total * 3 * 2, dtype=torch.float32).reshape(n_total, 3, 2)
-    full = gather_system_shards(full_ref[lo:hi].clone(), n_total)
-    assert torch.equal(full, full_ref), (rank, n_total)
+    full = gather_system_shards(full_ref[lo:hi].clone(), n_total, granule=g)
+    assert torch.equal(full, full_ref), (rank, n_total, g)
 dist.destroy_process_group()
 print("ok", rank)
 """
