@@ -86,6 +86,10 @@ SIGNATURES = {
         [_CFG, _HP, C.c_int32, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_uint64,
          C.c_uint64, c_f32p, c_f32p, C.c_void_p, C.c_void_p],
     ),
+    "bnn_train_noise": (
+        C.c_int,
+        [_CFG, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, c_f32p, c_f32p, c_f32p, C.c_void_p],
+    ),
     "bnn_eval_loss": (
         C.c_int,
         [_CFG, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_uint64, c_f32p, c_f32p, C.c_void_p,

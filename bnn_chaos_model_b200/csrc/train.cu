@@ -1,22 +1,800 @@
-// K4: fused SWAG training step -- placeholder until the kernels land.
+// K4: fused SWAG training step -- noisy forward + analytic backward + clip + SGD-momentum for n_seeds
+// independent models in one call, and the validation loss (bnn_eval_loss).
+//
+// Reference: SWAGModel.training_step (/root/reference/spock_reg_model.py:722-732) -> lossfnc (:579-583) ->
+// VarModel.forward(noisy_val=True) (:486-528) -> _lossfnc (:547-577); loss.backward(); Lightning's
+// gradient_clip_val = clip_grad_norm_ (run_swag.py:61,74-79); torch.optim.SGD(momentum, weight_decay) (:709-711).
+//
+// total = sum_b nll_b + beta_in * B * 1/2 sum_c (e^{lvin_c} - lvin_c - 1) + beta_out * sum_{b,j} 1/2 (s_bj^2 + e^{lvs_j} - lvs_j - 1)
+//
+// Backward (per system; T rows, n = T), derived by hand and checked against the reference's autograd gradient
+// (tests/golden/train_v50.npz):
+//   head:   g_r = (g_mu * (hi-lo)/2 (1 - tanh^2 r0), g_sd * ...);  dV2 += g_r r2^T;  g_a2 = (V2^T g_r) . [r2>0];
+//           dV1 += g_a2 r1^T;  g_a1 = (V1^T g_a2) . [r1>0];  dV0 += g_a1 s'^T;  g_s' = V0^T g_a1
+//   noise:  s' = s + eps_sum e^{lvs/2}:  g_s = g_s' + beta_out s;  dlvs += g_s' (s'-s)/2  (+ beta_out B (e^{lvs}-1)/2)
+//   stats:  s = [mu_s, sqrt(|v_s|+1e-5)], mu_s = eps1 sqrt(v/n) + m, v_s = eps2 sqrt(2 v^2/(n-1)) + v:
+//           g_m = g_mus;  g_v = g_mus eps1 / (2 n sqrt(v/n)) + g_vs (1 + eps2 2 v / ((n-1) sqrt(2 v^2/(n-1)))),
+//           g_vs = g_sds sign(v_s) / (2 sd_s);   g_f[t] = g_m / n + g_v 2 (f_t - m) / (n-1)      (v = std^2, unbiased)
+//   MLP:    dW2 += g_f^T h2; g_a2 = (g_f W2) . [h2>0]; dW1 += g_a2^T h1; g_a1 = (g_a2 W1) . [h1>0]; dW0 += g_a1^T x';
+//           g_x = g_a1 W0;  x' = mask(x) + eps_in e^{lvin/2}:  dlvin += g_x . (x' - mask(x)) / 2  (+ beta_in B (e^{lvin}-1)/2)
+//
+// Decomposition: one CTA owns a seed and walks that seed's systems (grid = n_cta x n_seeds); a system's T x 41
+// input, both hidden activations and the latent rows stay in shared memory (feature-major [feature][row]) for the
+// whole forward + backward; every thread accumulates its own block of every weight gradient in registers over all
+// systems of the CTA, writes one partial gradient vector per CTA, and a second kernel adds the partials in a fixed
+// order (bit-reproducible SWAG moments), a third computes the global norm, clips and applies SGD.
 #include "common.cuh"
+#include "loss_device.cuh"
+#include "predict_device.cuh"
+
+namespace bnn {
+namespace train {
+
+constexpr int NTHR = 288;          // 9 warps: 25 row quads x 11 column groups of the widest row GEMM (T = 100)
+constexpr int DPAD = 8;            // metric slots appended to each gradient partial
+constexpr int SLOT_NLL = 0, SLOT_SKL = 1;
+
+struct Params {
+    const float* theta;        // [n_seeds, d]
+    const float* X;            // [n_data, T, F]
+    const float* Y;            // [n_data, 2]
+    const int32_t* batch_index;  // [n_seeds, B] rows of X / Y, or null (row = b)
+    const float* eps_in;       // [n_seeds, B, T, F] or null
+    const float* eps12;        // [n_seeds, B, 2L] or null
+    const float* eps_sum;      // [n_seeds, B, 2L] or null
+    float* partial;            // [n_seeds, n_cta, d + DPAD]
+    int B, T, F, FP, n_cta;
+    uint64_t seed, step;
+    uint64_t zero_mask;
+    HeadConsts hc;
+    float beta_out;
+};
+
+// Philox key of one seed-model's noise streams; counters: (block, batch position, step, stream)
+__host__ __device__ inline uint64_t seed_key(uint64_t seed, int seed_index) {
+    return seed + 0x9E3779B97F4A7C15ull * (uint64_t)(seed_index + 1);
+}
+
+struct Smem {
+    // offsets in floats
+    int xT, nT, h1T, h2T, fT, W0T, b0, W1T, b1, W2T, b2, W2n, W1n, W0n, small, total;
+    __host__ __device__ Smem(int T, int F, int FP) {
+        int o = 0;
+        xT = o; o += F * T;
+        nT = o; o += F * T;
+        h1T = o; o += H * T;
+        h2T = o; o += H * T;
+        fT = o; o += L * T;
+        W0T = o; o += F * H;
+        b0 = o; o += H;
+        W1T = o; o += H * H;
+        b1 = o; o += H;
+        W2T = o; o += H * L;
+        b2 = o; o += L;
+        W2n = o; o += L * H;
+        W1n = o; o += H * H;
+        W0n = o; o += H * FP;
+        small = o; o += 768;
+        total = o;
+    }
+};
+// layout of the `small` region (floats)
+enum { SM_M = 0, SM_VAR = 20, SM_SIM = 40, SM_SIV = 60, SM_VS = 80, SM_S = 100, SM_SP = 140, SM_R1 = 180, SM_R2 = 220,
+       SM_G2 = 260, SM_G1 = 300, SM_GS = 340, SM_GM = 380, SM_GV = 400, SM_E12 = 420, SM_ESN = 460, SM_ELVH = 500,
+       SM_LVS = 540, SM_NSC = 580 /* exp(lv_in/2), up to 64 */, SM_R = 644, SM_GR = 648, SM_Y = 652 };
+
+// C[4 rows of quad q][4 columns of group cg] += sum_k AT[k][4q..4q+3] * W[k][4cg..4cg+3]
+__device__ __forceinline__ void rowgemm4x4(const float* __restrict__ AT, int RP, int K, const float* __restrict__ W,
+                                           int NP, int q, int cg, float (&acc)[4][4]) {
+    const float* ap = AT + 4 * q;
+    const float* wp = W + 4 * cg;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(ap + k * RP);
+        const float4 w = *reinterpret_cast<const float4*>(wp + k * NP);
+        const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+    }
+}
+
+// acc[jj][kk] += sum_r G[j0+jj][r] * Hm[krow[kk]][r]   (both feature-major with row pitch RP = T)
+__device__ __forceinline__ void outer_acc(const float* __restrict__ G, const float* __restrict__ Hm, int T, int j0,
+                                          const int (&krow)[4], float (&acc)[2][4]) {
+    const float* g0p = G + j0 * T;
+    const float* g1p = g0p + T;
+#pragma unroll 2
+    for (int r = 0; r < T; r += 4) {
+        const float4 g0 = *reinterpret_cast<const float4*>(g0p + r);
+        const float4 g1 = *reinterpret_cast<const float4*>(g1p + r);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float4 h = *reinterpret_cast<const float4*>(Hm + krow[kk] * T + r);
+            acc[0][kk] = fmaf(g0.x, h.x, acc[0][kk]); acc[0][kk] = fmaf(g0.y, h.y, acc[0][kk]);
+            acc[0][kk] = fmaf(g0.z, h.z, acc[0][kk]); acc[0][kk] = fmaf(g0.w, h.w, acc[0][kk]);
+            acc[1][kk] = fmaf(g1.x, h.x, acc[1][kk]); acc[1][kk] = fmaf(g1.y, h.y, acc[1][kk]);
+            acc[1][kk] = fmaf(g1.z, h.z, acc[1][kk]); acc[1][kk] = fmaf(g1.w, h.w, acc[1][kk]);
+        }
+    }
+}
+
+__device__ __forceinline__ float row_sum(const float* __restrict__ G, int T) {
+    float s = 0.f;
+    for (int r = 0; r < T; r += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(G + r);
+        s += (g.x + g.y) + (g.z + g.w);
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(NTHR, 2) train_fwd_bwd_kernel(const Params prm) {
+    extern __shared__ __align__(16) float sm[];
+    const int T = prm.T, F = prm.F, FP = prm.FP, NQ = T >> 2;
+    const Smem L_(T, F, FP);
+    const FlatLayout fl(F);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int sidx = blockIdx.y;
+    const float* th = prm.theta + (int64_t)sidx * fl.d;
+    float* xT = sm + L_.xT; float* nT = sm + L_.nT; float* h1T = sm + L_.h1T; float* h2T = sm + L_.h2T; float* fT = sm + L_.fT;
+    float* W0T = sm + L_.W0T; float* b0 = sm + L_.b0; float* W1T = sm + L_.W1T; float* b1 = sm + L_.b1;
+    float* W2T = sm + L_.W2T; float* b2 = sm + L_.b2; float* W2n = sm + L_.W2n; float* W1n = sm + L_.W1n; float* W0n = sm + L_.W0n;
+    float* sv = sm + L_.small;
+
+    // ---- stage this seed's feature weights (natural and transposed) and noise scales ----
+    for (int i = tid; i < H * F; i += NTHR) {
+        const int j = i / F, c = i - j * F;
+        const float w = __ldg(th + fl.W0 + i);
+        W0T[c * H + j] = w;
+        W0n[j * FP + c] = w;
+    }
+    for (int i = tid; i < H * (FP - F); i += NTHR) W0n[(i / (FP - F)) * FP + F + i % (FP - F)] = 0.f;
+    for (int i = tid; i < H * H; i += NTHR) {
+        const int j = i / H, k = i - j * H;
+        const float w = __ldg(th + fl.W1 + i);
+        W1T[k * H + j] = w;
+        W1n[i] = w;
+    }
+    for (int i = tid; i < L * H; i += NTHR) {
+        const int j = i / H, k = i - j * H;
+        const float w = __ldg(th + fl.W2 + i);
+        W2T[k * L + j] = w;
+        W2n[i] = w;
+    }
+    if (tid < H) { b0[tid] = __ldg(th + fl.b0 + tid); b1[tid] = __ldg(th + fl.b1 + tid); }
+    if (tid < L) b2[tid] = __ldg(th + fl.b2 + tid);
+    if (tid < S2) {
+        const float lv = __ldg(th + fl.lv_sum + tid);
+        sv[SM_LVS + tid] = lv;
+        sv[SM_ELVH + tid] = expf(__fdiv_rn(lv, 2.0f));
+    }
+    if (tid < F) sv[SM_NSC + tid] = expf(__fdiv_rn(__ldg(th + fl.lv_in + tid), 2.0f));
+
+    // ---- thread-owned gradient accumulators (summed over this CTA's systems) ----
+    float aW0[2][4] = {}, aW1[2][4] = {}, aW2[2][4] = {}, aV0[2][4] = {}, aV1[2][4] = {};
+    float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, aV2 = 0.f, ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, alvs = 0.f;
+    float alvin[4] = {0.f, 0.f, 0.f, 0.f};
+    float a_nll = 0.f, a_skl = 0.f;
+    // (j2 x k4) blocks of the 40x40 / 40xF / 20x40 gradients
+    const int jb = tid / 10, kb10 = tid % 10;      // dW1, dV0, dV1, dW2: 10 k-groups
+    const int KG0 = FP >> 2;                       // dW0: FP/4 k-groups (F = 41 -> 11); 20 * KG0 <= 248 threads
+    const int jb0 = tid / KG0, kb11 = tid % KG0;
+    int krow0[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) krow0[kk] = min(4 * kb11 + kk, F - 1);
+    const int krow10[4] = {4 * kb10, 4 * kb10 + 1, 4 * kb10 + 2, 4 * kb10 + 3};
+    const int q_rg = tid % NQ, cg_rg = tid / NQ;   // row-GEMM item of this thread
+    const float Tf = (float)T, Tm1 = (float)(T - 1);
+    const uint64_t key = seed_key(prm.seed, sidx);
+    __syncthreads();
+
+    for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
+        const int64_t sb = (int64_t)sidx * prm.B + b;
+        const int64_t row = prm.batch_index ? (int64_t)prm.batch_index[sb] : (int64_t)b;
+        // ---- S0: x' = mask(x) + eps_in * exp(lv_in/2), feature-major; noise term kept for dlv_in ----
+        {
+            const float* xs = prm.X + row * (int64_t)T * F;
+            const float* es = prm.eps_in ? prm.eps_in + sb * (int64_t)T * F : nullptr;
+            if (es) {
+                for (int i = tid; i < T * F; i += NTHR) {
+                    const int t = i / F, c = i - t * F;
+                    float xv = __ldg(xs + i);
+                    if ((prm.zero_mask >> c) & 1ull) xv = __fsub_rn(xv, xv);  // x - mask keeps NaN (:452-478)
+                    const float nz = __fmul_rn(__ldg(es + i), sv[SM_NSC + c]);
+                    nT[c * T + t] = nz;
+                    xT[c * T + t] = __fadd_rn(xv, nz);
+                }
+            } else {
+                const int F4 = (F + 3) >> 2;
+                for (int i = tid; i < T * F4; i += NTHR) {
+                    const int t = i / F4, c4 = i - t * F4;
+                    const float4 n4 = philox_normal4(key, STREAM_EPS_IN, (uint32_t)b, (uint32_t)prm.step, (uint32_t)i);
+                    const float e[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = 4 * c4 + u;
+                        if (c < F) {
+                            float xv = __ldg(xs + t * F + c);
+                            if ((prm.zero_mask >> c) & 1ull) xv = __fsub_rn(xv, xv);
+                            const float nz = __fmul_rn(e[u], sv[SM_NSC + c]);
+                            nT[c * T + t] = nz;
+                            xT[c * T + t] = __fadd_rn(xv, nz);
+                        }
+                    }
+                }
+            }
+            if (tid < S2 / 4) {
+                float4 a, c;
+                if (prm.eps12) {
+                    a = __ldg(reinterpret_cast<const float4*>(prm.eps12 + sb * S2) + tid);
+                    c = __ldg(reinterpret_cast<const float4*>(prm.eps_sum + sb * S2) + tid);
+                } else {
+                    a = philox_normal4(key, STREAM_EPS, (uint32_t)b, (uint32_t)prm.step, (uint32_t)tid);
+                    c = philox_normal4(key, STREAM_EPS_SUM, (uint32_t)b, (uint32_t)prm.step, (uint32_t)tid);
+                }
+                *reinterpret_cast<float4*>(sv + SM_E12 + 4 * tid) = a;
+                *reinterpret_cast<float4*>(sv + SM_ESN + 4 * tid) = c;
+            }
+            if (tid == 32) {
+                sv[SM_Y] = __ldg(prm.Y + row * 2);
+                sv[SM_Y + 1] = __ldg(prm.Y + row * 2 + 1);
+            }
+        }
+        __syncthreads();
+        // ---- S1..S3: feature_nn forward ----
+        if (cg_rg < 10) {
+            float acc[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const float bv = b0[4 * cg_rg + c]; for (int r = 0; r < 4; ++r) acc[r][c] = bv; }
+            rowgemm4x4(xT, T, F, W0T, H, q_rg, cg_rg, acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<float4*>(h1T + (4 * cg_rg + c) * T + 4 * q_rg) =
+                    make_float4(relu_nan(acc[0][c]), relu_nan(acc[1][c]), relu_nan(acc[2][c]), relu_nan(acc[3][c]));
+        }
+        __syncthreads();
+        if (cg_rg < 10) {
+            float acc[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const float bv = b1[4 * cg_rg + c]; for (int r = 0; r < 4; ++r) acc[r][c] = bv; }
+            rowgemm4x4(h1T, T, H, W1T, H, q_rg, cg_rg, acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<float4*>(h2T + (4 * cg_rg + c) * T + 4 * q_rg) =
+                    make_float4(relu_nan(acc[0][c]), relu_nan(acc[1][c]), relu_nan(acc[2][c]), relu_nan(acc[3][c]));
+        }
+        __syncthreads();
+        if (cg_rg < 5) {
+            float acc[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const float bv = b2[4 * cg_rg + c]; for (int r = 0; r < 4; ++r) acc[r][c] = bv; }
+            rowgemm4x4(h2T, T, H, W2T, L, q_rg, cg_rg, acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<float4*>(fT + (4 * cg_rg + c) * T + 4 * q_rg) =
+                    make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+        }
+        __syncthreads();
+        // ---- S4: pooling (two-pass mean / unbiased variance per latent column, :418-419) ----
+        if (tid < L * 8) {
+            const int c = tid >> 3, part = tid & 7;
+            const float* fc = fT + c * T;
+            float s = 0.f;
+            for (int r = part; r < T; r += 8) s += fc[r];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            const float mean = __fdiv_rn(s, Tf);
+            float m2 = 0.f;
+            for (int r = part; r < T; r += 8) { const float dl = fc[r] - mean; m2 = fmaf(dl, dl, m2); }
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
+            if (part == 0) {
+                const float sd = sqrtf(__fdiv_rn(m2, Tm1));
+                const float var = __fmul_rn(sd, sd);
+                const float sim = sqrtf(__fdiv_rn(var, Tf));                                   // :422
+                const float siv = sqrtf(__fdiv_rn(__fmul_rn(2.0f, __fmul_rn(var, var)), Tm1));   // :423
+                const float e1 = sv[SM_E12 + c], e2 = sv[SM_E12 + L + c];
+                const float mus = __fadd_rn(__fmul_rn(e1, sim), mean);                          // :426
+                const float vs = __fadd_rn(__fmul_rn(e2, siv), var);                            // :427
+                const float sds = sqrtf(__fadd_rn(fabsf(vs), 1e-5f));                           // :430
+                sv[SM_M + c] = mean; sv[SM_VAR + c] = var; sv[SM_SIM + c] = sim; sv[SM_SIV + c] = siv; sv[SM_VS + c] = vs;
+                sv[SM_S + c] = mus; sv[SM_S + L + c] = sds;
+                // summary noise (:448-450) and the KL terms of the clean summary (:515-520)
+                const float lv0 = sv[SM_LVS + c], lv1 = sv[SM_LVS + L + c];
+                sv[SM_SP + c] = __fadd_rn(mus, __fmul_rn(sv[SM_ESN + c], sv[SM_ELVH + c]));
+                sv[SM_SP + L + c] = __fadd_rn(sds, __fmul_rn(sv[SM_ESN + L + c], sv[SM_ELVH + L + c]));
+                a_skl += 0.5f * (mus * mus + expf(lv0) - lv0 - 1.0f) + 0.5f * (sds * sds + expf(lv1) - lv1 - 1.0f);
+            }
+        }
+        __syncthreads();
+        // ---- S6: regress_nn forward (head weights through L2: 13 kB per seed, shared by every CTA of the seed) ----
+        if (tid < H * 4) {
+            const int j = tid >> 2, part = tid & 3;
+            const float* w = th + fl.V0 + j * S2 + 10 * part;
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) a = fmaf(sv[SM_SP + 10 * part + k], __ldg(w + k), a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (part == 0) sv[SM_R1 + j] = relu_nan(a + __ldg(th + fl.c0 + j));
+        }
+        __syncthreads();
+        if (tid < H * 4) {
+            const int j = tid >> 2, part = tid & 3;
+            const float* w = th + fl.V1 + j * H + 10 * part;
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) a = fmaf(sv[SM_R1 + 10 * part + k], __ldg(w + k), a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (part == 0) sv[SM_R2 + j] = relu_nan(a + __ldg(th + fl.c1 + j));
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // o = lane >> 4 (two outputs), 16 lanes each: k = l16, l16+16, l16+32
+            const int o = lane >> 4, l16 = lane & 15;
+            float a = 0.f;
+            for (int k = l16; k < H; k += 16) a = fmaf(sv[SM_R2 + k], __ldg(th + fl.V2 + o * H + k), a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            const float r0 = __shfl_sync(0xffffffffu, a, 0) + __ldg(th + fl.c2);
+            const float r1 = __shfl_sync(0xffffffffu, a, 16) + __ldg(th + fl.c2 + 1);
+            if (lane == 0) {
+                const float t0 = tanhf(r0), t1 = tanhf(r1);
+                const float mu = soft_clamp_dev(r0, prm.hc.lo_mu, prm.hc.hi_mu);
+                const float sd = soft_clamp_dev(r1, prm.hc.lo_sd, prm.hc.hi_sd);
+                float l0, l1, dm0, dm1, ds0, ds1;
+                nll_terms(mu, sd, sv[SM_Y], l0, dm0, ds0);
+                nll_terms(mu, sd, sv[SM_Y + 1], l1, dm1, ds1);
+                a_nll += -(l0 + l1);
+                const float gmu = -(dm0 + dm1), gsd = -(ds0 + ds1);
+                sv[SM_GR] = gmu * 0.5f * (prm.hc.hi_mu - prm.hc.lo_mu) * (1.0f - t0 * t0);
+                sv[SM_GR + 1] = gsd * 0.5f * (prm.hc.hi_sd - prm.hc.lo_sd) * (1.0f - t1 * t1);
+            }
+        }
+        __syncthreads();
+        // ---- S7: regress_nn backward ----
+        const float gr0 = sv[SM_GR], gr1 = sv[SM_GR + 1];
+        if (tid < 2 * H) {
+            const int o = tid / H, k = tid - o * H;
+            aV2 = fmaf(o ? gr1 : gr0, sv[SM_R2 + k], aV2);
+            if (tid < H) {
+                const float g = gr0 * __ldg(th + fl.V2 + tid) + gr1 * __ldg(th + fl.V2 + H + tid);
+                sv[SM_G2 + tid] = sv[SM_R2 + tid] > 0.f ? g : 0.f;
+            }
+        }
+        if (tid == 2 * H) ac2 += gr0;
+        if (tid == 2 * H + 1) ac2 += gr1;
+        __syncthreads();
+        if (tid < H * 4) {
+            const int k = tid >> 2, part = tid & 3;
+            float a = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 10; ++jj) {
+                const int j = 10 * part + jj;
+                a = fmaf(sv[SM_G2 + j], __ldg(th + fl.V1 + j * H + k), a);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (part == 0) sv[SM_G1 + k] = sv[SM_R1 + k] > 0.f ? a : 0.f;
+        }
+        if (tid < 200) {  // dV1[j][k] += g_a2[j] r1[k]
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    aV1[jj][kk] = fmaf(sv[SM_G2 + 2 * jb + jj], sv[SM_R1 + krow10[kk]], aV1[jj][kk]);
+        }
+        if (tid >= 200 && tid < 200 + H) ac1 += sv[SM_G2 + tid - 200];
+        __syncthreads();
+        if (tid < S2 * 4) {
+            const int k = tid >> 2, part = tid & 3;
+            float a = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 10; ++jj) {
+                const int j = 10 * part + jj;
+                a = fmaf(sv[SM_G1 + j], __ldg(th + fl.V0 + j * S2 + k), a);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (part == 0) {
+                const float s = sv[SM_S + k], sp = sv[SM_SP + k];
+                alvs = fmaf(a, 0.5f * (sv[SM_ESN + k] * sv[SM_ELVH + k]), alvs);  // ds'/dlv = eps e^{lv/2} / 2
+                sv[SM_GS + k] = a + prm.beta_out * s;
+                (void)sp;
+            }
+        }
+        if (tid < 200) {  // dV0[j][k] += g_a1[j] s'[k]
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    aV0[jj][kk] = fmaf(sv[SM_G1 + 2 * jb + jj], sv[SM_SP + krow10[kk]], aV0[jj][kk]);
+        }
+        if (tid >= 200 && tid < 200 + H) ac0 += sv[SM_G1 + tid - 200];
+        __syncthreads();
+        if (tid < L) {
+            const int c = tid;
+            const float gmus = sv[SM_GS + c], gsds = sv[SM_GS + L + c];
+            const float vs = sv[SM_VS + c], sds = sv[SM_S + L + c], var = sv[SM_VAR + c];
+            const float sgn = vs > 0.f ? 1.0f : (vs < 0.f ? -1.0f : 0.f);
+            const float gvs = gsds * sgn / (2.0f * sds);
+            const float e1 = sv[SM_E12 + c], e2 = sv[SM_E12 + L + c];
+            const float gv = gmus * e1 / (2.0f * Tf * sv[SM_SIM + c]) +
+                             gvs * (1.0f + e2 * (2.0f * var) / (Tm1 * sv[SM_SIV + c]));
+            sv[SM_GM + c] = gmus / Tf;              // coefficient of 1
+            sv[SM_GV + c] = 2.0f * gv / Tm1;        // coefficient of (f - m)
+        }
+        __syncthreads();
+        // ---- S8: g_f in place over f ----
+        for (int i = tid; i < L * NQ; i += NTHR) {
+            const int c = i / NQ, q = i - c * NQ;
+            float4* p = reinterpret_cast<float4*>(fT + c * T + 4 * q);
+            const float m = sv[SM_M + c], A = sv[SM_GM + c], Bc = sv[SM_GV + c];
+            float4 f = *p;
+            f.x = fmaf(Bc, f.x - m, A); f.y = fmaf(Bc, f.y - m, A); f.z = fmaf(Bc, f.z - m, A); f.w = fmaf(Bc, f.w - m, A);
+            *p = f;
+        }
+        __syncthreads();
+        // ---- S9: dW2 += g_f^T h2, db2 ----
+        if (tid < 100) outer_acc(fT, h2T, T, 2 * jb, krow10, aW2);
+        else if (tid < 100 + L) ab2 += row_sum(fT + (tid - 100) * T, T);
+        __syncthreads();
+        // ---- S10: g_a2 = (g_f W2) . [h2 > 0], in place over h2 ----
+        if (cg_rg < 10) {
+            float acc[4][4] = {};
+            rowgemm4x4(fT, T, L, W2n, H, q_rg, cg_rg, acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4* p = reinterpret_cast<float4*>(h2T + (4 * cg_rg + c) * T + 4 * q_rg);
+                const float4 h = *p;
+                *p = make_float4(h.x > 0.f ? acc[0][c] : 0.f, h.y > 0.f ? acc[1][c] : 0.f, h.z > 0.f ? acc[2][c] : 0.f,
+                                 h.w > 0.f ? acc[3][c] : 0.f);
+            }
+        }
+        __syncthreads();
+        // ---- S11: dW1 += g_a2^T h1, db1 ----
+        if (tid < 200) outer_acc(h2T, h1T, T, 2 * jb, krow10, aW1);
+        else if (tid < 200 + H) ab1 += row_sum(h2T + (tid - 200) * T, T);
+        __syncthreads();
+        // ---- S12: g_a1 = (g_a2 W1) . [h1 > 0], in place over h1 ----
+        if (cg_rg < 10) {
+            float acc[4][4] = {};
+            rowgemm4x4(h2T, T, H, W1n, H, q_rg, cg_rg, acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4* p = reinterpret_cast<float4*>(h1T + (4 * cg_rg + c) * T + 4 * q_rg);
+                const float4 h = *p;
+                *p = make_float4(h.x > 0.f ? acc[0][c] : 0.f, h.y > 0.f ? acc[1][c] : 0.f, h.z > 0.f ? acc[2][c] : 0.f,
+                                 h.w > 0.f ? acc[3][c] : 0.f);
+            }
+        }
+        __syncthreads();
+        // ---- S13: dW0 += g_a1^T x', db0;  S14: dlv_in += sum_r (g_a1 W0)[r][c] * noise[r][c] / 2 ----
+        if (tid < 20 * KG0) outer_acc(h1T, xT, T, 2 * jb0, krow0, aW0);
+        else if (tid >= 248) ab0 += row_sum(h1T + (tid - 248) * T, T);
+        if (cg_rg < (FP >> 2)) {
+            float acc[4][4] = {};
+            rowgemm4x4(h1T, T, H, W0n, FP, q_rg, cg_rg, acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col = min(4 * cg_rg + c, F - 1);
+                const float4 nz = *reinterpret_cast<const float4*>(nT + col * T + 4 * q_rg);
+                alvin[c] += (acc[0][c] * nz.x + acc[1][c] * nz.y) + (acc[2][c] * nz.z + acc[3][c] * nz.w);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write this CTA's partial gradient (flatten() order) ----
+    float* part = prm.partial + ((int64_t)sidx * prm.n_cta + blockIdx.x) * (fl.d + DPAD);
+    // dlv_in: fixed-order sum over the row quads through shared memory (xT is free now)
+    float* red = xT;  // [FP][NQ]
+    if (cg_rg < (FP >> 2)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[(4 * cg_rg + c) * NQ + q_rg] = alvin[c];
+    }
+    __syncthreads();
+    if (tid < F) {
+        float s = 0.f;
+        for (int q = 0; q < NQ; ++q) s += red[tid * NQ + q];
+        part[fl.lv_in + tid] = 0.5f * s;
+    }
+    // lv_sum: owner = thread 4k (part == 0 of the k-th group of the g_s' GEMV)
+    if (tid < S2 * 4 && (tid & 3) == 0) part[fl.lv_sum + (tid >> 2)] = alvs;
+    if (tid < 20 * KG0) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int c = 4 * kb11 + kk;
+                if (c < F) part[fl.W0 + (2 * jb0 + jj) * F + c] = aW0[jj][kk];
+            }
+    }
+    if (tid < 200) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                part[fl.W1 + (2 * jb + jj) * H + krow10[kk]] = aW1[jj][kk];
+                part[fl.V0 + (2 * jb + jj) * S2 + krow10[kk]] = aV0[jj][kk];
+                part[fl.V1 + (2 * jb + jj) * H + krow10[kk]] = aV1[jj][kk];
+            }
+    }
+    if (tid < 100) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) part[fl.W2 + (2 * jb + jj) * H + krow10[kk]] = aW2[jj][kk];
+    }
+    if (tid >= 248) part[fl.b0 + tid - 248] = ab0;
+    if (tid >= 200 && tid < 200 + H) {
+        part[fl.b1 + tid - 200] = ab1;
+        part[fl.c0 + tid - 200] = ac0;
+        part[fl.c1 + tid - 200] = ac1;
+    }
+    if (tid >= 100 && tid < 100 + L) part[fl.b2 + tid - 100] = ab2;
+    if (tid < 2 * H) part[fl.V2 + tid] = aV2;
+    if (tid == 2 * H || tid == 2 * H + 1) part[fl.c2 + tid - 2 * H] = ac2;
+    // metrics: nll (lane 0 of warp 0) and the summary KL terms (threads 8c of the pooling groups)
+    float skl = (tid < L * 8 && (tid & 7) == 0) ? a_skl : 0.f;
+    __syncthreads();
+    red[tid] = skl;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int c = 0; c < L; ++c) s += red[8 * c];
+        part[fl.d + SLOT_NLL] = a_nll;
+        part[fl.d + SLOT_SKL] = s;
+        for (int i = 2; i < DPAD; ++i) part[fl.d + i] = 0.f;
+    }
+}
+
+// grad[s][i] = sum_c partial[s][c][i] (fixed order) + analytic KL terms; per-block sum of squares.
+__global__ void __launch_bounds__(256) train_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ theta,
+                                                           int n_cta, int d, int F, float kl_in_scale, float kl_sum_scale,
+                                                           float* __restrict__ grad, float* __restrict__ sq) {
+    __shared__ float sh[256];
+    const int s = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    const int DP = d + DPAD;
+    float g = 0.f;
+    if (i < DP) {
+        const float* p = partial + (int64_t)s * n_cta * DP + i;
+        for (int c = 0; c < n_cta; ++c) g += p[(int64_t)c * DP];
+        if (i < F) {  // input_kl * beta_in * B (:585-590, :726): d/dlv = (e^lv - 1)/2
+            g += kl_in_scale * 0.5f * (expf(theta[(int64_t)s * d + i]) - 1.0f);
+        } else if (i < F + S2) {  // summary_kl * beta_out, summed over the batch (:515-520, :727)
+            g += kl_sum_scale * 0.5f * (expf(theta[(int64_t)s * d + i]) - 1.0f);
+        }
+        grad[(int64_t)s * DP + i] = g;
+    }
+    sh[threadIdx.x] = (i < d) ? g * g : 0.f;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) sh[threadIdx.x] += sh[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sq[s * gridDim.x + blockIdx.x] = sh[0];
+}
+
+// clip_grad_norm_ (coef = clip / (norm + 1e-6), applied when < 1) + torch.optim.SGD with momentum / weight decay.
+__global__ void __launch_bounds__(256) train_update_kernel(const float* __restrict__ grad, const float* __restrict__ sq,
+                                                           int n_blocks, int d, int F, int B, bnn_train_hparams hp,
+                                                           float* __restrict__ theta, float* __restrict__ mom,
+                                                           float* __restrict__ grad_out, float* __restrict__ metrics) {
+    const int s = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    const int DP = d + DPAD;
+    float ss = 0.f;
+    for (int b = 0; b < n_blocks; ++b) ss += sq[s * n_blocks + b];
+    const float norm = sqrtf(ss);
+    const float coef = hp.clip_norm / (norm + 1e-6f);
+    const float* g = grad + (int64_t)s * DP;
+    if (i < d) {
+        const float gi = g[i];
+        if (grad_out) grad_out[(int64_t)s * d + i] = gi;
+        if (hp.apply_update) {
+            const int64_t o = (int64_t)s * d + i;
+            const float th = theta[o];
+            float dp = coef < 1.0f ? gi * coef : gi;
+            if (hp.weight_decay != 0.f) dp = fmaf(hp.weight_decay, th, dp);
+            const float buf = hp.first_step ? dp : fmaf(hp.momentum, mom[o], dp);
+            mom[o] = buf;
+            theta[o] = th - hp.lr * buf;
+        }
+    }
+    if (metrics && blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) {
+        float* m = metrics + s * 8;
+        const float nll = g[d + SLOT_NLL], skl = g[d + SLOT_SKL] * hp.beta_out;
+        m[0] = nll / (float)B;
+        m[3] = skl / (float)B;
+        m[4] = norm;
+        m[5] = coef < 1.0f ? coef : 1.0f;
+        m[6] = isfinite(nll + skl + norm) ? 0.f : 1.f;
+        m[7] = 0.f;
+        // m[1] (loss with reg) and m[2] (input_kl) are completed by train_metrics_kernel, which reads lv_in before the update
+    }
+}
+
+// input_kl * beta_in * B / B and the total, from the weights the step was evaluated at (runs BEFORE the update kernel)
+__global__ void train_metrics_kernel(const float* __restrict__ theta, const float* __restrict__ grad, int d, int F, int B,
+                                     bnn_train_hparams hp, float* __restrict__ metrics) {
+    const int s = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    float kl = 0.f;
+    for (int c = 0; c < F; ++c) {
+        const float lv = theta[(int64_t)s * d + c];
+        kl += expf(lv) - lv - 1.0f;
+    }
+    const float ikl = 0.5f * kl * hp.beta_in * (float)B;
+    const float* g = grad + (int64_t)s * (d + DPAD);
+    const float nll = g[d + SLOT_NLL], skl = g[d + SLOT_SKL] * hp.beta_out;
+    metrics[s * 8 + 1] = (nll + (ikl + skl)) / (float)B;
+    metrics[s * 8 + 2] = ikl / (float)B;
+}
+
+// the Philox draws of one training step, written out (parity tests feed them to the oracle)
+__global__ void train_noise_kernel(int B, int T, int F, uint64_t seed, uint64_t step, float* __restrict__ eps_in,
+                                   float* __restrict__ eps12, float* __restrict__ eps_sum) {
+    const int sidx = blockIdx.y, b = blockIdx.x;
+    const uint64_t key = seed_key(seed, sidx);
+    const int64_t sb = (int64_t)sidx * B + b;
+    const int F4 = (F + 3) >> 2;
+    for (int i = threadIdx.x; i < T * F4; i += blockDim.x) {
+        const int t = i / F4, c4 = i - t * F4;
+        const float4 n4 = philox_normal4(key, STREAM_EPS_IN, (uint32_t)b, (uint32_t)step, (uint32_t)i);
+        const float e[4] = {n4.x, n4.y, n4.z, n4.w};
+        for (int u = 0; u < 4; ++u)
+            if (4 * c4 + u < F) eps_in[(sb * T + t) * F + 4 * c4 + u] = e[u];
+    }
+    if (threadIdx.x < S2 / 4) {
+        reinterpret_cast<float4*>(eps12 + sb * S2)[threadIdx.x] =
+            philox_normal4(key, STREAM_EPS, (uint32_t)b, (uint32_t)step, threadIdx.x);
+        reinterpret_cast<float4*>(eps_sum + sb * S2)[threadIdx.x] =
+            philox_normal4(key, STREAM_EPS_SUM, (uint32_t)b, (uint32_t)step, threadIdx.x);
+    }
+}
+
+// loss_sum[u] = sum_b _lossfnc(out[u][b], y[b]) -- one block per unit, fixed order
+__global__ void __launch_bounds__(256) nll_sum_kernel(const float2* __restrict__ out, const float2* __restrict__ y, int64_t B,
+                                                      float* __restrict__ loss_sum) {
+    __shared__ float sh[256];
+    const float2* o = out + (int64_t)blockIdx.x * B;
+    float acc = 0.f;
+    for (int64_t b = threadIdx.x; b < B; b += 256) {
+        float l0, l1, a, c;
+        const float2 p = o[b], yy = y[b];
+        nll_terms(p.x, p.y, yy.x, l0, a, c);
+        nll_terms(p.x, p.y, yy.y, l1, a, c);
+        acc += -(l0 + l1);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) sh[threadIdx.x] += sh[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss_sum[blockIdx.x] = sh[0];
+}
+
+static int pick_n_cta(int64_t B, int n_seeds) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t n = (2ll * sms + n_seeds - 1) / n_seeds;  // two resident CTAs per SM over all seeds
+    if (n > B) n = B;
+    if (n < 1) n = 1;
+    return (int)n;
+}
+
+}  // namespace train
+}  // namespace bnn
 
 extern "C" {
 
-size_t bnn_train_workspace_bytes(const bnn_model_config*, int64_t, int32_t) { return 0; }
+size_t bnn_train_workspace_bytes(const bnn_model_config* cfg, int64_t B, int32_t n_seeds) {
+    using namespace bnn;
+    if (validate_config(cfg) != BNN_OK || B <= 0 || n_seeds <= 0) return 0;
+    const int d = FlatLayout(cfg->n_features).d;
+    const int n_cta = train::pick_n_cta(B, n_seeds);
+    const size_t DP = d + train::DPAD;
+    const size_t nb = (DP + 255) / 256;
+    return ((size_t)n_seeds * n_cta * DP + (size_t)n_seeds * DP + (size_t)n_seeds * nb + 64) * sizeof(float);
+}
 
-int bnn_train_step(const bnn_model_config*, const bnn_train_hparams*, int32_t, float*, float*, const float*,
-                   const float*, const int32_t*, int64_t, const float*, const float*, const float*, uint64_t,
-                   uint64_t, float*, float*, void*, void*) {
-    bnn::set_error("bnn_train_step: not built yet");
-    return BNN_E_CONFIG;
+int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int32_t n_seeds, float* d_theta,
+                   float* d_momentum, const float* d_x, const float* d_y, const int32_t* d_batch_index, int64_t B,
+                   const float* d_eps_in, const float* d_eps12, const float* d_eps_sum, uint64_t seed, uint64_t step,
+                   float* d_grad_out, float* d_metrics, void* d_workspace, void* stream) {
+    using namespace bnn;
+    int rc = validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    if ((rc = check_device()) != BNN_OK) return rc;
+    BNN_REQUIRE(hp && d_theta && d_x && d_y && d_workspace, BNN_E_ARG, "bnn_train_step: null pointer");
+    BNN_REQUIRE(n_seeds >= 1 && n_seeds <= 65535 && B >= 1 && B < (1ll << 30), BNN_E_ARG,
+                "bnn_train_step: n_seeds=%d B=%lld out of range", n_seeds, (long long)B);
+    BNN_REQUIRE(!hp->apply_update || d_momentum, BNN_E_ARG, "bnn_train_step: momentum buffer required to update");
+    const bool any = d_eps_in || d_eps12 || d_eps_sum, all = d_eps_in && d_eps12 && d_eps_sum;
+    BNN_REQUIRE(!any || all, BNN_E_ARG, "bnn_train_step: give all of eps_in, eps12, eps_sum or none");
+    BNN_REQUIRE(aligned16(d_workspace) && (!d_eps12 || (aligned16(d_eps12) && aligned16(d_eps_sum))), BNN_E_ALIGN,
+                "bnn_train_step: workspace / eps12 / eps_sum must be 16-byte aligned");
+    const int F = cfg->n_features, T = cfg->n_times, FP = (F + 3) & ~3;
+    BNN_REQUIRE((T / 4) * (FP / 4) <= train::NTHR && FP <= 48, BNN_E_CONFIG,
+                "bnn_train_step: T/4 * ceil(F/4) = %d exceeds the %d-thread tile, or F > 48", (T / 4) * (FP / 4),
+                train::NTHR);
+    const FlatLayout fl(F);
+    const train::Smem sl(T, F, FP);
+    const size_t smem = (size_t)sl.total * sizeof(float);
+    BNN_REQUIRE(smem <= 227 * 1024, BNN_E_CONFIG, "bnn_train_step: tile needs %zu bytes of shared memory", smem);
+    static bool attr_done = false;
+    if (!attr_done) {
+        BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_cta = train::pick_n_cta(B, n_seeds);
+    const int DP = fl.d + train::DPAD, nb = (DP + 255) / 256;
+    float* partial = (float*)d_workspace;
+    float* grad = partial + (size_t)n_seeds * n_cta * DP;
+    float* sq = grad + (size_t)n_seeds * DP;
+
+    train::Params prm;
+    prm.theta = d_theta; prm.X = d_x; prm.Y = d_y; prm.batch_index = d_batch_index;
+    prm.eps_in = d_eps_in; prm.eps12 = d_eps12; prm.eps_sum = d_eps_sum;
+    prm.partial = partial;
+    prm.B = (int)B; prm.T = T; prm.F = F; prm.FP = FP; prm.n_cta = n_cta;
+    prm.seed = seed; prm.step = step; prm.zero_mask = cfg->zero_mask;
+    prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
+    prm.beta_out = hp->beta_out;
+    train::train_fwd_bwd_kernel<<<dim3(n_cta, n_seeds), train::NTHR, smem, st>>>(prm);
+    BNN_CUDA(cudaGetLastError());
+    train::train_reduce_kernel<<<dim3(nb, n_seeds), 256, 0, st>>>(partial, d_theta, n_cta, fl.d, F,
+                                                                 hp->beta_in * (float)B, hp->beta_out * (float)B, grad, sq);
+    BNN_CUDA(cudaGetLastError());
+    if (d_metrics) {
+        train::train_metrics_kernel<<<n_seeds, 32, 0, st>>>(d_theta, grad, fl.d, F, (int)B, *hp, d_metrics);
+        BNN_CUDA(cudaGetLastError());
+    }
+    train::train_update_kernel<<<dim3(nb, n_seeds), 256, 0, st>>>(grad, sq, nb, fl.d, F, (int)B, *hp, d_theta, d_momentum,
+                                                                 d_grad_out, d_metrics);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+int bnn_train_noise(const bnn_model_config* cfg, int32_t n_seeds, int64_t B, uint64_t seed, uint64_t step,
+                    float* d_eps_in, float* d_eps12, float* d_eps_sum, void* stream) {
+    using namespace bnn;
+    int rc = validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    if ((rc = check_device()) != BNN_OK) return rc;
+    BNN_REQUIRE(d_eps_in && d_eps12 && d_eps_sum && n_seeds >= 1 && n_seeds <= 65535 && B >= 1, BNN_E_ARG,
+                "bnn_train_noise: null pointer or empty problem");
+    BNN_REQUIRE(aligned16(d_eps12) && aligned16(d_eps_sum), BNN_E_ALIGN, "bnn_train_noise: eps12 / eps_sum alignment");
+    train::train_noise_kernel<<<dim3((unsigned)B, n_seeds), 128, 0, (cudaStream_t)stream>>>(
+        (int)B, cfg->n_times, cfg->n_features, seed, step, d_eps_in, d_eps12, d_eps_sum);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
 }
 
 int bnn_eval_loss(const bnn_model_config* cfg, const float* d_x, const float* d_y, int64_t B,
                   const float* d_theta_packed, int64_t n_units, const float* d_eps, uint64_t seed,
                   float* d_out_mu_sd, float* d_loss_sum, void* d_workspace, void* stream) {
-    bnn::set_error("bnn_eval_loss: not built yet");
-    return BNN_E_CONFIG;
+    using namespace bnn;
+    BNN_REQUIRE(d_y && d_loss_sum, BNN_E_ARG, "bnn_eval_loss: null pointer");
+    BNN_REQUIRE(d_out_mu_sd || d_workspace, BNN_E_ARG,
+                "bnn_eval_loss: give d_out_mu_sd or a workspace of n_units*B*2 floats");
+    BNN_REQUIRE(n_units >= 1 && n_units < (1ll << 31), BNN_E_ARG, "bnn_eval_loss: n_units out of range");
+    float* out = d_out_mu_sd ? d_out_mu_sd : (float*)d_workspace;
+    int rc = bnn_predict(cfg, d_x, B, d_theta_packed, n_units, d_eps, nullptr, seed, 0, 0, 0, out, nullptr, nullptr, stream);
+    if (rc != BNN_OK) return rc;
+    train::nll_sum_kernel<<<(unsigned)n_units, 256, 0, (cudaStream_t)stream>>>((const float2*)out, (const float2*)d_y, B,
+                                                                              d_loss_sum);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
 }
 
 }  // extern "C"

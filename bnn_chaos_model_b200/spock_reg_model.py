@@ -62,6 +62,25 @@ def _param_stack(in_n, out_n, hidden, layers):
     return nn.Sequential(*mods)
 
 
+class _FusedLoss(torch.autograd.Function):
+    """Scalar training loss whose backward hands out the gradient the fused kernel already computed."""
+
+    @staticmethod
+    def forward(ctx, value, grad_flat, *params):
+        ctx.grad_flat = grad_flat
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        out, i = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp)) if len(shp) else 1
+            out.append((ctx.grad_flat[i:i + n] * gout).reshape(shp))
+            i += n
+        return (None, None, *out)
+
+
 class VarModel(nn.Module):
     """Bayesian neural network predicting instability time (reference :339-687)."""
 
@@ -124,8 +143,9 @@ class VarModel(nn.Module):
         self.ssy = None
         self.current_epoch = 0
         self.global_step = 0
-        for p in self.parameters():
-            p.requires_grad_(False)  # gradients come from the fused training kernels, not autograd
+        # gradients come from the fused training kernel (training_step installs them through a custom
+        # autograd.Function, so loss.backward() / clip_grad_norm_ / optimizer.step() work as in the reference)
+        self._train_ws = None
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -267,6 +287,54 @@ class VarModel(nn.Module):
         testy = self.forward(x, noisy_val=noisy_val)
         return self._lossfnc(testy, y).sum()
 
+    # ------------------------------------------------------------------ training (reference :595-614, :722-732)
+    def _fused_loss_and_grad(self, x, y, beta_in, beta_out):
+        """Noisy forward + analytic backward of one batch in one kernel launch (bnn_train_step with
+        apply_update=0).  Draw order as the reference's forward(noisy_val=True): eps_in [B,T,F] (:445), eps1,
+        eps2 [B,L] (:426-427), eps_sum [B,2L] (:449).  Returns (metrics[8], grad[d]) on the device."""
+        lib = _lib.load()
+        x = self._check_x(x)
+        _lib.require_cuda(y, "y")
+        y = y.contiguous().float()
+        B, T, _ = x.shape
+        L = self.hparams["latent"]
+        dev = x.device
+        with torch.cuda.device(dev):
+            eps_in = torch.randn_like(x)
+            eps12 = torch.cat((torch.randn((B, L), device=dev), torch.randn((B, L), device=dev)), dim=1).contiguous()
+            eps_sum = torch.randn((B, 2 * L), device=dev)
+            cfg = self.config(T)
+            theta = self._flat().contiguous().float()
+            hp = TrainHParams(lr=0.0, momentum=0.0, weight_decay=0.0, clip_norm=float("inf"), beta_in=float(beta_in),
+                              beta_out=float(beta_out), first_step=1, apply_update=0)
+            nbytes = lib.bnn_train_workspace_bytes(cfg, B, 1)
+            if self._train_ws is None or self._train_ws.numel() * 4 < nbytes or self._train_ws.device != dev:
+                self._train_ws = torch.empty((nbytes + 3) // 4, device=dev, dtype=torch.float32)
+            grad = torch.empty_like(theta)
+            metrics = torch.empty(8, device=dev, dtype=torch.float32)
+            _lib.check(
+                lib.bnn_train_step(cfg, hp, 1, _lib.ptr(theta), None, _lib.ptr(x), _lib.ptr(y), None, B,
+                                   _lib.ptr(eps_in), _lib.ptr(eps12), _lib.ptr(eps_sum), 0, 0, _lib.ptr(grad),
+                                   _lib.ptr(metrics), _lib.ptr(self._train_ws), _lib.current_stream_ptr()),
+                "bnn_train_step",
+            )
+        return metrics, grad
+
+    def _training_result(self, batch, beta_in, beta_out):
+        X_sample, y_sample = batch
+        n = len(X_sample)
+        metrics, grad = self._fused_loss_and_grad(X_sample, y_sample, beta_in, beta_out)
+        params = list(self.parameters())  # same order as state_dict() / flatten() (:734-746)
+        total = _FusedLoss.apply(metrics[1] * n, grad, *params)
+        logs = {"train_loss_no_reg": metrics[0], "train_loss_with_reg": metrics[1], "input_kl": metrics[2],
+                "summary_kl": metrics[3]}
+        return {"loss": total, "log": logs}
+
+    def training_step(self, batch, batch_idx):
+        """:595-614 (KL annealing over the first 30 % of the steps)."""
+        fraction = self.global_step / self.hparams["steps"]
+        return self._training_result(batch, min(1, fraction / 0.3) * self.beta_in, min(1, fraction / 0.3) * self.beta_out)
+
     def input_kl(self):
         """:585-590 (41 elements: plain tensor arithmetic)."""
         lv = self.input_noise_logvar.detach()
@@ -296,6 +364,42 @@ class SWAGModel(VarModel):
         self._momentum = None
         self._first_step = True
         return self
+
+    def configure_optimizers(self):
+        """:709-720."""
+        opt1 = torch.optim.SGD(self.parameters(), lr=self.swa_params["swa_lr"], momentum=self.hparams["momentum"],
+                               weight_decay=self.hparams["weight_decay"])
+        scheduler = torch.optim.lr_scheduler.MultiStepLR(opt1, [self.swa_params["swa_start"]],
+                                                         self.swa_params["swa_recording_lr_factor"])
+        return [opt1], [{"scheduler": scheduler, "name": "swa_record_lr", "interval": "steps"}]
+
+    def training_step(self, batch, batch_idx):
+        """:722-732 (no KL annealing in the SWAG phase).  ``res['loss'].backward()`` installs the analytic
+        gradient of the fused kernel in ``p.grad``; clip_grad_norm_ and the optimizer then act as usual."""
+        return self._training_result(batch, self.beta_in, self.beta_out)
+
+    def validation_step(self, batch, batch_idx):
+        """:787-799: loss at the current weights and at w_avg."""
+        X_sample, y_sample = batch
+        noisy = self.hparams["noisy_val"]
+        loss = self.lossfnc(X_sample, y_sample, noisy_val=noisy) / self.test_len
+        if self.w_avg is None:
+            swa_loss = loss
+        else:
+            tmp = self.flatten()
+            self.load(self.w_avg)
+            swa_loss = self.lossfnc(X_sample, y_sample, noisy_val=noisy) / self.test_len
+            self.load(tmp)
+        return {"val_loss": loss, "swa_loss": swa_loss}
+
+    def validation_epoch_end(self, outputs):
+        """:801-813: the collection gate reads hparams['swa_start']."""
+        avg_loss = torch.stack([x["val_loss"] for x in outputs]).sum()
+        swa_avg_loss = torch.stack([x["swa_loss"] for x in outputs]).sum()
+        logs = {"val_loss_no_reg": avg_loss, "swa_loss_no_reg": swa_avg_loss}
+        if self.global_step > self.hparams["swa_start"]:
+            self.aggregate_model()
+        return {"val_loss": avg_loss, "log": logs}
 
     # flatten / load (:734-761)
     def flatten(self):

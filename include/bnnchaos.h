@@ -139,20 +139,30 @@ int bnn_nll_fwd_bwd(const float* d_mu_sd, const float* d_y, int64_t B, float* d_
                     float* d_loss_sum, float* d_grad, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * SWAGModel.training_step (:722-732) + backward + clip_grad_norm_ + torch.optim.SGD
- * (:709-711; run_swag.py:61,74-79) for n_seeds independent models in one call.
- * State per seed (device, caller-owned): theta [d], momentum buffer [d].
- * d_x [B,T,F], d_y [B,2] shared by all seeds (d_batch_index [n_seeds,B] int32 gathers rows
- * of d_x per seed when not NULL).  Noise: explicit d_eps_in [n_seeds,B,T,F], d_eps12
- * [n_seeds,B,2L], d_eps_sum [n_seeds,B,2L], or all NULL: Philox keyed on (seed, step).
- * d_metrics [n_seeds,8]: loss_no_reg, loss_with_reg, input_kl, summary_kl (each /B, as
- * logged :731), grad_norm, clip_coef, non-finite flag, reserved.
+ * SWAGModel.training_step (:722-732) + loss.backward() + clip_grad_norm_ + torch.optim.SGD
+ * (:709-711; run_swag.py:61,74-79) for n_seeds independent models in one call:
+ *   total = sum_b _lossfnc(forward(x_b, noisy_val=True), y_b) + input_kl*beta_in*B + summary_kl*beta_out
+ *   g = d total / d theta (analytic);  g *= min(1, clip/(|g|_2 + 1e-6));  d_p = g + wd*theta;
+ *   buf = d_p (first step) | momentum*buf + d_p;  theta -= lr*buf.
+ * State per seed (device, caller-owned): d_theta [n_seeds,d] in flatten() order, d_momentum [n_seeds,d].
+ * d_x [n_data,T,F] normalised inputs, d_y [n_data,2]; seed s's batch row b is data row
+ * d_batch_index[s*B+b] (int32; NULL: row b, every seed sees the same batch).  The zero_* masks of cfg are
+ * applied before the input noise, like forward() (:487-506).
+ * Noise: explicit d_eps_in [n_seeds,B,T,F], d_eps12 [n_seeds,B,2L] (eps1 | eps2 of :426-427), d_eps_sum
+ * [n_seeds,B,2L] (the randn_like draws of :445, :426-427, :449), or all NULL: Philox4x32-10 keyed on
+ * (seed; seed index, batch position, step) -- bnn_train_noise writes exactly those draws out.
+ * d_grad_out [n_seeds,d] (may be NULL): the gradient before clipping.
+ * d_metrics [n_seeds,8] (may be NULL): train_loss_no_reg, train_loss_with_reg, input_kl, summary_kl (each
+ * / B, as logged :731), grad norm, clip coefficient (<= 1), non-finite flag (terminate_on_nan,
+ * run_swag.py:78, without a host sync), reserved.
+ * d_workspace: bnn_train_workspace_bytes() bytes, 16-byte aligned.  Gradient partials are reduced in a
+ * fixed order: the step is bit-reproducible.  T/4 * ceil(F/4) <= 288 and F <= 48 (else BNN_E_CONFIG).
  */
 typedef struct bnn_train_hparams {
     float lr, momentum, weight_decay, clip_norm; /* swa_lr, 0.9, hparams.weight_decay, 0.1*d */
     float beta_in, beta_out;                     /* find_minima.py:50-51                     */
     int32_t first_step;                          /* 1: momentum buffer is initialised (SGD)  */
-    int32_t apply_update;                        /* 0: gradients only (d_grad_out)           */
+    int32_t apply_update;                        /* 0: gradients / metrics only              */
 } bnn_train_hparams;
 
 size_t bnn_train_workspace_bytes(const bnn_model_config* cfg, int64_t B, int32_t n_seeds);
@@ -161,9 +171,15 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
                    const int32_t* d_batch_index, int64_t B, const float* d_eps_in,
                    const float* d_eps12, const float* d_eps_sum, uint64_t seed, uint64_t step,
                    float* d_grad_out, float* d_metrics, void* d_workspace, void* stream);
+/* The Philox draws bnn_train_step makes for (seed, step) when its eps pointers are NULL. */
+int bnn_train_noise(const bnn_model_config* cfg, int32_t n_seeds, int64_t B, uint64_t seed, uint64_t step,
+                    float* d_eps_in, float* d_eps12, float* d_eps_sum, void* stream);
 
-/* lossfnc(x, y, noisy_val) (:579-583) without gradients: validation_step (:787-799).
- * d_loss_sum [n_units]: sum over systems of _lossfnc for each unit's weights. */
+/* lossfnc(x, y, noisy_val=False) (:579-583) without gradients, for n_units weight vectors at once:
+ * validation_step (:787-799) evaluates it at the current weights and at w_avg.
+ * d_loss_sum [n_units]: sum over the B systems of _lossfnc.  d_eps [n_units,B,2L] or NULL (Philox).
+ * d_out_mu_sd [n_units,B,2] receives the predictions; when NULL, d_workspace must hold
+ * n_units*B*2 floats. */
 int bnn_eval_loss(const bnn_model_config* cfg, const float* d_x, const float* d_y, int64_t B,
                   const float* d_theta_packed, int64_t n_units, const float* d_eps, uint64_t seed,
                   float* d_out_mu_sd, float* d_loss_sum, void* d_workspace, void* stream);

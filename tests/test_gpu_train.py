@@ -1,0 +1,233 @@
+"""GPU parity of the fused SWAG training step (K4), the validation loss and the multi-seed trainer, through the
+C ABI.  Tolerances: logged losses 1e-5 relative; gradient 2e-4 of the gradient's max-norm (fp32 sums over
+B*T rows in a different order than autograd); theta after a step 1e-6; gradient norm 1e-5."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_swag_model, swag_stats
+from bnn_chaos_model_b200 import _lib, synth
+from bnn_chaos_model_b200._lib import TrainHParams
+from bnn_chaos_model_b200.swag_train import MultiSeedSWAGTrainer, seeds_of_rank
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _ws(lib, cfg, B, S, dev):
+    return torch.empty((lib.bnn_train_workspace_bytes(cfg, B, S) + 3) // 4, device=dev)
+
+
+def _step(lib, cfg, hp, S, theta, mom, x, y, idx, B, eps, seed, step, dev, want_grad=True):
+    grad = torch.empty_like(theta) if want_grad else None
+    metrics = torch.zeros((S, 8), device=dev)
+    ws = _ws(lib, cfg, B, S, dev)
+    e_in, e12, e_sum = eps if eps is not None else (None, None, None)
+    _lib.check(lib.bnn_train_step(cfg, hp, S, _lib.ptr(theta), _lib.ptr(mom), _lib.ptr(x), _lib.ptr(y), _lib.ptr(idx), B,
+                                  _lib.ptr(e_in), _lib.ptr(e12), _lib.ptr(e_sum), seed, step, _lib.ptr(grad),
+                                  _lib.ptr(metrics), _lib.ptr(ws), _lib.current_stream_ptr()), "bnn_train_step")
+    torch.cuda.synchronize()
+    return grad, metrics
+
+
+def test_train_steps_vs_reference_golden(gold_train, dev):
+    """Three SGD-momentum steps of the reference (autograd + clip_grad_norm_ + torch.optim.SGD) with all four
+    noise tensors fixed: logged scalars, full gradient, gradient norm and theta after every step."""
+    g = gold_train
+    lib = _lib.load()
+    m = make_swag_model(0, dev)
+    cfg = m.config(100)
+    B = int(g["B"])
+    x = torch.from_numpy(synth.make_systems(B, seed=int(g["x_seed"]))).to(dev)
+    y = torch.from_numpy(g["y"]).to(dev)
+    theta = torch.from_numpy(g["theta0"]).to(dev)[None].contiguous()
+    mom = torch.zeros_like(theta)
+    for s in range(3):
+        eps = (torch.from_numpy(g["eps_in"][s].astype(np.float32)).to(dev)[None].contiguous(),
+               torch.from_numpy(g["eps12"][s]).to(dev)[None].contiguous(),
+               torch.from_numpy(g["eps_sum"][s]).to(dev)[None].contiguous())
+        hp = TrainHParams(lr=float(g["lr"]), momentum=float(g["momentum"]), weight_decay=float(g["weight_decay"]),
+                          clip_norm=float(g["clip"]), beta_in=m.beta_in, beta_out=m.beta_out, first_step=int(s == 0),
+                          apply_update=1)
+        grad, met = _step(lib, cfg, hp, 1, theta, mom, x, y, None, B, eps, 0, s, dev)
+        gref = g[f"grad_ref_{s}"]
+        scale = np.abs(gref).max()
+        err = np.abs(grad[0].cpu().numpy() - gref).max() / scale
+        assert err < 2e-4, (s, err)
+        np.testing.assert_allclose(met[0, :4].cpu().numpy(), g[f"logs_ref_{s}"], rtol=1e-5)
+        assert float(met[0, 1]) * B == pytest.approx(float(g[f"loss_ref_{s}"]), rel=1e-5)
+        assert float(met[0, 4]) == pytest.approx(float(g[f"gradnorm_ref_{s}"]), rel=1e-5)
+        assert float(met[0, 6]) == 0.0
+        np.testing.assert_allclose(theta[0].cpu().numpy(), g[f"theta_ref_{s}"], rtol=1e-6, atol=1e-7)
+
+
+def test_gradient_by_parameter_group(gold_train, dev):
+    """Every parameter tensor's gradient on its own scale (a wrong small block would hide under a global max-norm)."""
+    g = gold_train
+    lib = _lib.load()
+    m = make_swag_model(0, dev)
+    cfg = m.config(100)
+    B = int(g["B"])
+    x = torch.from_numpy(synth.make_systems(B, seed=int(g["x_seed"]))).to(dev)
+    y = torch.from_numpy(g["y"]).to(dev)
+    theta = torch.from_numpy(g["theta0"]).to(dev)[None].contiguous()
+    eps = (torch.from_numpy(g["eps_in"][0].astype(np.float32)).to(dev)[None].contiguous(),
+           torch.from_numpy(g["eps12"][0]).to(dev)[None].contiguous(),
+           torch.from_numpy(g["eps_sum"][0]).to(dev)[None].contiguous())
+    hp = TrainHParams(lr=0.0, momentum=0.0, weight_decay=0.0, clip_norm=1e30, beta_in=m.beta_in, beta_out=m.beta_out,
+                      first_step=1, apply_update=0)
+    grad, _ = _step(lib, cfg, hp, 1, theta, None, x, y, None, B, eps, 0, 0, dev)
+    assert torch.equal(theta[0].cpu(), torch.from_numpy(g["theta0"]))  # apply_update=0 leaves the weights alone
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    got, ref = grad[0].cpu().numpy(), g["grad_ref_0"]
+    for name, (off, shp) in spec.offsets().items():
+        n = int(np.prod(shp))
+        a, b = got[off:off + n], ref[off:off + n]
+        assert np.abs(a - b).max() <= 3e-4 * np.abs(b).max() + 1e-7, name
+
+
+def test_training_step_dropin_backward_and_optimizer(dev):
+    """SWAGModel.training_step with torch draws in the reference's order; loss.backward() installs the fused
+    gradient, clip_grad_norm_ + the SGD of configure_optimizers() then match the oracle's step."""
+    m = make_swag_model(3, dev)
+    m.load(m.w_avg.clone())
+    spec = R.ModelSpec.from_hparams(swag_stats(3)["hparams"])
+    B = 32
+    x = torch.from_numpy(synth.make_systems(B, seed=41))
+    y = torch.from_numpy(synth.make_labels(B, seed=41))
+    theta0 = m.flatten().cpu()
+    (opt,), _ = m.configure_optimizers()
+    torch.manual_seed(5)
+    res = m.training_step((x.to(dev), y.to(dev)), 0)
+    res["loss"].backward()
+    clip = 0.1 * 7583
+    gn = torch.nn.utils.clip_grad_norm_(m.parameters(), clip)
+    opt.step()
+    # oracle with the same draws
+    torch.manual_seed(5)
+    eps_in = torch.randn_like(x.to(dev)).cpu()
+    e1 = torch.randn((B, 20), device=dev).cpu(); e2 = torch.randn((B, 20), device=dev).cpu()
+    es = torch.randn((B, 40), device=dev).cpu()
+    th = theta0.clone().requires_grad_(True)
+    total, logs = R.training_loss(spec, th, x, y, eps_in, e1, e2, es)
+    (gref,) = torch.autograd.grad(total, th)
+    assert float(res["loss"]) == pytest.approx(float(total), rel=1e-5)
+    for k in ("train_loss_no_reg", "train_loss_with_reg", "input_kl", "summary_kl"):
+        assert float(res["log"][k]) == pytest.approx(float(logs[k]), rel=1e-5), k
+    assert float(gn) == pytest.approx(float(gref.norm()), rel=1e-4)
+    th1, _, _ = R.clip_and_sgd_step(theta0, gref, None, m.swa_params["swa_lr"], m.hparams["momentum"],
+                                    m.hparams["weight_decay"], clip, True)
+    np.testing.assert_allclose(m.flatten().cpu().numpy(), th1.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_philox_noise_and_multi_seed_batches(dev):
+    """(a) NULL noise pointers == the draws bnn_train_noise writes out, bit for bit; (b) n_seeds models with
+    per-seed batch indices == each seed alone on its gathered batch; (c) the step is bit-reproducible."""
+    lib = _lib.load()
+    S, B, N = 3, 24, 90
+    models = [make_swag_model(s, dev) for s in (0, 3, 17)]
+    cfg = models[0].config(100)
+    x = torch.from_numpy(synth.make_systems(N, seed=51)).to(dev)
+    y = torch.from_numpy(synth.make_labels(N, seed=51)).to(dev)
+    theta0 = torch.stack([m.w_avg for m in models]).contiguous()
+    idx = torch.stack([torch.randperm(N, generator=torch.Generator().manual_seed(s))[:B] for s in range(S)]).to(torch.int32).to(dev)
+    hp = TrainHParams(lr=1e-4, momentum=0.9, weight_decay=1e-14, clip_norm=758.3, beta_in=1e-5, beta_out=1e-3,
+                      first_step=1, apply_update=1)
+    seed, step = 99, 7
+    th_a, mom_a = theta0.clone(), torch.zeros_like(theta0)
+    g_a, met_a = _step(lib, cfg, hp, S, th_a, mom_a, x, y, idx, B, None, seed, step, dev)
+    e_in = torch.empty((S, B, 100, 41), device=dev); e12 = torch.empty((S, B, 40), device=dev); e_sum = torch.empty((S, B, 40), device=dev)
+    _lib.check(lib.bnn_train_noise(cfg, S, B, seed, step, _lib.ptr(e_in), _lib.ptr(e12), _lib.ptr(e_sum), None))
+    assert abs(float(e_in.mean())) < 0.01 and abs(float(e_in.std()) - 1) < 0.01
+    th_b, mom_b = theta0.clone(), torch.zeros_like(theta0)
+    g_b, met_b = _step(lib, cfg, hp, S, th_b, mom_b, x, y, idx, B, (e_in, e12, e_sum), seed, step, dev)
+    assert torch.equal(g_a, g_b) and torch.equal(th_a, th_b) and torch.equal(met_a, met_b)
+    th_c, mom_c = theta0.clone(), torch.zeros_like(theta0)
+    g_c, _ = _step(lib, cfg, hp, S, th_c, mom_c, x, y, idx, B, None, seed, step, dev)
+    assert torch.equal(g_a, g_c) and torch.equal(th_a, th_c)
+    assert not torch.equal(e_in[0], e_in[1])  # seeds draw different noise
+    for s in range(S):  # each seed alone, batch gathered on the host side
+        xs, ys = x[idx[s].long()].contiguous(), y[idx[s].long()].contiguous()
+        th_s, mom_s = theta0[s:s + 1].clone(), torch.zeros((1, theta0.shape[1]), device=dev)
+        g_s, met_s = _step(lib, cfg, hp, 1, th_s, mom_s, xs, ys, None, B,
+                           (e_in[s:s + 1].contiguous(), e12[s:s + 1].contiguous(), e_sum[s:s + 1].contiguous()), 0, 0, dev)
+        # a seed alone runs on more CTAs (different partial-sum grouping): equal to rounding, not bit for bit
+        assert float((g_s[0] - g_a[s]).abs().max()) <= 2e-5 * float(g_a[s].abs().max())
+        np.testing.assert_allclose(met_s[0, :5].cpu().numpy(), met_a[s, :5].cpu().numpy(), rtol=2e-5)
+    # oracle cross-check of one seed with the Philox draws
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    th = theta0[0].cpu().clone().requires_grad_(True)
+    total, _ = R.training_loss(spec, th, x[idx[0].long()].cpu(), y[idx[0].long()].cpu(), e_in[0].cpu(), e12[0, :, :20].cpu(),
+                               e12[0, :, 20:].cpu(), e_sum[0].cpu())
+    (gref,) = torch.autograd.grad(total, th)
+    assert float((g_a[0].cpu() - gref).abs().max()) <= 3e-4 * float(gref.abs().max())
+    assert float(met_a[0, 1]) * B == pytest.approx(float(total), rel=1e-5)
+
+
+def test_eval_loss_vs_reference(gold_train, dev):
+    """validation_step (:787-799): lossfnc(noisy_val=False) at two weight vectors in one call."""
+    g = gold_train
+    lib = _lib.load()
+    m = make_swag_model(0, dev)
+    cfg = m.config(100)
+    B = int(g["B"])
+    x = torch.from_numpy(synth.make_systems(B, seed=int(g["x_seed"]))).to(dev)
+    y = torch.from_numpy(g["y"]).to(dev)
+    thetas = torch.stack([torch.from_numpy(g["theta0"]), torch.from_numpy(g["theta_ref_2"])]).to(dev)
+    thp = m._packed(cfg, thetas)
+    eps = torch.from_numpy(g["eps12"][0]).to(dev)[None].repeat(2, 1, 1).contiguous()
+    out = torch.empty((2, B, 2), device=dev); loss = torch.empty(2, device=dev)
+    _lib.check(lib.bnn_eval_loss(cfg, _lib.ptr(x), _lib.ptr(y), B, _lib.ptr(thp), 2, _lib.ptr(eps), 0, _lib.ptr(out),
+                                 _lib.ptr(loss), None, _lib.current_stream_ptr()))
+    assert float(loss[0]) == pytest.approx(float(g["val_loss_ref"]), rel=1e-5)
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    o1, _ = R.forward(spec, thetas[1].cpu(), x.cpu(), False, None, eps[1, :, :20].cpu(), eps[1, :, 20:].cpu(), None)
+    assert float(loss[1]) == pytest.approx(float(R.lossfnc_per_system(o1, y.cpu()).sum()), rel=1e-5)
+    # workspace variant (no prediction output)
+    ws = torch.empty(2 * B * 2, device=dev); loss2 = torch.empty(2, device=dev)
+    _lib.check(lib.bnn_eval_loss(cfg, _lib.ptr(x), _lib.ptr(y), B, _lib.ptr(thp), 2, _lib.ptr(eps), 0, None,
+                                 _lib.ptr(loss2), _lib.ptr(ws), _lib.current_stream_ptr()))
+    assert torch.equal(loss, loss2)
+
+
+def test_multi_seed_trainer_collects_reference_moments(dev):
+    """Trainer.fit replacement: per-epoch aggregate_model over the weights the fused steps produced; the
+    collected moments must equal the oracle's aggregate_model replayed on the recorded weight trajectory."""
+    torch.manual_seed(0)
+    models = [make_swag_model(s, dev) for s in (0, 17)]
+    for m in models:
+        m.load(m.w_avg.clone())
+        m.init_params({"K": 3, "c": 2, "swa_lr": 1e-4, "swa_start": 0})
+        m.hparams["swa_start"] = 2
+    N = 150
+    X = torch.from_numpy(synth.make_systems(N, seed=61)); y = torch.from_numpy(synth.make_labels(N, seed=61))
+    tr = MultiSeedSWAGTrainer(models, X[:120], y[:120], X[120:], y[120:], batch_size=50, device=dev, seed=4)
+    assert len(tr.epoch_batches()) == 3 and tr.epoch_batches()[-1][1] == 20  # ragged last batch
+    traj = []
+    states = [R.SwagState(K=3, c=2) for _ in models]
+    for epoch in range(6):
+        logs = tr.fit(1)
+        assert torch.isfinite(logs[0]["val_loss_no_reg"]).all()
+        traj.append(tr.theta.cpu().clone())
+        if tr.global_step > 2:
+            for i in range(2):
+                states[i] = R.aggregate_model(states[i], traj[-1][i], epoch)
+    assert not torch.equal(traj[0], traj[-1])
+    out = tr.export()
+    for i, m in enumerate(out):
+        st = states[i]
+        assert m.n_models == st.n_models and m.pre_D.shape[1] == st.pre_D.shape[1] == 3
+        np.testing.assert_allclose(m.w_avg.cpu().numpy(), st.w_avg.numpy(), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(m.w2_avg.cpu().numpy(), st.w2_avg.numpy(), rtol=1e-6, atol=1e-7)
+        assert torch.equal(m.pre_D.cpu(), st.pre_D)
+    # the exported mirrors sample and predict
+    o = out[0].forward_swag_fast(X[:8].to(dev), scale=0.5)
+    assert o.shape == (8, 2) and bool(torch.isfinite(o).all())
+    assert seeds_of_rank(30, 0, 8) == [0, 1, 2, 3] and seeds_of_rank(30, 7, 8) == [27, 28, 29]
