@@ -108,6 +108,103 @@ def cpu_oracle_arm(steps, warmup, n_sys=10000, n_samp=4):
                       f"oracle/restatement.py on torch CPU fp32, {steps} steps)"}, dt
 
 
+def cpu_train_arm(B=2000, steps=2):
+    """One SWAG-phase training step (noisy forward + loss + KL + autograd backward + clip + SGD) of the oracle
+    port on the host cores, same batch shape as BASELINE configs[3]."""
+    from bnn_chaos_model_b200 import synth
+    from oracle import restatement as R
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    z, hp, sp = load_stats(0)
+    spec = R.ModelSpec.from_hparams(hp)
+    x = torch.from_numpy(synth.make_systems(B, seed=2))
+    y = torch.from_numpy(synth.make_labels(B, seed=2))
+    theta = torch.from_numpy(z["w_avg"]).clone()
+    buf = None
+    g = torch.Generator().manual_seed(0)
+
+    def step(first):
+        nonlocal theta, buf
+        th = theta.clone().requires_grad_(True)
+        e_in = torch.randn(x.shape, generator=g)
+        e = torch.randn((B, 40), generator=g)
+        es = torch.randn((B, 40), generator=g)
+        total, _ = R.training_loss(spec, th, x, y, e_in, e[:, :20], e[:, 20:], es)
+        (grad,) = torch.autograd.grad(total, th)
+        theta, buf, _ = R.clip_and_sgd_step(theta, grad, buf, 1e-4, 0.9, 1e-14, 0.1 * spec.d, first)
+
+    step(True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(False)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 1.0 / dt, "unit": "seed-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of 1 seed, batch {B} x 100 x 41 (oracle/restatement.py training_loss + autograd + SGD)"}
+
+
+def gpu_train_arm(dev, n_seeds=4, B=2000, n_data=8000, iters=10):
+    """BASELINE configs[3] per GPU: n_seeds SWAG models trained in one fused call per step (K4)."""
+    from bnn_chaos_model_b200 import _lib, synth
+    from bnn_chaos_model_b200 import spock_reg_model as S
+    from bnn_chaos_model_b200._lib import TrainHParams
+
+    lib = _lib.load()
+    z, hp_, sp = load_stats(0)
+    m = S.SWAGModel(hp_).init_params(sp).to(dev)
+    cfg = m.config(100)
+    x = torch.from_numpy(synth.make_systems(n_data, seed=3)).to(dev)
+    y = torch.from_numpy(synth.make_labels(n_data, seed=3)).to(dev)
+    theta = torch.from_numpy(z["w_avg"]).to(dev)[None].repeat(n_seeds, 1).contiguous()
+    mom = torch.zeros_like(theta)
+    met = torch.zeros((n_seeds, 8), device=dev)
+    ws = torch.empty((lib.bnn_train_workspace_bytes(cfg, B, n_seeds) + 3) // 4, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0)
+    idx = torch.stack([torch.randperm(n_data, device=dev, generator=gen)[:B] for _ in range(n_seeds)]).to(torch.int32).contiguous()
+    hp = TrainHParams(lr=1e-4, momentum=0.9, weight_decay=1e-14, clip_norm=758.3, beta_in=1e-5, beta_out=1e-3,
+                      first_step=1, apply_update=1)
+
+    def step(i):
+        hp.first_step = int(i == 0)
+        _lib.check(lib.bnn_train_step(cfg, hp, n_seeds, _lib.ptr(theta), _lib.ptr(mom), _lib.ptr(x), _lib.ptr(y),
+                                      _lib.ptr(idx), B, None, None, None, 1, i, None, _lib.ptr(met), _lib.ptr(ws),
+                                      _lib.current_stream_ptr()))
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        step(3 + i)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    flop = 3 * 814_560 * B * n_seeds  # SURVEY 8d: 3 x dense forward FLOPs per system
+    tf = flop / (ms * 1e-3) / 1e12
+    assert bool((met[:, 6] == 0).all()) and bool(torch.isfinite(met).all())
+    return {"value": n_seeds / (ms * 1e-3), "unit": "seed-steps/s", "n_seeds": n_seeds, "batch": B, "ms_per_step": ms,
+            "gpu_launches_per_step": 4, "data": "synthetic, 8000 resident systems, per-seed index batches, Philox noise",
+            "roofline": {"bound": "fp32_fma", "achieved": tf, "peak": FP32_PEAK_NOMINAL, "unit": "TFLOP/s",
+                         "frac": tf / FP32_PEAK_NOMINAL, "flop_per_seed_step": 3 * 814_560 * B}}
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the predict kernel from the committed ncu --set full summary
+    (profiles/), per launch of this same workload; None when the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "r1_predict_tc3n4_ncu.txt")
+    try:
+        tot = 0.0
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+        return tot or None
+    except OSError:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -121,6 +218,7 @@ def run_reference(args):
                                "samples per GPU; this arm times a bounded sample of it on the host CPU"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "train": cpu_train_arm(),
     }
     print(json.dumps(line), flush=True)
 
@@ -234,6 +332,15 @@ def run_ours(args):
             tf = fl.value / (a.elapsed_time(b) * 1e-3) / 1e12
             ffma["f32x2" if packed else "f32"] = max(ffma.get("f32x2" if packed else "f32", 0.0), tf)
 
+    train = gpu_train_arm(dev) if not args.no_train else None
+    if train is not None and world > 1:  # seeds are sharded, no traffic: aggregate = sum over ranks, time = max
+        tt = torch.tensor([train["ms_per_step"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        train["ms_per_step"] = float(tt[0])
+        train["n_seeds"] *= world
+        train["value"] = train["n_seeds"] / (train["ms_per_step"] * 1e-3)
+        train["roofline"]["note"] = "per-GPU fraction; value is the aggregate over ranks"
+
     if rank == 0:
         evals = n_sys * n_samp * world
         achieved = FLOP_PER_EVAL_V50 * n_sys * n_samp / (k_ms * 1e-3) / 1e12
@@ -259,8 +366,13 @@ def run_ours(args):
                          "peak_source": "148 SM x 128 lanes x 2 x clocks.max.sm 1965 MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                         "no fp32 figure in MEASURED_PEAKS.json",
                          "measured_ffma_peak_tflops": ffma, "kernel_ms": k_ms,
-                         "flop_per_eval": FLOP_PER_EVAL_V50, "traffic": None},
+                         "flop_per_eval": FLOP_PER_EVAL_V50, "traffic": ncu_traffic_bytes(),
+                         "traffic_source": "profiles/r1_predict_tc3n4_ncu.txt (ncu --set full, same workload, per launch); "
+                                           "algorithmic HBM bytes per launch: 0.32e9",
+                         "note": "north_star's roofline for this kernel is the FP32 CUDA-core FMA peak; the kernel runs the "
+                                 "feature MLP as 3xTF32 on tcgen05 (tensor pipe active 27 %, profiles/)"},
             "cpu_baseline": cb,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -276,6 +388,7 @@ def main():
     ap.add_argument("--systems", type=int, default=N_SYS)
     ap.add_argument("--samples", type=int, default=N_SAMP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
