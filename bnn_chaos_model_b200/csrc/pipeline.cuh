@@ -57,6 +57,17 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     while (!mbar_test(bar, parity)) __nanosleep(ns);
 }
 
+// Named hardware barriers (bar.sync / bar.arrive, ids 1..15): a waiting warp sleeps in hardware and costs no issue
+// slots -- unlike an mbarrier try_wait loop, which ncu showed re-issuing on every mbarrier event of the CTA
+// (35 % of all executed instructions with 20 waiting warps).  Producer side: named_arrive (does not block);
+// consumer side: named_sync.  `threads` = arriving + syncing threads, a multiple of 32.
+__device__ __forceinline__ void named_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // global -> shared bulk copy (UBLKCP), completion counted in bytes on an mbarrier.
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

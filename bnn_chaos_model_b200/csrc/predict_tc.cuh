@@ -113,12 +113,28 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], uint32_t t_hi,
     uint32_t h[8], l[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float hi = tf32_rna(v[j]);
-        h[j] = __float_as_uint(hi);
-        l[j] = __float_as_uint(v[j] - hi);
+        // round to nearest tf32, ties away (= cvt.rna.tf32.f32 for every finite input; Inf / NaN are preserved):
+        // two integer instructions instead of the 5-instruction cvt expansion
+        const uint32_t hb = (__float_as_uint(v[j]) + 0x1000u) & 0xFFFFE000u;
+        h[j] = hb;
+        l[j] = __float_as_uint(v[j] - __uint_as_float(hb));
     }
     tmem_st8(t_hi, h);
     tmem_st8(t_lo, l);
+}
+
+template <bool RELU>
+__device__ __forceinline__ void split_store16(const uint32_t (&d)[16], uint32_t t_hi, uint32_t t_lo) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float v = RELU ? relu_nan(__uint_as_float(d[j])) : __uint_as_float(d[j]);
+        const uint32_t hb = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
+        h[j] = hb;
+        l[j] = __float_as_uint(v - __uint_as_float(hb));
+    }
+    tmem_st16(t_hi, h);
+    tmem_st16(t_lo, l);
 }
 
 // ---------------------------------------------------------------------------------------

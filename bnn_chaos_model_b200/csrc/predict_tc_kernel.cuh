@@ -14,6 +14,7 @@ namespace tc {
         }                                                                                            \
     } while (0)
 
+constexpr int BAR_A = 1, BAR_D = 5;  // named barrier ids: A-ready / D-ready of TMEM slot s are BAR_A + s / BAR_D + s
 constexpr int B_FLOATS = 2 * (TC_K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3);  // hi + lo B operands of one unit
 constexpr int B_BYTES = B_FLOATS * 4;
 
@@ -84,7 +85,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
             if (item != (int)blockIdx.x) {
                 for (int s = 0; s < 2; ++s) mbar_inval(&bars->w_full[s]);
                 for (int s = 0; s < NT; ++s) { mbar_inval(&bars->unit_done[s]); mbar_inval(&bars->rec_free[s]); }
-                for (int s = 0; s < NSLOT; ++s) { mbar_inval(&bars->a_ready[s]); mbar_inval(&bars->d_ready[s]); }
+                for (int s = 0; s < NSLOT; ++s) mbar_inval(&bars->d_ready[s]);
             }
             for (int s = 0; s < 2; ++s) mbar_init(&bars->w_full[s], 1);
             for (int s = 0; s < NT; ++s) {
@@ -92,7 +93,6 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                 mbar_init(&bars->rec_free[s], 1);        // the tail warp of the slot
             }
             for (int s = 0; s < NSLOT; ++s) {
-                mbar_init(&bars->a_ready[s], 4);         // 4 epilogue warps of the slot
                 mbar_init(&bars->d_ready[s], 1);         // tcgen05.commit
             }
             mbar_init_fence();
@@ -106,7 +106,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
             float* my_scratch = scratch + warp * TAIL_SCRATCH;
             for (int i = warp; i < n_units; i += NT) {
                 TC_STAMP(3 + (warp & 1), 1);
-                mbar_wait(&bars->unit_done[warp], (uint32_t)((i / NT) & 1));  // all 16 block records of unit i are written
+                mbar_wait_backoff(&bars->unit_done[warp], (uint32_t)((i / NT) & 1), 200);  // all 16 block records of unit i
                 TC_STAMP(3 + (warp & 1), 2);
                 const int64_t u = u_begin + i;
                 const float* eps_u = prm.eps ? prm.eps + u * prm.N * S2 : nullptr;
@@ -124,7 +124,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
             // slot i & 1 is free once every block record of unit i-2 is written (all its MMAs have completed)
             if (lane == 0) {
                 for (int i = 0; i < n_units; ++i) {
-                    if (i >= 2) mbar_wait(&bars->unit_done[(i - 2) % NT], (uint32_t)(((i - 2) / NT) & 1));
+                    if (i >= 2) mbar_wait_backoff(&bars->unit_done[(i - 2) % NT], (uint32_t)(((i - 2) / NT) & 1), 400);
                     mbar_arrive_expect_tx(&bars->w_full[i & 1], (uint32_t)B_BYTES);
                     bulk_g2s(ring + (size_t)(i & 1) * B_FLOATS, prm.thp + (u_begin + i) * pl.P + pl.B1h, (uint32_t)B_BYTES,
                              &bars->w_full[i & 1]);
@@ -149,8 +149,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                 }
 #pragma unroll 1
                 for (int layer = 0; layer < 3; ++layer) {
-                    mbar_wait(&bars->a_ready[s], pa);
-                    pa ^= 1;
+                    named_sync(BAR_A + s, 160);  // the slot's 4 epilogue warps have written A (they only arrive)
                     tc_fence_after();
                     uint32_t wb = ring_addr + (uint32_t)ws * (uint32_t)B_BYTES;
                     uint32_t ts = tmem + s * TM_SLOT;
@@ -165,6 +164,10 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                     TC_STAMP(7, 100 + 10 * s + layer);
                     if (elect_one_sync()) mma_commit(&bars->d_ready[s]);
                     __syncwarp();
+                    // this warp alone polls the commit barrier, then releases the epilogue warps through a named barrier
+                    mbar_wait_backoff(&bars->d_ready[s], pa, 20);
+                    pa ^= 1;
+                    named_arrive(BAR_D + s, 160);
                 }
             }
         } else if (warp >= W_EPI) {
@@ -172,14 +175,13 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
             const int slot = (warp - W_EPI) >> 2, quad = warp & 3;
             const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + slot * TM_SLOT;  // this lane's row of the slot
             float* my_fb = fb + (warp - W_EPI) * FB_FLOATS;
-            uint32_t pd = 0;
             int pend_i = -1, pend_m = 0;  // job whose latent rows sit in my_fb and still have to be pooled
 
             // pooled (mean, M2) records of one 32-row block, two-pass per segment like torch.mean / torch.std;
             // runs in the shadow of the next job's layer-1 MMAs
             auto pool_block = [&](int pi, int pm) {
                 const int rs = pi % NT;
-                if (pi >= NT) mbar_wait(&bars->rec_free[rs], (uint32_t)((pi / NT - 1) & 1));  // tail of unit pi-NT is done
+                if (pi >= NT) mbar_wait_backoff(&bars->rec_free[rs], (uint32_t)((pi / NT - 1) & 1), 100);  // tail of unit pi-NT done
                 if (lane < L) {
                     const int b = pm * 4 + quad;
                     int sysA, split, nvalid;
@@ -216,22 +218,25 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                 const int R = m * 128 + quad * 32 + lane;  // tile row of this thread
                 // ---- stage x -> A (hi 32 columns incl. the ones column, lo 32 columns) ----
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v[8];
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[16];
                     if (R < ROWS) {
-                        const float4 a = *reinterpret_cast<const float4*>(xs + R * 32 + (((2 * c) ^ (R & 7)) << 2));
-                        const float4 b = *reinterpret_cast<const float4*>(xs + R * 32 + (((2 * c + 1) ^ (R & 7)) << 2));
-                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            const float4 a = *reinterpret_cast<const float4*>(xs + R * 32 + (((4 * c + g4) ^ (R & 7)) << 2));
+                            v[4 * g4] = __float_as_uint(a.x); v[4 * g4 + 1] = __float_as_uint(a.y);
+                            v[4 * g4 + 2] = __float_as_uint(a.z); v[4 * g4 + 3] = __float_as_uint(a.w);
+                        }
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+                        for (int k = 0; k < 16; ++k) v[k] = 0u;
                     }
-                    split_store8(v, tl + TM_AHI + 8 * c, tl + TM_ALO + 8 * c);
+                    split_store16<false>(v, tl + TM_AHI + 16 * c, tl + TM_ALO + 16 * c);
                 }
+                if (quad == 0) TC_STAMP(slot, 34);
                 tc_wait_st();
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->a_ready[slot]);
+                named_arrive(BAR_A + slot, 160);
                 if (quad == 0) TC_STAMP(slot, 1);
 
                 // ---- pool the previous job's block while the tensor pipe works on layer 1 ----
@@ -241,44 +246,46 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                 // ---- layers 1 and 2: D -> ReLU -> hi/lo -> A ----
 #pragma unroll 1
                 for (int layer = 0; layer < 2; ++layer) {
-                    mbar_wait(&bars->d_ready[slot], pd);
+                    named_sync(BAR_D + slot, 160);
                     if (quad == 0) TC_STAMP(slot, 3 + 2 * layer);
-                    pd ^= 1;
                     tc_fence_after();
-                    uint32_t d[5][8];
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) tmem_ld8(tl + TM_D + 8 * c, d[c]);
+                    uint32_t d0[16], d1[16], d2[8];
+                    tmem_ld16(tl + TM_D, d0);
+                    tmem_ld16(tl + TM_D + 16, d1);
+                    tmem_ld8(tl + TM_D + 32, d2);
                     tc_wait_ld();
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
+                    if (quad == 0) TC_STAMP(slot, 31);
+                    split_store16<true>(d0, tl + TM_AHI, tl + TM_ALO);
+                    split_store16<true>(d1, tl + TM_AHI + 16, tl + TM_ALO + 16);
+                    {
                         float v[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = relu_nan(__uint_as_float(d[c][k]));
-                        split_store8(v, tl + TM_AHI + 8 * c, tl + TM_ALO + 8 * c);
+                        for (int k = 0; k < 8; ++k) v[k] = relu_nan(__uint_as_float(d2[k]));
+                        split_store8(v, tl + TM_AHI + 32, tl + TM_ALO + 32);
                     }
+                    if (quad == 0) TC_STAMP(slot, 32);
                     tc_wait_st();
+                    if (quad == 0) TC_STAMP(slot, 33);
                     tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->a_ready[slot]);
+                    named_arrive(BAR_A + slot, 160);
                     if (quad == 0) TC_STAMP(slot, 4 + 2 * layer);
                 }
 
                 // ---- layer 3: D (20 latent columns) -> my_fb (pooled after the next job's x is staged) ----
-                mbar_wait(&bars->d_ready[slot], pd);
+                named_sync(BAR_D + slot, 160);
                 if (quad == 0) TC_STAMP(slot, 7);
-                pd ^= 1;
                 tc_fence_after();
                 {
-                    uint32_t d[3][8];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) tmem_ld8(tl + TM_D + 8 * c, d[c]);
+                    uint32_t d0[16], d1[8];
+                    tmem_ld16(tl + TM_D, d0);
+                    tmem_ld8(tl + TM_D + 16, d1);
                     tc_wait_ld();
                     float4* dst = reinterpret_cast<float4*>(my_fb + lane * L);
-                    dst[0] = make_float4(__uint_as_float(d[0][0]), __uint_as_float(d[0][1]), __uint_as_float(d[0][2]), __uint_as_float(d[0][3]));
-                    dst[1] = make_float4(__uint_as_float(d[0][4]), __uint_as_float(d[0][5]), __uint_as_float(d[0][6]), __uint_as_float(d[0][7]));
-                    dst[2] = make_float4(__uint_as_float(d[1][0]), __uint_as_float(d[1][1]), __uint_as_float(d[1][2]), __uint_as_float(d[1][3]));
-                    dst[3] = make_float4(__uint_as_float(d[1][4]), __uint_as_float(d[1][5]), __uint_as_float(d[1][6]), __uint_as_float(d[1][7]));
-                    dst[4] = make_float4(__uint_as_float(d[2][0]), __uint_as_float(d[2][1]), __uint_as_float(d[2][2]), __uint_as_float(d[2][3]));
+                    dst[0] = make_float4(__uint_as_float(d0[0]), __uint_as_float(d0[1]), __uint_as_float(d0[2]), __uint_as_float(d0[3]));
+                    dst[1] = make_float4(__uint_as_float(d0[4]), __uint_as_float(d0[5]), __uint_as_float(d0[6]), __uint_as_float(d0[7]));
+                    dst[2] = make_float4(__uint_as_float(d0[8]), __uint_as_float(d0[9]), __uint_as_float(d0[10]), __uint_as_float(d0[11]));
+                    dst[3] = make_float4(__uint_as_float(d0[12]), __uint_as_float(d0[13]), __uint_as_float(d0[14]), __uint_as_float(d0[15]));
+                    dst[4] = make_float4(__uint_as_float(d1[0]), __uint_as_float(d1[1]), __uint_as_float(d1[2]), __uint_as_float(d1[3]));
                 }
                 __syncwarp();
                 if (quad == 0) TC_STAMP(slot, 8);

@@ -26,7 +26,7 @@ for role in range(8):
         v = int(d[role, 1 + k]); ev.append((v & 0xFFFFFFFFFFFF, role, v >> 48))
 ev.sort()
 t0 = ev[0][0]
-names = {1: "x staged", 2: "pooled", 3: "d1 wake", 4: "e1 done", 5: "d2 wake", 6: "e2 done", 7: "d3 wake", 8: "e3 done"}
+names = {1: "x staged", 2: "pooled", 3: "d1 wake", 4: "e1 done", 5: "d2 wake", 6: "e2 done", 7: "d3 wake", 8: "e3 done", 31: "  ld done", 32: "  st issued", 33: "  st done", 34: "  x st issued"}
 tnames = {1: "wait unit", 2: "unit ready", 3: "tail done"}
 xs = [t - t0 for t, role, code in ev if role == 0 and code == 1]
 print("slot0 x-staged times:", xs)
