@@ -84,20 +84,27 @@ enum { SM_M = 0, SM_VAR = 20, SM_SIM = 40, SM_SIV = 60, SM_VS = 80, SM_S = 100, 
        SM_LVS = 540, SM_NSC = 580 /* exp(lv_in/2), up to 64 */, SM_R = 644, SM_GR = 648, SM_Y = 652 };
 
 // C[4 rows of quad q][4 columns of group cg] += sum_k AT[k][4q..4q+3] * W[k][4cg..4cg+3]
+// Accumulators are column pairs (fma.rn.f32x2): 8 FFMA2 + 4 operand packs per k instead of 16 FFMA.
 __device__ __forceinline__ void rowgemm4x4(const float* __restrict__ AT, int RP, int K, const float* __restrict__ W,
                                            int NP, int q, int cg, float (&acc)[4][4]) {
     const float* ap = AT + 4 * q;
     const float* wp = W + 4 * cg;
+    u64 a2[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { a2[r][0] = pack2(acc[r][0], acc[r][1]); a2[r][1] = pack2(acc[r][2], acc[r][3]); }
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
         const float4 a = *reinterpret_cast<const float4*>(ap + k * RP);
-        const float4 w = *reinterpret_cast<const float4*>(wp + k * NP);
-        const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wp + k * NP);
+        const u64 av[4] = {pack2(a.x, a.x), pack2(a.y, a.y), pack2(a.z, a.z), pack2(a.w, a.w)};
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+        for (int r = 0; r < 4; ++r) {
+            a2[r][0] = fma2(av[r], w.x, a2[r][0]);
+            a2[r][1] = fma2(av[r], w.y, a2[r][1]);
+        }
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { unpack2(a2[r][0], acc[r][0], acc[r][1]); unpack2(a2[r][1], acc[r][2], acc[r][3]); }
 }
 
 // acc[jj][kk] += sum_r G[j0+jj][r] * Hm[krow[kk]][r]   (both feature-major with row pitch RP = T)
@@ -180,10 +187,13 @@ __global__ void __launch_bounds__(NTHR, 2) train_fwd_bwd_kernel(const Params prm
     const int jb = tid / 10, kb10 = tid % 10;      // dW1, dV0, dV1, dW2: 10 k-groups
     const int KG0 = FP >> 2;                       // dW0: FP/4 k-groups (F = 41 -> 11); 20 * KG0 <= 248 threads
     const int jb0 = tid / KG0, kb11 = tid % KG0;
+    // a thread's 4 k's are strided by the group count (k = kb + KG*kk): for a fixed kk the lanes of a warp then read
+    // CONSECUTIVE feature rows, whose 400-byte pitch (T = 100) walks the 16-byte bank groups -- contiguous k's per
+    // thread put rows 4 apart on the same banks (5-way conflicts, 79 % of the LSU wavefront peak in ncu)
     int krow0[4];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) krow0[kk] = min(4 * kb11 + kk, F - 1);
-    const int krow10[4] = {4 * kb10, 4 * kb10 + 1, 4 * kb10 + 2, 4 * kb10 + 3};
+    for (int kk = 0; kk < 4; ++kk) krow0[kk] = min(kb11 + KG0 * kk, F - 1);
+    const int krow10[4] = {kb10, kb10 + 10, kb10 + 20, kb10 + 30};
     const int q_rg = tid % NQ, cg_rg = tid / NQ;   // row-GEMM item of this thread
     const float Tf = (float)T, Tm1 = (float)(T - 1);
     const uint64_t key = seed_key(prm.seed, sidx);
@@ -512,7 +522,7 @@ __global__ void __launch_bounds__(NTHR, 2) train_fwd_bwd_kernel(const Params prm
         for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                const int c = 4 * kb11 + kk;
+                const int c = kb11 + KG0 * kk;
                 if (c < F) part[fl.W0 + (2 * jb0 + jj) * F + c] = aW0[jj][kk];
             }
     }
