@@ -266,7 +266,7 @@ size_t bnn_predict_workspace_bytes(const bnn_model_config*, int64_t, int64_t) { 
 static bool tc_selected(const bnn_model_config* cfg, int kin) {
     const char* force = getenv("BNN_PREDICT_VARIANT");
     if (force && strncmp(force, "tc", 2) != 0) return false;
-    return cfg->n_times == bnn::tc::T_FIXED && kin + 1 <= bnn::TC_K1;
+    return cfg->n_times == bnn::tc::T_FIXED && kin <= bnn::TC_K1;
 }
 
 int32_t bnn_predict_system_granule(const bnn_model_config* cfg) {
@@ -319,20 +319,20 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     if (tiles < 2 * 148) chunks = (2 * 148 + tiles - 1) / tiles;
     if (chunks > n_units) chunks = n_units;
     prm.units_per_cta = (int)((n_units + chunks - 1) / chunks);
-    // variant selection: tensor cores (tcgen05, 3xTF32; 3 TMEM slots, 4 tail warps) when T = 100 and at most 31
+    // variant selection: tensor cores (tcgen05, 3xTF32; 4 TMEM slots, 4 tail warps) when T = 100 and at most 31
     // live input columns; else the FFMA2 kernels: v2 (warp-specialised, TMA ring) when its tile fits in shared
-    // memory, else v1.  BNN_PREDICT_VARIANT=tc3n4|tc3n3|tc3n2|tc2n4|v1|v2c8|v2c12|v2c16 forces one (benchmarks /
+    // memory, else v1.  BNN_PREDICT_VARIANT=tc4n4|tc4n3|tc3n4|tc2n4|v1|v2c8|v2c12|v2c16 forces one (benchmarks /
     // cross-checks).
     const char* force = getenv("BNN_PREDICT_VARIANT");
     const int T = cfg->n_times;
     cudaStream_t st = (cudaStream_t)stream;
     auto fits = [&](int nc) { return v2_smem_bytes(prm.kin, prm.F, T, nc) <= 227 * 1024; };
     if (tc::tc_fits(prm, T)) {
+        if (force && !strcmp(force, "tc4n4")) return tc::launch_tc<4, 4>(prm, st);
+        if (force && !strcmp(force, "tc4n3")) return tc::launch_tc<4, 3>(prm, st);
         if (force && !strcmp(force, "tc3n4")) return tc::launch_tc<3, 4>(prm, st);
-        if (force && !strcmp(force, "tc3n3")) return tc::launch_tc<3, 3>(prm, st);
-        if (force && !strcmp(force, "tc3n2")) return tc::launch_tc<3, 2>(prm, st);
         if (force && !strcmp(force, "tc2n4")) return tc::launch_tc<2, 4>(prm, st);
-        if (!force) return tc::launch_tc<3, 4>(prm, st);
+        if (!force) return tc::launch_tc<4, 4>(prm, st);
     }
     if (force && !strcmp(force, "v1")) return launch_v1<8>(prm, T, st);
     if (force && !strcmp(force, "v2c8") && fits(8)) return launch_v2<8>(prm, T, st);

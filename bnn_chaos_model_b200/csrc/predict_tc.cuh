@@ -12,18 +12,18 @@
 // only run the per-row epilogue (ReLU + hi/lo split), 3 instructions per activation.
 //
 // One CTA per SM, 5 systems (500 time-step rows -> four 128-row M tiles) resident in shared memory
-// as fp32; per (unit, M tile) "job" a 3-deep ring of TMEM slots [A_hi 48 | A_lo 40 | D 48 columns]:
-//   epilogue warps (4 per slot, thread = row = TMEM lane):
-//       stage x: smem -> hi/lo -> tcgen05.st A          -> arrive a_ready
-//       after each layer: tcgen05.ld D -> ReLU -> hi/lo -> tcgen05.st A   -> arrive a_ready
-//       last layer: D -> per-32-row-block pooled (mean, M2) records
-//   MMA warps (one per slot, one elected lane): wait a_ready, issue 12/17/17 tcgen05.mma per layer, commit -> d_ready
-//   producer warp: cp.async.bulk of each unit's hi/lo B operands (43 KB) into a 2-slot ring
+// as fp32; per (unit, M tile) "job" one of NSLOT TMEM slots [A_hi 40 | A_lo 40 | D 48 columns]:
+//   epilogue warps (4 per slot, thread = row = TMEM lane; quadrant-0 warp also issues the slot's MMAs):
+//       stage x: smem -> hi/lo -> tcgen05.st A
+//       after each layer: tcgen05.ld D -> + bias -> ReLU -> hi/lo -> tcgen05.st A
+//       last layer: D + bias -> per-32-row-block pooled (mean, M2) records
+//       hand-offs inside a slot are named hardware barriers (bar.sync: waiting warps cost no issue slots); only
+//       the issuing warp polls the tcgen05.commit mbarrier
+//   MMA issue (one elected lane): 12/15/15 tcgen05.mma per layer (M=128, N=48/48/32, K=8)
+//   producer warp: cp.async.bulk of each unit's hi/lo B operands + biases (38 KB) into a 2-slot ring
 //   NT tail warps (unit i -> warp i % NT): merge the records per system, sampled summary statistics,
 //       regress_nn with the fp32 head weights read through L2, store (mu, std); records live in an NT-deep ring
 //       (unit_done / rec_free barriers give the epilogue back-pressure when the tails fall behind).
-// Biases ride in the GEMMs: x carries a ones column (index 31), the hidden activations a constant
-// ones block in TMEM columns 40..47 of A_hi.
 #pragma once
 #include "predict_device.cuh"
 #include "tc.cuh"
@@ -35,7 +35,7 @@ constexpr int SYS = 5;            // systems per CTA tile
 constexpr int MT = 4;             // 128-row M tiles per tile (5 * 100 rows -> 512)
 constexpr int T_FIXED = 100;      // time steps (the tiling is specific to T = 100)
 constexpr int ROWS = SYS * T_FIXED;
-constexpr int TM_AHI = 0, TM_ALO = 48, TM_D = 88, TM_SLOT = 136;
+constexpr int TM_AHI = 0, TM_ALO = 40, TM_D = 80, TM_SLOT = 128;  // TMEM columns of one slot
 constexpr int N_BLOCKS = MT * 4;  // 32-row blocks per tile
 constexpr int REC_FLOATS = N_BLOCKS * 2 * L * 2;  // [block][segment][col][mean, M2]
 constexpr int FB_FLOATS = 32 * L;                 // per epilogue warp
@@ -45,7 +45,7 @@ constexpr int MAX_NT = 4;
 struct Bars {
     uint64_t w_full[2];                                // B operands of unit i landed in ring slot i & 1
     uint64_t unit_done[MAX_NT], rec_free[MAX_NT];      // record ring slot i % NT: written by the epilogue / read by the tail
-    uint64_t a_ready[3], d_ready[3];
+    uint64_t d_ready[4];                               // tcgen05.commit of the slot's current layer
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -79,7 +79,7 @@ __device__ __forceinline__ void block_geom(int b, int& sysA, int& split, int& nv
 
 // ---------------------------------------------------------------------------------------
 // x tile: X[N,T,F] -> xs[row][32] fp32, 16-byte chunks XOR-swizzled by (row & 7) so that a warp's
-// 32 rows read conflict-free; live columns packed first, column 31 = 1.0 (bias), rest 0.
+// 32 rows read conflict-free; live columns packed first, the rest 0.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ int xs_index(int row, int c) { return row * 32 + ((((c >> 2) ^ (row & 7))) << 2) + (c & 3); }
 
@@ -101,7 +101,6 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
     }
     __syncthreads();
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
-        xs[xs_index(r, TC_K1 - 1)] = 1.0f;
         if (poison[r]) xs[xs_index(r, 0)] = __int_as_float(0x7fc00000);  // x - mask keeps NaN/Inf as NaN (:452-478)
     }
     __syncthreads();
@@ -123,18 +122,36 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], uint32_t t_hi,
     tmem_st8(t_lo, l);
 }
 
-template <bool RELU>
-__device__ __forceinline__ void split_store16(const uint32_t (&d)[16], uint32_t t_hi, uint32_t t_lo) {
+// (d + bias) -> ReLU -> hi/lo, 16 (8) consecutive columns; bias: 16-byte aligned shared memory, same for every lane
+template <bool EPI>
+__device__ __forceinline__ void split_store16(const uint32_t (&d)[16], const float* __restrict__ bias, uint32_t t_hi,
+                                              uint32_t t_lo) {
     uint32_t h[16], l[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float v = RELU ? relu_nan(__uint_as_float(d[j])) : __uint_as_float(d[j]);
-        const uint32_t hb = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
-        h[j] = hb;
-        l[j] = __float_as_uint(v - __uint_as_float(hb));
+    for (int g4 = 0; g4 < 4; ++g4) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI) b = *reinterpret_cast<const float4*>(bias + 4 * g4);
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = 4 * g4 + u;
+            const float v = EPI ? relu_nan(__uint_as_float(d[j]) + bv[u]) : __uint_as_float(d[j]);
+            const uint32_t hb = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
+            h[j] = hb;
+            l[j] = __float_as_uint(v - __uint_as_float(hb));
+        }
     }
     tmem_st16(t_hi, h);
     tmem_st16(t_lo, l);
+}
+__device__ __forceinline__ void split_store8_bias(const uint32_t (&d)[8], const float* __restrict__ bias, uint32_t t_hi,
+                                                  uint32_t t_lo) {
+    float v[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = relu_nan(__uint_as_float(d[k]) + bv[k]);
+    split_store8(v, t_hi, t_lo);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -146,22 +163,24 @@ __device__ __forceinline__ uint64_t bdesc(uint32_t base_addr, int N, int ks) {
     return smem_desc_kmajor(base_addr + (uint32_t)ks * 2u * chunk, chunk, 128u);
 }
 
-template <int N, int KS_HI, int KS_LO>
+template <int N, int KS>
 __device__ __forceinline__ void issue_layer(uint32_t ts, uint32_t bh_addr, uint32_t bl_addr) {
     constexpr uint32_t idesc = idesc_tf32(128, N);
     const uint32_t d = ts + TM_D, ahi = ts + TM_AHI, alo = ts + TM_ALO;
-    // descriptors advance by two 16-byte K chunks (2*N*16 bytes -> 2*N in the 16-byte address field) per
-    // K = 8 step; the loops stay rolled so that the 46 descriptors of a job are not all kept in registers
+    // descriptors advance by two 16-byte K chunks (2*N*16 bytes -> 2*N in the 16-byte address field) per K = 8 step
     const uint64_t dh = bdesc(bh_addr, N, 0), dl = bdesc(bl_addr, N, 0);
     constexpr uint64_t step = 2ull * N;
-    // called by the whole (converged) MMA warp; one elected lane issues
+    // called by a whole (converged) warp; one elected lane issues a_lo w_hi + a_hi w_lo + a_hi w_hi, the two
+    // small (2^-11) correction terms FIRST: the tensor core rounds its fp32 accumulator toward zero after every
+    // MMA, so only the last KS steps round at the full magnitude of the sum (measured: 3x smaller error than
+    // accumulating the corrections after the main term, tools/accuracy_study.py)
     if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < KS_HI; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dh + ks * step, idesc, ks > 0);
+        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, alo + 8 * ks, dh + ks * step, idesc, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < KS_LO; ++ks) mma_tf32_ts(d, alo + 8 * ks, dh + ks * step, idesc, true);
+        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dl + ks * step, idesc, true);
 #pragma unroll
-        for (int ks = 0; ks < KS_HI; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dl + ks * step, idesc, true);
+        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dh + ks * step, idesc, true);
     }
     __syncwarp();
 }

@@ -15,14 +15,17 @@ namespace tc {
     } while (0)
 
 constexpr int BAR_A = 1, BAR_D = 5;  // named barrier ids: A-ready / D-ready of TMEM slot s are BAR_A + s / BAR_D + s
-constexpr int B_FLOATS = 2 * (TC_K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3);  // hi + lo B operands of one unit
+constexpr int B_FLOATS = 2 * (TC_K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3) + TC_BIAS;  // hi + lo B operands + biases
 constexpr int B_BYTES = B_FLOATS * 4;
+constexpr int O_B1H = 0, O_B1L = O_B1H + TC_K1 * TC_N * 4, O_B2H = O_B1L + TC_K1 * TC_N * 4,
+              O_B2L = O_B2H + TC_K2 * TC_N * 4, O_B3H = O_B2L + TC_K2 * TC_N * 4, O_B3L = O_B3H + TC_K2 * TC_N3 * 4,
+              O_BIAS = O_B3L + TC_K2 * TC_N3 * 4;  // byte offsets inside a ring slot
 
 template <int NSLOT, int NT>
 struct SmemPlan {
     // byte offsets inside dynamic shared memory
     static constexpr int xs = 0;                                   // ROWS*32 floats
-    static constexpr int ring = xs + ROWS * 32 * 4;                // 2 slots of B operands
+    static constexpr int ring = xs + ROWS * 32 * 4;                // 2 slots of B operands + biases
     static constexpr int fb = ring + 2 * B_BYTES;                  // per epilogue warp: 32 rows x 20 latent columns
     static constexpr int rec = fb + NSLOT * 4 * FB_FLOATS * 4;     // NT slots of block records
     static constexpr int scratch = rec + NT * REC_FLOATS * 4;      // per tail warp
@@ -30,16 +33,17 @@ struct SmemPlan {
     static constexpr int total = bars + (int)sizeof(Bars);
 };
 
-// Warp roles (the issue arbiter favours high warp ids, B300_MICROARCH.md: the latency-critical roles sit high):
+// Warp roles (the issue arbiter favours high warp ids, B300_MICROARCH.md):
 //   [0, NT)                  tail warps (unit i -> warp i % NT)
-//   [NT0, NT0 + 4*NSLOT)     epilogue warps, NT0 = NT rounded up to 4 (slot = (w-NT0)/4, TMEM lane quadrant = w % 4)
-//   next NSLOT               MMA issuers, one per TMEM slot (the first also owns the TMEM allocation)
-//   last                     producer of the B-operand ring
+//   [NT0, NT0 + 4*NSLOT)     epilogue warps, NT0 = NT rounded up to 4 (slot = (w-NT0)/4, TMEM lane quadrant = w % 4);
+//                            the quadrant-0 warp of a slot issues that slot's MMAs
+// The B-operand ring is refilled by the quadrant-0 warp of slot 0 (it polls unit_done without blocking at its own
+// synchronisation points), so the CTA is exactly NT0 + 4*NSLOT warps (640 threads -> 96 registers at NSLOT = 4).
 template <int NSLOT, int NT>
-__global__ void __launch_bounds__((((NT + 3) & ~3) + 5 * NSLOT + 1) * 32, 1)
+__global__ void __launch_bounds__((((NT + 3) & ~3) + 4 * NSLOT) * 32, 1)
 predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
-    static_assert(NT >= 2 && NT <= MAX_NT && NSLOT <= 3 && MT >= NSLOT, "role layout");
+    static_assert(NT >= 2 && NT <= MAX_NT && NSLOT <= 4 && MT >= NSLOT && NSLOT * TM_SLOT <= 512, "role layout");
     const PackedLayout pl(prm.kin, prm.F);
     using Plan = SmemPlan<NSLOT, NT>;
     float* xs = reinterpret_cast<float*>(smem_tc + Plan::xs);
@@ -53,9 +57,9 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
     const int n_items = n_tiles * chunks;
     int dbg_n = 0;
 
-    constexpr int W_EPI = (NT + 3) & ~3, W_MMA = W_EPI + 4 * NSLOT, W_PROD = W_MMA + NSLOT;
-    // ---- one-time setup: TMEM allocation, constant ones block in every slot ----
-    if (warp == W_MMA) {
+    constexpr int W_EPI = (NT + 3) & ~3;
+    // ---- one-time setup: TMEM allocation ----
+    if (warp == W_EPI) {
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
@@ -63,13 +67,6 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-    if (warp >= W_EPI && warp < W_MMA) {
-        const int slot = (warp - W_EPI) >> 2, quad = warp & 3;
-        const uint32_t t = tmem + ((uint32_t)(quad * 32) << 16) + slot * TM_SLOT + TM_AHI + H;
-        uint32_t ones[8] = {__float_as_uint(1.0f), 0, 0, 0, 0, 0, 0, 0};
-        tmem_st8(t, ones);  // A_hi columns 40..47 = [1, 0 x7]: the bias column of layers 2 and 3
-        tc_wait_st();
-    }
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int tile = item / chunks, chunk = item % chunks;
@@ -92,9 +89,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                 mbar_init(&bars->unit_done[s], MT * 4);  // 4 epilogue warps per job, MT jobs per unit
                 mbar_init(&bars->rec_free[s], 1);        // the tail warp of the slot
             }
-            for (int s = 0; s < NSLOT; ++s) {
-                mbar_init(&bars->d_ready[s], 1);         // tcgen05.commit
-            }
+            for (int s = 0; s < NSLOT; ++s) mbar_init(&bars->d_ready[s], 1);  // tcgen05.commit
             mbar_init_fence();
         }
         load_x_tile_tc(prm.X, n0, n_valid, prm.F, prm.kin, prm.cm, xs, reinterpret_cast<int*>(fb));
@@ -105,9 +100,9 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
             // ---------------- tail warps ----------------
             float* my_scratch = scratch + warp * TAIL_SCRATCH;
             for (int i = warp; i < n_units; i += NT) {
-                TC_STAMP(3 + (warp & 1), 1);
+                TC_STAMP(4 + (warp & 1), 1);
                 mbar_wait_backoff(&bars->unit_done[warp], (uint32_t)((i / NT) & 1), 200);  // all 16 block records of unit i
-                TC_STAMP(3 + (warp & 1), 2);
+                TC_STAMP(4 + (warp & 1), 2);
                 const int64_t u = u_begin + i;
                 const float* eps_u = prm.eps ? prm.eps + u * prm.N * S2 : nullptr;
                 const float* eps_sum_u = prm.eps_sum ? prm.eps_sum + u * prm.N * S2 : nullptr;
@@ -117,64 +112,16 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                              prm.out + u * prm.out_unit_stride, prm.out_sys_stride);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->rec_free[warp]);  // the record slot may take unit i + NT
-                TC_STAMP(3 + (warp & 1), 3);
-            }
-        } else if (warp == W_PROD) {
-            // ---------------- producer: B operands of unit i -> ring slot i & 1 ----------------
-            // slot i & 1 is free once every block record of unit i-2 is written (all its MMAs have completed)
-            if (lane == 0) {
-                for (int i = 0; i < n_units; ++i) {
-                    if (i >= 2) mbar_wait_backoff(&bars->unit_done[(i - 2) % NT], (uint32_t)(((i - 2) / NT) & 1), 400);
-                    mbar_arrive_expect_tx(&bars->w_full[i & 1], (uint32_t)B_BYTES);
-                    bulk_g2s(ring + (size_t)(i & 1) * B_FLOATS, prm.thp + (u_begin + i) * pl.P + pl.B1h, (uint32_t)B_BYTES,
-                             &bars->w_full[i & 1]);
-                }
-            }
-        } else if (warp >= W_MMA) {
-            // ---------------- MMA issuers: one warp per TMEM slot (uniform control flow, one elected lane issues).
-            // The control overhead between two batches of one warp overlaps with the other warps' batches.
-            const int s = warp - W_MMA;
-            uint32_t pa = 0;
-            const uint32_t ring_addr = smem_u32(ring);
-            constexpr int o_b1h = 0, o_b1l = o_b1h + TC_K1 * TC_N * 4, o_b2h = o_b1l + TC_K1 * TC_N * 4,
-                          o_b2l = o_b2h + TC_K2 * TC_N * 4, o_b3h = o_b2l + TC_K2 * TC_N * 4,
-                          o_b3l = o_b3h + TC_K2 * TC_N3 * 4;
-            int seen_unit = -1;  // last unit whose weights this warp has waited for
-            for (int j = s; j < n_jobs; j += NSLOT) {
-                const int i = j / MT, ws = i & 1;
-                if (i != seen_unit) {
-                    // this warp visits every unit (MT >= NSLOT), in order, so its view of w_full[ws] never skips a phase
-                    mbar_wait(&bars->w_full[ws], (i >> 1) & 1);
-                    seen_unit = i;
-                }
-#pragma unroll 1
-                for (int layer = 0; layer < 3; ++layer) {
-                    named_sync(BAR_A + s, 160);  // the slot's 4 epilogue warps have written A (they only arrive)
-                    tc_fence_after();
-                    uint32_t wb = ring_addr + (uint32_t)ws * (uint32_t)B_BYTES;
-                    uint32_t ts = tmem + s * TM_SLOT;
-                    asm volatile("" : "+r"(wb), "+r"(ts));  // keep the descriptors out of loop-invariant hoisting
-                    TC_STAMP(7, 10 * s + layer);
-                    if (layer == 0)
-                        issue_layer<TC_N, TC_K1 / 8, TC_K1 / 8>(ts, wb + o_b1h, wb + o_b1l);
-                    else if (layer == 1)
-                        issue_layer<TC_N, TC_K2 / 8, H / 8>(ts, wb + o_b2h, wb + o_b2l);
-                    else
-                        issue_layer<TC_N3, TC_K2 / 8, H / 8>(ts, wb + o_b3h, wb + o_b3l);
-                    TC_STAMP(7, 100 + 10 * s + layer);
-                    if (elect_one_sync()) mma_commit(&bars->d_ready[s]);
-                    __syncwarp();
-                    // this warp alone polls the commit barrier, then releases the epilogue warps through a named barrier
-                    mbar_wait_backoff(&bars->d_ready[s], pa, 20);
-                    pa ^= 1;
-                    named_arrive(BAR_D + s, 160);
-                }
+                TC_STAMP(4 + (warp & 1), 3);
             }
         } else if (warp >= W_EPI) {
-            // ---------------- epilogue warps ----------------
+            // ---------------- epilogue warps (quadrant 0 also issues the MMAs of its slot) ----------------
             const int slot = (warp - W_EPI) >> 2, quad = warp & 3;
-            const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + slot * TM_SLOT;  // this lane's row of the slot
+            const uint32_t ts = tmem + slot * TM_SLOT;                     // slot base (lane 0)
+            const uint32_t tl = ts + ((uint32_t)(quad * 32) << 16);        // this warp's lane quadrant
             float* my_fb = fb + (warp - W_EPI) * FB_FLOATS;
+            const uint32_t ring_addr = smem_u32(ring);
+            uint32_t pd = 0;
             int pend_i = -1, pend_m = 0;  // job whose latent rows sit in my_fb and still have to be pooled
 
             // pooled (mean, M2) records of one 32-row block, two-pass per segment like torch.mean / torch.std;
@@ -212,11 +159,58 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->unit_done[rs]);
             };
+            // A of the slot is complete (named barrier over the slot's 4 warps); quadrant 0 issues the layer and the commit
+            auto issue = [&](int layer, int ws) {
+                named_sync(BAR_A + slot, 128);
+                if (quad == 0) {
+                    tc_fence_after();
+                    uint32_t wb = ring_addr + (uint32_t)ws * (uint32_t)B_BYTES;
+                    uint32_t tsv = ts;
+                    asm volatile("" : "+r"(wb), "+r"(tsv));  // keep the descriptors out of loop-invariant hoisting
+                    if (slot == 0) TC_STAMP(7, layer);
+                    if (layer == 0)
+                        issue_layer<TC_N, TC_K1 / 8>(tsv, wb + O_B1H, wb + O_B1L);
+                    else if (layer == 1)
+                        issue_layer<TC_N, TC_K2 / 8>(tsv, wb + O_B2H, wb + O_B2L);
+                    else
+                        issue_layer<TC_N3, TC_K2 / 8>(tsv, wb + O_B3H, wb + O_B3L);
+                    if (elect_one_sync()) mma_commit(&bars->d_ready[slot]);
+                    __syncwarp();
+                    if (slot == 0) TC_STAMP(7, 100 + layer);
+                }
+            };
+            // D of the slot is complete: quadrant 0 polls the commit barrier, the other three sleep on the named barrier
+            auto wait_d = [&]() {
+                if (quad == 0) {
+                    mbar_wait_backoff(&bars->d_ready[slot], pd, 20);
+                    pd ^= 1;
+                }
+                named_sync(BAR_D + slot, 128);
+                tc_fence_after();
+            };
 
+            // B operands + biases of unit i -> ring slot i & 1, free once every block record of unit i-2 is written
+            // (all its MMAs and bias reads are done).  Issued by one lane of slot 0's quadrant-0 warp whenever it passes.
+            int next_load = 0;
+            auto refill = [&]() {
+                if (slot == 0 && quad == 0 && lane == 0) {
+                    while (next_load < n_units &&
+                           (next_load < 2 || mbar_test(&bars->unit_done[(next_load - 2) % NT], (uint32_t)(((next_load - 2) / NT) & 1)))) {
+                        mbar_arrive_expect_tx(&bars->w_full[next_load & 1], (uint32_t)B_BYTES);
+                        bulk_g2s(ring + (size_t)(next_load & 1) * B_FLOATS, prm.thp + (u_begin + next_load) * pl.P + pl.B1h,
+                                 (uint32_t)B_BYTES, &bars->w_full[next_load & 1]);
+                        ++next_load;
+                    }
+                }
+            };
+            refill();
+
+            int seen_unit = -1;
             for (int j = slot; j < n_jobs; j += NSLOT) {
-                const int i = j / MT, m = j % MT;
+                const int i = j / MT, m = j % MT, ws = i & 1;
                 const int R = m * 128 + quad * 32 + lane;  // tile row of this thread
-                // ---- stage x -> A (hi 32 columns incl. the ones column, lo 32 columns) ----
+                const float* bias = ring + (size_t)ws * B_FLOATS + O_BIAS / 4;
+                // ---- stage x -> A (hi / lo, 32 columns each) ----
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t v[16];
@@ -231,64 +225,68 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
 #pragma unroll
                         for (int k = 0; k < 16; ++k) v[k] = 0u;
                     }
-                    split_store16<false>(v, tl + TM_AHI + 16 * c, tl + TM_ALO + 16 * c);
+                    split_store16<false>(v, nullptr, tl + TM_AHI + 16 * c, tl + TM_ALO + 16 * c);
                 }
-                if (quad == 0) TC_STAMP(slot, 34);
                 tc_wait_st();
                 tc_fence_before();
-                named_arrive(BAR_A + slot, 160);
-                if (quad == 0) TC_STAMP(slot, 1);
+                if (quad == 0 && slot < 3) TC_STAMP(slot, 1);
+                if (quad == 0 && i != seen_unit) {
+                    // a slot visits every unit (MT >= NSLOT), in order, so its view of w_full[ws] never skips a phase
+                    while (!mbar_test(&bars->w_full[ws], (i >> 1) & 1)) {
+                        refill();
+                        __nanosleep(20);
+                    }
+                    __syncwarp();
+                    seen_unit = i;
+                }
+                issue(0, ws);
+                refill();
 
                 // ---- pool the previous job's block while the tensor pipe works on layer 1 ----
                 if (pend_i >= 0) pool_block(pend_i, pend_m);
-                if (quad == 0) TC_STAMP(slot, 2);
+                if (quad == 0 && slot < 3) TC_STAMP(slot, 2);
 
-                // ---- layers 1 and 2: D -> ReLU -> hi/lo -> A ----
+                // ---- layers 1 and 2: D + bias -> ReLU -> hi/lo -> A ----
 #pragma unroll 1
                 for (int layer = 0; layer < 2; ++layer) {
-                    named_sync(BAR_D + slot, 160);
-                    if (quad == 0) TC_STAMP(slot, 3 + 2 * layer);
-                    tc_fence_after();
+                    wait_d();
+                    if (quad == 0 && slot < 3) TC_STAMP(slot, 3 + 2 * layer);
+                    const float* bl = bias + layer * TC_N;
                     uint32_t d0[16], d1[16], d2[8];
                     tmem_ld16(tl + TM_D, d0);
                     tmem_ld16(tl + TM_D + 16, d1);
                     tmem_ld8(tl + TM_D + 32, d2);
                     tc_wait_ld();
-                    if (quad == 0) TC_STAMP(slot, 31);
-                    split_store16<true>(d0, tl + TM_AHI, tl + TM_ALO);
-                    split_store16<true>(d1, tl + TM_AHI + 16, tl + TM_ALO + 16);
-                    {
-                        float v[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = relu_nan(__uint_as_float(d2[k]));
-                        split_store8(v, tl + TM_AHI + 32, tl + TM_ALO + 32);
-                    }
-                    if (quad == 0) TC_STAMP(slot, 32);
+                    split_store16<true>(d0, bl, tl + TM_AHI, tl + TM_ALO);
+                    split_store16<true>(d1, bl + 16, tl + TM_AHI + 16, tl + TM_ALO + 16);
+                    split_store8_bias(d2, bl + 32, tl + TM_AHI + 32, tl + TM_ALO + 32);
                     tc_wait_st();
-                    if (quad == 0) TC_STAMP(slot, 33);
                     tc_fence_before();
-                    named_arrive(BAR_A + slot, 160);
-                    if (quad == 0) TC_STAMP(slot, 4 + 2 * layer);
+                    if (quad == 0 && slot < 3) TC_STAMP(slot, 4 + 2 * layer);
+                    issue(layer + 1, ws);
+                    refill();
                 }
 
-                // ---- layer 3: D (20 latent columns) -> my_fb (pooled after the next job's x is staged) ----
-                named_sync(BAR_D + slot, 160);
-                if (quad == 0) TC_STAMP(slot, 7);
-                tc_fence_after();
+                // ---- layer 3: D + bias (20 latent columns) -> my_fb (pooled after the next job's x is staged) ----
+                wait_d();
+                if (quad == 0 && slot < 3) TC_STAMP(slot, 7);
                 {
                     uint32_t d0[16], d1[8];
                     tmem_ld16(tl + TM_D, d0);
                     tmem_ld8(tl + TM_D + 16, d1);
                     tc_wait_ld();
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + 2 * TC_N);
                     float4* dst = reinterpret_cast<float4*>(my_fb + lane * L);
-                    dst[0] = make_float4(__uint_as_float(d0[0]), __uint_as_float(d0[1]), __uint_as_float(d0[2]), __uint_as_float(d0[3]));
-                    dst[1] = make_float4(__uint_as_float(d0[4]), __uint_as_float(d0[5]), __uint_as_float(d0[6]), __uint_as_float(d0[7]));
-                    dst[2] = make_float4(__uint_as_float(d0[8]), __uint_as_float(d0[9]), __uint_as_float(d0[10]), __uint_as_float(d0[11]));
-                    dst[3] = make_float4(__uint_as_float(d0[12]), __uint_as_float(d0[13]), __uint_as_float(d0[14]), __uint_as_float(d0[15]));
-                    dst[4] = make_float4(__uint_as_float(d1[0]), __uint_as_float(d1[1]), __uint_as_float(d1[2]), __uint_as_float(d1[3]));
+#pragma unroll
+                    for (int g4 = 0; g4 < 5; ++g4) {
+                        const float4 b = b4[g4];
+                        const uint32_t* dd = g4 < 4 ? &d0[4 * g4] : &d1[0];
+                        dst[g4] = make_float4(__uint_as_float(dd[0]) + b.x, __uint_as_float(dd[1]) + b.y,
+                                              __uint_as_float(dd[2]) + b.z, __uint_as_float(dd[3]) + b.w);
+                    }
                 }
                 __syncwarp();
-                if (quad == 0) TC_STAMP(slot, 8);
+                if (quad == 0 && slot < 3) TC_STAMP(slot, 8);
                 pend_i = i;
                 pend_m = m;
             }
@@ -298,14 +296,14 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == W_MMA) tmem_dealloc(tmem, 512);
+    if (warp == W_EPI) tmem_dealloc(tmem, 512);
 }
 
 template <int NSLOT, int NT>
 static int launch_tc(const PredictParams& prm, cudaStream_t st) {
     constexpr size_t smem = (size_t)SmemPlan<NSLOT, NT>::total;
     static_assert(smem <= 227 * 1024, "tensor-core tile does not fit in shared memory");
-    constexpr int threads = (((NT + 3) & ~3) + 5 * NSLOT + 1) * 32;
+    constexpr int threads = (((NT + 3) & ~3) + 4 * NSLOT) * 32;
     static bool attr_done = false;
     static int n_sms = 0;
     if (!attr_done) {

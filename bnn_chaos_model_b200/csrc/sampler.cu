@@ -135,27 +135,33 @@ __global__ void pack_theta_kernel(const float* __restrict__ theta, int64_t n_uni
         int r = i - pl.lv_in;
         if (r < fl.F) src = fl.lv_in + r;
     } else {
+        if (i >= pl.Bb) {  // fp32 bias block b0[48] | b1[48] | b2[32]
+            const int r = i - pl.Bb;
+            float b = 0.f;
+            if (r < TC_N) { if (r < H) b = th[fl.b0 + r]; }
+            else if (r < 2 * TC_N) { if (r - TC_N < H) b = th[fl.b1 + r - TC_N]; }
+            else if (r - 2 * TC_N < L) b = th[fl.b2 + r - 2 * TC_N];
+            packed[idx] = b;
+            return;
+        }
         // tensor-core B operands: element (n, k) of a [N][K] matrix sits at ((k/4)*N + n)*4 + k%4
-        int r, N, kbias, nreal, wsrc, bsrc, kreal, ld;
+        int r, N, nreal, wsrc, kreal, ld;
         bool lo;
         if (i < pl.B2h) {
             r = i - pl.B1h; N = TC_N; lo = r >= TC_K1 * TC_N; r -= lo ? TC_K1 * TC_N : 0;
-            kbias = TC_K1 - 1; nreal = H; kreal = pl.kin; wsrc = fl.W0; bsrc = fl.b0; ld = fl.F;
+            nreal = H; kreal = pl.kin; wsrc = fl.W0; ld = fl.F;
         } else if (i < pl.B3h) {
             r = i - pl.B2h; N = TC_N; lo = r >= TC_K2 * TC_N; r -= lo ? TC_K2 * TC_N : 0;
-            kbias = H; nreal = H; kreal = H; wsrc = fl.W1; bsrc = fl.b1; ld = H;
+            nreal = H; kreal = H; wsrc = fl.W1; ld = H;
         } else {
             r = i - pl.B3h; N = TC_N3; lo = r >= TC_K2 * TC_N3; r -= lo ? TC_K2 * TC_N3 : 0;
-            kbias = H; nreal = L; kreal = H; wsrc = fl.W2; bsrc = fl.b2; ld = H;
+            nreal = L; kreal = H; wsrc = fl.W2; ld = H;
         }
         const int chunk = r / (N * 4), n = (r / 4) % N, k = chunk * 4 + (r & 3);
         float w = 0.f;
-        if (n < nreal) {
-            if (k < kreal) w = th[wsrc + n * ld + ((wsrc == fl.W0) ? (int)lc.col[k] : k)];
-            else if (k == kbias) w = th[bsrc + n];
-        }
+        if (n < nreal && k < kreal) w = th[wsrc + n * ld + ((wsrc == fl.W0) ? (int)lc.col[k] : k)];
         const float hi = tf32_rna(w);
-        packed[idx] = lo ? (w - hi) : hi;
+        packed[idx] = lo ? tf32_rna(w - hi) : hi;  // lo pre-rounded: the tensor core would truncate it
         return;
     }
     packed[idx] = src >= 0 ? th[src] : 0.f;

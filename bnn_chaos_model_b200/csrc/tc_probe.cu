@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(128) tc_time_kernel(int K, int N, int reps, in
         const uint32_t a_chunk = 128u * 16u;
         const uint32_t a_base = smem_u32(bs) + (uint32_t)N * K * 4;
         long long t0 = 0, t1 = 0;
+        const int nacc = (from_smem >> 1) + 1;
         // warp-uniform control flow and addresses, one elected lane per instruction (as in predict_tc)
         const uint64_t bd0 = smem_desc_kmajor(smem_u32(bs), chunk_bytes, 128u);
         const uint64_t ad0 = smem_desc_kmajor(a_base, a_chunk, 128u);
@@ -105,10 +106,13 @@ __global__ void __launch_bounds__(128) tc_time_kernel(int K, int N, int reps, in
             if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < 6; ++ks) {
-                    if (from_smem)
-                        mma_tf32_ss(tmem + 256, ad0 + ks * astep, bd0 + ks * bstep, idesc, (r | ks) > 0);
+                    // from_smem bit 0: A from shared memory; bits 1..: (number of independent accumulators - 1),
+                    // consecutive MMAs rotate over them (N <= 64) -- separates issue cost from the D dependency
+                    const uint32_t dcol = tmem + 256 + (uint32_t)(ks % nacc) * 64u;
+                    if (from_smem & 1)
+                        mma_tf32_ss(dcol, ad0 + ks * astep, bd0 + ks * bstep, idesc, (r | ks) > 0);
                     else
-                        mma_tf32_ts(tmem + 256, tmem + ks * 8, bd0 + ks * bstep, idesc, (r | ks) > 0);
+                        mma_tf32_ts(dcol, tmem + ks * 8, bd0 + ks * bstep, idesc, (r | ks) > 0);
                 }
             }
             __syncwarp();

@@ -266,7 +266,7 @@ def test_kernel_variants_agree_bitwise(dev, monkeypatch):
             assert torch.equal(outs[v], outs["v1"]), (v, N, S_)
 
 
-TC_VARIANTS = ("tc3n4", "tc3n3", "tc3n2", "tc2n4")
+TC_VARIANTS = ("tc4n4", "tc4n3", "tc3n4", "tc2n4")
 
 
 @pytest.mark.parametrize("variant", TC_VARIANTS)

@@ -5,7 +5,7 @@ import torch
 dev = torch.device("cuda:0")
 dbg = torch.zeros(8 * 512, dtype=torch.int64, device=dev)
 os.environ["BNN_TC_TIMELINE_PTR"] = str(dbg.data_ptr())
-os.environ["BNN_PREDICT_VARIANT"] = sys.argv[1] if len(sys.argv) > 1 else "tc3n4"
+os.environ["BNN_PREDICT_VARIANT"] = sys.argv[1] if len(sys.argv) > 1 else "tc4n4"
 from bench import load_stats
 from bnn_chaos_model_b200 import spock_reg_model as S, synth
 from bnn_chaos_model_b200.multiswag import MultiSWAG

@@ -13,7 +13,7 @@ from bench import FLOP_PER_EVAL_V50, load_stats  # noqa: E402
 from bnn_chaos_model_b200 import spock_reg_model as S, synth  # noqa: E402
 from bnn_chaos_model_b200.multiswag import MultiSWAG  # noqa: E402
 
-variants = sys.argv[1].split(",") if len(sys.argv) > 1 else ["v2c12", "tc3n4", "tc3n3", "tc3n2", "tc2n4"]
+variants = sys.argv[1].split(",") if len(sys.argv) > 1 else ["v2c12", "tc4n4", "tc4n3", "tc3n4", "tc2n4"]
 n_sys = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
 n_samp = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 dev = torch.device("cuda:0")
