@@ -100,6 +100,10 @@ SIGNATURES = {
         [c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, C.c_int32, C.c_int32,
          C.c_void_p],
     ),
+    "bnn_pack_inputs": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, c_f32p, C.c_void_p]),
+    "bnn_sample_instability": (
+        C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_float, C.c_int32, c_f32p, C.c_void_p]),
+    "bnn_summarize_instability": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     "bnn_ffma_peak": (C.c_int, [C.c_int32, C.c_int64, c_f32p, C.POINTER(C.c_int64), C.c_void_p]),
     "bnn_tc_probe": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bnn_tc_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -73,3 +73,66 @@ extern "C" int bnn_swag_collect(const float* d_w, int64_t d, int32_t n_seeds, in
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// K6: input packing -- the step immediately upstream of the predictive kernel.
+//
+// Reference: data_setup_kernel (/root/reference/figures/spock/regression.py:183-213) followed by
+// ssX.transform (:144, float64 sklearn StandardScaler) and torch.tensor(X).float() (:145):
+//   raw row = [26 time-series columns | 3 masses | isnotfinite(col 3), (col 6), (col 7)]   (32 columns)
+//   nan_to_num(posinf=0, neginf=0);  angle columns {11,12,13,17,18,19,23,24,25} -> (cos, sin)    (41 columns)
+//   x = float32((X - mean) / scale)        (all arithmetic in float64, like numpy)
+// HBM-bound: 232 B read + 164 B written per time-step row.
+// ---------------------------------------------------------------------------------------
+namespace bnn {
+
+__device__ __forceinline__ bool is_angle_col(int j) { return j >= 11 && j <= 25 && ((j - 11) % 6) < 3; }
+
+__global__ void __launch_bounds__(256) pack_inputs_kernel(const double* __restrict__ ts, const double* __restrict__ mass,
+                                                          const double* __restrict__ mean, const double* __restrict__ scale,
+                                                          int64_t n_rows, int T, float* __restrict__ x) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // (row, raw column j of 32)
+    if (idx >= n_rows * 32) return;
+    const int64_t row = idx >> 5;
+    const int j = (int)(idx & 31);
+    double v;
+    if (j < 26) {
+        v = ts[row * 26 + j];
+    } else if (j < 29) {
+        v = mass[(row / T) * 3 + (j - 26)];
+    } else {
+        const int src = (j == 29) ? 3 : (j == 30 ? 6 : 7);
+        v = isfinite(ts[row * 26 + src]) ? 0.0 : 1.0;  // flags are taken before nan_to_num
+    }
+    if (!isfinite(v)) v = 0.0;  // np.nan_to_num(posinf=0.0, neginf=0.0): NaN -> 0 too
+    // output column: every angle column before j adds one
+    int oc = j;
+    if (j > 11) oc += min(j - 11, 3);
+    if (j > 17) oc += min(j - 17, 3);
+    if (j > 23) oc += min(j - 23, 3);
+    float* o = x + row * 41;
+    if (is_angle_col(j)) {
+        o[oc] = (float)((cos(v) - mean[oc]) / scale[oc]);
+        o[oc + 1] = (float)((sin(v) - mean[oc + 1]) / scale[oc + 1]);
+    } else {
+        o[oc] = (float)((v - mean[oc]) / scale[oc]);
+    }
+}
+
+}  // namespace bnn
+
+extern "C" int bnn_pack_inputs(const double* d_tseries, const double* d_masses, const double* d_ss_mean,
+                               const double* d_ss_scale, int64_t n_systems, int32_t n_times, float* d_x, void* stream) {
+    using namespace bnn;
+    int rc = check_device();
+    if (rc != BNN_OK) return rc;
+    BNN_REQUIRE(d_tseries && d_masses && d_ss_mean && d_ss_scale && d_x, BNN_E_ARG, "bnn_pack_inputs: null pointer");
+    BNN_REQUIRE(n_systems > 0 && n_times > 0, BNN_E_ARG, "bnn_pack_inputs: empty input");
+    const int64_t total = n_systems * n_times * 32;
+    const int64_t blocks = (total + 255) / 256;
+    BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_pack_inputs: too many rows for one launch");
+    pack_inputs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_tseries, d_masses, d_ss_mean, d_ss_scale,
+                                                                          n_systems * n_times, n_times, d_x);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}

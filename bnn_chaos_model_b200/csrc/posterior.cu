@@ -1,0 +1,215 @@
+// K7: posterior post-processing, the step immediately downstream of the predictive kernel.
+//
+// Reference (numpy, on the host, over [samples, systems(, trios)] arrays copied back from the GPU):
+//   fast_truncnorm(mu, std, left=4, nsamp=40)     figures/main_figures.py:167-223, multiswag_5_planet.py:306-360
+//       draw up to nsamp normals x_k = z_k*std + mu, keep the first x_k > left (x_0 if none is)
+//   samples >= 9 are re-drawn from the analytic prior on [9, 100]                 main_figures.py:225-259, 5_planet:390-418
+//       prior(t) ~ 3.27086190404742 exp(-0.424033970670719 t) - 10.8793430454878 exp(-0.200351029031774 t^2)
+//       (the reference inverts a Riemann-sum table of 4*n_samples bins; this file inverts the closed-form CDF)
+//   5-planet: min over the adjacent trios of a system, per weight sample            multiswag_5_planet.py:421
+//   per system over the weight samples: average, median, percentiles 84 / 16 / 97.5 / 2.5   multiswag_5_planet.py:476-481
+//   "median of dists": median of mu and of std over the weight samples              main_figures.py:276-277
+//
+// Keeping this on the device turns the [N, U, 2] prediction block (48 GB at BASELINE config 3) into [N, 8].
+#include <math.h>
+
+#include "common.cuh"
+
+namespace bnn {
+
+enum : uint32_t { STREAM_TRUNC = 6, STREAM_PRIOR = 7 };
+
+// prior CDF on [9, inf), un-normalised:  F(t) = A/a (e^{-9a} - e^{-at}) - B sqrt(pi/b)/2 (erf(sqrt(b) t) - erf(9 sqrt(b)))
+struct PriorCdf {
+    double A = 3.27086190404742, a = 0.424033970670719, B = 10.8793430454878, b = 0.200351029031774;
+    __host__ __device__ double cdf(double t) const {
+        const double sb = sqrt(b);
+        return A / a * (exp(-9.0 * a) - exp(-a * t)) - B * 0.5 * sqrt(3.141592653589793 / b) * (erf(sb * t) - erf(9.0 * sb));
+    }
+};
+
+// inverse of the normalised prior CDF restricted to [9, 100] (the reference's table ends at top = 100)
+__device__ __forceinline__ float prior_inverse_cdf(double r) {
+    const PriorCdf p;
+    const double total = p.cdf(100.0);
+    const double target = r * total;
+    double lo = 9.0, hi = 100.0;
+#pragma unroll 1
+    for (int it = 0; it < 48; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (p.cdf(mid) < target) lo = mid; else hi = mid;
+    }
+    return (float)(0.5 * (lo + hi));
+}
+
+// t[row][u] for every (row = system*R + trio, unit) of pred[rows][U][2]
+__global__ void __launch_bounds__(256) sample_instability_kernel(const float2* __restrict__ pred, int64_t total, int64_t U,
+                                                                 uint64_t seed, int64_t row_offset, float left, int nsamp,
+                                                                 float* __restrict__ t) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const float2 ms = pred[idx];
+    const uint32_t row = (uint32_t)(row_offset + idx / U), u = (uint32_t)(idx % U);  // global row: shard-independent draws
+    float first = 0.f, val = 0.f;
+    bool found = false;
+    for (int k4 = 0; k4 * 4 < nsamp && !found; ++k4) {
+        const float4 z = philox_normal4(seed, STREAM_TRUNC, u, row, (uint32_t)k4);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (found || 4 * k4 + i >= nsamp) break;
+            const float x = __fadd_rn(__fmul_rn(zz[i], ms.y), ms.x);  // rand_out * scale + loc
+            if (k4 == 0 && i == 0) first = x;
+            if (x > left) { val = x; found = true; }
+        }
+    }
+    if (!found) val = first;  // mask.argmax(0) == 0 when no draw passes
+    if (val >= 9.0f) {        // stable_past_9: resample from the prior
+        const uint4 rr = philox4x32_10(make_uint4(0u, u, row, STREAM_PRIOR), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const double r = ((double)rr.x * 4294967296.0 + (double)rr.y) * (1.0 / 18446744073709551616.0);  // [0,1)
+        val = prior_inverse_cdf(r);
+    }
+    t[idx] = val;
+}
+
+// ---- per-system order statistics over the weight samples: bitonic sort in shared memory ----
+__device__ __forceinline__ void bitonic_sort(float* s, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const float a = s[i], b = s[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// numpy.percentile(method='linear'): virtual index q/100 (n-1), lerp with numpy's t >= 0.5 fix-up
+__device__ __forceinline__ float percentile_sorted(const float* s, int n, double q) {
+    const double pos = q / 100.0 * (double)(n - 1);
+    int lo = (int)floor(pos);
+    lo = max(0, min(lo, n - 1));
+    const int hi = min(lo + 1, n - 1);
+    const double tfrac = pos - (double)lo;
+    const double a = s[lo], b = s[hi];
+    const double d = b - a;
+    return (float)(tfrac >= 0.5 ? b - d * (1.0 - tfrac) : a + d * tfrac);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    __syncthreads();
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+        __syncthreads();
+    }
+    return red[0];
+}
+
+// one CTA per system.  t[(n*R + r)*U + u]; pred[(n*R + r)*U + u] = (mu, std).  stats[n][8]:
+// average, median, p84, p16, p97.5, p2.5 of min_r t; median over units of mu* = min_r mu and of its std.
+__global__ void __launch_bounds__(512) summarize_instability_kernel(const float* __restrict__ t, const float2* __restrict__ pred,
+                                                                    int R, int U, int n_pow2, float* __restrict__ stats) {
+    extern __shared__ float sh[];
+    float* s = sh;               // n_pow2 sort buffer
+    float* red = sh + n_pow2;    // blockDim.x
+    const int64_t n = blockIdx.x;
+    const float INF = __int_as_float(0x7f800000);
+    float* out = stats + n * 8;
+    // ---- min over trios of the sampled time ----
+    float part = 0.f;
+    for (int u = threadIdx.x; u < n_pow2; u += blockDim.x) {
+        float v = INF;
+        if (u < U) {
+            for (int r = 0; r < R; ++r) v = fminf(v, t[(n * R + r) * (int64_t)U + u]);
+            part += v;
+        }
+        s[u] = v;
+    }
+    const float total = block_sum(part, red);
+    bitonic_sort(s, n_pow2);
+    if (threadIdx.x == 0) {
+        out[0] = total / (float)U;
+        out[1] = percentile_sorted(s, U, 50.0);
+        out[2] = percentile_sorted(s, U, 50.0 + 68.0 / 2);
+        out[3] = percentile_sorted(s, U, 50.0 - 68.0 / 2);
+        out[4] = percentile_sorted(s, U, 50.0 + 95.0 / 2);
+        out[5] = percentile_sorted(s, U, 50.0 - 95.0 / 2);
+    }
+    __syncthreads();
+    // ---- median of dists: mu* = min over trios of mu, std* = std of that trio ----
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int u = threadIdx.x; u < n_pow2; u += blockDim.x) {
+            float v = INF;
+            if (u < U) {
+                float best = INF, bsd = 0.f;
+                for (int r = 0; r < R; ++r) {
+                    const float2 p = pred[(n * R + r) * (int64_t)U + u];
+                    if (p.x < best || r == 0) { best = p.x; bsd = p.y; }
+                }
+                v = pass == 0 ? best : bsd;
+                if (!(v == v)) v = INF;  // NaN predictions sort last
+            }
+            s[u] = v;
+        }
+        __syncthreads();
+        bitonic_sort(s, n_pow2);
+        if (threadIdx.x == 0) out[6 + pass] = percentile_sorted(s, U, 50.0);
+        __syncthreads();
+    }
+}
+
+}  // namespace bnn
+
+extern "C" {
+
+int bnn_sample_instability(const float* d_pred, int64_t n_rows, int64_t n_units, uint64_t seed, int64_t row_offset,
+                           float left, int32_t nsamp, float* d_t, void* stream) {
+    using namespace bnn;
+    int rc = check_device();
+    if (rc != BNN_OK) return rc;
+    BNN_REQUIRE(d_pred && d_t && n_rows > 0 && n_units > 0 && nsamp >= 1, BNN_E_ARG,
+                "bnn_sample_instability: null pointer or empty problem");
+    BNN_REQUIRE(row_offset >= 0 && row_offset + n_rows < (1ll << 32) && n_units < (1ll << 32), BNN_E_ARG,
+                "bnn_sample_instability: index exceeds 32 bits");
+    const int64_t total = n_rows * n_units;
+    const int64_t blocks = (total + 255) / 256;
+    BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_sample_instability: too many elements for one launch");
+    sample_instability_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float2*)d_pred, total, n_units, seed,
+                                                                                 row_offset, left, nsamp, d_t);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+int bnn_summarize_instability(const float* d_t, const float* d_pred, int64_t n_systems, int32_t n_trios, int32_t n_units,
+                              float* d_stats, void* stream) {
+    using namespace bnn;
+    int rc = check_device();
+    if (rc != BNN_OK) return rc;
+    BNN_REQUIRE(d_t && d_pred && d_stats && n_systems > 0 && n_trios > 0 && n_units > 0, BNN_E_ARG,
+                "bnn_summarize_instability: null pointer or empty problem");
+    int n_pow2 = 1;
+    while (n_pow2 < n_units) n_pow2 <<= 1;
+    const int threads = 512;
+    const size_t smem = (size_t)(n_pow2 + threads) * sizeof(float);
+    BNN_REQUIRE(smem <= 200 * 1024, BNN_E_CONFIG,
+                "bnn_summarize_instability: %d weight samples per system exceed the shared-memory sort (max 32768)", n_units);
+    BNN_REQUIRE(n_systems < (1ll << 31), BNN_E_ARG, "bnn_summarize_instability: too many systems for one launch");
+    static bool attr_done = false;
+    if (!attr_done) {
+        BNN_CUDA(cudaFuncSetAttribute(summarize_instability_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    summarize_instability_kernel<<<(unsigned)n_systems, threads, smem, (cudaStream_t)stream>>>(
+        d_t, (const float2*)d_pred, n_trios, n_units, n_pow2, d_stats);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+}  // extern "C"

@@ -159,6 +159,35 @@ class MultiSWAG:
             return local
         return gather_system_shards(local, n_total, group, granule)
 
+    def posterior_summary(self, x: torch.Tensor, samples_per_model: int, n_trios: int = 1, seed: int = 0,
+                          scale: float = 0.5, system_offset: int = 0):
+        """Predict + post-process on the device: x [N*n_trios, T, F] (rows = system*n_trios + trio, the
+        reshape(-1, 100, 41) of multiswag_5_planet.py:287) -> [N, 8] per-system statistics
+        (``posterior.STAT_NAMES``) of the sampled instability time, min over trios (figures/main_figures.py:
+        167-277, figures/multiswag_5_planet.py:306-481).  Only [N, 8] ever leaves the GPU."""
+        from . import posterior
+
+        pred = self.predict(x, samples_per_model, seed, scale, system_offset=system_offset * n_trios, system_major=True)
+        return posterior.posterior_summary(pred, n_trios, seed, row_offset=system_offset * n_trios)
+
+    def posterior_summary_sharded(self, x_local: torch.Tensor, n_total: int, samples_per_model: int, n_trios: int = 1,
+                                  seed: int = 0, scale: float = 0.5, group=None):
+        """Systems block-partitioned over ranks; the single all_gather moves [N, 8] instead of [N, U, 2]."""
+        import math
+
+        import torch.distributed as dist
+
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        g = self.system_granule(x_local.shape[1])
+        granule = g // math.gcd(g, n_trios)  # shard boundaries in SYSTEMS such that rows stay granule-aligned
+        lo, hi = shard_range(n_total, rank, world, granule)
+        assert x_local.shape[0] == (hi - lo) * n_trios, (x_local.shape, lo, hi)
+        local = self.posterior_summary(x_local, samples_per_model, n_trios, seed, scale, system_offset=lo)
+        if world == 1:
+            return local
+        return gather_system_shards(local, n_total, group, granule)
+
     # ------------------------------------------------------------------ drop-in per-call path
     def sample_full_swag(self, X_sample):
         """figures/spock/regression.py:74-92: pick a model with numpy's global RNG, sample its

@@ -196,6 +196,34 @@ int bnn_swag_collect(const float* d_w, int64_t d, int32_t n_seeds, int32_t K, fl
                      float* d_w2_avg, float* d_pre_D, int32_t* d_n_models, int32_t* d_n_cols,
                      int32_t current_epoch, int32_t c, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Input packing, the step upstream of bnn_predict: data_setup_kernel (figures/spock/regression.py:183-213)
+ * + ssX.transform (:144) + .float() (:145).  d_tseries [N,T,26] float64 raw time series (already sub-sampled
+ * to T steps, :141), d_masses [N,3] float64 planet/star mass ratios (:142), d_ss_mean / d_ss_scale [41]
+ * float64 StandardScaler constants (spock_reg_model.py:934-955) -> d_x [N,T,41] float32: 3 non-finite flags,
+ * nan_to_num, (cos, sin) of the 9 angle columns, standardisation; float64 arithmetic like numpy.
+ */
+int bnn_pack_inputs(const double* d_tseries, const double* d_masses, const double* d_ss_mean,
+                    const double* d_ss_scale, int64_t n_systems, int32_t n_times, float* d_x, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Posterior post-processing, the step downstream of bnn_predict (figures/main_figures.py:167-277,
+ * figures/multiswag_5_planet.py:306-481), on the system-major prediction block d_pred [n_rows, U, 2]
+ * (row = system * n_trios + trio; U weight samples):
+ * bnn_sample_instability: fast_truncnorm(mu, std, left, nsamp) -- the first of nsamp normal draws
+ *   x = z*std + mu that exceeds `left` (the first draw if none does) -- and, where the result is >= 9, a fresh
+ *   draw from the analytic prior on [9, 100] by inverse CDF.  Philox keyed on (seed; row_offset + row, unit).
+ *   d_t [n_rows, U].
+ * bnn_summarize_instability: per system, over the U weight samples of min-over-trios(t): d_stats [N, 8] =
+ *   average, median, percentiles 84, 16, 97.5, 2.5 (numpy 'linear'), then the median over weight samples of
+ *   mu* = min over trios of mu and of the std of that trio ("median of dists", main_figures.py:276-277).
+ *   U <= 32768 (shared-memory sort), else BNN_E_CONFIG.
+ */
+int bnn_sample_instability(const float* d_pred, int64_t n_rows, int64_t n_units, uint64_t seed, int64_t row_offset,
+                           float left, int32_t nsamp, float* d_t, void* stream);
+int bnn_summarize_instability(const float* d_t, const float* d_pred, int64_t n_systems, int32_t n_trios,
+                              int32_t n_units, float* d_stats, void* stream);
+
 /* Measured-FFMA-peak micro-kernel (roofline denominator check): runs `iters` dependent-free
  * fma.rn.f32x2 (packed=1) or fma.rn.f32 (packed=0) per thread on every SM, returns via
  * d_sink.  flops = 2 * grid*block*iters*16 ; time it with events around the call. */

@@ -198,6 +198,54 @@ def gen_train():
     np.savez_compressed(os.path.join(GOLD, "train_v50.npz"), **rec)
 
 
+def gen_pack():
+    """Input packing: the reference's own data_setup_kernel (figures/spock/regression.py:183-213), extracted from
+    the source file by AST (the module itself imports rebound / xgboost, which are not installed) and run with
+    plain numpy (numba's @jit dropped, np.float aliased), then StandardScaler.transform + .float() as :144-145."""
+    import ast
+
+    from sklearn.preprocessing import StandardScaler
+
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "figures", "spock", "regression.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "data_setup_kernel")
+    fn.decorator_list = []
+    ns = {"np": np}
+    if not hasattr(np, "float"):
+        np.float = float  # removed in numpy 1.24; the reference uses .astype(np.float)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "data_setup_kernel", "exec"), ns)
+    raw = synth.raw_systems(6, seed=9)
+    ts, ms = raw[:, :, :26].copy(), raw[:, 0, 26:29].copy()
+    ts[1, 5, 3] = np.nan; ts[1, 6, 6] = np.inf; ts[2, 7, 7] = -np.inf; ts[2, 8, 12] = np.nan; ts[3, 9, 0] = np.inf
+    ssX = StandardScaler()
+    ssX.mean_, ssX.scale_ = synth.SSX_MEAN.copy(), synth.SSX_SCALE.copy()
+    ssX.var_ = ssX.scale_ ** 2
+    outs = []
+    for i in range(ts.shape[0]):  # the reference packs one trio at a time (:136-145)
+        X = ns["data_setup_kernel"](ms[i], ts[None, i])
+        X = ssX.transform(X.reshape(-1, X.shape[-1])).reshape(X.shape)
+        outs.append(torch.tensor(X).float().numpy()[0])
+    np.savez_compressed(os.path.join(GOLD, "pack.npz"), tseries=ts, masses=ms, x_ref=np.stack(outs))
+
+
+def gen_posterior():
+    """fast_truncnorm of the reference (figures/main_figures.py:167-223, extracted by AST: the script itself needs
+    matplotlib / data files) under a fixed numpy seed, on a grid of (mu, std) that exercises accept-first,
+    accept-later and never-accept columns."""
+    import ast
+
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "figures", "main_figures.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "fast_truncnorm")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "fast_truncnorm", "exec"), ns)
+    rng = np.random.default_rng(3)
+    mu = rng.uniform(4.0, 12.0, (7, 33)).astype(np.float32)
+    sd = rng.uniform(0.5, 6.0, (7, 33)).astype(np.float32)
+    mu[0, :4] = -200.0  # no draw can pass left = 4: the first draw is returned
+    np.random.seed(123)
+    out = ns["fast_truncnorm"](mu, sd, left=4, d=100, nsamp=40)
+    np.savez_compressed(os.path.join(GOLD, "posterior.npz"), mu=mu, sd=sd, samples_ref=out, np_seed=123, d=100, nsamp=40)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # fixed summation order inside the reference's matmuls
@@ -206,5 +254,7 @@ if __name__ == "__main__":
     gen_loss()
     gen_aggregate()
     gen_train()
+    gen_pack()
+    gen_posterior()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -427,3 +427,109 @@ def draw_eps(seed: int, unit: np.ndarray, system: np.ndarray, n: int) -> np.ndar
         seed, STREAM_EPS, unit[:, None, None], system[None, :, None], np.arange(nblk)[None, None, :]
     )
     return z.reshape(len(unit), len(system), nblk * 4)[:, :, :n]
+
+
+# --------------------------------------------------------------------------------------
+# Input packing (figures/spock/regression.py:183-213 data_setup_kernel, :144-145 ssX + float)
+# --------------------------------------------------------------------------------------
+ANGLE_COLS = (11, 12, 13, 17, 18, 19, 23, 24, 25)  # :200
+
+
+def data_setup_kernel(mass_array: np.ndarray, cur_tseries: np.ndarray) -> np.ndarray:
+    """[N,3] masses, [N,T,26] raw series -> [N,T,41] float64 (flags, nan_to_num, cos/sin expansion)."""
+    n, t, _ = cur_tseries.shape
+    masses = np.broadcast_to(mass_array[:, None, :], (n, t, 3))
+    old_X = np.concatenate((cur_tseries, masses), axis=2)
+    for c in (3, 6, 7):  # :191-193 flags of the raw columns, before nan_to_num
+        old_X = np.concatenate((old_X, (~np.isfinite(old_X[:, :, [c]])).astype(np.float64)), axis=2)
+    old_X = np.nan_to_num(old_X, posinf=0.0, neginf=0.0)  # :195
+    cols = []
+    for j in range(old_X.shape[-1]):
+        if j in ANGLE_COLS:
+            cols.append(np.cos(old_X[:, :, [j]]))
+            cols.append(np.sin(old_X[:, :, [j]]))
+        else:
+            cols.append(old_X[:, :, [j]])
+    X = np.concatenate(cols, axis=2)
+    assert X.shape[-1] == 41
+    return X
+
+
+def pack_inputs(mass_array, cur_tseries, ss_mean, ss_scale) -> np.ndarray:
+    """data_setup_kernel + StandardScaler.transform (float64) + .float()."""
+    X = data_setup_kernel(np.asarray(mass_array, np.float64), np.asarray(cur_tseries, np.float64))
+    X = X - np.asarray(ss_mean)  # sklearn: X -= mean_; X /= scale_
+    X = X / np.asarray(ss_scale)
+    return X.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# Posterior post-processing (figures/main_figures.py:167-277, figures/multiswag_5_planet.py:306-481)
+# --------------------------------------------------------------------------------------
+def fast_truncnorm(loc, scale, left=np.inf, right=np.inf, d=10000, nsamp=50, rng=None):
+    """main_figures.py:167-223 with numpy's global RNG replaced by `rng` (np.random when None): the first of
+    nsamp draws z*scale + loc inside (left, right); the first draw when none is (mask.argmax == 0)."""
+    rng = np.random if rng is None else rng
+    oldscale = scale
+    scale = scale.reshape(-1)
+    loc = loc.reshape(-1)
+    samples = np.zeros_like(scale)
+    for start in range(0, scale.shape[0], d):
+        end = min(start + d, scale.shape[0])
+        cd = end - start
+        rand_out = rng.randn(nsamp, cd) if rng is np.random else rng.standard_normal((nsamp, cd))
+        rand_out = rand_out * scale[None, start:end] + loc[None, start:end]
+        if right == np.inf:
+            mask = rand_out > left
+        elif left == np.inf:
+            mask = rand_out < right
+        else:
+            mask = (rand_out > left) & (rand_out < right)
+        samples[start:end] = rand_out[mask.argmax(0), np.arange(cd)]
+    return samples.reshape(*oldscale.shape)
+
+
+def _prior_unnormalised(logT):  # main_figures.py:231-234
+    return 3.27086190404742 * np.exp(-0.424033970670719 * logT) - 10.8793430454878 * np.exp(-0.200351029031774 * logT**2)
+
+
+def prior_cdf(t):
+    """Closed-form CDF of the prior on [9, inf) (what the CUDA kernel inverts)."""
+    from scipy.special import erf
+
+    A, a, B, b = 3.27086190404742, 0.424033970670719, 10.8793430454878, 0.200351029031774
+    F = lambda x: A / a * (np.exp(-9 * a) - np.exp(-a * x)) - B * 0.5 * np.sqrt(np.pi / b) * (erf(np.sqrt(b) * x) - erf(9 * np.sqrt(b)))
+    return F(np.asarray(t, np.float64)) / F(np.inf)
+
+
+def prior_samples_table(r, n_samples=None):
+    """main_figures.py:236-257: inverse-CDF sampling through a Riemann-sum table with 4*n_samples bins."""
+    from scipy.integrate import quad
+    from scipy.interpolate import interp1d
+
+    n_samples = len(r) if n_samples is None else n_samples
+    normalization = quad(_prior_unnormalised, a=9, b=np.inf)[0]
+    bins = n_samples * 4
+    top = 100.0
+    bin_edges = np.linspace(9, top, num=bins)
+    cum_values = [0] + list(np.cumsum(_prior_unnormalised(bin_edges) / normalization * (bin_edges[1] - bin_edges[0]))) + [1]
+    bin_edges = [9.0] + list(bin_edges) + [top]
+    return interp1d(cum_values, bin_edges)(r)
+
+
+def posterior_stats(samps_time, pred=None):
+    """samps_time [U, N, R] -> per-system dict (multiswag_5_planet.py:421, :476-481); pred [U, N, R, 2] adds the
+    'median of dists' (main_figures.py:276-277) of mu* = min over trios of mu and the std of that trio."""
+    outs = np.min(samps_time, 2).T  # [N, U]
+    res = {
+        "average": np.average(outs, 1), "median": np.median(outs, 1),
+        "l": np.percentile(outs, 50 + 68 / 2, axis=1), "u": np.percentile(outs, 50 - 68 / 2, axis=1),
+        "ll": np.percentile(outs, 50 + 95 / 2, axis=1), "uu": np.percentile(outs, 50 - 95 / 2, axis=1),
+    }
+    if pred is not None:
+        arg = np.argmin(pred[..., 0], 2)  # [U, N]
+        mu = np.take_along_axis(pred[..., 0], arg[..., None], 2)[..., 0]
+        sd = np.take_along_axis(pred[..., 1], arg[..., None], 2)[..., 0]
+        res["median_mu"] = np.median(mu, 0)
+        res["median_std"] = np.median(sd, 0)
+    return res

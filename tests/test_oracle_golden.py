@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import swag_stats
+from conftest import load_golden, swag_stats
 from bnn_chaos_model_b200 import synth
 from oracle import restatement as R
 
@@ -118,3 +118,30 @@ def test_training_steps(gold_train):
         assert float(gn) == pytest.approx(float(g[f"gradnorm_ref_{s}"]), rel=1e-5)
         np.testing.assert_allclose(theta.numpy(), g[f"theta_ref_{s}"], rtol=1e-6, atol=1e-7)
         theta = torch.from_numpy(g[f"theta_ref_{s}"]).clone()
+
+
+def test_pack_inputs_oracle_vs_reference_golden():
+    """data_setup_kernel + ssX.transform + .float(): the oracle restatement reproduces the reference's own
+    function (run by oracle/make_golden.py::gen_pack) bit for bit, including NaN / Inf handling and flags."""
+    from bnn_chaos_model_b200 import synth
+
+    z = load_golden("pack.npz")
+    x = R.pack_inputs(z["masses"], z["tseries"], synth.SSX_MEAN, synth.SSX_SCALE)
+    assert x.dtype == np.float32 and np.array_equal(x, z["x_ref"])
+    # flags are taken before nan_to_num: system 1 has non-finite values in raw columns 3 and 6, system 2 in 7
+    un = lambda c: z["x_ref"][..., c] * synth.SSX_SCALE[c] + synth.SSX_MEAN[c]
+    assert un(38)[1].max() > 0.5 and un(39)[1].max() > 0.5 and un(40)[2].max() > 0.5 and un(38)[0].max() < 0.5
+
+
+def test_fast_truncnorm_oracle_vs_reference_golden():
+    """The oracle's fast_truncnorm under numpy's global RNG reproduces the reference function bit for bit
+    (golden written by oracle/make_golden.py::gen_posterior from figures/main_figures.py:167-223)."""
+    z = load_golden("posterior.npz")
+    np.random.seed(int(z["np_seed"]))
+    out = R.fast_truncnorm(z["mu"], z["sd"], left=4, d=int(z["d"]), nsamp=int(z["nsamp"]))
+    assert np.array_equal(out, z["samples_ref"])
+    assert (out[0, :4] < 4).all() and (out[1:] > 4).all()  # never-accepted columns return their first draw
+    # the reference's 4*n-bin table inversion of the prior agrees with the closed-form CDF the kernel inverts
+    r = np.random.default_rng(0).random(5000)
+    assert np.abs(R.prior_cdf(R.prior_samples_table(r)) - r).max() < 3e-3
+    assert R.prior_cdf(9.0) == 0.0 and abs(float(R.prior_cdf(100.0)) - 1.0) < 1e-12
