@@ -193,7 +193,7 @@ def gpu_train_arm(dev, n_seeds=4, B=2000, n_data=8000, iters=10):
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the predict kernel from the committed ncu --set full summary
     (profiles/), per launch of this same workload; None when the summary is absent."""
-    path = os.path.join(ROOT, "profiles", "r1_predict_tc3n4_ncu.txt")
+    path = os.path.join(ROOT, "profiles", "r1_predict_tc4n4_ncu.txt")
     try:
         tot = 0.0
         for line in open(path):
@@ -367,7 +367,7 @@ def run_ours(args):
                                         "no fp32 figure in MEASURED_PEAKS.json",
                          "measured_ffma_peak_tflops": ffma, "kernel_ms": k_ms,
                          "flop_per_eval": FLOP_PER_EVAL_V50, "traffic": ncu_traffic_bytes(),
-                         "traffic_source": "profiles/r1_predict_tc3n4_ncu.txt (ncu --set full, same workload, per launch); "
+                         "traffic_source": "profiles/r1_predict_tc4n4_ncu.txt (ncu --set full, same workload, per launch); "
                                            "algorithmic HBM bytes per launch: 0.32e9",
                          "note": "north_star's roofline for this kernel is the FP32 CUDA-core FMA peak; the kernel runs the "
                                  "feature MLP as 3xTF32 on tcgen05 (tensor pipe active 27 %, profiles/)"},

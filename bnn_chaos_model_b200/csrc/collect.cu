@@ -86,37 +86,63 @@ extern "C" int bnn_swag_collect(const float* d_w, int64_t d, int32_t n_seeds, in
 // ---------------------------------------------------------------------------------------
 namespace bnn {
 
-__device__ __forceinline__ bool is_angle_col(int j) { return j >= 11 && j <= 25 && ((j - 11) % 6) < 3; }
+constexpr int PACK_ROWS = 32;  // time-step rows per CTA tile
 
-__global__ void __launch_bounds__(256) pack_inputs_kernel(const double* __restrict__ ts, const double* __restrict__ mass,
-                                                          const double* __restrict__ mean, const double* __restrict__ scale,
-                                                          int64_t n_rows, int T, float* __restrict__ x) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // (row, raw column j of 32)
-    if (idx >= n_rows * 32) return;
-    const int64_t row = idx >> 5;
-    const int j = (int)(idx & 31);
-    double v;
-    if (j < 26) {
-        v = ts[row * 26 + j];
-    } else if (j < 29) {
-        v = mass[(row / T) * 3 + (j - 26)];
-    } else {
-        const int src = (j == 29) ? 3 : (j == 30 ? 6 : 7);
-        v = isfinite(ts[row * 26 + src]) ? 0.0 : 1.0;  // flags are taken before nan_to_num
-    }
-    if (!isfinite(v)) v = 0.0;  // np.nan_to_num(posinf=0.0, neginf=0.0): NaN -> 0 too
-    // output column: every angle column before j adds one
+// out column of raw column j: every angle column before j adds one
+__device__ __forceinline__ int pack_out_col(int j) {
     int oc = j;
     if (j > 11) oc += min(j - 11, 3);
     if (j > 17) oc += min(j - 17, 3);
     if (j > 23) oc += min(j - 23, 3);
-    float* o = x + row * 41;
-    if (is_angle_col(j)) {
-        o[oc] = (float)((cos(v) - mean[oc]) / scale[oc]);
-        o[oc + 1] = (float)((sin(v) - mean[oc + 1]) / scale[oc + 1]);
-    } else {
-        o[oc] = (float)((v - mean[oc]) / scale[oc]);
+    return oc;
+}
+
+// One CTA = 32 consecutive rows: coalesced load of the 32 x 26 doubles into shared memory, then warp-homogeneous
+// work lists (288 sincos items first, 736 plain items after) so that the fp64 trigonometry does not diverge against
+// the copy columns, results staged in shared memory and written back as one contiguous 32 x 41 float block.
+__global__ void __launch_bounds__(256) pack_inputs_kernel(const double* __restrict__ ts, const double* __restrict__ mass,
+                                                          const double* __restrict__ mean, const double* __restrict__ scale,
+                                                          int64_t n_rows, int T, float* __restrict__ x) {
+    __shared__ double raw[PACK_ROWS][26];
+    __shared__ float o[PACK_ROWS][41];
+    __shared__ double sm_mean[41], sm_scale[41];
+    const int64_t row0 = (int64_t)blockIdx.x * PACK_ROWS;
+    const int nr = (int)min((int64_t)PACK_ROWS, n_rows - row0);
+    for (int i = threadIdx.x; i < nr * 26; i += 256) (&raw[0][0])[i] = ts[row0 * 26 + i];
+    if (threadIdx.x < 41) { sm_mean[threadIdx.x] = mean[threadIdx.x]; sm_scale[threadIdx.x] = scale[threadIdx.x]; }
+    __syncthreads();
+    // angle columns {11,12,13,17,18,19,23,24,25}: (cos, sin)
+    for (int w = threadIdx.x; w < nr * 9; w += 256) {
+        const int r = w / 9, a = w - r * 9;
+        const int j = 11 + (a / 3) * 6 + a % 3;
+        double v = raw[r][j];
+        if (!isfinite(v)) v = 0.0;  // np.nan_to_num(posinf=0.0, neginf=0.0): NaN -> 0 too
+        double sn, cs;
+        sincos(v, &sn, &cs);
+        const int oc = pack_out_col(j);
+        o[r][oc] = (float)((cs - sm_mean[oc]) / sm_scale[oc]);
+        o[r][oc + 1] = (float)((sn - sm_mean[oc + 1]) / sm_scale[oc + 1]);
     }
+    // the 23 plain columns: 17 time-series columns, 3 masses, 3 non-finite flags
+    for (int w = threadIdx.x; w < nr * 23; w += 256) {
+        const int r = w / 23, p = w - r * 23;
+        // p -> raw column: 0..10, 14..16, 20..22, 26..31
+        const int j = p < 11 ? p : (p < 14 ? p + 3 : (p < 17 ? p + 6 : p + 9));
+        double v;
+        if (j < 26) {
+            v = raw[r][j];
+        } else if (j < 29) {
+            v = mass[((row0 + r) / T) * 3 + (j - 26)];
+        } else {
+            const int src = (j == 29) ? 3 : (j == 30 ? 6 : 7);
+            v = isfinite(raw[r][src]) ? 0.0 : 1.0;  // flags are taken before nan_to_num
+        }
+        if (!isfinite(v)) v = 0.0;
+        const int oc = pack_out_col(j);
+        o[r][oc] = (float)((v - sm_mean[oc]) / sm_scale[oc]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * 41; i += 256) x[row0 * 41 + i] = (&o[0][0])[i];
 }
 
 }  // namespace bnn
@@ -128,8 +154,7 @@ extern "C" int bnn_pack_inputs(const double* d_tseries, const double* d_masses, 
     if (rc != BNN_OK) return rc;
     BNN_REQUIRE(d_tseries && d_masses && d_ss_mean && d_ss_scale && d_x, BNN_E_ARG, "bnn_pack_inputs: null pointer");
     BNN_REQUIRE(n_systems > 0 && n_times > 0, BNN_E_ARG, "bnn_pack_inputs: empty input");
-    const int64_t total = n_systems * n_times * 32;
-    const int64_t blocks = (total + 255) / 256;
+    const int64_t blocks = (n_systems * n_times + PACK_ROWS - 1) / PACK_ROWS;
     BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_pack_inputs: too many rows for one launch");
     pack_inputs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_tseries, d_masses, d_ss_mean, d_ss_scale,
                                                                           n_systems * n_times, n_times, d_x);
