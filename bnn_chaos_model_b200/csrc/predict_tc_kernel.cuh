@@ -14,6 +14,15 @@ namespace tc {
         }                                                                                            \
     } while (0)
 
+// same, with its own counter: the MMA-issue stamps (role 7) come from the warp that also stamps role 0
+#define TC_STAMP_M(role, code)                                                                        \
+    do {                                                                                             \
+        if (prm.dbg && blockIdx.x == 0 && lane == 0 && dbg_m < 511) {                                 \
+            prm.dbg[(role) * 512 + 1 + dbg_m] = ((long long)(code) << 48) | (clock64() & 0xFFFFFFFFFFFFll); \
+            prm.dbg[(role) * 512] = ++dbg_m;                                                          \
+        }                                                                                            \
+    } while (0)
+
 constexpr int BAR_A = 1, BAR_D = 5;  // named barrier ids: A-ready / D-ready of TMEM slot s are BAR_A + s / BAR_D + s
 constexpr int B_FLOATS = 2 * (TC_K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3) + TC_BIAS;  // hi + lo B operands + biases
 constexpr int B_BYTES = B_FLOATS * 4;
@@ -55,7 +64,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = n_tiles * chunks;
-    int dbg_n = 0;
+    int dbg_n = 0, dbg_m = 0;
 
     constexpr int W_EPI = (NT + 3) & ~3;
     // ---- one-time setup: TMEM allocation ----
@@ -129,6 +138,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
             auto pool_block = [&](int pi, int pm) {
                 const int rs = pi % NT;
                 if (pi >= NT) mbar_wait_backoff(&bars->rec_free[rs], (uint32_t)((pi / NT - 1) & 1), 100);  // tail of unit pi-NT done
+                if (quad == 0 && slot < 3) TC_STAMP(slot, 21);
                 if (lane < L) {
                     const int b = pm * 4 + quad;
                     int sysA, split, nvalid;
@@ -157,6 +167,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                     }
                 }
                 __syncwarp();
+                if (quad == 0 && slot < 3) TC_STAMP(slot, 22);
                 if (lane == 0) mbar_arrive(&bars->unit_done[rs]);
             };
             // A of the slot is complete (named barrier over the slot's 4 warps); quadrant 0 issues the layer and the commit
@@ -167,7 +178,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                     uint32_t wb = ring_addr + (uint32_t)ws * (uint32_t)B_BYTES;
                     uint32_t tsv = ts;
                     asm volatile("" : "+r"(wb), "+r"(tsv));  // keep the descriptors out of loop-invariant hoisting
-                    if (slot == 0) TC_STAMP(7, layer);
+                    if (slot == 0) TC_STAMP_M(7, layer);
                     if (layer == 0)
                         issue_layer<TC_N, TC_K1 / 8>(tsv, wb + O_B1H, wb + O_B1L);
                     else if (layer == 1)
@@ -176,7 +187,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                         issue_layer<TC_N3, TC_K2 / 8>(tsv, wb + O_B3H, wb + O_B3L);
                     if (elect_one_sync()) mma_commit(&bars->d_ready[slot]);
                     __syncwarp();
-                    if (slot == 0) TC_STAMP(7, 100 + layer);
+                    if (slot == 0) TC_STAMP_M(7, 100 + layer);
                 }
             };
             // D of the slot is complete: quadrant 0 polls the commit barrier, the other three sleep on the named barrier

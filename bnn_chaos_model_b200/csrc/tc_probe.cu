@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__
 // out[0] = cycles from first issue to commit completion, out[1] = cycles spent issuing.
 __global__ void __launch_bounds__(128) tc_time_kernel(int K, int N, int reps, int from_smem, long long* out) {
     extern __shared__ __align__(128) float bs[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar, bar2;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) {
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(128) tc_time_kernel(int K, int N, int reps, in
     }
     if (tid == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&bar2, 1);
         mbar_init_fence();
     }
     for (int i = tid; i < (N + 128) * K; i += 128) bs[i] = 0.f;
@@ -90,37 +91,36 @@ __global__ void __launch_bounds__(128) tc_time_kernel(int K, int N, int reps, in
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    if (warp == 0) {
+    // from_smem bit 0: A from shared memory; bit 8: a second warp issues an identical, independent chain (its own D and
+    // A columns) at the same time -- tells a per-issuing-thread cost from a shared tensor-pipe service time
+    const bool two = (from_smem & 256) != 0;
+    if (warp == 0 || (two && warp == 1)) {
         const uint32_t idesc = idesc_tf32(128, N);
         const uint32_t chunk_bytes = (uint32_t)N * 16u;
         const uint32_t a_chunk = 128u * 16u;
         const uint32_t a_base = smem_u32(bs) + (uint32_t)N * K * 4;
         long long t0 = 0, t1 = 0;
-        const int nacc = (from_smem >> 1) + 1;
-        // warp-uniform control flow and addresses, one elected lane per instruction (as in predict_tc)
         const uint64_t bd0 = smem_desc_kmajor(smem_u32(bs), chunk_bytes, 128u);
         const uint64_t ad0 = smem_desc_kmajor(a_base, a_chunk, 128u);
         const uint64_t bstep = 2ull * (uint64_t)N, astep = 2ull * 128ull;
+        const uint32_t dcol = tmem + (warp == 0 ? 256u : 384u), acol = tmem + (warp == 0 ? 0u : 64u);
         t0 = clock64();
         for (int r = 0; r < reps; ++r) {
             if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < 6; ++ks) {
-                    // from_smem bit 0: A from shared memory; bits 1..: (number of independent accumulators - 1),
-                    // consecutive MMAs rotate over them (N <= 64) -- separates issue cost from the D dependency
-                    const uint32_t dcol = tmem + 256 + (uint32_t)(ks % nacc) * 64u;
                     if (from_smem & 1)
                         mma_tf32_ss(dcol, ad0 + ks * astep, bd0 + ks * bstep, idesc, (r | ks) > 0);
                     else
-                        mma_tf32_ts(dcol, tmem + ks * 8, bd0 + ks * bstep, idesc, (r | ks) > 0);
+                        mma_tf32_ts(dcol, acol + ks * 8, bd0 + ks * bstep, idesc, (r | ks) > 0);
                 }
             }
             __syncwarp();
         }
         t1 = clock64();
-        if (elect_one_sync()) mma_commit(&bar);
+        if (elect_one_sync()) mma_commit(warp == 0 ? &bar : &bar2);
         __syncwarp();
-        mbar_wait(&bar, 0);
+        mbar_wait(warp == 0 ? &bar : &bar2, 0);
         const long long t2 = clock64();
         if (tid == 0) {
             out[0] = t2 - t0;

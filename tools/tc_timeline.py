@@ -26,18 +26,17 @@ for role in range(8):
         v = int(d[role, 1 + k]); ev.append((v & 0xFFFFFFFFFFFF, role, v >> 48))
 ev.sort()
 t0 = ev[0][0]
-names = {1: "x staged", 2: "pooled", 3: "d1 wake", 4: "e1 done", 5: "d2 wake", 6: "e2 done", 7: "d3 wake", 8: "e3 done", 31: "  ld done", 32: "  st issued", 33: "  st done", 34: "  x st issued"}
+names = {1: "x staged", 2: "pooled", 3: "d1 wake", 4: "e1 done", 5: "d2 wake", 6: "e2 done", 7: "d3 wake", 8: "e3 done", 31: "  ld done", 32: "  st issued", 33: "  st done", 34: "  x st issued", 21: "  rec slot free", 22: "  pool sums done"}
 tnames = {1: "wait unit", 2: "unit ready", 3: "tail done"}
 xs = [t - t0 for t, role, code in ev if role == 0 and code == 1]
 print("slot0 x-staged times:", xs)
 print("slot0 job periods:", [b - a for a, b in zip(xs, xs[1:])])
-for r in (3, 4):
-    print(f"tail{r-3}:", [(code, t - t0) for t, role, code in ev if role == r][:40])
+for r in (4, 5):
+    print(f"tail{r-4}:", [(code, t - t0) for t, role, code in ev if role == r][:40])
 for t, role, code in ev[:int(os.environ.get("TL_N", "0"))]:
     if role == 7:
-        s, l = (code % 100) // 10, code % 10
-        kind = {0: "issue-start", 1: "issue-end  ", 2: "committed  ", 3: "loop-top   "}[code // 100]
-        print(f"{t - t0:8d}  MMA   {kind} slot{s} L{l + 1}")
+        kind = {0: "issue-start", 1: "issue-end  "}[code // 100]
+        print(f"{t - t0:8d}  MMA0     {kind} L{code % 100 + 1}")
     else:
-        who = f"EPI{role}   " if role < 3 else f"TAIL{role - 3}  "
+        who = f"EPI{role}   " if role < 3 else f"TAIL{role - 4}  "
         print(f"{t - t0:8d}  {who}  {(names if role < 3 else tnames).get(code, code)}")
