@@ -297,9 +297,8 @@ def run_ours(args):
     out_h = torch.empty((n_sys, n_samp, 2), dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
-        xd = xh.to(dev, non_blocking=True)
-        o = ens.predict(xd, n_samp, seed=i, system_offset=lo, system_major=True)  # samples theta inside
-        out_h.copy_(o, non_blocking=True)
+        # the public host-buffer entry: samples theta, pipelines H2D / predict / D2H over chunks of systems
+        ens.predict_host(xh, n_samp, seed=i, out_host=out_h, system_offset=lo)
 
     for i in range(max(1, args.warmup // 2)):
         e2e_step(i)

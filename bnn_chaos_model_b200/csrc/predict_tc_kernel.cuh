@@ -5,23 +5,24 @@
 namespace bnn {
 namespace tc {
 
-// timeline probe: role-major [8][512] int64 of clock64() stamps, CTA 0 lane 0 only (tools/tc_timeline.py)
-#define TC_STAMP(role, code)                                                                          \
+// timeline probe (tools/tc_timeline.py): role-major [8][512] int64 of clock64() stamps, CTA 0 lane 0 only.  Compiled in
+// only with -DBNN_TC_TIMELINE (make TIMELINE=1): the stamps cost registers in the hot loops (13 % of the kernel time
+// when they were always compiled).
+#ifdef BNN_TC_TIMELINE
+#define TC_STAMP_CTR(ctr, role, code)                                                                 \
     do {                                                                                             \
-        if (prm.dbg && blockIdx.x == 0 && lane == 0 && dbg_n < 511) {                                 \
-            prm.dbg[(role) * 512 + 1 + dbg_n] = ((long long)(code) << 48) | (clock64() & 0xFFFFFFFFFFFFll); \
-            prm.dbg[(role) * 512] = ++dbg_n;                                                          \
+        if (prm.dbg && blockIdx.x == 0 && lane == 0 && ctr < 511) {                                   \
+            prm.dbg[(role) * 512 + 1 + ctr] = ((long long)(code) << 48) | (clock64() & 0xFFFFFFFFFFFFll); \
+            prm.dbg[(role) * 512] = ++ctr;                                                            \
         }                                                                                            \
     } while (0)
-
-// same, with its own counter: the MMA-issue stamps (role 7) come from the warp that also stamps role 0
-#define TC_STAMP_M(role, code)                                                                        \
-    do {                                                                                             \
-        if (prm.dbg && blockIdx.x == 0 && lane == 0 && dbg_m < 511) {                                 \
-            prm.dbg[(role) * 512 + 1 + dbg_m] = ((long long)(code) << 48) | (clock64() & 0xFFFFFFFFFFFFll); \
-            prm.dbg[(role) * 512] = ++dbg_m;                                                          \
-        }                                                                                            \
-    } while (0)
+#define TC_STAMP(role, code) TC_STAMP_CTR(dbg_n, role, code)
+// own counter: the MMA-issue stamps (role 7) come from the warp that also stamps role 0
+#define TC_STAMP_M(role, code) TC_STAMP_CTR(dbg_m, role, code)
+#else
+#define TC_STAMP(role, code) do { } while (0)
+#define TC_STAMP_M(role, code) do { } while (0)
+#endif
 
 constexpr int BAR_A = 1, BAR_D = 5;  // named barrier ids: A-ready / D-ready of TMEM slot s are BAR_A + s / BAR_D + s
 constexpr int B_FLOATS = 2 * (TC_K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3) + TC_BIAS;  // hi + lo B operands + biases
@@ -64,7 +65,9 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = n_tiles * chunks;
+#ifdef BNN_TC_TIMELINE
     int dbg_n = 0, dbg_m = 0;
+#endif
 
     constexpr int W_EPI = (NT + 3) & ~3;
     // ---- one-time setup: TMEM allocation ----

@@ -303,3 +303,16 @@ def test_tensor_core_variants_vs_fp32_kernel(dev, monkeypatch):
                 got = ens.predict(x, S_, seed=N, thp=thp)
                 assert bool(torch.isnan(got[:, N // 2]).all()), (v, N)
                 assert rel_err(got[ok], want[ok]) < TOL, (v, N, S_, rep)
+
+
+def test_predict_host_pipelined_equals_single_launch(dev):
+    """Host-buffer entry with chunked H2D / compute / D2H overlap: bit-identical to one device-resident launch."""
+    ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(17, dev)], device=dev)
+    N, S_ = 203, 6
+    xh = torch.from_numpy(synth.make_systems(N, seed=31)).pin_memory()
+    want = ens.predict(xh.to(dev), S_, seed=12, system_major=True).cpu()
+    for n_chunks in (1, 3, 8, 64):
+        got = ens.predict_host(xh, S_, seed=12, n_chunks=n_chunks)
+        assert got.shape == (N, 2 * S_, 2) and torch.equal(got, want), n_chunks
+    out = torch.empty((N, 2 * S_, 2)).pin_memory()
+    assert ens.predict_host(xh, S_, seed=12, out_host=out) is out and torch.equal(out, want)

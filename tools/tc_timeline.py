@@ -1,4 +1,5 @@
-"""Dump a clock64 timeline of CTA 0 of the tensor-core kernel (debugging aid, GPU)."""
+"""Dump a clock64 timeline of CTA 0 of the tensor-core kernel (debugging aid, GPU).
+Needs a library built with the stamps compiled in:  make -C bnn_chaos_model_b200/csrc clean && make -C bnn_chaos_model_b200/csrc TIMELINE=1"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
