@@ -194,6 +194,16 @@ __device__ __forceinline__ u64 pack2(float lo, float hi) {
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     u64 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));

@@ -129,17 +129,31 @@ __device__ __forceinline__ void split_store16(const uint32_t (&d)[16], const flo
     uint32_t h[16], l[16];
 #pragma unroll
     for (int g4 = 0; g4 < 4; ++g4) {
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EPI) b = *reinterpret_cast<const float4*>(bias + 4 * g4);
-        const float bv[4] = {b.x, b.y, b.z, b.w};
+        // packed fp32x2 adds (Blackwell FADD2): one issue slot for two bias adds / two lo = v - hi subtractions
+        u64 v01 = pack2(__uint_as_float(d[4 * g4]), __uint_as_float(d[4 * g4 + 1]));
+        u64 v23 = pack2(__uint_as_float(d[4 * g4 + 2]), __uint_as_float(d[4 * g4 + 3]));
+        if (EPI) {
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bias + 4 * g4);
+            v01 = add2(v01, b.x);
+            v23 = add2(v23, b.y);
+        }
+        float v[4];
+        unpack2(v01, v[0], v[1]);
+        unpack2(v23, v[2], v[3]);
+        uint32_t hb[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int j = 4 * g4 + u;
-            const float v = EPI ? relu_nan(__uint_as_float(d[j]) + bv[u]) : __uint_as_float(d[j]);
-            const uint32_t hb = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
-            h[j] = hb;
-            l[j] = __float_as_uint(v - __uint_as_float(hb));
+            if (EPI) v[u] = relu_nan(v[u]);
+            hb[u] = (__float_as_uint(v[u]) + 0x1000u) & 0xFFFFE000u;
+            h[4 * g4 + u] = hb[u];
         }
+        const u64 l01 = sub2(pack2(v[0], v[1]), pack2(__uint_as_float(hb[0]), __uint_as_float(hb[1])));
+        const u64 l23 = sub2(pack2(v[2], v[3]), pack2(__uint_as_float(hb[2]), __uint_as_float(hb[3])));
+        float lo[4];
+        unpack2(l01, lo[0], lo[1]);
+        unpack2(l23, lo[2], lo[3]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) l[4 * g4 + u] = __float_as_uint(lo[u]);
     }
     tmem_st16(t_hi, h);
     tmem_st16(t_lo, l);

@@ -116,7 +116,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
             float* my_scratch = scratch + tw * TAIL_SCRATCH;
             for (int i = tw; i < n_units; i += NT) {
                 TC_STAMP(4 + (tw & 1), 1);
-                mbar_wait_backoff(&bars->unit_done[tw], (uint32_t)((i / NT) & 1), 200);  // all 16 block records of unit i
+                mbar_wait_backoff(&bars->unit_done[tw], (uint32_t)((i / NT) & 1), 400);  // all 16 block records of unit i
                 TC_STAMP(4 + (tw & 1), 2);
                 const int64_t u = u_begin + i;
                 const float* eps_u = prm.eps ? prm.eps + u * prm.N * S2 : nullptr;
@@ -199,7 +199,11 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
             // D of the slot is complete: quadrant 0 polls the commit barrier, the other three sleep on the named barrier
             auto wait_d = [&]() {
                 if (quad == 0) {
-                    mbar_wait_backoff(&bars->d_ready[slot], pd, 20);
+                    // a layer's MMAs take >= 0.3 us behind the other slots' queues: one long nap, then short ones
+                    if (!mbar_test(&bars->d_ready[slot], pd)) {
+                        __nanosleep(120);
+                        mbar_wait_backoff(&bars->d_ready[slot], pd, 20);
+                    }
                     pd ^= 1;
                 }
                 named_sync(BAR_D + slot, 128);
