@@ -12,6 +12,8 @@
 //
 // Keeping this on the device turns the [N, U, 2] prediction block (48 GB at BASELINE config 3) into [N, 8].
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -165,6 +167,138 @@ __global__ void __launch_bounds__(512) summarize_instability_kernel(const float*
     }
 }
 
+// ---- the same statistics for any U: exact order statistics by 3-pass radix select (11 + 11 + 10 bits of an
+// order-preserving key) with shared-memory histograms, one per requested rank; nothing is sorted or stored ----
+constexpr int SEL_MAXT = 10;  // ranks per array: floor / ceil neighbours of 5 percentiles
+
+__device__ __forceinline__ uint32_t order_key(float v) {
+    if (!(v == v)) v = __int_as_float(0x7f800000);  // NaN predictions rank last, like the sort path
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// which: 0 = min over trios of t, 1 = mu* (min over trios of mu), 2 = std of the arg-min trio
+__device__ __forceinline__ float summary_value(const float* __restrict__ t, const float2* __restrict__ pred, int64_t n, int R,
+                                               int U, int u, int which) {
+    if (which == 0) {
+        float v = __int_as_float(0x7f800000);
+        for (int r = 0; r < R; ++r) v = fminf(v, t[(n * R + r) * (int64_t)U + u]);
+        return v;
+    }
+    float best = 0.f, bsd = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const float2 p = pred[(n * R + r) * (int64_t)U + u];
+        if (r == 0 || p.x < best) { best = p.x; bsd = p.y; }
+    }
+    return which == 1 ? best : bsd;
+}
+
+// warp `w` finds the bin holding rank[w] in hist (nbins <= 2048 counts): returns the bin, updates the rank to the
+// rank inside the bin
+__device__ __forceinline__ int select_bin(const uint32_t* __restrict__ hist, int nbins, uint32_t& rank) {
+    const int lane = threadIdx.x & 31;
+    const int per = nbins / 32;
+    uint32_t mine = 0;
+    for (int i = 0; i < per; ++i) mine += hist[lane * per + i];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const uint32_t excl = incl - mine;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, rank < incl);
+    const int src = __ffs(ballot) - 1;  // first lane whose inclusive count exceeds the rank
+    int bin = 0;
+    uint32_t r = 0;
+    if (lane == src) {
+        r = rank - excl;
+        for (int i = 0; i < per; ++i) {
+            const uint32_t c = hist[lane * per + i];
+            if (r < c) { bin = lane * per + i; break; }
+            r -= c;
+        }
+    }
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    rank = __shfl_sync(0xffffffffu, r, src);
+    return bin;
+}
+
+__global__ void __launch_bounds__(512) summarize_select_kernel(const float* __restrict__ t, const float2* __restrict__ pred,
+                                                               int R, int U, float* __restrict__ stats) {
+    extern __shared__ uint32_t hist[];            // [SEL_MAXT][2048]
+    __shared__ uint32_t s_rank[SEL_MAXT], s_prefix[SEL_MAXT];
+    __shared__ float s_val[SEL_MAXT], red[512];
+    const int64_t n = blockIdx.x;
+    const int warp = threadIdx.x >> 5;
+    float* out = stats + n * 8;
+    const double qs[5] = {50.0, 50.0 + 68.0 / 2, 50.0 - 68.0 / 2, 50.0 + 95.0 / 2, 50.0 - 95.0 / 2};
+    for (int which = 0; which < 3; ++which) {
+        const int nq = which == 0 ? 5 : 1, nt = 2 * nq;
+        if (threadIdx.x < nt) {
+            const double pos = qs[threadIdx.x >> 1] / 100.0 * (double)(U - 1);
+            int lo = (int)floor(pos);
+            lo = max(0, min(lo, U - 1));
+            s_rank[threadIdx.x] = (threadIdx.x & 1) ? min(lo + 1, U - 1) : lo;
+            s_prefix[threadIdx.x] = 0;
+        }
+        // pass 1: top 11 bits, one histogram for every target (+ the sum for the average)
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        float part = 0.f;
+        for (int u = threadIdx.x; u < U; u += blockDim.x) {
+            const float v = summary_value(t, pred, n, R, U, u, which);
+            part += v;
+            atomicAdd(&hist[order_key(v) >> 21], 1u);
+        }
+        if (which == 0) {
+            const float total = block_sum(part, red);
+            if (threadIdx.x == 0) out[0] = total / (float)U;
+        }
+        __syncthreads();
+        if (warp < nt) {
+            uint32_t r = s_rank[warp];
+            const int b = select_bin(hist, 2048, r);
+            if ((threadIdx.x & 31) == 0) { s_rank[warp] = r; s_prefix[warp] = (uint32_t)b; }
+        }
+        __syncthreads();
+        // pass 2: next 11 bits, pass 3: last 10 bits -- one histogram per target, restricted to its prefix
+        for (int pass = 0; pass < 2; ++pass) {
+            const int bits = pass == 0 ? 11 : 10, shift = pass == 0 ? 10 : 0, nb = 1 << bits;
+            for (int i = threadIdx.x; i < nt * 2048; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            for (int u = threadIdx.x; u < U; u += blockDim.x) {
+                const uint32_t k = order_key(summary_value(t, pred, n, R, U, u, which));
+                const uint32_t pre = k >> (shift + bits);
+                for (int tt = 0; tt < nt; ++tt)
+                    if (pre == s_prefix[tt]) atomicAdd(&hist[tt * 2048 + ((k >> shift) & (nb - 1))], 1u);
+            }
+            __syncthreads();
+            if (warp < nt) {
+                uint32_t r = s_rank[warp];
+                const int b = select_bin(hist + warp * 2048, nb, r);
+                if ((threadIdx.x & 31) == 0) { s_rank[warp] = r; s_prefix[warp] = (s_prefix[warp] << bits) | (uint32_t)b; }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < nt) s_val[threadIdx.x] = key_value(s_prefix[threadIdx.x]);
+        __syncthreads();
+        if (threadIdx.x < nq) {
+            const double pos = qs[threadIdx.x] / 100.0 * (double)(U - 1);
+            int lo = (int)floor(pos);
+            lo = max(0, min(lo, U - 1));
+            const double tfrac = pos - (double)lo;
+            const double a = s_val[2 * threadIdx.x], b = s_val[2 * threadIdx.x + 1], d = b - a;
+            const float v = (float)(tfrac >= 0.5 ? b - d * (1.0 - tfrac) : a + d * tfrac);  // numpy's lerp
+            if (which == 0) out[1 + threadIdx.x] = v; else out[5 + which] = v;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace bnn
 
 extern "C" {
@@ -198,9 +332,23 @@ int bnn_summarize_instability(const float* d_t, const float* d_pred, int64_t n_s
     while (n_pow2 < n_units) n_pow2 <<= 1;
     const int threads = 512;
     const size_t smem = (size_t)(n_pow2 + threads) * sizeof(float);
-    BNN_REQUIRE(smem <= 200 * 1024, BNN_E_CONFIG,
-                "bnn_summarize_instability: %d weight samples per system exceed the shared-memory sort (max 32768)", n_units);
     BNN_REQUIRE(n_systems < (1ll << 31), BNN_E_ARG, "bnn_summarize_instability: too many systems for one launch");
+    const char* force = getenv("BNN_SUMMARY_VARIANT");  // sort | select (tests cross-check the two)
+    const bool use_select = (force && !strcmp(force, "select")) || smem > 200 * 1024;
+    if (use_select) {
+        // more weight samples than the shared-memory sort holds (30 models x 2000 samples = 60000 at BASELINE config 3):
+        // exact order statistics by radix select, nothing is stored
+        const size_t hsm = (size_t)SEL_MAXT * 2048 * sizeof(uint32_t);
+        static bool attr2_done = false;
+        if (!attr2_done) {
+            BNN_CUDA(cudaFuncSetAttribute(summarize_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr2_done = true;
+        }
+        summarize_select_kernel<<<(unsigned)n_systems, threads, hsm, (cudaStream_t)stream>>>(d_t, (const float2*)d_pred, n_trios,
+                                                                                         n_units, d_stats);
+        BNN_CUDA(cudaGetLastError());
+        return BNN_OK;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         BNN_CUDA(cudaFuncSetAttribute(summarize_instability_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -628,24 +628,39 @@ __device__ __forceinline__ void rowgemm4x4_c(const float* __restrict__ AT, const
     for (int r = 0; r < 4; ++r) { unpack2(a2[r][0], acc[r][0], acc[r][1]); unpack2(a2[r][1], acc[r][2], acc[r][3]); }
 }
 
-// acc[jj][kk] += sum_r G[j0+jj][r] * Hm[krow[kk]][r], feature-major with row pitch RP, r < n_rows (multiple of 4)
+// acc[jj][kk] += sum_r G[j0+jj][r] * Hm[krow[kk]][r], feature-major with row pitch RP, r < n_rows (multiple of 4).
+// Packed fp32x2 accumulators over even / odd rows (row pairs come straight out of the LDS.128): 16 FFMA2 per
+// 4-row step instead of 32 FFMA; the two halves are added when the step's 2T rows are done.
 __device__ __forceinline__ void outer_acc_p(const float* __restrict__ G, const float* __restrict__ Hm, int RP, int n_rows,
                                             int j0, const int (&krow)[4], float (&acc)[2][4]) {
     const float* g0p = G + j0 * RP;
     const float* g1p = g0p + RP;
+    u64 a2[2][4];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) a2[jj][kk] = pack2(acc[jj][kk], 0.f);
 #pragma unroll 2
     for (int r = 0; r < n_rows; r += 4) {
-        const float4 g0 = *reinterpret_cast<const float4*>(g0p + r);
-        const float4 g1 = *reinterpret_cast<const float4*>(g1p + r);
+        const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(g0p + r);
+        const ulonglong2 g1 = *reinterpret_cast<const ulonglong2*>(g1p + r);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            const float4 h = *reinterpret_cast<const float4*>(Hm + krow[kk] * RP + r);
-            acc[0][kk] = fmaf(g0.x, h.x, acc[0][kk]); acc[0][kk] = fmaf(g0.y, h.y, acc[0][kk]);
-            acc[0][kk] = fmaf(g0.z, h.z, acc[0][kk]); acc[0][kk] = fmaf(g0.w, h.w, acc[0][kk]);
-            acc[1][kk] = fmaf(g1.x, h.x, acc[1][kk]); acc[1][kk] = fmaf(g1.y, h.y, acc[1][kk]);
-            acc[1][kk] = fmaf(g1.z, h.z, acc[1][kk]); acc[1][kk] = fmaf(g1.w, h.w, acc[1][kk]);
+            const ulonglong2 h = *reinterpret_cast<const ulonglong2*>(Hm + krow[kk] * RP + r);
+            a2[0][kk] = fma2(g0.x, h.x, a2[0][kk]);
+            a2[0][kk] = fma2(g0.y, h.y, a2[0][kk]);
+            a2[1][kk] = fma2(g1.x, h.x, a2[1][kk]);
+            a2[1][kk] = fma2(g1.y, h.y, a2[1][kk]);
         }
     }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            float lo, hi;
+            unpack2(a2[jj][kk], lo, hi);
+            acc[jj][kk] = lo + hi;
+        }
 }
 
 // compiled for one (T, F): every pitch and loop bound is a constant, which removes the address arithmetic that made up

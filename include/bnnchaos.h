@@ -217,7 +217,7 @@ int bnn_pack_inputs(const double* d_tseries, const double* d_masses, const doubl
  * bnn_summarize_instability: per system, over the U weight samples of min-over-trios(t): d_stats [N, 8] =
  *   average, median, percentiles 84, 16, 97.5, 2.5 (numpy 'linear'), then the median over weight samples of
  *   mu* = min over trios of mu and of the std of that trio ("median of dists", main_figures.py:276-277).
- *   U <= 32768 (shared-memory sort), else BNN_E_CONFIG.
+ *   U <= 32768: shared-memory bitonic sort; larger U (30 models x 2000 samples): exact 3-pass radix select.
  */
 int bnn_sample_instability(const float* d_pred, int64_t n_rows, int64_t n_units, uint64_t seed, int64_t row_offset,
                            float left, int32_t nsamp, float* d_t, void* stream);

@@ -30,6 +30,27 @@ def test_summary_statistics_vs_numpy(dev, N, Rt, U):
         np.testing.assert_allclose(got[:, i], ref[name], rtol=2e-6, err_msg=name)
 
 
+def test_radix_select_summary_for_many_weight_samples(dev, monkeypatch):
+    """U = 60000 (30 models x 2000 samples, BASELINE config 3) exceeds the shared-memory sort: exact radix select.
+    Also cross-checked against the sort path at a size both support, with ties, negatives and a NaN."""
+    N, Rt, U = 2, 2, 60000
+    rng = np.random.default_rng(7)
+    t = rng.uniform(4.0, 30.0, (N * Rt, U)).astype(np.float32)
+    pred = np.stack([rng.uniform(4.0, 12.0, (N * Rt, U)), rng.uniform(0.5, 6.0, (N * Rt, U))], -1).astype(np.float32)
+    got = summarize_instability(torch.from_numpy(t).to(dev), torch.from_numpy(pred).to(dev), Rt).cpu().numpy()
+    ref = R.posterior_stats(t.reshape(N, Rt, U).transpose(2, 0, 1), pred.reshape(N, Rt, U, 2).transpose(2, 0, 1, 3))
+    for i, name in enumerate(STAT_NAMES):
+        np.testing.assert_allclose(got[:, i], ref[name], rtol=2e-6, err_msg=name)
+    U = 3001
+    t = np.round(rng.uniform(-3.0, 12.0, (3, U)), 1).astype(np.float32)  # many ties, negative values
+    pred = np.stack([np.round(rng.uniform(4, 12, (3, U)), 1), rng.uniform(0.5, 6, (3, U))], -1).astype(np.float32)
+    pred[1, 5, 0] = np.nan
+    a = summarize_instability(torch.from_numpy(t).to(dev), torch.from_numpy(pred).to(dev), 1)
+    monkeypatch.setenv("BNN_SUMMARY_VARIANT", "select")
+    b = summarize_instability(torch.from_numpy(t).to(dev), torch.from_numpy(pred).to(dev), 1)
+    assert torch.equal(a[:, 1:], b[:, 1:]) and torch.allclose(a[:, 0], b[:, 0], rtol=1e-6)
+
+
 def test_sampling_matches_reference_distribution(dev):
     # (a) one (mu, std) repeated: KS against the oracle's fast_truncnorm + prior resampling
     U = 200_000
