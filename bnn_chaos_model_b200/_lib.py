@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbnnchaos.so")
+# BNN_CHAOS_LIB selects a diagnostic build of the same library (e.g. libbnnchaos_tl.so); there is no other backend
+LIB_PATH = os.environ.get("BNN_CHAOS_LIB") or os.path.join(_HERE, "libbnnchaos.so")
 
 c_f32p = C.c_void_p  # device / host float* (passed as integers from tensor.data_ptr())
 c_i32p = C.c_void_p
@@ -107,6 +108,7 @@ SIGNATURES = {
     "bnn_ffma_peak": (C.c_int, [C.c_int32, C.c_int64, c_f32p, C.POINTER(C.c_int64), C.c_void_p]),
     "bnn_tc_probe": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bnn_tc_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bnn_train_timeline": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int32]),
 }
 
 _lib = None

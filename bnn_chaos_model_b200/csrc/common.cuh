@@ -168,6 +168,24 @@ __device__ __forceinline__ float4 box_muller(uint4 u) {
     return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
 }
 
+// Box-Muller on the special-function unit (lg2 / sin / cos approximations, ~1e-6 absolute): for the bulk training
+// noise (STREAM_EPS_IN), where 4 normals otherwise cost ~370 instructions.  The angle is reduced to (-pi, pi], the
+// range the approximations are specified on.  Every consumer of a stream must use the same variant.
+__device__ __forceinline__ float4 box_muller_fast(uint4 u) {
+    float a0 = u01(u.x), b0 = u01(u.y), a1 = u01(u.z), b1 = u01(u.w);
+    float r0 = sqrtf(-2.0f * __logf(a0)), r1 = sqrtf(-2.0f * __logf(a1));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * (b0 - 0.5f), &s0, &c0);   // sin(2 pi b) = -sin(2 pi (b - 1/2))
+    __sincosf(6.283185307179586f * (b1 - 0.5f), &s1, &c1);
+    return make_float4(-r0 * c0, -r0 * s0, -r1 * c1, -r1 * s1);
+}
+
+__device__ __forceinline__ float4 philox_normal4_fast(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b,
+                                                      uint32_t blk) {
+    uint4 r = philox4x32_10(make_uint4(blk, a, b, stream), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    return box_muller_fast(r);
+}
+
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b,
                                                  uint32_t blk) {
     uint4 r = philox4x32_10(make_uint4(blk, a, b, stream), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));

@@ -46,6 +46,8 @@ struct Params {
     const float* eps12;        // [n_seeds, B, 2L] or null
     const float* eps_sum;      // [n_seeds, B, 2L] or null
     float* partial;            // [n_seeds, n_cta, d + DPAD]
+    float* head_rec;           // [n_seeds, B, REC] per-system head vectors (v3 only)
+    float* xprod;              // [n_seeds, n_cta, 2, 2, F, 2T] input-tile scratch of the producer warps (v3 only)
     int B, T, F, FP, n_cta;
     uint64_t seed, step;
     uint64_t zero_mask;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(NTHR, 2) train_fwd_bwd_kernel(const Params prm
                 const int F4 = (F + 3) >> 2;
                 for (int i = tid; i < T * F4; i += NTHR) {
                     const int t = i / F4, c4 = i - t * F4;
-                    const float4 n4 = philox_normal4(key, STREAM_EPS_IN, (uint32_t)b, (uint32_t)prm.step, (uint32_t)i);
+                    const float4 n4 = philox_normal4_fast(key, STREAM_EPS_IN, (uint32_t)b, (uint32_t)prm.step, (uint32_t)i);
                     const float e[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(NTHR2, 1) train_fwd_bwd2_kernel(const Params p
                 const int F4 = (F + 3) >> 2;
                 for (int i = lt; i < T * F4; i += HALF2) {
                     const int t = i / F4, c4 = i - t * F4;
-                    const float4 n4 = philox_normal4(key, STREAM_EPS_IN, (uint32_t)b, (uint32_t)prm.step, (uint32_t)i);
+                    const float4 n4 = philox_normal4_fast(key, STREAM_EPS_IN, (uint32_t)b, (uint32_t)prm.step, (uint32_t)i);
                     const float e[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -1157,6 +1159,12 @@ __global__ void __launch_bounds__(NTHR2, 1) train_fwd_bwd2_kernel(const Params p
     }
 }
 
+}  // namespace train
+}  // namespace bnn
+#include "train_v3.cuh"
+namespace bnn {
+namespace train {
+
 // grad[s][i] = sum_c partial[s][c][i] (fixed order) + analytic KL terms; per-block sum of squares.
 __global__ void __launch_bounds__(256) train_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ theta,
                                                            int n_cta, int d, int F, float kl_in_scale, float kl_sum_scale,
@@ -1248,7 +1256,7 @@ __global__ void train_noise_kernel(int B, int T, int F, uint64_t seed, uint64_t 
     const int F4 = (F + 3) >> 2;
     for (int i = threadIdx.x; i < T * F4; i += blockDim.x) {
         const int t = i / F4, c4 = i - t * F4;
-        const float4 n4 = philox_normal4(key, STREAM_EPS_IN, (uint32_t)b, (uint32_t)step, (uint32_t)i);
+        const float4 n4 = philox_normal4_fast(key, STREAM_EPS_IN, (uint32_t)b, (uint32_t)step, (uint32_t)i);
         const float e[4] = {n4.x, n4.y, n4.z, n4.w};
         for (int u = 0; u < 4; ++u)
             if (4 * c4 + u < F) eps_in[(sb * T + t) * F + 4 * c4 + u] = e[u];
@@ -1283,7 +1291,14 @@ __global__ void __launch_bounds__(256) nll_sum_kernel(const float2* __restrict__
     if (threadIdx.x == 0) loss_sum[blockIdx.x] = sh[0];
 }
 
-// v2 (two systems per iteration, one CTA per SM) when its tile fits; BNN_TRAIN_VARIANT=v1|v2 forces one
+// v3 (large register tiles) for the reference's shape; BNN_TRAIN_VARIANT=v1|v2|v3 forces one
+static bool use_v3(const bnn_model_config* cfg) {
+    const char* force = getenv("BNN_TRAIN_VARIANT");
+    if (force && (!strcmp(force, "v1") || !strcmp(force, "v2"))) return false;
+    return cfg->n_times == 100 && cfg->n_features == 41;
+}
+
+// v2 (two systems per iteration, one CTA per SM) when its tile fits
 static bool use_v2(const bnn_model_config* cfg) {
     const char* force = getenv("BNN_TRAIN_VARIANT");
     if (force && !strcmp(force, "v1")) return false;
@@ -1297,7 +1312,7 @@ static int pick_n_cta(const bnn_model_config* cfg, int64_t B, int n_seeds) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool v2 = use_v2(cfg);
+    const bool v2 = use_v2(cfg) || use_v3(cfg);
     // v1: two resident CTAs per SM, one system per iteration; v2: one CTA per SM, two systems per iteration
     int64_t n = ((v2 ? 1ll : 2ll) * sms + n_seeds - 1) / n_seeds;
     const int64_t cap = v2 ? (B + 1) / 2 : B;
@@ -1318,7 +1333,10 @@ size_t bnn_train_workspace_bytes(const bnn_model_config* cfg, int64_t B, int32_t
     const int n_cta = train::pick_n_cta(cfg, B, n_seeds);
     const size_t DP = d + train::DPAD;
     const size_t nb = (DP + 255) / 256;
-    return ((size_t)n_seeds * n_cta * DP + (size_t)n_seeds * DP + (size_t)n_seeds * nb + 64) * sizeof(float);
+    // partial | grad | sq | pad | head records (v3)
+    return ((size_t)n_seeds * n_cta * DP + (size_t)n_seeds * DP + (size_t)n_seeds * nb + 64 +
+            (size_t)n_seeds * B * train::REC + 4 +
+            (size_t)n_seeds * n_cta * (8 * cfg->n_features * cfg->n_times + 2 * train::XSM)) * sizeof(float);
 }
 
 int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int32_t n_seeds, float* d_theta,
@@ -1356,16 +1374,29 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
     float* partial = (float*)d_workspace;
     float* grad = partial + (size_t)n_seeds * n_cta * DP;
     float* sq = grad + (size_t)n_seeds * DP;
+    float* head_rec = sq + (size_t)n_seeds * nb;
+    head_rec += (4 - ((uintptr_t)head_rec / sizeof(float)) % 4) % 4;  // 16-byte aligned records
 
     train::Params prm;
     prm.theta = d_theta; prm.X = d_x; prm.Y = d_y; prm.batch_index = d_batch_index;
     prm.eps_in = d_eps_in; prm.eps12 = d_eps12; prm.eps_sum = d_eps_sum;
     prm.partial = partial;
+    prm.head_rec = head_rec;
+    prm.xprod = head_rec + (size_t)n_seeds * B * train::REC;   // REC is a multiple of 4: stays 16-byte aligned
     prm.B = (int)B; prm.T = T; prm.F = F; prm.FP = FP; prm.n_cta = n_cta;
     prm.seed = seed; prm.step = step; prm.zero_mask = cfg->zero_mask;
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
     prm.beta_out = hp->beta_out;
-    if (train::use_v2(cfg)) {
+    if (train::use_v3(cfg)) {
+        const size_t smem3 = (size_t)train::Smem3(T, F).total * sizeof(float);
+        static bool attr3_done = false;
+        if (!attr3_done) {
+            BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd3_kernel<100, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024));
+            attr3_done = true;
+        }
+        train::train_fwd_bwd3_kernel<100, 41><<<dim3(n_cta, n_seeds), train::NTHR3, smem3, st>>>(prm);
+    } else if (train::use_v2(cfg)) {
         const size_t smem2 = (size_t)train::Smem2(T, F, FP).total * sizeof(float);
         static bool attr2_done = false;
         if (!attr2_done) {
@@ -1388,6 +1419,19 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
     train::train_update_kernel<<<dim3(nb, n_seeds), 256, 0, st>>>(grad, sq, nb, fl.d, F, (int)B, *hp, d_theta, d_momentum,
                                                                  d_grad_out, d_metrics);
     BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+int bnn_train_timeline(unsigned long long* host_out, int32_t n) {
+    using namespace bnn;
+    BNN_REQUIRE(host_out && n >= 0, BNN_E_ARG, "bnn_train_timeline: null pointer");
+    for (int i = 0; i < n; ++i) host_out[i] = 0;
+#ifdef BNN_TRAIN_TIMELINE
+    BNN_CUDA(cudaDeviceSynchronize());
+    unsigned long long tmp[train::TL_N];
+    BNN_CUDA(cudaMemcpyFromSymbol(tmp, train::g_train_tl, sizeof(tmp)));
+    for (int i = 0; i < n && i < train::TL_N; ++i) host_out[i] = tmp[i];
+#endif
     return BNN_OK;
 }
 

@@ -1,0 +1,1028 @@
+// K4 v3: the fused training forward + backward with large register tiles (included by train.cu, namespace bnn::train).
+//
+// Same math, boundary and partial-gradient format as train_fwd_bwd2_kernel (derivation in the header of train.cu;
+// reference: /root/reference/spock_reg_model.py:486-528,547-593,722-732).  What changed, and why (ncu of v2:
+// shared-memory scoreboard stalls 28 %, barrier stalls 24 %, FMAs only 41 % of the executed instructions):
+// The kernel is bound by shared-memory wavefronts, not FMA issue: an LDS.128 costs four wavefronts (one per quarter
+// warp, 128 B each, no broadcast across quarters -- ncu: "ideal" = 4 per instruction), i.e. shared memory fills 32
+// register words per cycle per SM against 128 FMA lanes, so a thread needs >= 4 FMAs per loaded word.
+//   * row GEMMs (feature_nn forward, the two activation-gradient GEMMs, g_x): 4 rows x 8 columns per thread
+//     (3 LDS.128 per 16 FFMA2 = 2.7 FMA per word) instead of 4 x 4 (2.0); thread = (column group, row quad) with the
+//     quad fastest, so a quarter warp reads 8 consecutive 16-byte chunks of activations and ONE weight address, and
+//     its epilogue STS.128 are conflict-free (quad-slowest ordering cost 2x on weight loads, 5x on the stores);
+//   * weight-gradient outer products: 8 x 8 blocks of dW per thread in plain FFMA (16 LDS.128 per 256 FFMA = 4.0 FMA
+//     per word) instead of 2 x 4 (1.3); the 2T rows are split over six row groups (five for dW2) so that 375 of the
+//     384 threads own a block of ONE matrix;
+//   * the Philox input noise of the NEXT pair of systems is drawn by the four warps that have no row-GEMM tile, while
+//     the other eight run the GEMMs, into an L2-resident scratch (x' and x' - mask(x), feature-major); the load phase
+//     is a float4 copy (it was 19 % of the kernel when every thread drew noise between two barriers);
+//   * regress_nn weights live in shared memory (six L2-latency-bound mat-vec phases per pair of systems before);
+//   * the head's weight gradients are rank-1 updates per system: the vectors they need go to a 1 kB record per
+//     system in the workspace and the outer products run once, at the end of the kernel, over the CTA's records --
+//     no head accumulators live through the main loop;
+//   * bias gradients and the 41st input column are row sums done by the two warps that have no g_x tile.
+// One CTA per SM, 384 threads (<= 168 registers), two systems (2T rows) per iteration.
+#pragma once
+#include "tc.cuh"
+
+namespace bnn {
+namespace train {
+
+constexpr int NTHR3 = 384, HALF3 = 192;
+constexpr int REC = 256;     // floats per system record (head vectors for the deferred outer products)
+constexpr int SMALL3 = 512;  // per-system-slot scratch (floats)
+constexpr int XSM = 192;    // per-parity small inputs in the tile scratch: 2 slots x (eps12[40] eps_sum[40] y[2] pad)
+constexpr int W0NP = 44;     // pitch of the natural-layout W0 rows (g_x GEMM reads 48 columns; the tail is discarded)
+
+// per-slot scratch layout (floats); [V3_REC0, V3_REC0 + 242) is copied verbatim into the system's record
+enum { V3_M = 0, V3_VAR = 20, V3_SIM = 40, V3_SIV = 60, V3_VS = 80, V3_S = 100, V3_GS = 140, V3_GM = 180, V3_GV = 200,
+       V3_E12 = 220, V3_ESN = 260, V3_Y = 300,
+       V3_REC0 = 304, V3_SP = 304, V3_R1 = 344, V3_R2 = 384, V3_G1 = 424, V3_G2 = 464 };
+// record layout: s'[40] r1[40] r2[40] g_a1[40] g_a2[40] | dlvs[40] g_r[2] live right behind G2 in the record only
+enum { R_SP = 0, R_R1 = 40, R_R2 = 80, R_G1 = 120, R_G2 = 160, R_DLVS = 200, R_GR = 240 };
+// shared constants (floats, one copy)
+enum { C3_ELVH = 0, C3_LVS = 40, C3_NSC = 80, C3_TOTAL = 144 };
+
+struct Smem3 {
+    int RP, xT, h1T, h2T, fT, g2T, g1T, W0T, b0, W1T, b1, W2T, b2, W2n, W1n, W0n, V0, V1, V2, cb, consts, small, prod, total;
+    __host__ __device__ Smem3(int T, int F) {
+        RP = 2 * T + 4;
+        int o = 0;
+        xT = o; o += F * RP;
+        h1T = o; o += H * RP;
+        h2T = o; o += H * RP;
+        fT = o; o += L * RP;
+        g2T = o; o += H * RP;
+        g1T = o; o += H * RP;
+        W0T = o; o += F * H;
+        b0 = o; o += H;
+        W1T = o; o += H * H;
+        b1 = o; o += H;
+        W2T = o; o += H * L;
+        b2 = o; o += L;
+        W2n = o; o += L * H;
+        W1n = o; o += H * H;
+        W0n = o; o += H * W0NP;
+        V0 = o; o += H * S2;
+        V1 = o; o += H * H;
+        V2 = o; o += 2 * H;
+        cb = o; o += 2 * H + 4;   // c0[40] c1[40] c2[2]
+        consts = o; o += C3_TOTAL;
+        small = o; o += 2 * SMALL3;
+        prod = o; o += 32;        // ProdArgs of the tile being produced
+        total = o;
+    }
+};
+
+#ifdef BNN_TRAIN_TIMELINE
+constexpr int TL_N = 24;
+__device__ unsigned long long g_train_tl[TL_N];
+// volatile + memory clobber: the read stays on its side of the neighbouring barrier
+__device__ __forceinline__ long long tl_clock() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
+    return t;
+}
+#define TL3(i)                                                 \
+    do {                                                       \
+        if (tid == 0) {                                        \
+            const long long t_now_ = tl_clock();               \
+            tl[i] += (unsigned long long)(t_now_ - tl_prev);   \
+            tl_prev = t_now_;                                  \
+        }                                                      \
+    } while (0)
+// producer-side stamps (thread 256): cycles inside produce call i -> slot 18 + i
+#define TLP_BEGIN() const long long tp0_ = tl_clock()
+#define TLP_END(i) do { const long long tp1_ = tl_clock(); if (tid == 256) tl[18 + (i)] += (unsigned long long)(tp1_ - tp0_); } while (0)
+#else
+#define TL3(i) do { } while (0)
+#define TLP_BEGIN() do { } while (0)
+#define TLP_END(i) do { } while (0)
+#endif
+
+// acc2[r][i] (columns c0 + 2i, c0 + 2i + 1 of row 4q + r) += sum_k AT[k][4q + r] * W[k][c0 + 2i .. +1]
+template <int RP, int K, int NP, int NC>
+__device__ __forceinline__ void rowgemm4(const float* __restrict__ AT, const float* __restrict__ W, int q, int c0,
+                                         u64 (&a2)[4][NC / 2]) {
+    const float* ap = AT + 4 * q;
+    const float* wp = W + c0;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(ap + k * RP);
+        u64 w[NC / 2];
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i) {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(wp + k * NP + 4 * i);
+            w[2 * i] = t.x;
+            w[2 * i + 1] = t.y;
+        }
+        const u64 av[4] = {pack2(a.x, a.x), pack2(a.y, a.y), pack2(a.z, a.z), pack2(a.w, a.w)};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < NC / 2; ++i) a2[r][i] = fma2(av[r], w[i], a2[r][i]);
+    }
+}
+
+#ifndef V3_OUTER
+#define V3_OUTER 88
+#endif
+// 4 x 8 variant: even / odd rows accumulate in the two halves of an fp32x2 register (no packing moves)
+__device__ __forceinline__ void outer4x8(const float* __restrict__ Gp, int gstr, const float* __restrict__ Hp, int hstr,
+                                         int q0, int q1, float (&acc)[4][8]) {
+    u64 a2[4][8];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) a2[jj][kk] = pack2(acc[jj][kk], 0.f);
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+        ulonglong2 g[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) g[jj] = *reinterpret_cast<const ulonglong2*>(Gp + jj * gstr + 4 * q);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const ulonglong2 h = *reinterpret_cast<const ulonglong2*>(Hp + kk * hstr + 4 * q);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                a2[jj][kk] = fma2(g[jj].x, h.x, a2[jj][kk]);
+                a2[jj][kk] = fma2(g[jj].y, h.y, a2[jj][kk]);
+            }
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            float lo, hi;
+            unpack2(a2[jj][kk], lo, hi);
+            acc[jj][kk] = lo + hi;
+        }
+}
+
+// acc[jj][kk] += sum over the rows of quads [q0, q1) of G[jj * gstr][r] * Hm[kk * hstr][r]  (feature-major, pitch RP)
+__device__ __forceinline__ void outer8x8(const float* __restrict__ Gp, int gstr, const float* __restrict__ Hp, int hstr,
+                                         int q0, int q1, float (&acc)[8][8]) {
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+        float4 g[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) g[jj] = *reinterpret_cast<const float4*>(Gp + jj * gstr + 4 * q);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const float4 h = *reinterpret_cast<const float4*>(Hp + kk * hstr + 4 * q);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                float a = acc[jj][kk];
+                a = fmaf(g[jj].x, h.x, a);
+                a = fmaf(g[jj].y, h.y, a);
+                a = fmaf(g[jj].z, h.z, a);
+                a = fmaf(g[jj].w, h.w, a);
+                acc[jj][kk] = a;
+            }
+        }
+    }
+}
+
+// Tensor memory as a register stash: a thread's block of weight-gradient accumulators lives in its own TMEM lane
+// (columns [col, col + NV)) between the outer-product phases, so that no other phase carries those registers.
+template <int NV>
+__device__ __forceinline__ void stash_load(uint32_t taddr, float* v) {
+#pragma unroll
+    for (int i = 0; i < NV / 16; ++i) {
+        uint32_t u[16];
+        tmem_ld16(taddr + 16 * i, u);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * i + j] = __uint_as_float(u[j]);
+    }
+}
+template <int NV>
+__device__ __forceinline__ void stash_store(uint32_t taddr, const float* v) {
+#pragma unroll
+    for (int i = 0; i < NV / 16; ++i) {
+        uint32_t u[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) u[j] = __float_as_uint(v[16 * i + j]);
+        tmem_st16(taddr + 16 * i, u);
+    }
+    tc_wait_st();
+}
+
+// Input tile producer: x' = mask(x) + eps_in * exp(lv_in / 2) (:486-500) and n = x' - mask(x) for the two systems
+// b0n, b0n + 1 (data rows row0 / row1, -1 = past the batch), written feature-major ([c][2T]) to this CTA's scratch.
+// Work items are (system slot, 4-column group, time step); item ids first + stride * round, round in [r0, r0 + NR).
+// All loads of the NR rounds are issued before the first Philox block (the rounds were latency-bound one by one).
+// Philox counters as in train_noise_kernel.  Not inlined: six call sites, ~500 instructions each.
+struct ProdArgs {
+    const float* X; const float* eps_in; float* xp; float* np; const float* nsc;
+    const float* Y; const float* eps12; const float* eps_sum; float* sm_out;
+    uint64_t key, zero_mask; int64_t sb0; int row0, row1, b0n, step;
+};
+static_assert(sizeof(ProdArgs) <= 32 * sizeof(float), "ProdArgs must fit its shared-memory slot");
+template <int T, int F, int NR>
+__device__ __noinline__ void produce_tile(const ProdArgs* __restrict__ ap, int first, int stride, int r0) {
+    const ProdArgs a = *ap;
+    constexpr int F4 = (F + 3) >> 2, RT = 2 * T, PER = T * F4;
+    float xv[NR][4], ev[NR][4];
+    int off[NR], c4s[NR];
+    uint4 ctr[NR];
+    bool live[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        const int id = first + stride * (r0 + k);
+        const bool ok = id < 2 * PER;
+        const int hs = id >= PER ? 1 : 0, rem = id - hs * PER;
+        const int c4 = rem / T, t = rem - c4 * T;
+        const int row = hs ? a.row1 : a.row0;
+        c4s[k] = c4;
+        off[k] = ok ? hs * T + t : -1;
+        live[k] = ok && row >= 0;
+        ctr[k] = make_uint4((uint32_t)(t * F4 + c4), (uint32_t)(a.b0n + hs), (uint32_t)a.step, STREAM_EPS_IN);
+        const float* xs = a.X + ((int64_t)(live[k] ? row : 0) * T + t) * F + 4 * c4;
+        const float* es = a.eps_in ? a.eps_in + ((a.sb0 + hs) * T + t) * (int64_t)F + 4 * c4 : nullptr;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool in = live[k] && 4 * c4 + u < F;
+            xv[k][u] = in ? __ldg(xs + u) : 0.f;
+            ev[k][u] = (in && es) ? __ldg(es + u) : 0.f;
+        }
+    }
+    if (!a.eps_in) {
+        // NR Philox4x32-10 blocks, rounds interleaved across the blocks (one warp per scheduler runs this: the
+        // instruction-level parallelism has to come from here)
+        constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+        uint32_t k0 = (uint32_t)a.key, k1 = (uint32_t)(a.key >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+                const uint4 c = ctr[k];
+                const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+                const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+                ctr[k] = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+            }
+            k0 += W0;
+            k1 += W1;
+        }
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const float4 n4 = box_muller_fast(ctr[k]);
+            ev[k][0] = n4.x; ev[k][1] = n4.y; ev[k][2] = n4.z; ev[k][3] = n4.w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = 4 * c4s[k] + u;
+            if (c < F && off[k] >= 0) {
+                float x = xv[k][u];
+                if ((a.zero_mask >> c) & 1ull) x = __fsub_rn(x, x);  // x - mask keeps NaN (:452-478)
+                const float xpv = live[k] ? __fadd_rn(x, __fmul_rn(ev[k][u], a.nsc[c])) : 0.f;
+                a.xp[c * RT + off[k]] = xpv;
+                a.np[c * RT + off[k]] = live[k] ? __fsub_rn(xpv, x) : 0.f;
+            }
+        }
+    }
+}
+
+// The per-system vectors of the same tile: eps1|eps2 (:426-427), the summary noise (:522) and the labels, for both slots.
+// Threads p < 20 (two slots x 10 float4) draw / load the noise, p = 32, 33 fetch the labels.
+__device__ __noinline__ void produce_small(const ProdArgs* __restrict__ ap, int p) {
+    const ProdArgs a = *ap;
+    if (p < 20) {
+        const int hs = p / 10, l = p - 10 * hs;
+        const int row = hs ? a.row1 : a.row0;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f), c = e;
+        if (row >= 0) {
+            if (a.eps12) {
+                e = __ldg(reinterpret_cast<const float4*>(a.eps12 + (a.sb0 + hs) * S2) + l);
+                c = __ldg(reinterpret_cast<const float4*>(a.eps_sum + (a.sb0 + hs) * S2) + l);
+            } else {
+                e = philox_normal4(a.key, STREAM_EPS, (uint32_t)(a.b0n + hs), (uint32_t)a.step, (uint32_t)l);
+                c = philox_normal4(a.key, STREAM_EPS_SUM, (uint32_t)(a.b0n + hs), (uint32_t)a.step, (uint32_t)l);
+            }
+        }
+        reinterpret_cast<float4*>(a.sm_out + hs * (XSM / 2))[l] = e;
+        reinterpret_cast<float4*>(a.sm_out + hs * (XSM / 2) + S2)[l] = c;
+    } else if (p == 32 || p == 33) {
+        const int hs = p - 32;
+        const int row = hs ? a.row1 : a.row0;
+        float2 y = make_float2(0.f, 0.f);
+        if (row >= 0) y = __ldg(reinterpret_cast<const float2*>(a.Y) + row);
+        *reinterpret_cast<float2*>(a.sm_out + hs * (XSM / 2) + 2 * S2) = y;
+    }
+}
+
+template <int T, int F>
+__global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params prm) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int NQ = T >> 2, NQ2 = 2 * NQ, RT = 2 * T, RP = 2 * T + 4;
+    static_assert(F == 41 && T == 100, "thread maps below are laid out for the reference's shape");
+    const Smem3 L_(T, F);
+    const FlatLayout fl(F);
+    const int tid = threadIdx.x;
+    const int half = tid >= HALF3 ? 1 : 0, lt = tid - half * HALF3;
+    const int lane = tid & 31;
+    const int sidx = blockIdx.y;
+    const float* th = prm.theta + (int64_t)sidx * fl.d;
+    float* xT = sm + L_.xT; float* h1T = sm + L_.h1T; float* h2T = sm + L_.h2T; float* fT = sm + L_.fT;
+    float* g2T = sm + L_.g2T; float* g1T = sm + L_.g1T;
+    float* W0T = sm + L_.W0T; float* b0 = sm + L_.b0; float* W1T = sm + L_.W1T; float* b1 = sm + L_.b1;
+    float* W2T = sm + L_.W2T; float* b2 = sm + L_.b2; float* W2n = sm + L_.W2n; float* W1n = sm + L_.W1n; float* W0n = sm + L_.W0n;
+    float* V0s = sm + L_.V0; float* V1s = sm + L_.V1; float* V2s = sm + L_.V2; float* cbs = sm + L_.cb;
+    float* cst = sm + L_.consts;
+    float* sv = sm + L_.small + half * SMALL3;
+#ifdef BNN_TRAIN_TIMELINE
+    unsigned long long tl[TL_N];
+#pragma unroll
+    for (int i = 0; i < TL_N; ++i) tl[i] = 0;
+    long long tl_prev = tl_clock();
+#endif
+
+    // ---- stage this seed's weights (feature matrices natural and transposed, the head natural) ----
+    for (int i = tid; i < H * F; i += NTHR3) {
+        const int j = i / F, c = i - j * F;
+        const float w = __ldg(th + fl.W0 + i);
+        W0T[c * H + j] = w;
+        W0n[j * W0NP + c] = w;
+    }
+    for (int i = tid; i < H * (W0NP - F); i += NTHR3) W0n[(i / (W0NP - F)) * W0NP + F + i % (W0NP - F)] = 0.f;
+    for (int i = tid; i < H * H; i += NTHR3) {
+        const int j = i / H, k = i - j * H;
+        const float w = __ldg(th + fl.W1 + i);
+        W1T[k * H + j] = w;
+        W1n[i] = w;
+        V1s[i] = __ldg(th + fl.V1 + i);
+        V0s[i] = __ldg(th + fl.V0 + i);   // H * S2 == H * H
+    }
+    for (int i = tid; i < L * H; i += NTHR3) {
+        const int j = i / H, k = i - j * H;
+        const float w = __ldg(th + fl.W2 + i);
+        W2T[k * L + j] = w;
+        W2n[i] = w;
+    }
+    if (tid < H) {
+        b0[tid] = __ldg(th + fl.b0 + tid); b1[tid] = __ldg(th + fl.b1 + tid);
+        cbs[tid] = __ldg(th + fl.c0 + tid); cbs[H + tid] = __ldg(th + fl.c1 + tid);
+    }
+    if (tid < 2 * H) V2s[tid] = __ldg(th + fl.V2 + tid);
+    if (tid < 2) cbs[2 * H + tid] = __ldg(th + fl.c2 + tid);
+    if (tid < L) b2[tid] = __ldg(th + fl.b2 + tid);
+    if (tid < S2) {
+        const float lv = __ldg(th + fl.lv_sum + tid);
+        cst[C3_LVS + tid] = lv;
+        cst[C3_ELVH + tid] = expf(__fdiv_rn(lv, 2.0f));
+    }
+    if (tid < F) cst[C3_NSC + tid] = expf(__fdiv_rn(__ldg(th + fl.lv_in + tid), 2.0f));
+    // the 4 pad rows of every feature row are never read (row GEMMs and outer products stop at 2T)
+
+    // ---- thread roles ----
+    // row GEMMs: column group cg_rg (8 columns; 4 for the latent layer), quad q_rg of the 2T rows, quad fastest
+    const int cg_rg = tid / NQ2, q_rg = tid - NQ2 * cg_rg;   // 5 groups: tid < 250; g_x (48 columns, 6 groups): tid < 300
+    // outer products: one block of one matrix over one row group
+    const float* opG; const float* opH; int op_gstr, op_q0, op_q1, op_role, op_jb, op_kb;
+#if V3_OUTER == 88
+    // 8 x 8 blocks, six row groups (dW2: five)
+    {
+        int r = tid, rg;
+        if (tid < 150) { op_role = 0; rg = r / 25; r -= 25 * rg; opG = g1T; opH = xT; }
+        else if (tid < 300) { op_role = 1; r -= 150; rg = r / 25; r -= 25 * rg; opG = g2T; opH = h1T; }
+        else if (tid < 375) { op_role = 2; r -= 300; rg = r / 15; r -= 15 * rg; opG = fT; opH = h2T; }
+        else { op_role = 3; rg = 0; r = 0; opG = fT; opH = h2T; }
+        op_jb = r / 5; op_kb = r - 5 * op_jb;
+        op_gstr = (op_role >= 2 ? 3 : 5) * RP;   // dW2: rows j = jb + 3 jj (j >= 20 is discarded), else j = jb + 5 jj
+        opG += op_jb * RP; opH += op_kb * RP;
+        if (op_role < 2) { op_q0 = rg < 2 ? 9 * rg : 18 + 8 * (rg - 2); op_q1 = rg < 2 ? 9 * rg + 9 : 26 + 8 * (rg - 2); }
+        else if (op_role == 2) { op_q0 = 10 * rg; op_q1 = 10 * rg + 10; }
+        else { op_q0 = 0; op_q1 = 0; }
+    }
+    constexpr int OJ = 8;
+#else
+    // 4 x 8 blocks (fp32x2 accumulators), three row groups
+    {
+        int r = tid, rg;
+        if (tid < 150) { op_role = 0; rg = r / 50; r -= 50 * rg; op_jb = r / 5; op_kb = r - 5 * op_jb; opG = g1T; opH = xT; op_gstr = 10 * RP; }
+        else if (tid < 300) { op_role = 1; r -= 150; rg = r / 50; r -= 50 * rg; op_jb = r / 5; op_kb = r - 5 * op_jb; opG = g2T; opH = h1T; op_gstr = 10 * RP; }
+        else if (tid < 375) { op_role = 2; r -= 300; rg = r / 25; r -= 25 * rg; op_jb = r / 5; op_kb = r - 5 * op_jb; opG = fT; opH = h2T; op_gstr = 5 * RP; }
+        else { op_role = 3; rg = 0; op_jb = 0; op_kb = 0; opG = fT; opH = h2T; op_gstr = 5 * RP; }
+        opG += op_jb * RP; opH += op_kb * RP;
+        op_q0 = rg == 0 ? 0 : (rg == 1 ? 17 : 34);
+        op_q1 = op_role == 3 ? 0 : (rg == 0 ? 17 : (rg == 1 ? 34 : NQ2));
+    }
+    constexpr int OJ = 4;
+#endif
+    // the block's accumulators: OJ * 8 columns of this thread's TMEM lane (three warps share a lane quadrant)
+    constexpr int NV = OJ * 8, TCOLS = NV == 32 ? 128 : 256;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + L_.prod + 30);
+    if (tid < 32) { tmem_alloc(tslot, TCOLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+    const uint32_t taddr = tbase + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * NV);
+    {
+        float z[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) z[i] = 0.f;
+        stash_store<NV>(taddr, z);
+    }
+    // tid < 300: dlv_in partial sums of this thread's 8 g_x columns; tid >= 300: two of the 120 row sums
+    // (rows 0..39: b0 = sum g_a1, 40..79: column 40 of dW0 = sum g_a1 x'[40], 80..119: b1 = sum g_a2)
+    float aux[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float ab2 = 0.f, a_nll = 0.f, a_skl = 0.f;
+    const float Tf = (float)T, Tm1 = (float)(T - 1);
+    const uint64_t key = seed_key(prm.seed, sidx);
+    // this CTA's input-tile scratch: [parity][x' | n][F][2T]
+    constexpr int XPAR = 2 * F * RT + XSM;   // floats per parity: x' | n | small inputs
+    float* xprod = prm.xprod + ((int64_t)sidx * prm.n_cta + blockIdx.x) * (2 * XPAR);
+    __syncthreads();   // cst[C3_NSC] is staged
+    ProdArgs* pas = reinterpret_cast<ProdArgs*>(sm + L_.prod);
+    if (tid == 0) {   // first tile
+        const int bq = 2 * blockIdx.x;
+        const int64_t sbq = (int64_t)sidx * prm.B + bq;
+        pas->X = prm.X; pas->eps_in = prm.eps_in; pas->nsc = cst + C3_NSC; pas->key = key; pas->zero_mask = prm.zero_mask;
+        pas->step = (int)prm.step; pas->Y = prm.Y; pas->eps12 = prm.eps12; pas->eps_sum = prm.eps_sum;
+        pas->b0n = bq; pas->sb0 = sbq; pas->xp = xprod; pas->np = xprod + F * RT; pas->sm_out = xprod + 2 * F * RT;
+        pas->row0 = bq < prm.B ? (prm.batch_index ? prm.batch_index[sbq] : bq) : -1;
+        pas->row1 = bq + 1 < prm.B ? (prm.batch_index ? prm.batch_index[sbq + 1] : bq + 1) : -1;
+    }
+    __syncthreads();
+    produce_small(pas, tid);
+    produce_tile<T, F, 6>(pas, tid, NTHR3, 0);   // every thread helps with the first tile
+    int parity = 0;
+    __syncthreads();
+    TL3(0);
+
+    for (int b0i = 2 * blockIdx.x; b0i < prm.B; b0i += 2 * gridDim.x) {
+        const int b = b0i + half;
+        const bool act = b < prm.B;
+        const int64_t sb = (int64_t)sidx * prm.B + (act ? b : b0i);
+        // ---- S0: copy this iteration's x' tile from the scratch (written one iteration ago by the producer warps) ----
+        const float* xp_cur = xprod + parity * XPAR;
+        const float* np_cur = xp_cur + F * RT;
+        float* xp_nxt = xprod + (parity ^ 1) * XPAR;
+        const int b0n = b0i + 2 * gridDim.x;
+        const bool have_next = b0n < prm.B;
+        const int ptid = tid - 256;   // producer lane id (warps 8..11)
+        if (ptid >= 0 && have_next) {
+            if (ptid == 0) {   // the next tile's descriptor (read by the producer calls after the barrier)
+                const int64_t sbn = (int64_t)sidx * prm.B + b0n;
+                pas->b0n = b0n; pas->sb0 = sbn; pas->xp = xp_nxt; pas->np = xp_nxt + F * RT; pas->sm_out = xp_nxt + 2 * F * RT;
+                pas->row0 = prm.batch_index ? prm.batch_index[sbn] : b0n;
+                pas->row1 = b0n + 1 < prm.B ? (prm.batch_index ? prm.batch_index[sbn + 1] : b0n + 1) : -1;
+            }
+            // pull the rows of the tile after next into L2 (the producer's loads are its critical path)
+            const int b2n = b0n + 2 * gridDim.x;
+            constexpr int LINES = (T * F * 4 + 127) / 128;   // 129 lines of 128 B per system
+            for (int i = ptid; i < 2 * LINES; i += 128) {
+                const int hs = i >= LINES ? 1 : 0, ln = i - hs * LINES;
+                if (b2n + hs < prm.B) {
+                    const int64_t sb2 = (int64_t)sidx * prm.B + b2n + hs;
+                    const int64_t r2 = prm.batch_index ? (int64_t)prm.batch_index[sb2] : (int64_t)(b2n + hs);
+                    const char* p2 = reinterpret_cast<const char*>(prm.X + r2 * T * F) + 128 * ln;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
+                }
+            }
+        }
+        {
+            for (int i = tid; i < F * NQ2; i += NTHR3) {
+                const int c = i / NQ2, q = i - c * NQ2;
+                *reinterpret_cast<float4*>(xT + c * RP + 4 * q) = __ldcg(reinterpret_cast<const float4*>(xp_cur) + i);
+            }
+            if (tid < 2 * 21) {   // the small inputs of both slots: eps12 | eps_sum (20 float4) and the labels
+                const int hs = tid / 21, w = tid - 21 * hs;
+                const float* src = xp_cur + 2 * F * RT + hs * (XSM / 2);
+                float* dst = sm + L_.small + hs * SMALL3;
+                if (w < 20) *reinterpret_cast<float4*>(dst + (w < 10 ? V3_E12 + 4 * w : V3_ESN + 4 * (w - 10))) =
+                                __ldcg(reinterpret_cast<const float4*>(src) + w);
+                else *reinterpret_cast<float2*>(dst + V3_Y) = __ldcg(reinterpret_cast<const float2*>(src + 2 * S2));
+            }
+        }
+        __syncthreads();
+        TL3(1);
+        // ---- S1..S3: feature_nn forward over the 2T rows ----
+        if (tid < 5 * NQ2) {
+            u64 a2[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const u64 bv = *reinterpret_cast<const u64*>(b0 + 8 * cg_rg + 2 * i);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) a2[r][i] = bv;
+            }
+            rowgemm4<RP, F, H, 8>(xT, W0T, q_rg, 8 * cg_rg, a2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) unpack2(a2[r][i], v[r][0], v[r][1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    *reinterpret_cast<float4*>(h1T + (8 * cg_rg + 2 * i + e) * RP + 4 * q_rg) =
+                        make_float4(relu_nan(v[0][e]), relu_nan(v[1][e]), relu_nan(v[2][e]), relu_nan(v[3][e]));
+            }
+        } else if (ptid >= 0 && have_next) {
+            { TLP_BEGIN();
+            produce_small(pas, ptid);
+            produce_tile<T, F, 6>(pas, ptid, 128, 0);
+            TLP_END(0); }
+        }
+        __syncthreads();
+        TL3(2);
+        if (tid < 5 * NQ2) {
+            u64 a2[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const u64 bv = *reinterpret_cast<const u64*>(b1 + 8 * cg_rg + 2 * i);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) a2[r][i] = bv;
+            }
+            rowgemm4<RP, H, H, 8>(h1T, W1T, q_rg, 8 * cg_rg, a2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) unpack2(a2[r][i], v[r][0], v[r][1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    *reinterpret_cast<float4*>(h2T + (8 * cg_rg + 2 * i + e) * RP + 4 * q_rg) =
+                        make_float4(relu_nan(v[0][e]), relu_nan(v[1][e]), relu_nan(v[2][e]), relu_nan(v[3][e]));
+            }
+        } else if (ptid >= 0 && have_next) {
+            { TLP_BEGIN();
+            produce_tile<T, F, 6>(pas, ptid, 128, 6);
+            TLP_END(1); }
+        }
+        __syncthreads();
+        TL3(3);
+        if (tid < 5 * NQ2) {
+            u64 a2[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const u64 bv = *reinterpret_cast<const u64*>(b2 + 4 * cg_rg + 2 * i);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) a2[r][i] = bv;
+            }
+            rowgemm4<RP, H, L, 4>(h2T, W2T, q_rg, 4 * cg_rg, a2);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                float v[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) unpack2(a2[r][i], v[r][0], v[r][1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    *reinterpret_cast<float4*>(fT + (4 * cg_rg + 2 * i + e) * RP + 4 * q_rg) =
+                        make_float4(v[0][e], v[1][e], v[2][e], v[3][e]);
+            }
+        } else if (ptid >= 0 && have_next) {
+            { TLP_BEGIN();
+            produce_tile<T, F, 6>(pas, ptid, 128, 12);
+            TLP_END(2); }
+        }
+        __syncthreads();
+        TL3(4);
+        // ---- S4: pooling per system (two-pass mean / unbiased variance per latent column, :418-419) ----
+        if (lt < L * 8) {
+            const int c = lt >> 3, part = lt & 7;
+            const float* fc = fT + c * RP + half * T;
+            // the column's 25 row quads: this lane takes quads part, part + 8, part + 16 (and 24 when part == 0)
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                v[i] = (part + 8 * i < NQ) ? *reinterpret_cast<const float4*>(fc + 4 * (part + 8 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            const float mean = __fdiv_rn(s, Tf);
+            float m2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (part + 8 * i < NQ) {
+                    const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+                    m2 = fmaf(d0, d0, m2); m2 = fmaf(d1, d1, m2); m2 = fmaf(d2, d2, m2); m2 = fmaf(d3, d3, m2);
+                }
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
+            if (part == 0) {
+                const float sd = sqrtf(__fdiv_rn(m2, Tm1));
+                const float var = __fmul_rn(sd, sd);
+                const float sim = sqrtf(__fdiv_rn(var, Tf));                                   // :422
+                const float siv = sqrtf(__fdiv_rn(__fmul_rn(2.0f, __fmul_rn(var, var)), Tm1));   // :423
+                const float e1 = sv[V3_E12 + c], e2 = sv[V3_E12 + L + c];
+                const float mus = __fadd_rn(__fmul_rn(e1, sim), mean);                          // :426
+                const float vs = __fadd_rn(__fmul_rn(e2, siv), var);                            // :427
+                const float sds = sqrtf(__fadd_rn(fabsf(vs), 1e-5f));                           // :430
+                sv[V3_M + c] = mean; sv[V3_VAR + c] = var; sv[V3_SIM + c] = sim; sv[V3_SIV + c] = siv; sv[V3_VS + c] = vs;
+                sv[V3_S + c] = mus; sv[V3_S + L + c] = sds;
+                const float lv0 = cst[C3_LVS + c], lv1 = cst[C3_LVS + L + c];
+                sv[V3_SP + c] = __fadd_rn(mus, __fmul_rn(sv[V3_ESN + c], cst[C3_ELVH + c]));
+                sv[V3_SP + L + c] = __fadd_rn(sds, __fmul_rn(sv[V3_ESN + L + c], cst[C3_ELVH + L + c]));
+                if (act) a_skl += 0.5f * (mus * mus + expf(lv0) - lv0 - 1.0f) + 0.5f * (sds * sds + expf(lv1) - lv1 - 1.0f);
+            }
+        }
+        __syncthreads();
+        TL3(11);
+        // ---- S6: regress_nn forward ----
+        if (lt < H * 4) {
+            const int j = lt >> 2, part = lt & 3;
+            const float* w = V0s + j * S2 + 10 * part;
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) a = fmaf(sv[V3_SP + 10 * part + k], w[k], a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (part == 0) sv[V3_R1 + j] = relu_nan(a + cbs[j]);
+        }
+        __syncthreads();
+        TL3(12);
+        if (lt < H * 4) {
+            const int j = lt >> 2, part = lt & 3;
+            const float* w = V1s + j * H + 10 * part;
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) a = fmaf(sv[V3_R1 + 10 * part + k], w[k], a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (part == 0) sv[V3_R2 + j] = relu_nan(a + cbs[H + j]);
+        }
+        __syncthreads();
+        TL3(13);
+        float gr0 = 0.f, gr1 = 0.f;   // valid in the first warp of each half
+        if (lt < 32) {
+            const int o = lane >> 4, l16 = lane & 15;
+            float a = 0.f;
+            for (int k = l16; k < H; k += 16) a = fmaf(sv[V3_R2 + k], V2s[o * H + k], a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            const float r0 = __shfl_sync(0xffffffffu, a, 0) + cbs[2 * H];
+            const float r1 = __shfl_sync(0xffffffffu, a, 16) + cbs[2 * H + 1];
+            {
+                // lanes 0 and 1 each take one label's truncated-normal term (the longest single-lane chain of the head)
+                const float t0 = tanhf(r0), t1 = tanhf(r1);
+                const float mu = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, __fadd_rn(t0, 1.0f)), __fsub_rn(prm.hc.hi_mu, prm.hc.lo_mu)), prm.hc.lo_mu);
+                const float sd = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, __fadd_rn(t1, 1.0f)), __fsub_rn(prm.hc.hi_sd, prm.hc.lo_sd)), prm.hc.lo_sd);
+                float l = 0.f, dm = 0.f, ds = 0.f;
+                if (lane < 2) nll_terms(mu, sd, sv[V3_Y + lane], l, dm, ds);
+                const float l1 = __shfl_sync(0xffffffffu, l, 1), dm1 = __shfl_sync(0xffffffffu, dm, 1), ds1 = __shfl_sync(0xffffffffu, ds, 1);
+                if (lane == 0) {
+                    if (act) a_nll += -(l + l1);
+                    const float gmu = -(dm + dm1), gsd = -(ds + ds1);
+                    // an inactive slot (odd batch tail) contributes nothing: zero upstream gradient
+                    gr0 = act ? gmu * 0.5f * (prm.hc.hi_mu - prm.hc.lo_mu) * (1.0f - t0 * t0) : 0.f;
+                    gr1 = act ? gsd * 0.5f * (prm.hc.hi_sd - prm.hc.lo_sd) * (1.0f - t1 * t1) : 0.f;
+                }
+            }
+            // ---- S7: regress_nn backward (the same warp carries on: g_a2 = (V2^T g_r) . [r2 > 0]) ----
+            gr0 = __shfl_sync(0xffffffffu, gr0, 0);
+            gr1 = __shfl_sync(0xffffffffu, gr1, 0);
+            for (int k = lane; k < H; k += 32) {
+                const float g = gr0 * V2s[k] + gr1 * V2s[H + k];
+                sv[V3_G2 + k] = sv[V3_R2 + k] > 0.f ? g : 0.f;
+            }
+        }
+        __syncthreads();
+        TL3(14);
+        if (lt < H * 4) {
+            const int k = lt >> 2, part = lt & 3;
+            float a = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 10; ++jj) {
+                const int j = 10 * part + jj;
+                a = fmaf(sv[V3_G2 + j], V1s[j * H + k], a);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (part == 0) sv[V3_G1 + k] = sv[V3_R1 + k] > 0.f ? a : 0.f;
+        }
+        __syncthreads();
+        TL3(15);
+        float* rec = prm.head_rec + sb * REC;
+        if (lt < S2 * 4) {
+            const int k = lt >> 2, part = lt & 3;
+            float a = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 10; ++jj) {
+                const int j = 10 * part + jj;
+                a = fmaf(sv[V3_G1 + j], V0s[j * S2 + k], a);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (part == 0) {
+                if (act) rec[R_DLVS + k] = a * (0.5f * (sv[V3_ESN + k] * cst[C3_ELVH + k]));  // ds'/dlv = eps e^{lv/2} / 2
+                sv[V3_GS + k] = a + (act ? prm.beta_out * sv[V3_S + k] : 0.f);
+            }
+        } else if (act) {
+            // the other warp of the half writes the record (s', r1, r2, g_a1, g_a2 are complete)
+            const int i0 = lt - S2 * 4;  // 0..31
+            for (int i = i0; i < R_DLVS; i += HALF3 - S2 * 4) rec[i] = sv[V3_REC0 + i];
+        }
+        if (lt == 0 && act) { rec[R_GR] = gr0; rec[R_GR + 1] = gr1; }
+        __syncthreads();
+        TL3(16);
+        if (lt < L) {
+            const int c = lt;
+            const float gmus = sv[V3_GS + c], gsds = sv[V3_GS + L + c];
+            const float vs = sv[V3_VS + c], sds = sv[V3_S + L + c], var = sv[V3_VAR + c];
+            const float sgn = vs > 0.f ? 1.0f : (vs < 0.f ? -1.0f : 0.f);
+            const float gvs = gsds * sgn / (2.0f * sds);
+            const float e1 = sv[V3_E12 + c], e2 = sv[V3_E12 + L + c];
+            const float gv = gmus * e1 / (2.0f * Tf * sv[V3_SIM + c]) +
+                             gvs * (1.0f + e2 * (2.0f * var) / (Tm1 * sv[V3_SIV + c]));
+            sv[V3_GM + c] = act ? gmus / Tf : 0.f;        // coefficient of 1
+            sv[V3_GV + c] = act ? 2.0f * gv / Tm1 : 0.f;  // coefficient of (f - m)
+        }
+        __syncthreads();
+        TL3(17);
+        // ---- S8: g_f in place over f (each half its own system); b2 gradient = column sums of g_f ----
+        for (int i = lt; i < L * NQ; i += HALF3) {
+            const int c = i / NQ, q = i - c * NQ;
+            float4* p = reinterpret_cast<float4*>(fT + c * RP + half * T + 4 * q);
+            const float m = sv[V3_M + c], A = sv[V3_GM + c], Bc = sv[V3_GV + c];
+            float4 f = *p;
+            f.x = fmaf(Bc, f.x - m, A); f.y = fmaf(Bc, f.y - m, A); f.z = fmaf(Bc, f.z - m, A); f.w = fmaf(Bc, f.w - m, A);
+            *p = f;
+        }
+        __syncthreads();
+        TL3(5);
+        if (tid >= 256 && tid < 256 + L) {  // b2 gradient: fixed-order column sums of g_f (a warp without a GEMM tile)
+            const float* g = fT + (tid - 256) * RP;
+            float s = 0.f;
+            for (int r = 0; r < RT; r += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(g + r);
+                s += (v.x + v.y) + (v.z + v.w);
+            }
+            ab2 += s;
+        }
+        // ---- S10: g_a2 = (g_f W2) . [h2 > 0] ----
+        if (tid < 5 * NQ2) {
+            u64 a2[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a2[r][i] = 0ull;
+            rowgemm4<RP, L, H, 8>(fT, W2n, q_rg, 8 * cg_rg, a2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) unpack2(a2[r][i], v[r][0], v[r][1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * cg_rg + 2 * i + e;
+                    const float4 h = *reinterpret_cast<const float4*>(h2T + col * RP + 4 * q_rg);
+                    *reinterpret_cast<float4*>(g2T + col * RP + 4 * q_rg) =
+                        make_float4(h.x > 0.f ? v[0][e] : 0.f, h.y > 0.f ? v[1][e] : 0.f, h.z > 0.f ? v[2][e] : 0.f,
+                                    h.w > 0.f ? v[3][e] : 0.f);
+                }
+            }
+        }
+        __syncthreads();
+        TL3(6);
+        // ---- S12: g_a1 = (g_a2 W1) . [h1 > 0] ----
+        if (tid < 5 * NQ2) {
+            u64 a2[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a2[r][i] = 0ull;
+            rowgemm4<RP, H, H, 8>(g2T, W1n, q_rg, 8 * cg_rg, a2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) unpack2(a2[r][i], v[r][0], v[r][1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * cg_rg + 2 * i + e;
+                    const float4 h = *reinterpret_cast<const float4*>(h1T + col * RP + 4 * q_rg);
+                    *reinterpret_cast<float4*>(g1T + col * RP + 4 * q_rg) =
+                        make_float4(h.x > 0.f ? v[0][e] : 0.f, h.y > 0.f ? v[1][e] : 0.f, h.z > 0.f ? v[2][e] : 0.f,
+                                    h.w > 0.f ? v[3][e] : 0.f);
+                }
+            }
+        }
+        __syncthreads();
+        TL3(7);
+        // ---- S13: all weight-gradient outer products in one phase ----
+        {
+            float aW[OJ][8];
+            stash_load<NV>(taddr, &aW[0][0]);
+#if V3_OUTER == 88
+            outer8x8(opG, op_gstr, opH, 5 * RP, op_q0, op_q1, aW);
+#else
+            outer4x8(opG, op_gstr, opH, 5 * RP, op_q0, op_q1, aW);
+#endif
+            stash_store<NV>(taddr, &aW[0][0]);
+        }
+        TL3(8);
+        // ---- S14: g_x = g_a1 W0, dlv_in += sum g_x . (x' - mask(x)) / 2; the two spare warps do the row sums ----
+        if (tid < 6 * NQ2) {
+            u64 a2[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a2[r][i] = 0ull;
+            rowgemm4<RP, H, W0NP, 8>(g1T, W0n, q_rg, 8 * cg_rg, a2);
+            // n = x' - mask(x) of these rows comes back from the scratch (inactive slots hold zeros)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) unpack2(a2[r][i], v[r][0], v[r][1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * cg_rg + 2 * i + e;
+                    if (col < F) {
+                        const float4 nn = __ldcg(reinterpret_cast<const float4*>(np_cur + col * RT) + q_rg);
+                        aux[2 * i + e] += fmaf(v[0][e], nn.x, fmaf(v[1][e], nn.y, fmaf(v[2][e], nn.z, v[3][e] * nn.w)));
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = tid - 6 * NQ2 + e * (NTHR3 - 6 * NQ2);  // 84 threads, rows r and r + 84 of 120
+                if (r < 3 * H) {
+                    const float* g = r < 2 * H ? g1T + (r < H ? r : r - H) * RP : g2T + (r - 2 * H) * RP;
+                    float s0 = 0.f, s1 = 0.f;
+                    if (r >= H && r < 2 * H) {
+                        const float* xc = xT + (F - 1) * RP;
+                        for (int t = 0; t < RT; t += 4) {
+                            const float4 v = *reinterpret_cast<const float4*>(g + t);
+                            const float4 x = *reinterpret_cast<const float4*>(xc + t);
+                            s0 = fmaf(v.x, x.x, s0); s1 = fmaf(v.y, x.y, s1); s0 = fmaf(v.z, x.z, s0); s1 = fmaf(v.w, x.w, s1);
+                        }
+                    } else {
+                        for (int t = 0; t < RT; t += 4) {
+                            const float4 v = *reinterpret_cast<const float4*>(g + t);
+                            s0 += v.x + v.z; s1 += v.y + v.w;
+                        }
+                    }
+                    aux[e] += s0 + s1;
+                }
+            }
+        }
+        __syncthreads();
+        TL3(9);
+        parity ^= 1;
+    }
+
+    // =====================================================================================================
+    // Epilogue: this CTA's partial gradient in flatten() order.  The activation buffers are dead: scratch.
+    // =====================================================================================================
+    float* part = prm.partial + ((int64_t)sidx * prm.n_cta + blockIdx.x) * (fl.d + DPAD);
+    float* red = sm;  // up to 45,084 floats
+    // (1) feature matrices: add the row groups in a fixed order
+    float aW[OJ][8];
+    stash_load<NV>(taddr, &aW[0][0]);
+    if (op_role < 3) {
+        float* o = red + tid * (OJ * 8);
+#pragma unroll
+        for (int jj = 0; jj < OJ; ++jj)
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) o[jj * 8 + kk] = aW[jj][kk];
+    }
+    __syncthreads();
+    if (op_role < 3) {
+#if V3_OUTER == 88
+        const int nblk = op_role == 2 ? 15 : 25, ngrp = op_role == 2 ? 5 : 6;
+        const int jstr = op_role == 2 ? 3 : 5;
+#else
+        const int nblk = op_role == 2 ? 25 : 50, ngrp = 3;
+        const int jstr = op_role == 2 ? 5 : 10;
+#endif
+        const int jmax = op_role == 2 ? L : H;
+        const int base = op_role == 0 ? 0 : (op_role == 1 ? 150 : 300);
+        if (tid - base < nblk) {  // the row-group-0 owner of the block sums and writes
+            const int off = op_role == 0 ? fl.W0 : (op_role == 1 ? fl.W1 : fl.W2);
+            const int pitch = op_role == 0 ? F : H;
+#pragma unroll
+            for (int jj = 0; jj < OJ; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    float a = aW[jj][kk];
+                    for (int g = 1; g < ngrp; ++g) a += red[(tid + g * nblk) * (OJ * 8) + jj * 8 + kk];
+                    const int j = op_jb + jstr * jj;
+                    if (j < jmax) part[off + j * pitch + op_kb + 5 * kk] = a;
+                }
+        }
+    }
+    __syncthreads();
+    // (2) dlv_in (fixed-order sum over the row quads), b0 / b1 / column 40 of dW0, b2
+    if (tid < 6 * NQ2) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red[(8 * cg_rg + c) * NQ2 + q_rg] = aux[c];
+    } else {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int r = tid - 6 * NQ2 + e * (NTHR3 - 6 * NQ2);
+            if (r < H) part[fl.b0 + r] = aux[e];
+            else if (r < 2 * H) part[fl.W0 + (r - H) * F + (F - 1)] = aux[e];
+            else if (r < 3 * H) part[fl.b1 + r - 2 * H] = aux[e];
+        }
+    }
+    if (tid >= 256 && tid < 256 + L) part[fl.b2 + tid - 256] = ab2;
+    __syncthreads();
+    if (tid < F) {
+        float s = 0.f;
+        for (int q = 0; q < NQ2; ++q) s += red[tid * NQ2 + q];
+        part[fl.lv_in + tid] = 0.5f * s;
+    }
+    __syncthreads();
+    // (3) metrics: nll (lane 0 of the first warp of each half) and the summary KL (pooling threads with part == 0)
+    red[tid] = (lt < L * 8 && (lt & 7) == 0) ? a_skl : 0.f;
+    red[NTHR3 + tid] = (lt == 0) ? a_nll : 0.f;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int h = 0; h < 2; ++h)
+            for (int c = 0; c < L; ++c) s += red[h * HALF3 + 8 * c];
+        part[fl.d + SLOT_NLL] = red[NTHR3] + red[NTHR3 + HALF3];
+        part[fl.d + SLOT_SKL] = s;
+        for (int i = 2; i < DPAD; ++i) part[fl.d + i] = 0.f;
+    }
+    __syncthreads();
+    // (4) head gradients from the records of this CTA's systems, in system order:
+    //     dV0 += g_a1 s'^T, c0 += g_a1; dV1 += g_a2 r1^T, c1 += g_a2; dV2 += g_r r2^T, c2 += g_r; dlv_sum += dlvs
+    {
+        constexpr int CH = 128;  // records staged per chunk (128 kB)
+        // roles: tid < 200: 2 x 4 blocks of dV0 and dV1; 200..239: c0, c1; 240..319: dV2; 320..321: c2; 322..361: dlv_sum
+        const int jbh = tid / 10, kb = tid % 10;
+        float aV0[2][4] = {}, aV1[2][4] = {};
+        float s0 = 0.f, s1 = 0.f;
+        const int n_it = (prm.B - 2 * (int)blockIdx.x + 2 * (int)gridDim.x - 1) / (2 * (int)gridDim.x);  // loop trips
+        const int n_sys = 2 * n_it;  // slots (the last one may be past the batch)
+        for (int c0i = 0; c0i < n_sys; c0i += CH) {
+            const int nc = min(CH, n_sys - c0i);
+            for (int i = tid; i < nc * (REC / 4); i += NTHR3) {
+                const int s = c0i + i / (REC / 4), w = i % (REC / 4);
+                const int bsys = 2 * blockIdx.x + 2 * gridDim.x * (s >> 1) + (s & 1);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bsys < prm.B)
+                    v = __ldcg(reinterpret_cast<const float4*>(prm.head_rec + ((int64_t)sidx * prm.B + bsys) * REC) + w);
+                reinterpret_cast<float4*>(red)[i] = v;
+            }
+            __syncthreads();
+            if (tid < 200) {
+                for (int s = 0; s < nc; ++s) {
+                    const float* r = red + s * REC;
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            aV0[jj][kk] = fmaf(r[R_G1 + 2 * jbh + jj], r[R_SP + kb + 10 * kk], aV0[jj][kk]);
+                            aV1[jj][kk] = fmaf(r[R_G2 + 2 * jbh + jj], r[R_R1 + kb + 10 * kk], aV1[jj][kk]);
+                        }
+                }
+            } else if (tid < 240) {
+                for (int s = 0; s < nc; ++s) { s0 += red[s * REC + R_G1 + tid - 200]; s1 += red[s * REC + R_G2 + tid - 200]; }
+            } else if (tid < 320) {
+                const int o = (tid - 240) / H, k = (tid - 240) % H;
+                for (int s = 0; s < nc; ++s) s0 = fmaf(red[s * REC + R_GR + o], red[s * REC + R_R2 + k], s0);
+            } else if (tid < 322) {
+                for (int s = 0; s < nc; ++s) s0 += red[s * REC + R_GR + tid - 320];
+            } else if (tid < 322 + S2) {
+                for (int s = 0; s < nc; ++s) s0 += red[s * REC + R_DLVS + tid - 322];
+            }
+            __syncthreads();
+        }
+        if (tid < 200) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    part[fl.V0 + (2 * jbh + jj) * S2 + kb + 10 * kk] = aV0[jj][kk];
+                    part[fl.V1 + (2 * jbh + jj) * H + kb + 10 * kk] = aV1[jj][kk];
+                }
+        } else if (tid < 240) {
+            part[fl.c0 + tid - 200] = s0;
+            part[fl.c1 + tid - 200] = s1;
+        } else if (tid < 320) {
+            part[fl.V2 + tid - 240] = s0;
+        } else if (tid < 322) {
+            part[fl.c2 + tid - 320] = s0;
+        } else if (tid < 322 + S2) {
+            part[fl.lv_sum + tid - 322] = s0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tbase, TCOLS);
+    TL3(10);
+#ifdef BNN_TRAIN_TIMELINE
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        for (int i = 0; i < 18; ++i) g_train_tl[i] = tl[i];
+    if (tid == 256 && blockIdx.x == 0 && blockIdx.y == 0)
+        for (int i = 18; i < TL_N; ++i) g_train_tl[i] = tl[i];
+#endif
+}
+
+}  // namespace train
+}  // namespace bnn

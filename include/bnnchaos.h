@@ -239,6 +239,11 @@ int bnn_tc_probe(const float* d_A, const float* d_B, float* d_D, int32_t K, int3
  * d_out[0] = issue-to-completion cycles, d_out[1] = cycles spent issuing.  from_smem: A from shared memory. */
 int bnn_tc_time(int32_t K, int32_t N, int32_t reps, int32_t from_smem, long long* d_out, void* stream);
 
+/* Diagnostic: per-phase cycle totals of CTA (0,0) of the last bnn_train_step (v3 kernel), copied to host_out[n].
+ * All zeros unless the library was built with `make TRAIN_TIMELINE=1` (the stamps are compiled out by default).
+ * Synchronises the device. */
+int bnn_train_timeline(unsigned long long* host_out, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,10 +37,10 @@ def _step(lib, cfg, hp, S, theta, mom, x, y, idx, B, eps, seed, step, dev, want_
     return grad, metrics
 
 
-@pytest.fixture(params=["v2", "v1"], autouse=True)
+@pytest.fixture(params=["v3", "v2", "v1"], autouse=True)
 def train_variant(request, monkeypatch):
-    """Every test of this file runs on both training kernels (v2: two systems per iteration, one outer-product
-    phase; v1: one system per iteration)."""
+    """Every test of this file runs on all three training kernels (v3: large register tiles, deferred head
+    gradients -- the default; v2: two systems per iteration, one outer-product phase; v1: one system per iteration)."""
     monkeypatch.setenv("BNN_TRAIN_VARIANT", request.param)
     return request.param
 

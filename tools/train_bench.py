@@ -1,5 +1,5 @@
 """Time the fused training step (K4): BASELINE config 4 shape -- B=2000 systems x 100 x 41, n_seeds models per GPU."""
-import json, os, sys
+import ctypes, json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -40,3 +40,11 @@ flop = 3 * 814_560 * B * n_seeds
 print(json.dumps({"n_seeds": n_seeds, "B": B, "ms_per_step": round(ms, 4), "seed_steps_per_s": n_seeds / (ms * 1e-3),
                   "tflops": flop / (ms * 1e-3) / 1e12, "frac_fp32_peak": flop / (ms * 1e-3) / 1e12 / 74.45,
                   "loss": met[:, 0].tolist()[:2], "nonfinite": met[:, 6].tolist()[:2]}))
+tl = (ctypes.c_ulonglong * 24)()
+_lib.check(lib.bnn_train_timeline(tl, 24))
+if any(tl):
+    names = ["stage", "S0 load", "L1 fwd", "L2 fwd", "L3 fwd", "head tail (g_f)", "B1 g_a2", "B2 g_a1", "outer", "g_x+sums", "epilogue",
+             "pool", "head V0", "head V1", "head V2+nll", "bwd V1", "bwd V0+rec", "gm/gv", "prod L1", "prod L2", "prod L3", "prod B2", "p22", "p23"]
+    tot = float(sum(tl[:18]))
+    print(json.dumps({"timeline_cycles_cta0_last_step": {n: int(v) for n, v in zip(names, tl)},
+                      "share": {n: round(v / tot, 3) for n, v in zip(names, tl)}}))
