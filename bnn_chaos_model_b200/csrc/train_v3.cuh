@@ -28,7 +28,7 @@
 namespace bnn {
 namespace train {
 
-constexpr int NTHR3 = 384, HALF3 = 192;
+constexpr int NMAIN = 384, NPROD = 128, NTHR3 = NMAIN + NPROD, HALF3 = 192;   // 12 pipeline warps + 4 producer warps
 constexpr int REC = 256;     // floats per system record (head vectors for the deferred outer products)
 constexpr int SMALL3 = 512;  // per-system-slot scratch (floats)
 constexpr int XSM = 192;    // per-parity small inputs in the tile scratch: 2 slots x (eps12[40] eps_sum[40] y[2] pad)
@@ -69,7 +69,7 @@ struct Smem3 {
         cb = o; o += 2 * H + 4;   // c0[40] c1[40] c2[2]
         consts = o; o += C3_TOTAL;
         small = o; o += 2 * SMALL3;
-        prod = o; o += 32;        // ProdArgs of the tile being produced
+        prod = o; o += 2 * 32;    // ProdArgs of the tiles being produced (by parity), TMEM base in the last word
         total = o;
     }
 };
@@ -93,7 +93,7 @@ __device__ __forceinline__ long long tl_clock() {
     } while (0)
 // producer-side stamps (thread 256): cycles inside produce call i -> slot 18 + i
 #define TLP_BEGIN() const long long tp0_ = tl_clock()
-#define TLP_END(i) do { const long long tp1_ = tl_clock(); if (tid == 256) tl[18 + (i)] += (unsigned long long)(tp1_ - tp0_); } while (0)
+#define TLP_END(i) do { const long long tp1_ = tl_clock(); if (tid == NMAIN) tl[18 + (i)] += (unsigned long long)(tp1_ - tp0_); } while (0)
 #else
 #define TL3(i) do { } while (0)
 #define TLP_BEGIN() do { } while (0)
@@ -125,7 +125,7 @@ __device__ __forceinline__ void rowgemm4(const float* __restrict__ AT, const flo
 }
 
 #ifndef V3_OUTER
-#define V3_OUTER 88
+#define V3_OUTER 48
 #endif
 // 4 x 8 variant: even / odd rows accumulate in the two halves of an fp32x2 register (no packing moves)
 __device__ __forceinline__ void outer4x8(const float* __restrict__ Gp, int gstr, const float* __restrict__ Hp, int hstr,
@@ -228,24 +228,30 @@ __device__ __noinline__ void produce_tile(const ProdArgs* __restrict__ ap, int f
     int off[NR], c4s[NR];
     uint4 ctr[NR];
     bool live[NR];
+    // straight-line loads: out-of-range items / columns are clamped to a valid address and masked at the store
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-        const int id = first + stride * (r0 + k);
-        const bool ok = id < 2 * PER;
+        const int id0 = first + stride * (r0 + k);
+        const bool ok = id0 < 2 * PER;
+        const int id = ok ? id0 : 2 * PER - 1;
         const int hs = id >= PER ? 1 : 0, rem = id - hs * PER;
         const int c4 = rem / T, t = rem - c4 * T;
         const int row = hs ? a.row1 : a.row0;
         c4s[k] = c4;
         off[k] = ok ? hs * T + t : -1;
-        live[k] = ok && row >= 0;
+        live[k] = row >= 0;
         ctr[k] = make_uint4((uint32_t)(t * F4 + c4), (uint32_t)(a.b0n + hs), (uint32_t)a.step, STREAM_EPS_IN);
-        const float* xs = a.X + ((int64_t)(live[k] ? row : 0) * T + t) * F + 4 * c4;
-        const float* es = a.eps_in ? a.eps_in + ((a.sb0 + hs) * T + t) * (int64_t)F + 4 * c4 : nullptr;
+        const float* xs = a.X + ((int64_t)(row >= 0 ? row : 0) * T + t) * F;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const bool in = live[k] && 4 * c4 + u < F;
-            xv[k][u] = in ? __ldg(xs + u) : 0.f;
-            ev[k][u] = (in && es) ? __ldg(es + u) : 0.f;
+        for (int u = 0; u < 4; ++u) xv[k][u] = __ldg(xs + min(4 * c4 + u, F - 1));
+    }
+    if (a.eps_in) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const int t = (int)ctr[k].x / F4, hs = (int)ctr[k].y - a.b0n;
+            const float* es = a.eps_in + ((a.sb0 + (live[k] ? hs : 0)) * T + t) * (int64_t)F;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ev[k][u] = __ldg(es + min(4 * c4s[k] + u, F - 1));
         }
     }
     if (!a.eps_in) {
@@ -314,6 +320,12 @@ __device__ __noinline__ void produce_small(const ProdArgs* __restrict__ ap, int 
         *reinterpret_cast<float2*>(a.sm_out + hs * (XSM / 2) + 2 * S2) = y;
     }
 }
+
+// Named barriers.  0: whole CTA (prologue only); 1, 2: tile of parity 0 / 1 is ready (producers arrive, pipeline waits);
+// 3, 4: scratch of parity 0 / 1 is free again (pipeline arrives, producers wait); 5: the 12 pipeline warps; 6: the producers.
+__device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+#define MAIN_SYNC() nb_sync(5, NMAIN)
 
 template <int T, int F>
 __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params prm) {
@@ -415,12 +427,78 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
 #endif
     // the block's accumulators: OJ * 8 columns of this thread's TMEM lane (three warps share a lane quadrant)
     constexpr int NV = OJ * 8, TCOLS = NV == 32 ? 128 : 256;
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + L_.prod + 30);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + L_.prod + 63);
     if (tid < 32) { tmem_alloc(tslot, TCOLS); tmem_relinquish(); }
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();   // whole CTA: weights, noise scales and the TMEM base are staged
     tc_fence_after();
     const uint32_t tbase = *tslot;
+    const uint64_t key = seed_key(prm.seed, sidx);
+    // this CTA's input-tile scratch: [parity][x' | n | small inputs]
+    constexpr int XPAR = 2 * F * RT + XSM;
+    float* xprod = prm.xprod + ((int64_t)sidx * prm.n_cta + blockIdx.x) * (2 * XPAR);
+
+    // =====================================================================================================
+    // Producer warps (12..15): run up to two tiles ahead of the pipeline, never touch its barriers.
+    // =====================================================================================================
+    if (tid >= NMAIN) {
+        const int ptid = tid - NMAIN;
+#ifdef BNN_TRAIN_TIMELINE
+        long long tp_wait = 0, tp_work = 0;
+#endif
+        int it = 0;
+        for (int b0p = 2 * blockIdx.x; b0p < prm.B; b0p += 2 * gridDim.x, ++it) {
+            const int par = it & 1;
+#ifdef BNN_TRAIN_TIMELINE
+            const long long t0 = tl_clock();
+#endif
+            if (it >= 2) nb_sync(3 + par, NTHR3);   // the pipeline is done with the tile that used this parity
+#ifdef BNN_TRAIN_TIMELINE
+            const long long t1 = tl_clock();
+#endif
+            ProdArgs* pas = reinterpret_cast<ProdArgs*>(sm + L_.prod) + par;
+            float* xo = xprod + par * XPAR;
+            if (ptid == 0) {
+                const int64_t sbq = (int64_t)sidx * prm.B + b0p;
+                pas->X = prm.X; pas->eps_in = prm.eps_in; pas->nsc = cst + C3_NSC; pas->key = key; pas->zero_mask = prm.zero_mask;
+                pas->step = (int)prm.step; pas->Y = prm.Y; pas->eps12 = prm.eps12; pas->eps_sum = prm.eps_sum;
+                pas->b0n = b0p; pas->sb0 = sbq; pas->xp = xo; pas->np = xo + F * RT; pas->sm_out = xo + 2 * F * RT;
+                pas->row0 = prm.batch_index ? prm.batch_index[sbq] : b0p;
+                pas->row1 = b0p + 1 < prm.B ? (prm.batch_index ? prm.batch_index[sbq + 1] : b0p + 1) : -1;
+            }
+            {   // pull the rows of the next tile into L2
+                const int b2n = b0p + 2 * gridDim.x;
+                constexpr int LINES = (T * F * 4 + 127) / 128;   // 129 lines of 128 B per system
+                for (int i = ptid; i < 2 * LINES; i += NPROD) {
+                    const int hs = i >= LINES ? 1 : 0, ln = i - hs * LINES;
+                    if (b2n + hs < prm.B) {
+                        const int64_t sb2 = (int64_t)sidx * prm.B + b2n + hs;
+                        const int64_t r2 = prm.batch_index ? (int64_t)prm.batch_index[sb2] : (int64_t)(b2n + hs);
+                        const char* p2 = reinterpret_cast<const char*>(prm.X + r2 * T * F) + 128 * ln;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
+                    }
+                }
+            }
+            nb_sync(6, NPROD);                       // descriptor visible to the four warps
+            produce_small(pas, ptid);
+            produce_tile<T, F, 6>(pas, ptid, NPROD, 0);
+            produce_tile<T, F, 6>(pas, ptid, NPROD, 6);
+            produce_tile<T, F, 6>(pas, ptid, NPROD, 12);
+            __threadfence_block();
+            nb_arrive(1 + par, NTHR3);               // tile ready
+#ifdef BNN_TRAIN_TIMELINE
+            tp_wait += t1 - t0; tp_work += tl_clock() - t1;
+#endif
+        }
+#ifdef BNN_TRAIN_TIMELINE
+        if (tid == NMAIN && blockIdx.x == 0 && blockIdx.y == 0) { g_train_tl[18] = tp_work; g_train_tl[19] = tp_wait; }
+#endif
+        return;
+    }
+
+    // =====================================================================================================
+    // Pipeline warps (0..11)
+    // =====================================================================================================
     const uint32_t taddr = tbase + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * NV);
     {
         float z[NV];
@@ -433,26 +511,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     float aux[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float ab2 = 0.f, a_nll = 0.f, a_skl = 0.f;
     const float Tf = (float)T, Tm1 = (float)(T - 1);
-    const uint64_t key = seed_key(prm.seed, sidx);
-    // this CTA's input-tile scratch: [parity][x' | n][F][2T]
-    constexpr int XPAR = 2 * F * RT + XSM;   // floats per parity: x' | n | small inputs
-    float* xprod = prm.xprod + ((int64_t)sidx * prm.n_cta + blockIdx.x) * (2 * XPAR);
-    __syncthreads();   // cst[C3_NSC] is staged
-    ProdArgs* pas = reinterpret_cast<ProdArgs*>(sm + L_.prod);
-    if (tid == 0) {   // first tile
-        const int bq = 2 * blockIdx.x;
-        const int64_t sbq = (int64_t)sidx * prm.B + bq;
-        pas->X = prm.X; pas->eps_in = prm.eps_in; pas->nsc = cst + C3_NSC; pas->key = key; pas->zero_mask = prm.zero_mask;
-        pas->step = (int)prm.step; pas->Y = prm.Y; pas->eps12 = prm.eps12; pas->eps_sum = prm.eps_sum;
-        pas->b0n = bq; pas->sb0 = sbq; pas->xp = xprod; pas->np = xprod + F * RT; pas->sm_out = xprod + 2 * F * RT;
-        pas->row0 = bq < prm.B ? (prm.batch_index ? prm.batch_index[sbq] : bq) : -1;
-        pas->row1 = bq + 1 < prm.B ? (prm.batch_index ? prm.batch_index[sbq + 1] : bq + 1) : -1;
-    }
-    __syncthreads();
-    produce_small(pas, tid);
-    produce_tile<T, F, 6>(pas, tid, NTHR3, 0);   // every thread helps with the first tile
     int parity = 0;
-    __syncthreads();
     TL3(0);
 
     for (int b0i = 2 * blockIdx.x; b0i < prm.B; b0i += 2 * gridDim.x) {
@@ -462,34 +521,23 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         // ---- S0: copy this iteration's x' tile from the scratch (written one iteration ago by the producer warps) ----
         const float* xp_cur = xprod + parity * XPAR;
         const float* np_cur = xp_cur + F * RT;
-        float* xp_nxt = xprod + (parity ^ 1) * XPAR;
-        const int b0n = b0i + 2 * gridDim.x;
-        const bool have_next = b0n < prm.B;
-        const int ptid = tid - 256;   // producer lane id (warps 8..11)
-        if (ptid >= 0 && have_next) {
-            if (ptid == 0) {   // the next tile's descriptor (read by the producer calls after the barrier)
-                const int64_t sbn = (int64_t)sidx * prm.B + b0n;
-                pas->b0n = b0n; pas->sb0 = sbn; pas->xp = xp_nxt; pas->np = xp_nxt + F * RT; pas->sm_out = xp_nxt + 2 * F * RT;
-                pas->row0 = prm.batch_index ? prm.batch_index[sbn] : b0n;
-                pas->row1 = b0n + 1 < prm.B ? (prm.batch_index ? prm.batch_index[sbn + 1] : b0n + 1) : -1;
-            }
-            // pull the rows of the tile after next into L2 (the producer's loads are its critical path)
-            const int b2n = b0n + 2 * gridDim.x;
-            constexpr int LINES = (T * F * 4 + 127) / 128;   // 129 lines of 128 B per system
-            for (int i = ptid; i < 2 * LINES; i += 128) {
-                const int hs = i >= LINES ? 1 : 0, ln = i - hs * LINES;
-                if (b2n + hs < prm.B) {
-                    const int64_t sb2 = (int64_t)sidx * prm.B + b2n + hs;
-                    const int64_t r2 = prm.batch_index ? (int64_t)prm.batch_index[sb2] : (int64_t)(b2n + hs);
-                    const char* p2 = reinterpret_cast<const char*>(prm.X + r2 * T * F) + 128 * ln;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
-                }
-            }
-        }
+        nb_sync(1 + parity, NTHR3);   // the producers have finished this tile
         {
-            for (int i = tid; i < F * NQ2; i += NTHR3) {
-                const int c = i / NQ2, q = i - c * NQ2;
-                *reinterpret_cast<float4*>(xT + c * RP + 4 * q) = __ldcg(reinterpret_cast<const float4*>(xp_cur) + i);
+            // all loads first (L2 latency once, not once per float4)
+            constexpr int NCP = (F * NQ2 + NMAIN - 1) / NMAIN;
+            float4 cp[NCP];
+#pragma unroll
+            for (int k = 0; k < NCP; ++k) {
+                const int i = tid + k * NMAIN;
+                cp[k] = __ldcg(reinterpret_cast<const float4*>(xp_cur) + min(i, F * NQ2 - 1));
+            }
+#pragma unroll
+            for (int k = 0; k < NCP; ++k) {
+                const int i = tid + k * NMAIN;
+                if (i < F * NQ2) {
+                    const int c = i / NQ2, q = i - c * NQ2;
+                    *reinterpret_cast<float4*>(xT + c * RP + 4 * q) = cp[k];
+                }
             }
             if (tid < 2 * 21) {   // the small inputs of both slots: eps12 | eps_sum (20 float4) and the labels
                 const int hs = tid / 21, w = tid - 21 * hs;
@@ -500,7 +548,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 else *reinterpret_cast<float2*>(dst + V3_Y) = __ldcg(reinterpret_cast<const float2*>(src + 2 * S2));
             }
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(1);
         // ---- S1..S3: feature_nn forward over the 2T rows ----
         if (tid < 5 * NQ2) {
@@ -522,13 +570,8 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                     *reinterpret_cast<float4*>(h1T + (8 * cg_rg + 2 * i + e) * RP + 4 * q_rg) =
                         make_float4(relu_nan(v[0][e]), relu_nan(v[1][e]), relu_nan(v[2][e]), relu_nan(v[3][e]));
             }
-        } else if (ptid >= 0 && have_next) {
-            { TLP_BEGIN();
-            produce_small(pas, ptid);
-            produce_tile<T, F, 6>(pas, ptid, 128, 0);
-            TLP_END(0); }
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(2);
         if (tid < 5 * NQ2) {
             u64 a2[4][4];
@@ -549,12 +592,8 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                     *reinterpret_cast<float4*>(h2T + (8 * cg_rg + 2 * i + e) * RP + 4 * q_rg) =
                         make_float4(relu_nan(v[0][e]), relu_nan(v[1][e]), relu_nan(v[2][e]), relu_nan(v[3][e]));
             }
-        } else if (ptid >= 0 && have_next) {
-            { TLP_BEGIN();
-            produce_tile<T, F, 6>(pas, ptid, 128, 6);
-            TLP_END(1); }
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(3);
         if (tid < 5 * NQ2) {
             u64 a2[4][2];
@@ -575,12 +614,8 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                     *reinterpret_cast<float4*>(fT + (4 * cg_rg + 2 * i + e) * RP + 4 * q_rg) =
                         make_float4(v[0][e], v[1][e], v[2][e], v[3][e]);
             }
-        } else if (ptid >= 0 && have_next) {
-            { TLP_BEGIN();
-            produce_tile<T, F, 6>(pas, ptid, 128, 12);
-            TLP_END(2); }
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(4);
         // ---- S4: pooling per system (two-pass mean / unbiased variance per latent column, :418-419) ----
         if (lt < L * 8) {
@@ -625,7 +660,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 if (act) a_skl += 0.5f * (mus * mus + expf(lv0) - lv0 - 1.0f) + 0.5f * (sds * sds + expf(lv1) - lv1 - 1.0f);
             }
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(11);
         // ---- S6: regress_nn forward ----
         if (lt < H * 4) {
@@ -638,7 +673,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             if (part == 0) sv[V3_R1 + j] = relu_nan(a + cbs[j]);
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(12);
         if (lt < H * 4) {
             const int j = lt >> 2, part = lt & 3;
@@ -650,7 +685,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             if (part == 0) sv[V3_R2 + j] = relu_nan(a + cbs[H + j]);
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(13);
         float gr0 = 0.f, gr1 = 0.f;   // valid in the first warp of each half
         if (lt < 32) {
@@ -687,7 +722,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 sv[V3_G2 + k] = sv[V3_R2 + k] > 0.f ? g : 0.f;
             }
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(14);
         if (lt < H * 4) {
             const int k = lt >> 2, part = lt & 3;
@@ -701,7 +736,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             if (part == 0) sv[V3_G1 + k] = sv[V3_R1 + k] > 0.f ? a : 0.f;
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(15);
         float* rec = prm.head_rec + sb * REC;
         if (lt < S2 * 4) {
@@ -724,7 +759,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             for (int i = i0; i < R_DLVS; i += HALF3 - S2 * 4) rec[i] = sv[V3_REC0 + i];
         }
         if (lt == 0 && act) { rec[R_GR] = gr0; rec[R_GR + 1] = gr1; }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(16);
         if (lt < L) {
             const int c = lt;
@@ -738,7 +773,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             sv[V3_GM + c] = act ? gmus / Tf : 0.f;        // coefficient of 1
             sv[V3_GV + c] = act ? 2.0f * gv / Tm1 : 0.f;  // coefficient of (f - m)
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(17);
         // ---- S8: g_f in place over f (each half its own system); b2 gradient = column sums of g_f ----
         for (int i = lt; i < L * NQ; i += HALF3) {
@@ -749,7 +784,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             f.x = fmaf(Bc, f.x - m, A); f.y = fmaf(Bc, f.y - m, A); f.z = fmaf(Bc, f.z - m, A); f.w = fmaf(Bc, f.w - m, A);
             *p = f;
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(5);
         if (tid >= 256 && tid < 256 + L) {  // b2 gradient: fixed-order column sums of g_f (a warp without a GEMM tile)
             const float* g = fT + (tid - 256) * RP;
@@ -783,7 +818,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 }
             }
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(6);
         // ---- S12: g_a1 = (g_a2 W1) . [h1 > 0] ----
         if (tid < 5 * NQ2) {
@@ -808,7 +843,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 }
             }
         }
-        __syncthreads();
+        MAIN_SYNC();
         TL3(7);
         // ---- S13: all weight-gradient outer products in one phase ----
         {
@@ -848,7 +883,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         } else {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int r = tid - 6 * NQ2 + e * (NTHR3 - 6 * NQ2);  // 84 threads, rows r and r + 84 of 120
+                const int r = tid - 6 * NQ2 + e * (NMAIN - 6 * NQ2);  // 84 threads, rows r and r + 84 of 120
                 if (r < 3 * H) {
                     const float* g = r < 2 * H ? g1T + (r < H ? r : r - H) * RP : g2T + (r - 2 * H) * RP;
                     float s0 = 0.f, s1 = 0.f;
@@ -869,7 +904,8 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 }
             }
         }
-        __syncthreads();
+        if (b0i + 4 * (int)gridDim.x < prm.B) nb_arrive(3 + parity, NTHR3);   // this parity's scratch may be overwritten
+        MAIN_SYNC();
         TL3(9);
         parity ^= 1;
     }
@@ -889,7 +925,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) o[jj * 8 + kk] = aW[jj][kk];
     }
-    __syncthreads();
+    MAIN_SYNC();
     if (op_role < 3) {
 #if V3_OUTER == 88
         const int nblk = op_role == 2 ? 15 : 25, ngrp = op_role == 2 ? 5 : 6;
@@ -914,7 +950,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 }
         }
     }
-    __syncthreads();
+    MAIN_SYNC();
     // (2) dlv_in (fixed-order sum over the row quads), b0 / b1 / column 40 of dW0, b2
     if (tid < 6 * NQ2) {
 #pragma unroll
@@ -922,33 +958,33 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     } else {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int r = tid - 6 * NQ2 + e * (NTHR3 - 6 * NQ2);
+            const int r = tid - 6 * NQ2 + e * (NMAIN - 6 * NQ2);
             if (r < H) part[fl.b0 + r] = aux[e];
             else if (r < 2 * H) part[fl.W0 + (r - H) * F + (F - 1)] = aux[e];
             else if (r < 3 * H) part[fl.b1 + r - 2 * H] = aux[e];
         }
     }
     if (tid >= 256 && tid < 256 + L) part[fl.b2 + tid - 256] = ab2;
-    __syncthreads();
+    MAIN_SYNC();
     if (tid < F) {
         float s = 0.f;
         for (int q = 0; q < NQ2; ++q) s += red[tid * NQ2 + q];
         part[fl.lv_in + tid] = 0.5f * s;
     }
-    __syncthreads();
+    MAIN_SYNC();
     // (3) metrics: nll (lane 0 of the first warp of each half) and the summary KL (pooling threads with part == 0)
     red[tid] = (lt < L * 8 && (lt & 7) == 0) ? a_skl : 0.f;
-    red[NTHR3 + tid] = (lt == 0) ? a_nll : 0.f;
-    __syncthreads();
+    red[NMAIN + tid] = (lt == 0) ? a_nll : 0.f;
+    MAIN_SYNC();
     if (tid == 0) {
         float s = 0.f;
         for (int h = 0; h < 2; ++h)
             for (int c = 0; c < L; ++c) s += red[h * HALF3 + 8 * c];
-        part[fl.d + SLOT_NLL] = red[NTHR3] + red[NTHR3 + HALF3];
+        part[fl.d + SLOT_NLL] = red[NMAIN] + red[NMAIN + HALF3];
         part[fl.d + SLOT_SKL] = s;
         for (int i = 2; i < DPAD; ++i) part[fl.d + i] = 0.f;
     }
-    __syncthreads();
+    MAIN_SYNC();
     // (4) head gradients from the records of this CTA's systems, in system order:
     //     dV0 += g_a1 s'^T, c0 += g_a1; dV1 += g_a2 r1^T, c1 += g_a2; dV2 += g_r r2^T, c2 += g_r; dlv_sum += dlvs
     {
@@ -961,7 +997,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         const int n_sys = 2 * n_it;  // slots (the last one may be past the batch)
         for (int c0i = 0; c0i < n_sys; c0i += CH) {
             const int nc = min(CH, n_sys - c0i);
-            for (int i = tid; i < nc * (REC / 4); i += NTHR3) {
+            for (int i = tid; i < nc * (REC / 4); i += NMAIN) {
                 const int s = c0i + i / (REC / 4), w = i % (REC / 4);
                 const int bsys = 2 * blockIdx.x + 2 * gridDim.x * (s >> 1) + (s & 1);
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -969,7 +1005,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                     v = __ldcg(reinterpret_cast<const float4*>(prm.head_rec + ((int64_t)sidx * prm.B + bsys) * REC) + w);
                 reinterpret_cast<float4*>(red)[i] = v;
             }
-            __syncthreads();
+            MAIN_SYNC();
             if (tid < 200) {
                 for (int s = 0; s < nc; ++s) {
                     const float* r = red + s * REC;
@@ -991,7 +1027,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             } else if (tid < 322 + S2) {
                 for (int s = 0; s < nc; ++s) s0 += red[s * REC + R_DLVS + tid - 322];
             }
-            __syncthreads();
+            MAIN_SYNC();
         }
         if (tid < 200) {
 #pragma unroll
@@ -1013,14 +1049,13 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         }
     }
     tc_fence_before();
-    __syncthreads();
+    MAIN_SYNC();
     if (tid < 32) tmem_dealloc(tbase, TCOLS);
     TL3(10);
 #ifdef BNN_TRAIN_TIMELINE
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
         for (int i = 0; i < 18; ++i) g_train_tl[i] = tl[i];
-    if (tid == 256 && blockIdx.x == 0 && blockIdx.y == 0)
-        for (int i = 18; i < TL_N; ++i) g_train_tl[i] = tl[i];
+
 #endif
 }
 

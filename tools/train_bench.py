@@ -44,7 +44,7 @@ tl = (ctypes.c_ulonglong * 24)()
 _lib.check(lib.bnn_train_timeline(tl, 24))
 if any(tl):
     names = ["stage", "S0 load", "L1 fwd", "L2 fwd", "L3 fwd", "head tail (g_f)", "B1 g_a2", "B2 g_a1", "outer", "g_x+sums", "epilogue",
-             "pool", "head V0", "head V1", "head V2+nll", "bwd V1", "bwd V0+rec", "gm/gv", "prod L1", "prod L2", "prod L3", "prod B2", "p22", "p23"]
+             "pool", "head V0", "head V1", "head V2+nll", "bwd V1", "bwd V0+rec", "gm/gv", "producer: work", "producer: wait for free scratch", "p20", "p21", "p22", "p23"]
     tot = float(sum(tl[:18]))
     print(json.dumps({"timeline_cycles_cta0_last_step": {n: int(v) for n, v in zip(names, tl)},
                       "share": {n: round(v / tot, 3) for n, v in zip(names, tl)}}))
