@@ -1314,7 +1314,8 @@ static int pick_n_cta(const bnn_model_config* cfg, int64_t B, int n_seeds) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const bool v2 = use_v2(cfg) || use_v3(cfg);
     // v1: two resident CTAs per SM, one system per iteration; v2: one CTA per SM, two systems per iteration
-    int64_t n = ((v2 ? 1ll : 2ll) * sms + n_seeds - 1) / n_seeds;
+    // one-CTA-per-SM kernels: never more CTAs than SMs (a 149th CTA would run alone in a second wave)
+    int64_t n = v2 ? sms / n_seeds : (2ll * sms + n_seeds - 1) / n_seeds;
     const int64_t cap = v2 ? (B + 1) / 2 : B;
     if (n > cap) n = cap;
     if (n < 1) n = 1;

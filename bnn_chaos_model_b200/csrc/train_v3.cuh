@@ -864,8 +864,13 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) a2[r][i] = 0ull;
+            // n = x' - mask(x) of these rows comes back from the scratch (inactive slots hold zeros); the L2 loads are
+            // issued before the GEMM so that their latency hides under it
+            float4 nn[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                nn[c] = __ldcg(reinterpret_cast<const float4*>(np_cur + min(8 * cg_rg + c, F - 1) * RT) + q_rg);
             rowgemm4<RP, H, W0NP, 8>(g1T, W0n, q_rg, 8 * cg_rg, a2);
-            // n = x' - mask(x) of these rows comes back from the scratch (inactive slots hold zeros)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float v[4][2];
@@ -875,8 +880,8 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 for (int e = 0; e < 2; ++e) {
                     const int col = 8 * cg_rg + 2 * i + e;
                     if (col < F) {
-                        const float4 nn = __ldcg(reinterpret_cast<const float4*>(np_cur + col * RT) + q_rg);
-                        aux[2 * i + e] += fmaf(v[0][e], nn.x, fmaf(v[1][e], nn.y, fmaf(v[2][e], nn.z, v[3][e] * nn.w)));
+                        const float4 n4 = nn[2 * i + e];
+                        aux[2 * i + e] += fmaf(v[0][e], n4.x, fmaf(v[1][e], n4.y, fmaf(v[2][e], n4.z, v[3][e] * n4.w)));
                     }
                 }
             }
