@@ -10,12 +10,14 @@ state yields the same draws as the reference on the same device (SURVEY.md secti
 fact 5).  There is no CPU fallback: tensors on the CPU raise ``BnnChaosError``.
 
 Not mirrored (outside the hot path): the Lightning trainer hooks, the
-dataloaders / ``get_data``, ``CustomOneCycleLR``, ``VarModel.sample``, ``augment`` and the
-megno side channel (``fix_megno=True``).
+dataloaders / ``get_data``, ``VarModel.sample``, ``augment`` and the megno side channel
+(``fix_megno=True``).  ``CustomOneCycleLR`` (:27-159) is mirrored for the pre-training phase
+(find_minima.py): host-side scalars that drive the fused step.
 """
 from __future__ import annotations
 
 import io
+import math
 import pickle
 import random
 from collections import OrderedDict
@@ -48,6 +50,76 @@ class AttributeDict(dict):
 
     def __setattr__(self, key, val):
         self[key] = val
+
+
+def one_cycle_lr_momentum(step_num, max_lr, total_steps, pct_start=0.3, div_factor=25.0, final_div_factor=1e4,
+                          base_momentum=0.85, max_momentum=0.95, anneal_strategy="cos"):
+    """(lr, momentum) of the reference's one-cycle schedule at optimizer step ``step_num`` (:131-158): up from
+    max_lr/div_factor to max_lr over ``pct_start*total_steps - 1`` steps, down to max_lr/div_factor/final_div_factor
+    over the rest, momentum moving the opposite way.  Past ``total_steps`` it raises ValueError like :137-139 --
+    find_minima.py relies on that to end the run (find_minima.py:79-82)."""
+    if step_num > total_steps:
+        raise ValueError("Tried to step {} times. The specified number of total steps is {}".format(step_num + 1, total_steps))
+    size_up = float(pct_start * total_steps) - 1
+    size_down = float(total_steps - size_up) - 1
+    lr0 = max_lr / div_factor
+    lr_min = lr0 / final_div_factor
+    if anneal_strategy == "cos":
+        def anneal(a, b, pct):
+            return b if pct >= 1.0 else b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1)
+    elif anneal_strategy == "linear":
+        def anneal(a, b, pct):
+            return b if pct >= 1.0 else (b - a) * pct + a
+    else:
+        raise ValueError("anneal_strategy must by one of 'cos' or 'linear', instead got {}".format(anneal_strategy))
+    if step_num <= size_up:
+        pct = step_num / size_up
+        return anneal(lr0, max_lr, pct), anneal(max_momentum, base_momentum, pct)
+    pct = (step_num - size_up) / size_down
+    return anneal(max_lr, lr_min, pct), anneal(base_momentum, max_momentum, pct)
+
+
+class CustomOneCycleLR(torch.optim.lr_scheduler.LRScheduler):
+    """Drop-in for the reference's scheduler (:27-159; "custom version of one-cycle learning rate to stop early"):
+    same constructor arguments, same lr / momentum per step, same ValueError once stepped past ``swa_steps_start``."""
+
+    def __init__(self, optimizer, max_lr, swa_steps_start, pct_start=0.3, anneal_strategy="cos", cycle_momentum=True,
+                 base_momentum=0.85, max_momentum=0.95, div_factor=25.0, final_div_factor=1e4, last_epoch=-1):
+        if not isinstance(swa_steps_start, int) or swa_steps_start <= 0:
+            raise ValueError("Expected non-negative integer total_steps, but got {}".format(swa_steps_start))
+        if not isinstance(pct_start, float) or pct_start < 0 or pct_start > 1:
+            raise ValueError("Expected float between 0 and 1 pct_start, but got {}".format(pct_start))
+        if anneal_strategy not in ("cos", "linear"):
+            raise ValueError("anneal_strategy must by one of 'cos' or 'linear', instead got {}".format(anneal_strategy))
+        self.total_steps = swa_steps_start
+        self._cfg = dict(pct_start=pct_start, div_factor=div_factor, final_div_factor=final_div_factor,
+                         base_momentum=base_momentum, max_momentum=max_momentum, anneal_strategy=anneal_strategy)
+        self._max_lrs = list(max_lr) if isinstance(max_lr, (list, tuple)) else [max_lr] * len(optimizer.param_groups)
+        if len(self._max_lrs) != len(optimizer.param_groups):
+            raise ValueError("expected {} values for max_lr, got {}".format(len(optimizer.param_groups), len(self._max_lrs)))
+        self.cycle_momentum = cycle_momentum
+        if cycle_momentum:
+            if "momentum" not in optimizer.defaults and "betas" not in optimizer.defaults:
+                raise ValueError("optimizer must support momentum with `cycle_momentum` option enabled")
+            self.use_beta1 = "betas" in optimizer.defaults
+        if last_epoch == -1:
+            for g, mx in zip(optimizer.param_groups, self._max_lrs):
+                g["initial_lr"] = mx / div_factor
+                g["max_lr"] = mx
+                g["min_lr"] = g["initial_lr"] / final_div_factor
+        super().__init__(optimizer, last_epoch)
+
+    def get_lr(self):
+        lrs = []
+        for g, mx in zip(self.optimizer.param_groups, self._max_lrs):
+            lr, mom = one_cycle_lr_momentum(self.last_epoch, mx, self.total_steps, **self._cfg)
+            lrs.append(lr)
+            if self.cycle_momentum:
+                if self.use_beta1:
+                    g["betas"] = (mom, g["betas"][1])
+                else:
+                    g["momentum"] = mom
+        return lrs
 
 
 def _param_stack(in_n, out_n, hidden, layers):
@@ -334,6 +406,14 @@ class VarModel(nn.Module):
         """:595-614 (KL annealing over the first 30 % of the steps)."""
         fraction = self.global_step / self.hparams["steps"]
         return self._training_result(batch, min(1, fraction / 0.3) * self.beta_in, min(1, fraction / 0.3) * self.beta_out)
+
+    def configure_optimizers(self):
+        """:630-644: SGD(momentum) under the custom one-cycle schedule over 0.9 * steps."""
+        opt1 = torch.optim.SGD(self.parameters(), lr=self.lr, momentum=self.hparams["momentum"],
+                               weight_decay=self.hparams["weight_decay"])
+        assert self.hparams["scheduler_choice"] == "swa"
+        scheduler = CustomOneCycleLR(opt1, self.lr, int(0.9 * self.steps), final_div_factor=1e4)
+        return [opt1], [{"scheduler": scheduler, "name": "swa_lr", "interval": "steps"}]
 
     def input_kl(self):
         """:585-590 (41 elements: plain tensor arithmetic)."""

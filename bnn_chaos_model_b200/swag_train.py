@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import BnnChaosError, TrainHParams
 from .multiswag import shard_range
-from .spock_reg_model import SWAGModel
+from .spock_reg_model import SWAGModel, VarModel, one_cycle_lr_momentum
 
 
 def seeds_of_rank(n_seeds: int, rank: int, world: int):
@@ -56,7 +56,7 @@ class MultiSeedSWAGTrainer:
         if noisy_val:
             raise NotImplementedError("batched validation is noise-free (bnn_eval_loss); use SWAGModel.validation_step")
         self.swa_start = int(m0.hparams["swa_start"] if swa_start is None else swa_start)  # :808 reads hparams
-        self.theta = torch.stack([m.flatten().float() for m in self.models]).to(dev).contiguous()  # [S,d]
+        self.theta = torch.stack([m._flat().detach().float() for m in self.models]).to(dev).contiguous()  # [S,d]
         self.momentum = torch.zeros_like(self.theta)
         d = self.theta.shape[1]
         self.w_avg = torch.zeros((self.S, d), device=dev)
@@ -80,7 +80,7 @@ class MultiSeedSWAGTrainer:
         lib = _lib.load()
         cfg = self.models[0].config(self.X.shape[1])
         hp = TrainHParams(lr=self.lr if lr is None else float(lr), first_step=int(self.first_step), apply_update=1,
-                          **self.hp)
+                          **self.step_hparams())
         with torch.cuda.device(self.device):
             nbytes = lib.bnn_train_workspace_bytes(cfg, B, self.S)
             if self._ws is None or self._ws.numel() * 4 < nbytes:
@@ -94,6 +94,10 @@ class MultiSeedSWAGTrainer:
             )
         self.first_step = False
         self.global_step += 1
+
+    def step_hparams(self):
+        """momentum, weight decay, clip and KL weights of the coming step (constant in the SWAG phase, :722-732)."""
+        return self.hp
 
     def epoch_batches(self):
         """Per-seed shuffles of the training set (DataLoader(shuffle=True), :276): [n_batches] of ([S,B] int32, B)."""
@@ -178,3 +182,93 @@ class MultiSeedSWAGTrainer:
                 m._pre_D_buf = None
             m.global_step, m.current_epoch = self.global_step, self.current_epoch
         return self.models
+
+
+class MultiSeedPretrainer(MultiSeedSWAGTrainer):
+    """The pre-training phase of several seed models at once (find_minima.py:26-84; 300,000 of the 350,000 steps of
+    a seed in train.sh:3-6).  Same fused step as the SWAG phase; what changes per step are host-side scalars:
+
+    * KL annealing of ``VarModel.training_step`` (:595-598): both KL weights ramp over the first 30 % of ``steps``;
+    * the custom one-cycle schedule (:27-159, :634) over ``int(0.9 * steps)`` optimizer steps: lr AND momentum
+      (0.95 -> 0.85 -> 0.95) change every step;
+    * no moment collection; validation once per epoch, the weights of the best epoch are kept
+      (ModelCheckpoint, find_minima.py:67,82);
+    * the run ends when the scheduler is stepped past its total -- the reference's ValueError
+      (:137-139, caught at find_minima.py:79-82) -- after which every seed is reset to its best checkpoint.
+    """
+
+    def __init__(self, models: Sequence[VarModel], X_train, y_train, X_val=None, y_val=None, batch_size=None,
+                 device=None, seed=0):
+        m0 = models[0]
+        for m in models:  # the SWAG bookkeeping of the base class reads these; unused here
+            if not hasattr(m, "K"):
+                m.K, m.c, m.swa_params = 1, 1, {"swa_lr": m.lr}
+        super().__init__(models, X_train, y_train, X_val, y_val, batch_size=batch_size or m0.batch_size, device=device,
+                         seed=seed, swa_start=1 << 62)
+        self.steps = int(m0.steps)
+        self.max_lr = float(m0.lr)
+        self.total_sched = int(0.9 * self.steps)
+        self.best_val = torch.full((self.S,), float("inf"), device=self.device)
+        self.best_theta = self.theta.clone()
+        self.finished = False
+
+    def schedule(self, step: Optional[int] = None):
+        """(lr, momentum, beta_in, beta_out) of optimizer step ``step`` (default: the coming one)."""
+        g = self.global_step if step is None else int(step)
+        lr, mom = one_cycle_lr_momentum(g, self.max_lr, self.total_sched)
+        f = min([1, (g / self.steps) / 0.3])
+        return lr, mom, f * self.hp["beta_in"], f * self.hp["beta_out"]
+
+    def step_hparams(self):
+        _, mom, b_in, b_out = self.schedule()
+        return dict(self.hp, momentum=mom, beta_in=b_in, beta_out=b_out)
+
+    def train_step(self, batch_index, B, lr=None):
+        if lr is None:
+            lr = self.schedule()[0]  # raises ValueError past the schedule's end, like scheduler.step() does
+        super().train_step(batch_index, B, lr)
+
+    def fit(self, epochs: Optional[int] = None, validate: bool = True, check_nan_every: int = 1):
+        """Trainer.fit of find_minima.py: epochs = 1 + steps / steps_per_epoch unless given; stops at the schedule's end."""
+        if epochs is None:
+            epochs = int(1 + self.steps / len(self.epoch_batches()))
+        logs = []
+        for _ in range(epochs):
+            try:
+                self.train_epoch()
+            except ValueError:
+                self.finished = True
+            entry = {"epoch": self.current_epoch, "global_step": self.global_step}
+            if not self.finished and validate and self.Xv is not None:
+                v, _ = self.validation_losses()
+                better = v < self.best_val
+                self.best_val = torch.where(better, v, self.best_val)
+                self.best_theta = torch.where(better[:, None], self.theta, self.best_theta)
+                entry["val_loss_no_reg"] = v.cpu()
+            if check_nan_every and bool((self.metrics[:, 6] != 0).any()):
+                raise ValueError(f"non-finite training loss at epoch {self.current_epoch}")
+            logs.append(entry)
+            self.current_epoch += 1
+            if self.finished:
+                if self.Xv is not None and bool(torch.isfinite(self.best_val).all()):
+                    self.theta.copy_(self.best_theta)  # load_state_dict(best_model_path), find_minima.py:82
+                break
+        return logs
+
+    def export(self):
+        for i, m in enumerate(self.models):
+            m.to(self.device)
+            m.load(self.theta[i]) if hasattr(m, "load") else _load_flat(m, self.theta[i])
+            m.global_step, m.current_epoch = self.global_step, self.current_epoch
+        return self.models
+
+
+def _load_flat(model: VarModel, p_vec: torch.Tensor):
+    """SWAGModel.load (:748-761) for a plain VarModel: split the flat vector over the state_dict in order."""
+    off = 0
+    sd = model.state_dict()
+    for k, v in sd.items():
+        n = v.numel()
+        sd[k] = p_vec[off:off + n].reshape(v.shape).to(v.device)
+        off += n
+    model.load_state_dict(sd)

@@ -246,6 +246,37 @@ def gen_posterior():
     np.savez_compressed(os.path.join(GOLD, "posterior.npz"), mu=mu, sd=sd, samples_ref=out, np_seed=123, d=100, nsamp=40)
 
 
+def gen_schedule():
+    """lr / momentum sequences of the reference's CustomOneCycleLR on a real torch SGD optimizer, stepped like
+    Lightning does (scheduler.step() after every optimizer step), incl. the step at which it raises."""
+    ref = ref_shim.import_reference()
+    rec = {}
+    for tag, (max_lr, total, mom) in {"a": (5e-4, 90, 0.9), "b": (1e-3, 27, 0.9), "c": (5e-4, 270000, 0.9)}.items():
+        w = torch.nn.Parameter(torch.zeros(3))
+        opt = torch.optim.SGD([w], lr=max_lr, momentum=mom, weight_decay=1e-14)
+        sch = ref.CustomOneCycleLR(opt, max_lr, total, final_div_factor=1e4)
+        n_rec = total if total < 1000 else 2000
+        stride = 1 if total < 1000 else total // n_rec
+        lrs, moms, steps = [], [], []
+        raised_at = -1
+        for i in range(total + 3):
+            if i % stride == 0 and len(steps) < n_rec + 1:
+                steps.append(i); lrs.append(opt.param_groups[0]["lr"]); moms.append(opt.param_groups[0]["momentum"])
+            opt.step()
+            try:
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    sch.step()
+            except ValueError:
+                raised_at = i + 1
+                break
+        rec[f"{tag}_max_lr"] = max_lr; rec[f"{tag}_total"] = total
+        rec[f"{tag}_steps"] = np.array(steps); rec[f"{tag}_lr_ref"] = np.array(lrs, dtype=np.float64)
+        rec[f"{tag}_momentum_ref"] = np.array(moms, dtype=np.float64); rec[f"{tag}_raised_at"] = raised_at
+    np.savez_compressed(os.path.join(GOLD, "schedule.npz"), **rec)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # fixed summation order inside the reference's matmuls
@@ -256,5 +287,6 @@ if __name__ == "__main__":
     gen_train()
     gen_pack()
     gen_posterior()
+    gen_schedule()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -307,6 +307,40 @@ def clip_and_sgd_step(theta, grad, buf, lr, momentum, weight_decay, clip, first_
 
 
 # --------------------------------------------------------------------------------------
+# Pre-training schedule (find_minima.py:26-84): CustomOneCycleLR (spock_reg_model.py:27-159) and the KL annealing
+# of VarModel.training_step (:595-598)
+# --------------------------------------------------------------------------------------
+def one_cycle(step_num: int, max_lr: float, total_steps: int, pct_start: float = 0.3, div_factor: float = 25.0,
+              final_div_factor: float = 1e4, base_momentum: float = 0.85, max_momentum: float = 0.95):
+    """(lr, momentum) the scheduler installs for optimizer step `step_num` (= its last_epoch; 0 at construction):
+    cosine from max_lr/25 up to max_lr over step_size_up = pct_start*total - 1 steps, then cosine down to
+    max_lr/25/1e4 over the rest, momentum cycling the other way (:64-65, :133-158).  Raises like :137-139 once
+    step_num > total_steps -- that ValueError is how find_minima.py's run ends (find_minima.py:79-82)."""
+    if step_num > total_steps:
+        raise ValueError("Tried to step {} times. The specified number of total steps is {}".format(step_num + 1, total_steps))
+    up = float(pct_start * total_steps) - 1
+    down = float(total_steps - up) - 1
+    initial_lr = max_lr / div_factor
+    min_lr = initial_lr / final_div_factor
+
+    def cos_anneal(start, end, pct):  # :119-124
+        if pct >= 1.0:
+            return end
+        return end + (start - end) / 2.0 * (math.cos(math.pi * pct) + 1)
+
+    if step_num <= up:
+        return cos_anneal(initial_lr, max_lr, step_num / up), cos_anneal(max_momentum, base_momentum, step_num / up)
+    d = step_num - up
+    return cos_anneal(max_lr, min_lr, d / down), cos_anneal(base_momentum, max_momentum, d / down)
+
+
+def kl_annealing(global_step: int, steps: int, beta_in: float, beta_out: float):
+    """:596-598: both KL weights ramp linearly over the first 30 % of `steps`."""
+    f = min([1, (global_step / steps) / 0.3])
+    return f * beta_in, f * beta_out
+
+
+# --------------------------------------------------------------------------------------
 # SWAG moment collection (spock_reg_model.py:763-785)
 # --------------------------------------------------------------------------------------
 @dataclass

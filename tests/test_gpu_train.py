@@ -239,3 +239,61 @@ def test_multi_seed_trainer_collects_reference_moments(dev):
     o = out[0].forward_swag_fast(X[:8].to(dev), scale=0.5)
     assert o.shape == (8, 2) and bool(torch.isfinite(o).all())
     assert seeds_of_rank(30, 0, 8) == [0, 1, 2, 3] and seeds_of_rank(30, 7, 8) == [27, 28, 29]
+
+
+def test_multi_seed_pretrainer_vs_oracle_schedule(dev):
+    """find_minima.py phase: fused steps under the custom one-cycle schedule (lr AND momentum per step) and the KL
+    annealing, for two seeds at once; replayed step by step on the oracle (autograd + clip + SGD) with the Philox draws
+    the kernel made; ends at the schedule's ValueError and restores the best-validation weights."""
+    from bnn_chaos_model_b200.swag_train import MultiSeedPretrainer
+
+    lib = _lib.load()
+    models = [make_swag_model(s, dev) for s in (0, 3)]
+    for m in models:
+        m.load(m.w_avg.clone())
+        m.steps = m.hparams["steps"] = 10      # schedule over int(0.9 * 10) = 9 optimizer steps
+        m.lr = m.hparams["lr"] = 1e-3
+    N, B = 60, 20
+    X = torch.from_numpy(synth.make_systems(N, seed=71)); y = torch.from_numpy(synth.make_labels(N, seed=71))
+    tr = MultiSeedPretrainer(models, X[:40], y[:40], X[40:], y[40:], batch_size=B, device=dev, seed=11)
+    assert tr.total_sched == 9 and len(tr.epoch_batches()) == 2
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    cfg = models[0].config(100)
+    th_o = [tr.theta[i].cpu().clone() for i in range(2)]
+    buf_o = [torch.zeros_like(t) for t in th_o]
+    d = th_o[0].numel()
+    Xc, yc = X[:40], y[:40]
+    n_checked = 0
+    for epoch in range(3):
+        for idx, Bb in tr.epoch_batches():
+            g = tr.global_step
+            lr, mom, b_in, b_out = tr.schedule()
+            assert (lr, mom) == R.one_cycle(g, 1e-3, 9)
+            assert (b_in, b_out) == pytest.approx(R.kl_annealing(g, 10, models[0].beta_in, models[0].beta_out))
+            e_in = torch.empty((2, Bb, 100, 41), device=dev); e12 = torch.empty((2, Bb, 40), device=dev); e_sum = torch.empty((2, Bb, 40), device=dev)
+            _lib.check(lib.bnn_train_noise(cfg, 2, Bb, tr.seed, g, _lib.ptr(e_in), _lib.ptr(e12), _lib.ptr(e_sum), None))
+            tr.train_step(idx, Bb)
+            torch.cuda.synchronize()
+            for i in range(2):
+                sel = idx[i].long().cpu()
+                th = th_o[i].clone().requires_grad_(True)
+                total, _ = R.training_loss(spec, th, Xc[sel], yc[sel], e_in[i].cpu(), e12[i, :, :20].cpu(), e12[i, :, 20:].cpu(),
+                                           e_sum[i].cpu(), beta_in=b_in, beta_out=b_out)
+                (gr,) = torch.autograd.grad(total, th)
+                th_o[i], buf_o[i], _ = R.clip_and_sgd_step(th_o[i], gr, buf_o[i], lr, mom, 1e-14, 0.1 * d, g == 0)
+                np.testing.assert_allclose(tr.theta[i].cpu().numpy(), th_o[i].numpy(), rtol=1e-5, atol=2e-6)
+                th_o[i] = tr.theta[i].cpu().clone()   # no drift: every step is compared from the same start
+                buf_o[i] = tr.momentum[i].cpu().clone()
+            n_checked += 1
+            if n_checked == 4:
+                break
+        if n_checked == 4:
+            break
+    assert n_checked == 4 and tr.global_step == 4
+    logs = tr.fit()                       # runs to the end of the schedule
+    assert tr.finished and tr.global_step == 10   # steps 0..9 ran, step 10 raised
+    with pytest.raises(ValueError):
+        tr.schedule(10)
+    assert torch.isfinite(tr.best_val).all() and torch.equal(tr.theta, tr.best_theta)
+    out = tr.export()
+    assert torch.equal(out[1].flatten().to(dev), tr.theta[1])

@@ -174,3 +174,33 @@ def test_gather_system_shards_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_custom_one_cycle_lr_mirror_vs_reference_golden():
+    """The mirrored scheduler on a real torch SGD, stepped like Lightning steps it: lr and momentum of every step
+    equal the reference's (tests/golden/schedule.npz), and it raises at the same step."""
+    from conftest import load_golden
+    from bnn_chaos_model_b200 import spock_reg_model as S
+
+    z = load_golden("schedule.npz")
+    for t in "ab":
+        mx, tot = float(z[f"{t}_max_lr"]), int(z[f"{t}_total"])
+        w = torch.nn.Parameter(torch.zeros(3))
+        opt = torch.optim.SGD([w], lr=mx, momentum=0.9, weight_decay=1e-14)
+        sch = S.CustomOneCycleLR(opt, mx, tot, final_div_factor=1e4)
+        raised_at = -1
+        for i in range(tot + 3):
+            assert opt.param_groups[0]["lr"] == pytest.approx(float(z[f"{t}_lr_ref"][i]), rel=1e-14)
+            assert opt.param_groups[0]["momentum"] == pytest.approx(float(z[f"{t}_momentum_ref"][i]), rel=1e-14)
+            opt.step()
+            try:
+                sch.step()
+            except ValueError:
+                raised_at = i + 1
+                break
+        assert raised_at == int(z[f"{t}_raised_at"])
+    lr, mom = S.one_cycle_lr_momentum(1000, 5e-4, 270000)
+    i = list(z["c_steps"]).index(1080)
+    assert S.one_cycle_lr_momentum(1080, 5e-4, 270000)[0] == pytest.approx(float(z["c_lr_ref"][i]), rel=1e-14)
+    with pytest.raises(ValueError):
+        S.CustomOneCycleLR(torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0), 1.0, 10, pct_start=2.0)

@@ -145,3 +145,21 @@ def test_fast_truncnorm_oracle_vs_reference_golden():
     r = np.random.default_rng(0).random(5000)
     assert np.abs(R.prior_cdf(R.prior_samples_table(r)) - r).max() < 3e-3
     assert R.prior_cdf(9.0) == 0.0 and abs(float(R.prior_cdf(100.0)) - 1.0) < 1e-12
+
+
+def test_one_cycle_schedule_vs_reference_golden():
+    """oracle one_cycle == the reference's CustomOneCycleLR stepped on a torch SGD (lr and cycled momentum per step,
+    and the step at which it raises), for a short, an odd and the production-length (0.9 * 300,000) schedule."""
+    z = load_golden("schedule.npz")
+    for t in "abc":
+        mx, tot = float(z[f"{t}_max_lr"]), int(z[f"{t}_total"])
+        for st, lr, mom in zip(z[f"{t}_steps"], z[f"{t}_lr_ref"], z[f"{t}_momentum_ref"]):
+            a, b = R.one_cycle(int(st), mx, tot)
+            assert a == pytest.approx(float(lr), rel=1e-14) and b == pytest.approx(float(mom), rel=1e-14)
+        assert int(z[f"{t}_raised_at"]) == tot + 1
+        R.one_cycle(tot, mx, tot)
+        with pytest.raises(ValueError):
+            R.one_cycle(tot + 1, mx, tot)
+    assert R.kl_annealing(0, 100, 1e-5, 1e-3) == (0.0, 0.0)
+    assert R.kl_annealing(15, 100, 1e-5, 1e-3) == pytest.approx((0.5e-5, 0.5e-3))
+    assert R.kl_annealing(60, 100, 1e-5, 1e-3) == (1e-5, 1e-3)
