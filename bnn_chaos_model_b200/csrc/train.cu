@@ -48,6 +48,9 @@ struct Params {
     float* partial;            // [n_seeds, n_cta, d + DPAD]
     float* head_rec;           // [n_seeds, B, REC] per-system head vectors (v3 only)
     float* xprod;              // [n_seeds, n_cta, 2, 2, F, 2T] input-tile scratch of the producer warps (v3 only)
+    int saliency;              // v3 only: d mu / d x instead of the training gradient (bnn_saliency)
+    float* gx_out;             // [n_seeds, B, T, F] or null
+    float* mu_out;             // [n_seeds, B]
     int B, T, F, FP, n_cta;
     uint64_t seed, step;
     uint64_t zero_mask;
@@ -1291,6 +1294,17 @@ __global__ void __launch_bounds__(256) nll_sum_kernel(const float2* __restrict__
     if (threadIdx.x == 0) loss_sum[blockIdx.x] = sh[0];
 }
 
+// sumsq[s][c] = sum over the CTAs' partial sums of (d mu / d x)^2 in column c (the v3 kernel parks them, halved, in the
+// dlv_in slot of its partial), fixed order
+__global__ void saliency_finish_kernel(const float* __restrict__ partial, int n_cta, int d, int F, float* __restrict__ sumsq) {
+    const int s = blockIdx.x, c = threadIdx.x;
+    if (c >= F) return;
+    const float* p = partial + (int64_t)s * n_cta * (d + DPAD) + c;
+    float a = 0.f;
+    for (int i = 0; i < n_cta; ++i) a += p[(int64_t)i * (d + DPAD)];
+    sumsq[s * F + c] = 2.0f * a;
+}
+
 // v3 (large register tiles) for the reference's shape; BNN_TRAIN_VARIANT=v1|v2|v3 forces one
 static bool use_v3(const bnn_model_config* cfg) {
     const char* force = getenv("BNN_TRAIN_VARIANT");
@@ -1388,6 +1402,7 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
     prm.seed = seed; prm.step = step; prm.zero_mask = cfg->zero_mask;
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
     prm.beta_out = hp->beta_out;
+    prm.saliency = 0; prm.gx_out = nullptr; prm.mu_out = nullptr;
     if (train::use_v3(cfg)) {
         const size_t smem3 = (size_t)train::Smem3(T, F).total * sizeof(float);
         static bool attr3_done = false;
@@ -1419,6 +1434,55 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
     }
     train::train_update_kernel<<<dim3(nb, n_seeds), 256, 0, st>>>(grad, sq, nb, fl.d, F, (int)B, *hp, d_theta, d_momentum,
                                                                  d_grad_out, d_metrics);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+int bnn_saliency(const bnn_model_config* cfg, int32_t n_models, const float* d_theta, const float* d_x, int64_t B,
+                 const float* d_eps12, uint64_t seed, float* d_grad_x, float* d_sumsq, float* d_mu, void* d_workspace,
+                 void* stream) {
+    using namespace bnn;
+    int rc = validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    if ((rc = check_device()) != BNN_OK) return rc;
+    BNN_REQUIRE(d_theta && d_x && d_sumsq && d_mu && d_workspace, BNN_E_ARG, "bnn_saliency: null pointer");
+    BNN_REQUIRE(n_models >= 1 && n_models <= 65535 && B >= 1 && B < (1ll << 30), BNN_E_ARG,
+                "bnn_saliency: n_models=%d B=%lld out of range", n_models, (long long)B);
+    BNN_REQUIRE(cfg->n_times == 100 && cfg->n_features == 41, BNN_E_CONFIG,
+                "bnn_saliency: compiled for T=100, F=41 (got T=%d, F=%d)", cfg->n_times, cfg->n_features);
+    BNN_REQUIRE(aligned16(d_workspace) && (!d_eps12 || aligned16(d_eps12)), BNN_E_ALIGN, "bnn_saliency: alignment");
+    const int F = cfg->n_features, T = cfg->n_times;
+    const FlatLayout fl(F);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t n_cta = sms / n_models;
+    if (n_cta > (B + 1) / 2) n_cta = (B + 1) / 2;
+    if (n_cta < 1) n_cta = 1;
+    const int DP = fl.d + train::DPAD;
+    float* partial = (float*)d_workspace;
+    float* xprod = partial + (size_t)n_models * n_cta * DP;
+    xprod += (4 - ((uintptr_t)xprod / sizeof(float)) % 4) % 4;
+    train::Params prm;
+    prm.theta = d_theta; prm.X = d_x; prm.Y = nullptr; prm.batch_index = nullptr;
+    prm.eps_in = nullptr; prm.eps12 = d_eps12; prm.eps_sum = nullptr;
+    prm.partial = partial; prm.head_rec = nullptr; prm.xprod = xprod;
+    prm.B = (int)B; prm.T = T; prm.F = F; prm.FP = (F + 3) & ~3; prm.n_cta = (int)n_cta;
+    prm.seed = seed; prm.step = 0; prm.zero_mask = cfg->zero_mask;
+    prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
+    prm.beta_out = 0.f;
+    prm.saliency = 1; prm.gx_out = d_grad_x; prm.mu_out = d_mu;
+    static bool attr_done = false;
+    if (!attr_done) {
+        BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd3_kernel<100, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
+        attr_done = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem3 = (size_t)train::Smem3(T, F).total * sizeof(float);
+    train::train_fwd_bwd3_kernel<100, 41><<<dim3((unsigned)n_cta, n_models), train::NTHR3, smem3, st>>>(prm);
+    BNN_CUDA(cudaGetLastError());
+    train::saliency_finish_kernel<<<n_models, 64, 0, st>>>(partial, (int)n_cta, fl.d, F, d_sumsq);
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }

@@ -217,9 +217,9 @@ __device__ __forceinline__ void stash_store(uint32_t taddr, const float* v) {
 struct ProdArgs {
     const float* X; const float* eps_in; float* xp; float* np; const float* nsc;
     const float* Y; const float* eps12; const float* eps_sum; float* sm_out;
-    uint64_t key, zero_mask; int64_t sb0; int row0, row1, b0n, step;
+    uint64_t key, zero_mask; int64_t sb0; int row0, row1, b0n, step, saliency;
 };
-static_assert(sizeof(ProdArgs) <= 32 * sizeof(float), "ProdArgs must fit its shared-memory slot");
+static_assert(sizeof(ProdArgs) <= 31 * sizeof(float), "ProdArgs must fit its shared-memory slot");
 template <int T, int F, int NR>
 __device__ __noinline__ void produce_tile(const ProdArgs* __restrict__ ap, int first, int stride, int r0) {
     const ProdArgs a = *ap;
@@ -245,7 +245,7 @@ __device__ __noinline__ void produce_tile(const ProdArgs* __restrict__ ap, int f
 #pragma unroll
         for (int u = 0; u < 4; ++u) xv[k][u] = __ldg(xs + min(4 * c4 + u, F - 1));
     }
-    if (a.eps_in) {
+    if (a.eps_in && !a.saliency) {
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
             const int t = (int)ctr[k].x / F4, hs = (int)ctr[k].y - a.b0n;
@@ -254,7 +254,12 @@ __device__ __noinline__ void produce_tile(const ProdArgs* __restrict__ ap, int f
             for (int u = 0; u < 4; ++u) ev[k][u] = __ldg(es + min(4 * c4s[k] + u, F - 1));
         }
     }
-    if (!a.eps_in) {
+    if (a.saliency) {   // noise-free input (feature_importance.py: gradforward has no input noise)
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ev[k][u] = 0.f;
+    } else if (!a.eps_in) {
         // NR Philox4x32-10 blocks, rounds interleaved across the blocks (one warp per scheduler runs this: the
         // instruction-level parallelism has to come from here)
         constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -304,11 +309,12 @@ __device__ __noinline__ void produce_small(const ProdArgs* __restrict__ ap, int 
         if (row >= 0) {
             if (a.eps12) {
                 e = __ldg(reinterpret_cast<const float4*>(a.eps12 + (a.sb0 + hs) * S2) + l);
-                c = __ldg(reinterpret_cast<const float4*>(a.eps_sum + (a.sb0 + hs) * S2) + l);
+                if (a.eps_sum) c = __ldg(reinterpret_cast<const float4*>(a.eps_sum + (a.sb0 + hs) * S2) + l);
             } else {
                 e = philox_normal4(a.key, STREAM_EPS, (uint32_t)(a.b0n + hs), (uint32_t)a.step, (uint32_t)l);
                 c = philox_normal4(a.key, STREAM_EPS_SUM, (uint32_t)(a.b0n + hs), (uint32_t)a.step, (uint32_t)l);
             }
+            if (a.saliency) c = make_float4(0.f, 0.f, 0.f, 0.f);   // partforward adds no summary noise
         }
         reinterpret_cast<float4*>(a.sm_out + hs * (XSM / 2))[l] = e;
         reinterpret_cast<float4*>(a.sm_out + hs * (XSM / 2) + S2)[l] = c;
@@ -316,7 +322,7 @@ __device__ __noinline__ void produce_small(const ProdArgs* __restrict__ ap, int 
         const int hs = p - 32;
         const int row = hs ? a.row1 : a.row0;
         float2 y = make_float2(0.f, 0.f);
-        if (row >= 0) y = __ldg(reinterpret_cast<const float2*>(a.Y) + row);
+        if (row >= 0 && a.Y) y = __ldg(reinterpret_cast<const float2*>(a.Y) + row);
         *reinterpret_cast<float2*>(a.sm_out + hs * (XSM / 2) + 2 * S2) = y;
     }
 }
@@ -462,6 +468,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 const int64_t sbq = (int64_t)sidx * prm.B + b0p;
                 pas->X = prm.X; pas->eps_in = prm.eps_in; pas->nsc = cst + C3_NSC; pas->key = key; pas->zero_mask = prm.zero_mask;
                 pas->step = (int)prm.step; pas->Y = prm.Y; pas->eps12 = prm.eps12; pas->eps_sum = prm.eps_sum;
+                pas->saliency = prm.saliency;
                 pas->b0n = b0p; pas->sb0 = sbq; pas->xp = xo; pas->np = xo + F * RT; pas->sm_out = xo + 2 * F * RT;
                 pas->row0 = prm.batch_index ? prm.batch_index[sbq] : b0p;
                 pas->row1 = b0p + 1 < prm.B ? (prm.batch_index ? prm.batch_index[sbq + 1] : b0p + 1) : -1;
@@ -704,7 +711,10 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 const float mu = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, __fadd_rn(t0, 1.0f)), __fsub_rn(prm.hc.hi_mu, prm.hc.lo_mu)), prm.hc.lo_mu);
                 const float sd = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, __fadd_rn(t1, 1.0f)), __fsub_rn(prm.hc.hi_sd, prm.hc.lo_sd)), prm.hc.lo_sd);
                 float l = 0.f, dm = 0.f, ds = 0.f;
-                if (lane < 2) nll_terms(mu, sd, sv[V3_Y + lane], l, dm, ds);
+                if (prm.saliency) {   // upstream gradient of mu.sum(): d mu = 1, d sd = 0 (feature_importance.py:109-110)
+                    dm = lane == 0 ? -1.0f : 0.f;
+                    if (lane == 0 && act) prm.mu_out[sb] = mu;
+                } else if (lane < 2) nll_terms(mu, sd, sv[V3_Y + lane], l, dm, ds);
                 const float l1 = __shfl_sync(0xffffffffu, l, 1), dm1 = __shfl_sync(0xffffffffu, dm, 1), ds1 = __shfl_sync(0xffffffffu, ds, 1);
                 if (lane == 0) {
                     if (act) a_nll += -(l + l1);
@@ -750,15 +760,15 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             if (part == 0) {
-                if (act) rec[R_DLVS + k] = a * (0.5f * (sv[V3_ESN + k] * cst[C3_ELVH + k]));  // ds'/dlv = eps e^{lv/2} / 2
+                if (act && !prm.saliency) rec[R_DLVS + k] = a * (0.5f * (sv[V3_ESN + k] * cst[C3_ELVH + k]));  // ds'/dlv = eps e^{lv/2} / 2
                 sv[V3_GS + k] = a + (act ? prm.beta_out * sv[V3_S + k] : 0.f);
             }
-        } else if (act) {
+        } else if (act && !prm.saliency) {
             // the other warp of the half writes the record (s', r1, r2, g_a1, g_a2 are complete)
             const int i0 = lt - S2 * 4;  // 0..31
             for (int i = i0; i < R_DLVS; i += HALF3 - S2 * 4) rec[i] = sv[V3_REC0 + i];
         }
-        if (lt == 0 && act) { rec[R_GR] = gr0; rec[R_GR + 1] = gr1; }
+        if (lt == 0 && act && !prm.saliency) { rec[R_GR] = gr0; rec[R_GR + 1] = gr1; }
         MAIN_SYNC();
         TL3(16);
         if (lt < L) {
@@ -846,7 +856,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         MAIN_SYNC();
         TL3(7);
         // ---- S13: all weight-gradient outer products in one phase ----
-        {
+        if (!prm.saliency) {
             float aW[OJ][8];
             stash_load<NV>(taddr, &aW[0][0]);
 #if V3_OUTER == 88
@@ -880,12 +890,22 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 for (int e = 0; e < 2; ++e) {
                     const int col = 8 * cg_rg + 2 * i + e;
                     if (col < F) {
-                        const float4 n4 = nn[2 * i + e];
-                        aux[2 * i + e] += fmaf(v[0][e], n4.x, fmaf(v[1][e], n4.y, fmaf(v[2][e], n4.z, v[3][e] * n4.w)));
+                        if (prm.saliency) {   // d mu / d x: sum of squares per column, and the rows themselves if asked for
+                            aux[2 * i + e] += fmaf(v[0][e], v[0][e], fmaf(v[1][e], v[1][e], fmaf(v[2][e], v[2][e], v[3][e] * v[3][e])));
+                            const int hs = q_rg / NQ, bb = b0i + hs;
+                            if (prm.gx_out && bb < prm.B) {
+                                float* o = prm.gx_out + (((int64_t)sidx * prm.B + bb) * T + 4 * (q_rg - hs * NQ)) * F + col;
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) o[r * F] = v[r][e];
+                            }
+                        } else {
+                            const float4 n4 = nn[2 * i + e];
+                            aux[2 * i + e] += fmaf(v[0][e], n4.x, fmaf(v[1][e], n4.y, fmaf(v[2][e], n4.z, v[3][e] * n4.w)));
+                        }
                     }
                 }
             }
-        } else {
+        } else if (!prm.saliency) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int r = tid - 6 * NQ2 + e * (NMAIN - 6 * NQ2);  // 84 threads, rows r and r + 84 of 120
@@ -992,7 +1012,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     MAIN_SYNC();
     // (4) head gradients from the records of this CTA's systems, in system order:
     //     dV0 += g_a1 s'^T, c0 += g_a1; dV1 += g_a2 r1^T, c1 += g_a2; dV2 += g_r r2^T, c2 += g_r; dlv_sum += dlvs
-    {
+    if (!prm.saliency) {
         constexpr int CH = 128;  // records staged per chunk (128 kB)
         // roles: tid < 200: 2 x 4 blocks of dV0 and dV1; 200..239: c0, c1; 240..319: dV2; 320..321: c2; 322..361: dlv_sum
         const int jbh = tid / 10, kb = tid % 10;

@@ -270,3 +270,28 @@ def load_ensemble(paths: Sequence[str], device=None) -> MultiSWAG:
     from .spock_reg_model import load_swag
 
     return MultiSWAG([load_swag(p) for p in paths], device=device)
+
+
+def feature_importance(models, X, seed: int = 0, device=None):
+    """figures/feature_importance.py:118-131 for the whole ensemble in one launch: every model evaluated at its SWA
+    mean w_avg (:45-47), saliency = d mu / d x over the given (validation) systems, importance[m, c] =
+    (saliency**2).mean((0, 1)).  eps1, eps2 are counter-based Philox draws keyed on (seed; model, system).
+    Returns (importance [M, F], mu [M, N])."""
+    lib = _lib.load()
+    m0 = models[0]
+    dev = torch.device(device) if device is not None else X.device
+    if dev.type != "cuda":
+        raise _lib.BnnChaosError("feature_importance needs a CUDA device: there is no CPU fallback")
+    X = X.to(dev).contiguous().float()
+    N, T, F = X.shape
+    theta = torch.stack([(m.w_avg if getattr(m, "w_avg", None) is not None else m._flat()).to(dev).float() for m in models])
+    theta = theta.contiguous()
+    M = theta.shape[0]
+    with torch.cuda.device(dev):
+        cfg = m0.config(T)
+        ws = torch.empty((lib.bnn_train_workspace_bytes(cfg, N, M) + 3) // 4, device=dev)
+        sumsq = torch.empty((M, F), device=dev)
+        mu = torch.empty((M, N), device=dev)
+        _lib.check(lib.bnn_saliency(cfg, M, _lib.ptr(theta), _lib.ptr(X), N, None, int(seed), None, _lib.ptr(sumsq),
+                                    _lib.ptr(mu), _lib.ptr(ws), _lib.current_stream_ptr()), "bnn_saliency")
+    return sumsq / float(N * T), mu

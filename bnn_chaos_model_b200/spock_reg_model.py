@@ -298,6 +298,30 @@ class VarModel(nn.Module):
             _, summ = self._predict(x, self._packed(cfg), eps, cfg=cfg, want_summary=True)
         return summ[0]
 
+    def gradforward(self, x, want_grad=True):
+        """figures/feature_importance.py:93-131 (``gradforward`` / ``partforward``): the zero_* masks, then
+        ``mu = predict_instability(compute_summary_stats(x))[0]`` with eps1, eps2 drawn like compute_summary_stats
+        (no input / summary noise) and ``grad(mu.sum(), x)`` with respect to the masked input, all F columns.
+        Returns (grad [B,T,F] or None, mu [B], sumsq [F] = (grad**2).sum((0, 1)))."""
+        lib = _lib.load()
+        x = self._check_x(x)
+        B, T, F = x.shape
+        L = self.hparams["latent"]
+        with torch.cuda.device(x.device):
+            cfg = self.config(T)
+            eps1 = torch.randn((B, L), device=x.device)
+            eps2 = torch.randn((B, L), device=x.device)
+            eps = torch.cat((eps1, eps2), dim=1)[None].contiguous()
+            theta = self._flat().contiguous().float()[None].contiguous()
+            ws = torch.empty((lib.bnn_train_workspace_bytes(cfg, B, 1) + 3) // 4, device=x.device)
+            g = torch.empty((1, B, T, F), device=x.device) if want_grad else None
+            sumsq = torch.empty((1, F), device=x.device)
+            mu = torch.empty((1, B), device=x.device)
+            _lib.check(lib.bnn_saliency(cfg, 1, _lib.ptr(theta), _lib.ptr(x), B, _lib.ptr(eps), 0, _lib.ptr(g),
+                                        _lib.ptr(sumsq), _lib.ptr(mu), _lib.ptr(ws), _lib.current_stream_ptr()),
+                       "bnn_saliency")
+        return (g[0] if want_grad else None), mu[0], sumsq[0]
+
     def predict_instability(self, summary_stats):
         """:437-442 -> (mu[B,1], std[B,1])."""
         lib = _lib.load()

@@ -171,6 +171,17 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
                    const int32_t* d_batch_index, int64_t B, const float* d_eps_in,
                    const float* d_eps12, const float* d_eps_sum, uint64_t seed, uint64_t step,
                    float* d_grad_out, float* d_metrics, void* d_workspace, void* stream);
+/* Saliency (figures/feature_importance.py:93-131, gradforward): for each of n_models weight vectors d_theta[m]
+ * (flatten() order; the script uses w_avg) and each system b: mu_b = predict_instability(compute_summary_stats(
+ * mask(x_b)))[0] and g = d mu_b / d x (all F columns of the masked input; no input noise, no summary noise).
+ * eps1 | eps2 of compute_summary_stats (:426-427): explicit d_eps12 [n_models,B,2L] or NULL (Philox on (seed; model,
+ * system)).  Outputs: d_grad_x [n_models,B,T,F] (may be NULL), d_sumsq [n_models,F] = sum over systems and time steps
+ * of g^2 (the script's importance is this / (B*T)), d_mu [n_models,B].  Workspace: bnn_train_workspace_bytes(cfg, B,
+ * n_models).  T = 100, F = 41 only (else BNN_E_CONFIG). */
+int bnn_saliency(const bnn_model_config* cfg, int32_t n_models, const float* d_theta, const float* d_x, int64_t B,
+                 const float* d_eps12, uint64_t seed, float* d_grad_x, float* d_sumsq, float* d_mu, void* d_workspace,
+                 void* stream);
+
 /* The Philox draws bnn_train_step makes for (seed, step) when its eps pointers are NULL. */
 int bnn_train_noise(const bnn_model_config* cfg, int32_t n_seeds, int64_t B, uint64_t seed, uint64_t step,
                     float* d_eps_in, float* d_eps12, float* d_eps_sum, void* stream);

@@ -297,3 +297,37 @@ def test_multi_seed_pretrainer_vs_oracle_schedule(dev):
     assert torch.isfinite(tr.best_val).all() and torch.equal(tr.theta, tr.best_theta)
     out = tr.export()
     assert torch.equal(out[1].flatten().to(dev), tr.theta[1])
+
+
+def test_saliency_vs_oracle_autograd(dev):
+    """feature_importance.py's gradforward: d mu / d x through compute_summary_stats (fixed eps1, eps2) and
+    predict_instability at w_avg, against torch autograd on the oracle; then the ensemble entry (Philox eps)."""
+    from bnn_chaos_model_b200.multiswag import feature_importance
+
+    m = make_swag_model(3, dev)
+    m.load(m.w_avg.clone())
+    spec = R.ModelSpec.from_hparams(swag_stats(3)["hparams"])
+    B = 37   # odd: the last pair has an inactive slot
+    x = torch.from_numpy(synth.make_systems(B, seed=81)).to(dev)
+    torch.manual_seed(5)
+    g, mu, sumsq = m.gradforward(x)
+    torch.manual_seed(5)
+    eps1 = torch.randn((B, 20), device=dev).cpu(); eps2 = torch.randn((B, 20), device=dev).cpu()
+    p = R.unflatten(spec, m.w_avg.cpu())
+    xz = R.zero_columns(spec, x.cpu()).clone().requires_grad_(True)
+    s = R.compute_summary_stats(spec, p, xz, eps1, eps2)
+    mu_o, _ = R.predict_instability(spec, p, s)
+    (g_o,) = torch.autograd.grad(mu_o.sum(), xz)
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_o.detach().reshape(-1).numpy(), rtol=1e-5)
+    scale = float(g_o.abs().max())
+    assert float((g.cpu() - g_o).abs().max()) <= 2e-5 * scale
+    for c in range(41):   # every column on its own scale (the zeroed columns carry gradient too)
+        assert float((g[:, :, c].cpu() - g_o[:, :, c]).abs().max()) <= 1e-4 * float(g_o[:, :, c].abs().max()) + 1e-9
+    np.testing.assert_allclose(sumsq.cpu().numpy(), (g_o ** 2).sum((0, 1)).numpy(), rtol=1e-4)
+    # ensemble: three models, Philox eps; importance is positive, finite, and reproducible
+    models = [make_swag_model(sd, dev) for sd in (0, 3, 17)]
+    imp, mus = feature_importance(models, x, seed=9)
+    imp2, _ = feature_importance(models, x, seed=9)
+    assert imp.shape == (3, 41) and mus.shape == (3, B) and torch.equal(imp, imp2)
+    assert bool(torch.isfinite(imp).all()) and bool((imp > 0).all())
+    assert 4.0 <= float(mus.min()) and float(mus.max()) <= 12.0
