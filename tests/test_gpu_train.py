@@ -331,3 +331,34 @@ def test_saliency_vs_oracle_autograd(dev):
     assert imp.shape == (3, 41) and mus.shape == (3, B) and torch.equal(imp, imp2)
     assert bool(torch.isfinite(imp).all()) and bool((imp > 0).all())
     assert 4.0 <= float(mus.min()) and float(mus.max()) <= 12.0
+
+
+def test_full_size_step_properties(dev, monkeypatch):
+    """BASELINE configs[3] per GPU (4 seeds x batch 2000 of 8000 resident systems, Philox noise), where the oracle is
+    too slow: (a) the step is bit-reproducible; (b) the three independently written kernels agree on the full
+    gradient and the logged scalars to rounding; (c) seeds with equal weights but different batches differ."""
+    lib = _lib.load()
+    S, B, N = 4, 2000, 8000
+    m = make_swag_model(0, dev)
+    cfg = m.config(100)
+    x = torch.from_numpy(synth.make_systems(N, seed=3)).to(dev)
+    y = torch.from_numpy(synth.make_labels(N, seed=3)).to(dev)
+    theta0 = m.w_avg[None].repeat(S, 1).contiguous()
+    gen = torch.Generator(device=dev); gen.manual_seed(0)
+    idx = torch.stack([torch.randperm(N, device=dev, generator=gen)[:B] for _ in range(S)]).to(torch.int32).contiguous()
+    hp = TrainHParams(lr=1e-4, momentum=0.9, weight_decay=1e-14, clip_norm=758.3, beta_in=1e-5, beta_out=1e-3,
+                      first_step=1, apply_update=0)
+    res = {}
+    for v in ("v3", "v2", "v1"):
+        monkeypatch.setenv("BNN_TRAIN_VARIANT", v)
+        g, met = _step(lib, cfg, hp, S, theta0.clone(), None, x, y, idx, B, None, 5, 11, dev)
+        g2, met2 = _step(lib, cfg, hp, S, theta0.clone(), None, x, y, idx, B, None, 5, 11, dev)
+        assert torch.equal(g, g2) and torch.equal(met, met2), v
+        assert bool(torch.isfinite(g).all()) and bool((met[:, 6] == 0).all())
+        res[v] = (g, met)
+    for v in ("v2", "v1"):
+        for s in range(S):
+            scale = float(res["v3"][0][s].abs().max())
+            assert float((res[v][0][s] - res["v3"][0][s]).abs().max()) <= 5e-5 * scale, (v, s)
+        np.testing.assert_allclose(res[v][1][:, :5].cpu().numpy(), res["v3"][1][:, :5].cpu().numpy(), rtol=2e-5)
+    assert not torch.equal(res["v3"][0][0], res["v3"][0][1])
