@@ -313,12 +313,32 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
         const char* dbgp = getenv("BNN_TC_TIMELINE_PTR");  // device pointer (decimal) to 8*512 int64, debugging only
         prm.dbg = dbgp ? reinterpret_cast<long long*>(strtoull(dbgp, nullptr, 10)) : nullptr;
     }
+    // Units are processed in chunks whose weights stay resident in L2: every system tile streams the weights of all
+    // units of a launch (~52 kB per unit: tensor-core operands + head), so with 60,000 units (BASELINE configs[2]) one
+    // launch would pull 3 GB per tile from HBM; per chunk only x is re-read (16.4 kB per system).  Results do not
+    // depend on the chunking (Philox is keyed on the global unit index).  BNN_PREDICT_UNIT_CHUNK overrides (tests).
+    int64_t unit_chunk = 1024;
+    if (const char* uc = getenv("BNN_PREDICT_UNIT_CHUNK")) unit_chunk = strtoll(uc, nullptr, 10);
+    if (unit_chunk < 1 || n_units <= unit_chunk + unit_chunk / 2) unit_chunk = n_units;
+    const PredictParams prm_all = prm;
+    const int L2_ = 2 * L;
+    for (int64_t u0 = 0; u0 < n_units; u0 += unit_chunk) {
+    const int64_t n_units_launch = n_units - u0 < unit_chunk ? n_units - u0 : unit_chunk;
+    prm = prm_all;
+    prm.U = n_units_launch;
+    prm.unit_offset = unit_offset + u0;
+    prm.thp = d_theta_packed + u0 * (int64_t)PackedLayout(lc.n, cfg->n_features).P;
+    prm.out = d_out + u0 * prm_all.out_unit_stride;
+    if (d_eps) prm.eps = d_eps + u0 * n_systems * L2_;
+    if (d_eps_sum) prm.eps_sum = d_eps_sum + u0 * n_systems * L2_;
+    if (d_summary_out) prm.summary = d_summary_out + u0 * n_systems * L2_;
+    int rc_launch = BNN_OK;
     // split units over CTAs only when the tiles alone cannot fill the GPU twice
     const int64_t tiles = (n_systems + SYS_TILE - 1) / SYS_TILE;
     int64_t chunks = 1;
     if (tiles < 2 * 148) chunks = (2 * 148 + tiles - 1) / tiles;
-    if (chunks > n_units) chunks = n_units;
-    prm.units_per_cta = (int)((n_units + chunks - 1) / chunks);
+    if (chunks > n_units_launch) chunks = n_units_launch;
+    prm.units_per_cta = (int)((n_units_launch + chunks - 1) / chunks);
     // variant selection: tensor cores (tcgen05, 3xTF32; 4 TMEM slots, 4 tail warps) when T = 100 and at most 31
     // live input columns; else the FFMA2 kernels: v2 (warp-specialised, TMA ring) when its tile fits in shared
     // memory, else v1.  BNN_PREDICT_VARIANT=tc4n4|tc4n3|tc3n4|tc2n4|v1|v2c8|v2c12|v2c16 forces one (benchmarks /
@@ -327,19 +347,20 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     const int T = cfg->n_times;
     cudaStream_t st = (cudaStream_t)stream;
     auto fits = [&](int nc) { return v2_smem_bytes(prm.kin, prm.F, T, nc) <= 227 * 1024; };
-    if (tc::tc_fits(prm, T)) {
-        if (force && !strcmp(force, "tc4n4")) return tc::launch_tc<4, 4>(prm, st);
-        if (force && !strcmp(force, "tc4n3")) return tc::launch_tc<4, 3>(prm, st);
-        if (force && !strcmp(force, "tc3n4")) return tc::launch_tc<3, 4>(prm, st);
-        if (force && !strcmp(force, "tc2n4")) return tc::launch_tc<2, 4>(prm, st);
-        if (!force) return tc::launch_tc<4, 4>(prm, st);
-    }
-    if (force && !strcmp(force, "v1")) return launch_v1<8>(prm, T, st);
-    if (force && !strcmp(force, "v2c8") && fits(8)) return launch_v2<8>(prm, T, st);
-    if (force && !strcmp(force, "v2c16") && fits(16)) return launch_v2<16>(prm, T, st);
-    if (fits(12)) return launch_v2<12>(prm, T, st);
-    if (fits(8)) return launch_v2<8>(prm, T, st);
-    return launch_v1<8>(prm, T, st);
+    if (tc::tc_fits(prm, T) && (!force || !strncmp(force, "tc", 2))) {
+        if (force && !strcmp(force, "tc4n3")) rc_launch = tc::launch_tc<4, 3>(prm, st);
+        else if (force && !strcmp(force, "tc3n4")) rc_launch = tc::launch_tc<3, 4>(prm, st);
+        else if (force && !strcmp(force, "tc2n4")) rc_launch = tc::launch_tc<2, 4>(prm, st);
+        else rc_launch = tc::launch_tc<4, 4>(prm, st);
+    } else if (force && !strcmp(force, "v1")) rc_launch = launch_v1<8>(prm, T, st);
+    else if (force && !strcmp(force, "v2c8") && fits(8)) rc_launch = launch_v2<8>(prm, T, st);
+    else if (force && !strcmp(force, "v2c16") && fits(16)) rc_launch = launch_v2<16>(prm, T, st);
+    else if (fits(12)) rc_launch = launch_v2<12>(prm, T, st);
+    else if (fits(8)) rc_launch = launch_v2<8>(prm, T, st);
+    else rc_launch = launch_v1<8>(prm, T, st);
+    if (rc_launch != BNN_OK) return rc_launch;
+    }  // unit chunks
+    return BNN_OK;
 }
 
 }  // extern "C"

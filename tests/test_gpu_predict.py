@@ -184,6 +184,35 @@ def test_sharded_equals_single_bitwise(dev):
         assert torch.equal(got, full.permute(1, 0, 2))
 
 
+def test_unit_chunked_launches_equal_single_launch(dev, monkeypatch):
+    """bnn_predict walks many units in L2-sized chunks (60,000 units at BASELINE configs[2]); the chunking must not show
+    in the results: both output layouts, the explicit-eps path and the summary output, bit for bit."""
+    ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(3, dev), make_swag_model(17, dev)], device=dev)
+    N, S_ = 43, 9   # 27 units
+    x = torch.from_numpy(synth.make_systems(N, seed=19)).to(dev)
+    _, thp = ens.sample_thetas(S_, 6)
+    ref_um = ens.predict(x, S_, seed=6, thp=thp)
+    ref_sm = ens.predict(x, S_, seed=6, thp=thp, system_major=True)
+    lib = _lib.load()
+    cfg = ens.config(100)
+    U = thp.shape[0]
+    eps = torch.randn((U, N, 40), device=dev)
+    def explicit():
+        out = torch.empty((U, N, 2), device=dev); summ = torch.empty((U, N, 40), device=dev)
+        _lib.check(lib.bnn_predict(cfg, _lib.ptr(x), N, _lib.ptr(thp), U, _lib.ptr(eps), None, 0, 0, 0, 0, _lib.ptr(out),
+                                   _lib.ptr(summ), None, _lib.current_stream_ptr()))
+        torch.cuda.synchronize()
+        return out, summ
+    ref_e, ref_s = explicit()
+    for chunk in ("4", "5", "13"):
+        monkeypatch.setenv("BNN_PREDICT_UNIT_CHUNK", chunk)
+        assert torch.equal(ens.predict(x, S_, seed=6, thp=thp), ref_um), chunk
+        assert torch.equal(ens.predict(x, S_, seed=6, thp=thp, system_major=True), ref_sm), chunk
+        o, sm_ = explicit()
+        assert torch.equal(o, ref_e) and torch.equal(sm_, ref_s), chunk
+    assert torch.equal(ref_sm, ref_um.permute(1, 0, 2))
+
+
 def test_edge_cases(dev):
     m = make_swag_model(0, dev)
     m.load(m.w_avg.clone())
