@@ -31,6 +31,19 @@ int check_device();  // BNN_OK or BNN_E_ARCH
         }                                 \
     } while (0)
 
+// One-time, per-device setup (cudaFuncSetAttribute applies to the current device): need() is true the first time it
+// is called with a given device current.  Two racing first calls may both return true; the setup is idempotent.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long b = 1ull << (d & 63);
+        const unsigned long long old = __atomic_fetch_or(&mask, b, __ATOMIC_RELAXED);
+        return !(old & b);
+    }
+};
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------------------

@@ -339,20 +339,18 @@ int bnn_summarize_instability(const float* d_t, const float* d_pred, int64_t n_s
         // more weight samples than the shared-memory sort holds (30 models x 2000 samples = 60000 at BASELINE config 3):
         // exact order statistics by radix select, nothing is stored
         const size_t hsm = (size_t)SEL_MAXT * 2048 * sizeof(uint32_t);
-        static bool attr2_done = false;
-        if (!attr2_done) {
+        static PerDeviceOnce attr2_done;
+        if (attr2_done.need()) {
             BNN_CUDA(cudaFuncSetAttribute(summarize_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr2_done = true;
         }
         summarize_select_kernel<<<(unsigned)n_systems, threads, hsm, (cudaStream_t)stream>>>(d_t, (const float2*)d_pred, n_trios,
                                                                                          n_units, d_stats);
         BNN_CUDA(cudaGetLastError());
         return BNN_OK;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         BNN_CUDA(cudaFuncSetAttribute(summarize_instability_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
     }
     summarize_instability_kernel<<<(unsigned)n_systems, threads, smem, (cudaStream_t)stream>>>(
         d_t, (const float2*)d_pred, n_trios, n_units, n_pow2, d_stats);

@@ -89,10 +89,9 @@ template <int NW>
 static int launch_v1(const PredictParams& prm, int T, cudaStream_t st) {
     const size_t smem = v1_smem_bytes(prm.kin, T, NW);
     BNN_REQUIRE(smem <= 227 * 1024, BNN_E_CONFIG, "predict tile needs %zu bytes of shared memory (> 227 KB)", smem);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         BNN_CUDA(cudaFuncSetAttribute(predict_v1_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     const int64_t tiles = (prm.N + SYS_TILE - 1) / SYS_TILE;
     const int64_t chunks = (prm.U + prm.units_per_cta - 1) / prm.units_per_cta;
@@ -223,14 +222,15 @@ static size_t v2_smem_bytes(int kin, int F, int T, int NC) {
 template <int NC>
 static int launch_v2(const PredictParams& prm, int T, cudaStream_t st) {
     const size_t smem = v2_smem_bytes(prm.kin, prm.F, T, NC);
-    static bool attr_done = false;
-    static int n_sms = 0;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         BNN_CUDA(cudaFuncSetAttribute(predict_v2_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    int n_sms = 0;
+    {
         int dev = 0;
         BNN_CUDA(cudaGetDevice(&dev));
         BNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
     }
     const int64_t tiles = (prm.N + SYS_TILE - 1) / SYS_TILE;
     BNN_REQUIRE(tiles < (1ll << 24), BNN_E_ARG, "too many system tiles for one launch (%lld)", (long long)tiles);

@@ -325,14 +325,15 @@ static int launch_tc(const PredictParams& prm, cudaStream_t st) {
     constexpr size_t smem = (size_t)SmemPlan<NSLOT, NT>::total;
     static_assert(smem <= 227 * 1024, "tensor-core tile does not fit in shared memory");
     constexpr int threads = (((NT + 3) & ~3) + 4 * NSLOT) * 32;
-    static bool attr_done = false;
-    static int n_sms = 0;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         BNN_CUDA(cudaFuncSetAttribute(predict_tc_kernel<NSLOT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    int n_sms = 0;
+    {
         int dev = 0;
         BNN_CUDA(cudaGetDevice(&dev));
         BNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
     }
     const int64_t tiles = (prm.N + SYS - 1) / SYS;
     BNN_REQUIRE(tiles < (1ll << 24), BNN_E_ARG, "too many system tiles for one launch (%lld)", (long long)tiles);

@@ -1378,10 +1378,9 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
     const train::Smem sl(T, F, FP);
     const size_t smem = (size_t)sl.total * sizeof(float);
     BNN_REQUIRE(smem <= 227 * 1024, BNN_E_CONFIG, "bnn_train_step: tile needs %zu bytes of shared memory", smem);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int n_cta = train::pick_n_cta(cfg, B, n_seeds);
@@ -1405,20 +1404,18 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
     prm.saliency = 0; prm.gx_out = nullptr; prm.mu_out = nullptr;
     if (train::use_v3(cfg)) {
         const size_t smem3 = (size_t)train::Smem3(T, F).total * sizeof(float);
-        static bool attr3_done = false;
-        if (!attr3_done) {
+        static PerDeviceOnce attr3_done;
+        if (attr3_done.need()) {
             BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd3_kernel<100, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           227 * 1024));
-            attr3_done = true;
         }
         train::train_fwd_bwd3_kernel<100, 41><<<dim3(n_cta, n_seeds), train::NTHR3, smem3, st>>>(prm);
     } else if (train::use_v2(cfg)) {
         const size_t smem2 = (size_t)train::Smem2(T, F, FP).total * sizeof(float);
-        static bool attr2_done = false;
-        if (!attr2_done) {
+        static PerDeviceOnce attr2_done;
+        if (attr2_done.need()) {
             BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd2_kernel<100, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           227 * 1024));
-            attr2_done = true;
         }
         train::train_fwd_bwd2_kernel<100, 41><<<dim3(n_cta, n_seeds), train::NTHR2, smem2, st>>>(prm);
     } else {
@@ -1472,11 +1469,10 @@ int bnn_saliency(const bnn_model_config* cfg, int32_t n_models, const float* d_t
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
     prm.beta_out = 0.f;
     prm.saliency = 1; prm.gx_out = d_grad_x; prm.mu_out = d_mu;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd3_kernel<100, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
-        attr_done = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem3 = (size_t)train::Smem3(T, F).total * sizeof(float);
