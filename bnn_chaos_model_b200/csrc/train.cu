@@ -1165,6 +1165,7 @@ __global__ void __launch_bounds__(NTHR2, 1) train_fwd_bwd2_kernel(const Params p
 }  // namespace train
 }  // namespace bnn
 #include "train_v3.cuh"
+#include "train_v4.cuh"
 namespace bnn {
 namespace train {
 
@@ -1305,10 +1306,16 @@ __global__ void saliency_finish_kernel(const float* __restrict__ partial, int n_
     sumsq[s * F + c] = 2.0f * a;
 }
 
-// v3 (large register tiles) for the reference's shape; BNN_TRAIN_VARIANT=v1|v2|v3 forces one
+// v4 (two CTAs per SM, one system per iteration): BNN_TRAIN_VARIANT=v4
+static bool use_v4(const bnn_model_config* cfg) {
+    const char* force = getenv("BNN_TRAIN_VARIANT");
+    return force && !strcmp(force, "v4") && cfg->n_times == 100 && cfg->n_features == 41;
+}
+
+// v3 (large register tiles) for the reference's shape; BNN_TRAIN_VARIANT=v1|v2|v3|v4 forces one
 static bool use_v3(const bnn_model_config* cfg) {
     const char* force = getenv("BNN_TRAIN_VARIANT");
-    if (force && (!strcmp(force, "v1") || !strcmp(force, "v2"))) return false;
+    if (force && (!strcmp(force, "v1") || !strcmp(force, "v2") || !strcmp(force, "v4"))) return false;
     return cfg->n_times == 100 && cfg->n_features == 41;
 }
 
@@ -1326,6 +1333,11 @@ static int pick_n_cta(const bnn_model_config* cfg, int64_t B, int n_seeds) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (use_v4(cfg)) {   // two resident CTAs per SM, one system per iteration
+        int64_t n4 = 2ll * sms / n_seeds;
+        if (n4 > B) n4 = B;
+        return (int)(n4 < 1 ? 1 : n4);
+    }
     const bool v2 = use_v2(cfg) || use_v3(cfg);
     // v1: two resident CTAs per SM, one system per iteration; v2: one CTA per SM, two systems per iteration
     // one-CTA-per-SM kernels: never more CTAs than SMs (a 149th CTA would run alone in a second wave)
@@ -1402,7 +1414,17 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
     prm.beta_out = hp->beta_out;
     prm.saliency = 0; prm.gx_out = nullptr; prm.mu_out = nullptr;
-    if (train::use_v3(cfg)) {
+    if (train::use_v4(cfg)) {
+        const size_t smem4 = (size_t)train::Smem4(T, F).total * sizeof(float);
+        static PerDeviceOnce attr4_done;
+        if (attr4_done.need()) {
+            BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd4_kernel<100, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem4));
+            BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd4_kernel<100, 41>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+        }
+        train::train_fwd_bwd4_kernel<100, 41><<<dim3(n_cta, n_seeds), train::NTHR4, smem4, st>>>(prm);
+    } else if (train::use_v3(cfg)) {
         const size_t smem3 = (size_t)train::Smem3(T, F).total * sizeof(float);
         static PerDeviceOnce attr3_done;
         if (attr3_done.need()) {

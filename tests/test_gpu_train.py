@@ -37,7 +37,7 @@ def _step(lib, cfg, hp, S, theta, mom, x, y, idx, B, eps, seed, step, dev, want_
     return grad, metrics
 
 
-@pytest.fixture(params=["v3", "v2", "v1"], autouse=True)
+@pytest.fixture(params=["v3", "v4", "v2", "v1"], autouse=True)
 def train_variant(request, monkeypatch):
     """Every test of this file runs on all three training kernels (v3: large register tiles, deferred head
     gradients -- the default; v2: two systems per iteration, one outer-product phase; v1: one system per iteration)."""
@@ -349,14 +349,14 @@ def test_full_size_step_properties(dev, monkeypatch):
     hp = TrainHParams(lr=1e-4, momentum=0.9, weight_decay=1e-14, clip_norm=758.3, beta_in=1e-5, beta_out=1e-3,
                       first_step=1, apply_update=0)
     res = {}
-    for v in ("v3", "v2", "v1"):
+    for v in ("v3", "v4", "v2", "v1"):
         monkeypatch.setenv("BNN_TRAIN_VARIANT", v)
         g, met = _step(lib, cfg, hp, S, theta0.clone(), None, x, y, idx, B, None, 5, 11, dev)
         g2, met2 = _step(lib, cfg, hp, S, theta0.clone(), None, x, y, idx, B, None, 5, 11, dev)
         assert torch.equal(g, g2) and torch.equal(met, met2), v
         assert bool(torch.isfinite(g).all()) and bool((met[:, 6] == 0).all())
         res[v] = (g, met)
-    for v in ("v2", "v1"):
+    for v in ("v4", "v2", "v1"):
         for s in range(S):
             scale = float(res["v3"][0][s].abs().max())
             assert float((res[v][0][s] - res["v3"][0][s]).abs().max()) <= 5e-5 * scale, (v, s)
