@@ -369,7 +369,7 @@ def run_ours(args):
                          "traffic_source": "profiles/r1_predict_tc4n4_ncu.txt (ncu --set full, same workload, per launch); "
                                            "algorithmic HBM bytes per launch: 0.32e9",
                          "note": "north_star's roofline for this kernel is the FP32 CUDA-core FMA peak; the kernel runs the "
-                                 "feature MLP as 3xTF32 on tcgen05 (tensor pipe active 27 %, profiles/)"},
+                                 "feature MLP as 3xTF32 on tcgen05 (tensor pipe active 33 %, profiles/)"},
             "cpu_baseline": cb,
             "train": train,
         }
