@@ -159,3 +159,55 @@ extern "C" int bnn_tc_probe(const float* d_A, const float* d_B, float* d_D, int3
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Warp-level mma.sync.m16n8k8 (tf32, fp32 accumulate) issue-rate probe: every warp of the CTA runs `iters` rounds of
+// NACC independent MMAs (operands in registers).  out[0] = cycles of warp 0, out[1] = MMAs per warp.
+// ---------------------------------------------------------------------------------------
+namespace bnn {
+template <int NACC>
+__global__ void mma_sync_rate_kernel(int iters, long long* out, float* sink) {
+    float c[NACC][4];
+    uint32_t a[4], b[2];
+    for (int i = 0; i < 4; ++i) a[i] = __float_as_uint(1.0f + 0.001f * (float)((threadIdx.x + i) & 7));
+    for (int i = 0; i < 2; ++i) b[i] = __float_as_uint(0.5f + 0.001f * (float)((threadIdx.x + i) & 3));
+#pragma unroll
+    for (int n = 0; n < NACC; ++n)
+        for (int i = 0; i < 4; ++i) c[n][i] = 0.f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int n = 0; n < NACC; ++n)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[n][0]), "+f"(c[n][1]), "+f"(c[n][2]), "+f"(c[n][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int n = 0; n < NACC; ++n) s += c[n][0] + c[n][1] + c[n][2] + c[n][3];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        out[0] = t1 - t0;
+        out[1] = (long long)iters * NACC;
+    }
+}
+}  // namespace bnn
+
+extern "C" int bnn_mma_sync_rate(int32_t warps_per_cta, int32_t n_acc, int32_t iters, long long* d_out, float* d_sink,
+                                 void* stream) {
+    using namespace bnn;
+    int rc = check_device();
+    if (rc != BNN_OK) return rc;
+    BNN_REQUIRE(d_out && d_sink && warps_per_cta >= 1 && warps_per_cta <= 32 && iters >= 1, BNN_E_ARG,
+                "bnn_mma_sync_rate: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_acc == 1) mma_sync_rate_kernel<1><<<148, 32 * warps_per_cta, 0, st>>>(iters, d_out, d_sink);
+    else if (n_acc == 4) mma_sync_rate_kernel<4><<<148, 32 * warps_per_cta, 0, st>>>(iters, d_out, d_sink);
+    else if (n_acc == 8) mma_sync_rate_kernel<8><<<148, 32 * warps_per_cta, 0, st>>>(iters, d_out, d_sink);
+    else if (n_acc == 15) mma_sync_rate_kernel<15><<<148, 32 * warps_per_cta, 0, st>>>(iters, d_out, d_sink);
+    else BNN_REQUIRE(false, BNN_E_ARG, "bnn_mma_sync_rate: n_acc must be 1, 4, 8 or 15");
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}

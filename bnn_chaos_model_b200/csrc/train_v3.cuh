@@ -124,8 +124,10 @@ __device__ __forceinline__ void rowgemm4(const float* __restrict__ AT, const flo
     }
 }
 
+// outer-product variant: 16 = warp-level tensor-core tiles (mma.sync 3xTF32, default), 48 = 4 x 8 FFMA2 blocks,
+// 88 = 8 x 8 FFMA blocks
 #ifndef V3_OUTER
-#define V3_OUTER 48
+#define V3_OUTER 16
 #endif
 // 4 x 8 variant: even / odd rows accumulate in the two halves of an fp32x2 register (no packing moves)
 __device__ __forceinline__ void outer4x8(const float* __restrict__ Gp, int gstr, const float* __restrict__ Hp, int hstr,
@@ -179,6 +181,61 @@ __device__ __forceinline__ void outer8x8(const float* __restrict__ Gp, int gstr,
                 a = fmaf(g[jj].z, h.z, a);
                 a = fmaf(g[jj].w, h.w, a);
                 acc[jj][kk] = a;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-level tensor-core tiles: mma.sync.m16n8k8, tf32 x tf32 -> fp32, operands in registers (512 MAC per cycle per SM
+// measured, tools/mma_sync_rate.py: 4 x the FP32 FMA rate).  Full fp32 accuracy comes from the 3xTF32 split done in
+// registers (hi = cvt.rna.tf32, lo = x - hi; lo.hi + hi.lo first, hi.hi last), so that three MMAs = one fp32-grade
+// 16 x 8 x 8 tile: 1.33 x the FP32 roofline, with 22 LDS.32 per 15 tiles instead of 12 LDS.128 per 4 x 8 x 4 block.
+// Fragment layout (g = lane / 4, t = lane % 4): A a0 = (g, t) a1 = (g+8, t) a2 = (g, t+4) a3 = (g+8, t+4);
+// B b0 = (k = t, n = g) b1 = (t+4, g); D c0 = (g, 2t) c1 = (g, 2t+1) c2 = (g+8, 2t) c3 = (g+8, 2t+1).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// acc[mt][nt] (16 x 8 tiles of D[m][n]) += sum over the rows of k-steps [ks0, ks1) (8 rows each) of
+// Ms[(16 mt + m)][r] * Ns[(8 nt + n)][r]; both operands feature-major with pitch RP: dW[j = n][k = m] of one layer.
+// RP = 12 mod 32 makes every fragment LDS.32 one conflict-free wavefront (bank = 12 g + t).
+template <int RP, int NNT>
+__device__ __forceinline__ void outer_mma(const float* __restrict__ Ms, const float* __restrict__ Ns, int ks0, int ks1,
+                                          int lane, float (&acc)[3][NNT][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const float* mp = Ms + g * RP + t;
+    const float* np_ = Ns + g * RP + t;
+#pragma unroll 1
+    for (int ks = ks0; ks < ks1; ++ks) {
+        const int r0 = 8 * ks;
+        uint32_t ah[3][4], al[3][4];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {
+            const float* p = mp + 16 * mt * RP + r0;
+            split_tf32(p[0], ah[mt][0], al[mt][0]);
+            split_tf32(p[8 * RP], ah[mt][1], al[mt][1]);
+            split_tf32(p[4], ah[mt][2], al[mt][2]);
+            split_tf32(p[8 * RP + 4], ah[mt][3], al[mt][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NNT; ++nt) {
+            const float* p = np_ + 8 * nt * RP + r0;
+            uint32_t bh[2], bl[2];
+            split_tf32(p[0], bh[0], bl[0]);
+            split_tf32(p[4], bh[1], bl[1]);
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+                mma_tf32(acc[mt][nt], al[mt], bh);
+                mma_tf32(acc[mt][nt], ah[mt], bl);
+                mma_tf32(acc[mt][nt], ah[mt], bh);
             }
         }
     }
@@ -401,7 +458,18 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     const int cg_rg = tid / NQ2, q_rg = tid - NQ2 * cg_rg;   // 5 groups: tid < 250; g_x (48 columns, 6 groups): tid < 300
     // outer products: one block of one matrix over one row group
     const float* opG; const float* opH; int op_gstr, op_q0, op_q1, op_role, op_jb, op_kb;
-#if V3_OUTER == 88
+#if V3_OUTER == 16
+    // warp-level tensor-core tiles: warps 0..4 dW0 (M side x', 48 x 40), 5..9 dW1 (h1, 48 x 40), five k-steps of 8 rows
+    // each; warps 10, 11 dW2 (h2 x g_f, 48 x 24), 13 / 12 k-steps.  60 accumulators per thread (36 for dW2).
+    const int owarp = tid >> 5;
+    op_role = owarp < 5 ? 0 : (owarp < 10 ? 1 : 2);
+    opG = op_role == 0 ? g1T : (op_role == 1 ? g2T : fT);    // N side (output index j)
+    opH = op_role == 0 ? xT : (op_role == 1 ? h1T : h2T);    // M side (input index k)
+    op_q0 = op_role == 0 ? 5 * owarp : (op_role == 1 ? 5 * (owarp - 5) : (owarp == 10 ? 0 : 13));
+    op_q1 = op_role == 0 ? 5 * owarp + 5 : (op_role == 1 ? 5 * (owarp - 5) + 5 : (owarp == 10 ? 13 : 25));
+    op_gstr = 0; op_jb = 0; op_kb = 0;
+    constexpr int OJ = 8;   // 64 stash columns per thread
+#elif V3_OUTER == 88
     // 8 x 8 blocks, six row groups (dW2: five)
     {
         int r = tid, rg;
@@ -859,7 +927,10 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         if (!prm.saliency) {
             float aW[OJ][8];
             stash_load<NV>(taddr, &aW[0][0]);
-#if V3_OUTER == 88
+#if V3_OUTER == 16
+            if (op_role < 2) outer_mma<RP, 5>(opH, opG, op_q0, op_q1, lane, *reinterpret_cast<float (*)[3][5][4]>(&aW[0][0]));
+            else outer_mma<RP, 3>(opH, opG, op_q0, op_q1, lane, *reinterpret_cast<float (*)[3][3][4]>(&aW[0][0]));
+#elif V3_OUTER == 88
             outer8x8(opG, op_gstr, opH, 5 * RP, op_q0, op_q1, aW);
 #else
             outer4x8(opG, op_gstr, opH, 5 * RP, op_q0, op_q1, aW);
@@ -943,6 +1014,32 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     // (1) feature matrices: add the row groups in a fixed order
     float aW[OJ][8];
     stash_load<NV>(taddr, &aW[0][0]);
+#if V3_OUTER == 16
+    {
+        // every warp parks its 60 partial sums; the first warp of a matrix adds its partners' in warp order and writes
+        float* o = red + tid * 64;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) o[i] = (&aW[0][0])[i];
+        MAIN_SYNC();
+        const int first = op_role == 0 ? 0 : (op_role == 1 ? 5 : 10), nw = op_role == 2 ? 2 : 5;
+        if (owarp == first) {
+            const int nnt = op_role == 2 ? 3 : 5;
+            const int g = lane >> 2, t = lane & 3;
+            const int off = op_role == 0 ? fl.W0 : (op_role == 1 ? fl.W1 : fl.W2);
+            const int pitch = op_role == 0 ? F : H, mmax = op_role == 0 ? F : H, nmax = op_role == 2 ? L : H;
+            for (int mt = 0; mt < 3; ++mt)
+                for (int nt = 0; nt < nnt; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = (mt * nnt + nt) * 4 + i;
+                        float a = 0.f;
+                        for (int w = 0; w < nw; ++w) a += red[((first + w) * 32 + lane) * 64 + idx];
+                        const int m = 16 * mt + g + (i & 2 ? 8 : 0), n = 8 * nt + 2 * t + (i & 1);
+                        if (m < mmax && n < nmax) part[off + n * pitch + m] = a;
+                    }
+        }
+    }
+#else
     if (op_role < 3) {
         float* o = red + tid * (OJ * 8);
 #pragma unroll
@@ -950,7 +1047,9 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) o[jj * 8 + kk] = aW[jj][kk];
     }
+#endif
     MAIN_SYNC();
+#if V3_OUTER != 16
     if (op_role < 3) {
 #if V3_OUTER == 88
         const int nblk = op_role == 2 ? 15 : 25, ngrp = op_role == 2 ? 5 : 6;
@@ -975,6 +1074,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 }
         }
     }
+#endif
     MAIN_SYNC();
     // (2) dlv_in (fixed-order sum over the row quads), b0 / b1 / column 40 of dW0, b2
     if (tid < 6 * NQ2) {
@@ -985,7 +1085,11 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         for (int e = 0; e < 2; ++e) {
             const int r = tid - 6 * NQ2 + e * (NMAIN - 6 * NQ2);
             if (r < H) part[fl.b0 + r] = aux[e];
-            else if (r < 2 * H) part[fl.W0 + (r - H) * F + (F - 1)] = aux[e];
+            else if (r < 2 * H) {
+#if V3_OUTER != 16
+                part[fl.W0 + (r - H) * F + (F - 1)] = aux[e];   // (the tensor-core tiles cover column 40 themselves)
+#endif
+            }
             else if (r < 3 * H) part[fl.b1 + r - 2 * H] = aux[e];
         }
     }

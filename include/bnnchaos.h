@@ -250,6 +250,11 @@ int bnn_tc_probe(const float* d_A, const float* d_B, float* d_D, int32_t K, int3
  * d_out[0] = issue-to-completion cycles, d_out[1] = cycles spent issuing.  from_smem: A from shared memory. */
 int bnn_tc_time(int32_t K, int32_t N, int32_t reps, int32_t from_smem, long long* d_out, void* stream);
 
+/* Diagnostic: issue rate of the warp-level mma.sync.m16n8k8 (tf32 x tf32 -> fp32, operands in registers): 148 CTAs of
+ * warps_per_cta warps each run iters rounds of n_acc (1, 4, 8 or 15) independent MMAs; d_out[0] = cycles of warp 0 of
+ * CTA 0, d_out[1] = MMAs per warp; d_sink: 148 * 32 * warps_per_cta floats. */
+int bnn_mma_sync_rate(int32_t warps_per_cta, int32_t n_acc, int32_t iters, long long* d_out, float* d_sink, void* stream);
+
 /* Diagnostic: per-phase cycle totals of CTA (0,0) of the last bnn_train_step (v3 kernel), copied to host_out[n].
  * All zeros unless the library was built with `make TRAIN_TIMELINE=1` (the stamps are compiled out by default).
  * Synchronises the device. */
