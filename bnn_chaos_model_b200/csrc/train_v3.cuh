@@ -200,16 +200,19 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    // round to nearest on the 13 dropped mantissa bits with two integer ops (cvt.rna.tf32 goes through the
+    // conversion unit at a fraction of the ALU rate and was as expensive as the MMAs it feeds)
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-// acc[mt][nt] (16 x 8 tiles of D[m][n]) += sum over the rows of k-steps [ks0, ks1) (8 rows each) of
-// Ms[(16 mt + m)][r] * Ns[(8 nt + n)][r]; both operands feature-major with pitch RP: dW[j = n][k = m] of one layer.
-// RP = 12 mod 32 makes every fragment LDS.32 one conflict-free wavefront (bank = 12 g + t).
-template <int RP, int NNT>
+// acc[nt][4 mt + i] (16 x 8 tiles of D[m][n], three row tiles mt per column tile nt; 16 stash columns per nt, 12 used)
+// += sum over the rows of k-steps [ks0, ks1) (8 rows each) of Ms[(16 mt + m)][r] * Ns[(8 nt + n)][r]; both operands
+// feature-major with pitch RP: dW[j = n][k = m] of one layer.  RP = 12 mod 32 makes every fragment LDS.32 one
+// conflict-free wavefront (bank = 12 g + t).  NN column tiles per call: 36 accumulators in registers at most.
+template <int RP, int NN>
 __device__ __forceinline__ void outer_mma(const float* __restrict__ Ms, const float* __restrict__ Ns, int ks0, int ks1,
-                                          int lane, float (&acc)[3][NNT][4]) {
+                                          int lane, float (&acc)[NN][16]) {
     const int g = lane >> 2, t = lane & 3;
     const float* mp = Ms + g * RP + t;
     const float* np_ = Ns + g * RP + t;
@@ -225,19 +228,114 @@ __device__ __forceinline__ void outer_mma(const float* __restrict__ Ms, const fl
             split_tf32(p[4], ah[mt][2], al[mt][2]);
             split_tf32(p[8 * RP + 4], ah[mt][3], al[mt][3]);
         }
+        uint32_t bh[NN][2], bl[NN][2];
+#pragma unroll
+        for (int nt = 0; nt < NN; ++nt) {
+            const float* p = np_ + 8 * nt * RP + r0;
+            split_tf32(p[0], bh[nt][0], bl[nt][0]);
+            split_tf32(p[4], bh[nt][1], bl[nt][1]);
+        }
+        // three passes over the 3 NN independent tiles: consecutive MMAs never touch the same accumulator
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+            for (int nt = 0; nt < NN; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 3; ++mt) {
+                    float (&c)[4] = *reinterpret_cast<float (*)[4]>(&acc[nt][4 * mt]);
+                    if (pass == 0) mma_tf32(c, al[mt], bh[nt]);
+                    else if (pass == 1) mma_tf32(c, ah[mt], bl[nt]);
+                    else mma_tf32(c, ah[mt], bh[nt]);
+                }
+    }
+}
+
+// Row GEMM on the same tiles: C[row][n] = sum_k AT[k][row] * W[k][n] over the 2T = 200 rows (12 full 16-row tiles +
+// one half-used tile), K padded to a multiple of 8 with zero operands, N = 8 * NNT columns (pad columns read whatever
+// follows W and are dropped by the epilogue).  Warp w owns rows [16 w, 16 w + 16) with all NNT column tiles (its A
+// fragments are loaded and split once per k-step) and, for w < NNT, the tile (rows 192.., columns 8 w..) of the 13th
+// row tile (accx).  The caller runs the epilogue over acc[nt] (rows 16 w + g (+8), columns 8 nt + 2 t (+1)) and accx.
+// V3_GEMM: 0 = the six row GEMMs on 4 x 8 FFMA2 register tiles (default), 1 = on the same mma.sync tiles as the outer
+// products.  Measured (4 seeds x 2000): 0.754 ms vs 1.115 ms per step -- for the row GEMMs the 3xTF32 tile rate of the
+// legacy tensor path (three 8-cycle MMAs per 16 x 8 x 8 = 1.33 x the FP32 FMA rate, 0.85 of it left after padding
+// 200 x 41 / 20 to tile multiples) does not beat FFMA2 tiles that already run from registers, and every layer pays
+// two splits per operand word; the outer products win because their operand traffic drops 8-fold.
+#ifndef V3_GEMM
+#define V3_GEMM 0
+#endif
+template <int RP, int K, int NP, int NNT>
+__device__ __forceinline__ void rowgemm_mma(const float* __restrict__ AT, const float* __restrict__ W, int warp, int lane,
+                                            float (&acc)[NNT][4], float (&accx)[4]) {
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int KS = (K + 7) / 8;
+    constexpr bool KPAD = (K % 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accx[i] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NNT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const bool has_x = warp < NNT;
+    const float* ap = AT + t * RP + 16 * warp + g;
+    const float* axp = AT + t * RP + 192 + g;
+    const float* wp = W + t * NP + g;
+#pragma unroll 1
+    for (int ks = 0; ks < KS; ++ks) {
+        const int k0 = 8 * ks;
+        const bool v0 = !KPAD || (k0 + t < K), v1 = !KPAD || (k0 + t + 4 < K);
+        uint32_t ah[4], al[4], xh[4], xl[4];
+        split_tf32(v0 ? ap[k0 * RP] : 0.f, ah[0], al[0]);
+        split_tf32(v0 ? ap[k0 * RP + 8] : 0.f, ah[1], al[1]);
+        split_tf32(v1 ? ap[(k0 + 4) * RP] : 0.f, ah[2], al[2]);
+        split_tf32(v1 ? ap[(k0 + 4) * RP + 8] : 0.f, ah[3], al[3]);
+        if (has_x) {
+            split_tf32(v0 ? axp[k0 * RP] : 0.f, xh[0], xl[0]);
+            split_tf32(v0 ? axp[k0 * RP + 8] : 0.f, xh[1], xl[1]);
+            split_tf32(v1 ? axp[(k0 + 4) * RP] : 0.f, xh[2], xl[2]);
+            split_tf32(v1 ? axp[(k0 + 4) * RP + 8] : 0.f, xh[3], xl[3]);
+        }
+        uint32_t bh[NNT][2], bl[NNT][2];
 #pragma unroll
         for (int nt = 0; nt < NNT; ++nt) {
-            const float* p = np_ + 8 * nt * RP + r0;
-            uint32_t bh[2], bl[2];
-            split_tf32(p[0], bh[0], bl[0]);
-            split_tf32(p[4], bh[1], bl[1]);
+            split_tf32(v0 ? wp[k0 * NP + 8 * nt] : 0.f, bh[nt][0], bl[nt][0]);
+            split_tf32(v1 ? wp[(k0 + 4) * NP + 8 * nt] : 0.f, bh[nt][1], bl[nt][1]);
+        }
+        // three passes over the independent tiles: consecutive MMAs never touch the same accumulator
 #pragma unroll
-            for (int mt = 0; mt < 3; ++mt) {
-                mma_tf32(acc[mt][nt], al[mt], bh);
-                mma_tf32(acc[mt][nt], ah[mt], bl);
-                mma_tf32(acc[mt][nt], ah[mt], bh);
+        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+            for (int nt = 0; nt < NNT; ++nt) {
+                if (pass == 0) mma_tf32(acc[nt], al, bh[nt]);
+                else if (pass == 1) mma_tf32(acc[nt], ah, bl[nt]);
+                else mma_tf32(acc[nt], ah, bh[nt]);
+                if (has_x && nt == warp) {
+                    if (pass == 0) mma_tf32(accx, xl, bh[nt]);
+                    else if (pass == 1) mma_tf32(accx, xh, bl[nt]);
+                    else mma_tf32(accx, xh, bh[nt]);
+                }
             }
         }
+    }
+}
+// epilogues of one tile: c0 = (row, col), c1 = (row, col + 1), c2 = (row + 8, col), c3 = (row + 8, col + 1); full = rows + 8 exist
+template <int RP, bool RELU>
+__device__ __forceinline__ void tile_store_bias(float* __restrict__ out, const float* __restrict__ bias, int row, int col,
+                                                const float (&c)[4], bool full) {
+    const float bA = bias[col], bB = bias[col + 1];
+    float v0 = c[0] + bA, v1 = c[1] + bB, v2 = c[2] + bA, v3 = c[3] + bB;
+    if (RELU) { v0 = relu_nan(v0); v1 = relu_nan(v1); v2 = relu_nan(v2); v3 = relu_nan(v3); }
+    out[col * RP + row] = v0;
+    out[(col + 1) * RP + row] = v1;
+    if (full) { out[col * RP + row + 8] = v2; out[(col + 1) * RP + row + 8] = v3; }
+}
+template <int RP>
+__device__ __forceinline__ void tile_store_masked(float* __restrict__ out, const float* __restrict__ hT, int row, int col,
+                                                  const float (&c)[4], bool full) {
+    out[col * RP + row] = hT[col * RP + row] > 0.f ? c[0] : 0.f;
+    out[(col + 1) * RP + row] = hT[(col + 1) * RP + row] > 0.f ? c[1] : 0.f;
+    if (full) {
+        out[col * RP + row + 8] = hT[col * RP + row + 8] > 0.f ? c[2] : 0.f;
+        out[(col + 1) * RP + row + 8] = hT[(col + 1) * RP + row + 8] > 0.f ? c[3] : 0.f;
     }
 }
 
@@ -468,7 +566,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     op_q0 = op_role == 0 ? 5 * owarp : (op_role == 1 ? 5 * (owarp - 5) : (owarp == 10 ? 0 : 13));
     op_q1 = op_role == 0 ? 5 * owarp + 5 : (op_role == 1 ? 5 * (owarp - 5) + 5 : (owarp == 10 ? 13 : 25));
     op_gstr = 0; op_jb = 0; op_kb = 0;
-    constexpr int OJ = 8;   // 64 stash columns per thread
+    constexpr int OJ = 10;   // 80 stash columns per thread: 5 column tiles x 16 (12 used)
 #elif V3_OUTER == 88
     // 8 x 8 blocks, six row groups (dW2: five)
     {
@@ -500,7 +598,11 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     constexpr int OJ = 4;
 #endif
     // the block's accumulators: OJ * 8 columns of this thread's TMEM lane (three warps share a lane quadrant)
-    constexpr int NV = OJ * 8, TCOLS = NV == 32 ? 128 : 256;
+#if V3_GEMM == 1
+    constexpr int NV = OJ * 8, TSTRIDE = NV + 16, TCOLS = 512;   // + 16 columns per thread for the dlv_in partial sums
+#else
+    constexpr int NV = OJ * 8, TSTRIDE = NV, TCOLS = NV == 32 ? 128 : 256;   // three warps per lane quadrant: 3 NV <= TCOLS
+#endif
     uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + L_.prod + 63);
     if (tid < 32) { tmem_alloc(tslot, TCOLS); tmem_relinquish(); }
     tc_fence_before();
@@ -574,16 +676,25 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     // =====================================================================================================
     // Pipeline warps (0..11)
     // =====================================================================================================
-    const uint32_t taddr = tbase + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * NV);
+    const uint32_t taddr = tbase + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * TSTRIDE);
     {
         float z[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) z[i] = 0.f;
         stash_store<NV>(taddr, z);
+#if V3_GEMM == 1
+        stash_store<16>(taddr + NV, z);
+#endif
     }
     // tid < 300: dlv_in partial sums of this thread's 8 g_x columns; tid >= 300: two of the 120 row sums
     // (rows 0..39: b0 = sum g_a1, 40..79: column 40 of dW0 = sum g_a1 x'[40], 80..119: b1 = sum g_a2)
     float aux[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#if V3_GEMM == 1
+    // tensor-core row GEMMs: the dlv_in partial sums per (column tile slot, column of the pair) live in 16 stash
+    // columns and are in registers only inside the g_x phase; b0 / b1 row sums (tid < 80)
+    float arow = 0.f;
+    (void)aux;
+#endif
     float ab2 = 0.f, a_nll = 0.f, a_skl = 0.f;
     const float Tf = (float)T, Tm1 = (float)(T - 1);
     int parity = 0;
@@ -626,6 +737,39 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         MAIN_SYNC();
         TL3(1);
         // ---- S1..S3: feature_nn forward over the 2T rows ----
+#if V3_GEMM == 1
+        {
+            const int wrp = tid >> 5, mg = lane >> 2, mt2 = 2 * (lane & 3);
+            float acc[5][4], accx[4];
+            rowgemm_mma<RP, F, H, 5>(xT, W0T, wrp, lane, acc, accx);
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) tile_store_bias<RP, true>(h1T, b0, 16 * wrp + mg, 8 * nt + mt2, acc[nt], true);
+            if (wrp < 5) tile_store_bias<RP, true>(h1T, b0, 192 + mg, 8 * wrp + mt2, accx, false);
+        }
+        MAIN_SYNC();
+        TL3(2);
+        {
+            const int wrp = tid >> 5, mg = lane >> 2, mt2 = 2 * (lane & 3);
+            float acc[5][4], accx[4];
+            rowgemm_mma<RP, H, H, 5>(h1T, W1T, wrp, lane, acc, accx);
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) tile_store_bias<RP, true>(h2T, b1, 16 * wrp + mg, 8 * nt + mt2, acc[nt], true);
+            if (wrp < 5) tile_store_bias<RP, true>(h2T, b1, 192 + mg, 8 * wrp + mt2, accx, false);
+        }
+        MAIN_SYNC();
+        TL3(3);
+        {
+            const int wrp = tid >> 5, mg = lane >> 2, mt2 = 2 * (lane & 3);
+            float acc[3][4], accx[4];
+            rowgemm_mma<RP, H, L, 3>(h2T, W2T, wrp, lane, acc, accx);
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+                if (8 * nt + mt2 < L) tile_store_bias<RP, false>(fT, b2, 16 * wrp + mg, 8 * nt + mt2, acc[nt], true);   // columns 20..23: padding
+            if (wrp < 3 && 8 * wrp + mt2 < L) tile_store_bias<RP, false>(fT, b2, 192 + mg, 8 * wrp + mt2, accx, false);
+        }
+        MAIN_SYNC();
+        TL3(4);
+#else
         if (tid < 5 * NQ2) {
             u64 a2[4][4];
 #pragma unroll
@@ -692,6 +836,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         }
         MAIN_SYNC();
         TL3(4);
+#endif
         // ---- S4: pooling per system (two-pass mean / unbiased variance per latent column, :418-419) ----
         if (lt < L * 8) {
             const int c = lt >> 3, part = lt & 7;
@@ -874,6 +1019,18 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             ab2 += s;
         }
         // ---- S10: g_a2 = (g_f W2) . [h2 > 0] ----
+#if V3_GEMM == 1
+        {
+            const int wrp = tid >> 5, mg = lane >> 2, mt2 = 2 * (lane & 3);
+            float acc[5][4], accx[4];
+            rowgemm_mma<RP, L, H, 5>(fT, W2n, wrp, lane, acc, accx);
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) tile_store_masked<RP>(g2T, h2T, 16 * wrp + mg, 8 * nt + mt2, acc[nt], true);
+            if (wrp < 5) tile_store_masked<RP>(g2T, h2T, 192 + mg, 8 * wrp + mt2, accx, false);
+        }
+        MAIN_SYNC();
+        TL3(6);
+#else
         if (tid < 5 * NQ2) {
             u64 a2[4][4];
 #pragma unroll
@@ -898,7 +1055,20 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         }
         MAIN_SYNC();
         TL3(6);
+#endif
         // ---- S12: g_a1 = (g_a2 W1) . [h1 > 0] ----
+#if V3_GEMM == 1
+        {
+            const int wrp = tid >> 5, mg = lane >> 2, mt2 = 2 * (lane & 3);
+            float acc[5][4], accx[4];
+            rowgemm_mma<RP, H, H, 5>(g2T, W1n, wrp, lane, acc, accx);
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) tile_store_masked<RP>(g1T, h1T, 16 * wrp + mg, 8 * nt + mt2, acc[nt], true);
+            if (wrp < 5) tile_store_masked<RP>(g1T, h1T, 192 + mg, 8 * wrp + mt2, accx, false);
+        }
+        MAIN_SYNC();
+        TL3(7);
+#else
         if (tid < 5 * NQ2) {
             u64 a2[4][4];
 #pragma unroll
@@ -923,22 +1093,96 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         }
         MAIN_SYNC();
         TL3(7);
+#endif
         // ---- S13: all weight-gradient outer products in one phase ----
         if (!prm.saliency) {
+#if V3_OUTER == 16
+            {   // column tiles 0..2, then 3..4 (dW2 has three): at most 36 accumulators in registers at a time
+                float a3[3][16];
+                stash_load<48>(taddr, &a3[0][0]);
+                outer_mma<RP, 3>(opH, opG, op_q0, op_q1, lane, a3);
+                stash_store<48>(taddr, &a3[0][0]);
+            }
+            if (op_role < 2) {
+                float a2[2][16];
+                stash_load<32>(taddr + 48, &a2[0][0]);
+                outer_mma<RP, 2>(opH, opG + 24 * RP, op_q0, op_q1, lane, a2);
+                stash_store<32>(taddr + 48, &a2[0][0]);
+            }
+#else
             float aW[OJ][8];
             stash_load<NV>(taddr, &aW[0][0]);
-#if V3_OUTER == 16
-            if (op_role < 2) outer_mma<RP, 5>(opH, opG, op_q0, op_q1, lane, *reinterpret_cast<float (*)[3][5][4]>(&aW[0][0]));
-            else outer_mma<RP, 3>(opH, opG, op_q0, op_q1, lane, *reinterpret_cast<float (*)[3][3][4]>(&aW[0][0]));
-#elif V3_OUTER == 88
+#if V3_OUTER == 88
             outer8x8(opG, op_gstr, opH, 5 * RP, op_q0, op_q1, aW);
 #else
             outer4x8(opG, op_gstr, opH, 5 * RP, op_q0, op_q1, aW);
 #endif
             stash_store<NV>(taddr, &aW[0][0]);
+#endif
         }
         TL3(8);
         // ---- S14: g_x = g_a1 W0, dlv_in += sum g_x . (x' - mask(x)) / 2; the two spare warps do the row sums ----
+#if V3_GEMM == 1
+        {
+            const int wrp = tid >> 5, mg = lane >> 2, mt2 = 2 * (lane & 3);
+            // n = x' - mask(x) of this thread's elements, from the L2 scratch: issued before the GEMM so that the latency
+            // hides under it (slot nt: columns 8 nt + 2 t + e, rows 16 w + g (+8); slot 6: the 13th row tile)
+            float nn[7][4];
+            if (!prm.saliency) {
+#pragma unroll
+                for (int nt = 0; nt < 7; ++nt) {
+                    const int row = nt < 6 ? 16 * wrp + mg : 192 + mg, col = nt < 6 ? 8 * nt + mt2 : 8 * wrp + mt2;
+                    const bool full = nt < 6;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cc = min(col + e, F - 1);
+                        nn[nt][e] = (nt < 6 || wrp < 6) ? __ldcg(np_cur + cc * RT + row) : 0.f;
+                        nn[nt][2 + e] = full ? __ldcg(np_cur + cc * RT + row + 8) : 0.f;
+                    }
+                }
+            }
+            float acc[6][4], accx[4];
+            rowgemm_mma<RP, H, W0NP, 6>(g1T, W0n, wrp, lane, acc, accx);
+            float agx[8][2];
+            stash_load<16>(taddr + NV, &agx[0][0]);
+            // one tile: d mu / d x (saliency) or dlv_in += g_x . (x' - mask(x)), with n = x' - mask(x) from the L2 scratch
+            auto tile = [&](int row, int col, const float (&c)[4], bool full, float (&ag)[2], const float (&nv)[4]) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int cc = col + e;
+                    if (cc < F) {
+                        const float v0 = c[e], v1 = full ? c[2 + e] : 0.f;
+                        if (prm.saliency) {
+                            ag[e] += fmaf(v0, v0, v1 * v1);
+                            if (prm.gx_out) {
+#pragma unroll
+                                for (int h8 = 0; h8 < 2; ++h8) {
+                                    const int rr = row + 8 * h8, hs = rr >= T ? 1 : 0, bb = b0i + hs;
+                                    if ((h8 == 0 || full) && bb < prm.B)
+                                        prm.gx_out[(((int64_t)sidx * prm.B + bb) * T + rr - hs * T) * F + cc] = h8 ? v1 : v0;
+                                }
+                            }
+                        } else {
+                            ag[e] += fmaf(v0, nv[e], v1 * nv[2 + e]);
+                        }
+                    }
+                }
+            };
+#pragma unroll
+            for (int nt = 0; nt < 6; ++nt) tile(16 * wrp + mg, 8 * nt + mt2, acc[nt], true, agx[nt], nn[nt]);
+            if (wrp < 6) tile(192 + mg, 8 * wrp + mt2, accx, false, agx[6], nn[6]);
+            stash_store<16>(taddr + NV, &agx[0][0]);
+            if (!prm.saliency && tid < 2 * H) {   // b0 = row sums of g_a1, b1 = row sums of g_a2
+                const float* gsrc = tid < H ? g1T + tid * RP : g2T + (tid - H) * RP;
+                float s0 = 0.f, s1 = 0.f;
+                for (int tt = 0; tt < RT; tt += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(gsrc + tt);
+                    s0 += v.x + v.z; s1 += v.y + v.w;
+                }
+                arow += s0 + s1;
+            }
+        }
+#else
         if (tid < 6 * NQ2) {
             u64 a2[4][4];
 #pragma unroll
@@ -1000,6 +1244,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 }
             }
         }
+#endif
         if (b0i + 4 * (int)gridDim.x < prm.B) nb_arrive(3 + parity, NTHR3);   // this parity's scratch may be overwritten
         MAIN_SYNC();
         TL3(9);
@@ -1017,9 +1262,9 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
 #if V3_OUTER == 16
     {
         // every warp parks its 60 partial sums; the first warp of a matrix adds its partners' in warp order and writes
-        float* o = red + tid * 64;
+        float* o = red + tid * 80;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) o[i] = (&aW[0][0])[i];
+        for (int i = 0; i < 80; ++i) o[i] = (&aW[0][0])[i];
         MAIN_SYNC();
         const int first = op_role == 0 ? 0 : (op_role == 1 ? 5 : 10), nw = op_role == 2 ? 2 : 5;
         if (owarp == first) {
@@ -1031,9 +1276,9 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 for (int nt = 0; nt < nnt; ++nt)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int idx = (mt * nnt + nt) * 4 + i;
+                        const int idx = nt * 16 + mt * 4 + i;
                         float a = 0.f;
-                        for (int w = 0; w < nw; ++w) a += red[((first + w) * 32 + lane) * 64 + idx];
+                        for (int w = 0; w < nw; ++w) a += red[((first + w) * 32 + lane) * 80 + idx];
                         const int m = 16 * mt + g + (i & 2 ? 8 : 0), n = 8 * nt + 2 * t + (i & 1);
                         if (m < mmax && n < nmax) part[off + n * pitch + m] = a;
                     }
@@ -1077,6 +1322,33 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
 #endif
     MAIN_SYNC();
     // (2) dlv_in (fixed-order sum over the row quads), b0 / b1 / column 40 of dW0, b2
+#if V3_GEMM == 1
+    {
+        // thread (warp w, g, t) holds, for column tile nt (slot nt) and e: the sum over its rows of column 8 nt + 2 t + e;
+        // slot 6 (warps 0..5): the 13th row tile, column 8 w + 2 t + e.  red[col][w * 8 + g] / red[col][96 + g].
+        const int wrp = tid >> 5, g = lane >> 2, t = lane & 3;
+        float agx[8][2];
+        stash_load<16>(taddr + NV, &agx[0][0]);
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) red[(8 * nt + 2 * t + e) * 104 + wrp * 8 + g] = agx[nt][e];
+        if (wrp < 6) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) red[(8 * wrp + 2 * t + e) * 104 + 96 + g] = agx[6][e];
+        }
+        if (tid < H) part[fl.b0 + tid] = arow;
+        else if (tid < 2 * H) part[fl.b1 + tid - H] = arow;
+        if (tid >= 256 && tid < 256 + L) part[fl.b2 + tid - 256] = ab2;
+        MAIN_SYNC();
+        if (tid < F) {
+            float sacc = 0.f;
+            for (int i = 0; i < 104; ++i) sacc += red[tid * 104 + i];
+            part[fl.lv_in + tid] = 0.5f * sacc;
+        }
+        MAIN_SYNC();
+    }
+#else
     if (tid < 6 * NQ2) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) red[(8 * cg_rg + c) * NQ2 + q_rg] = aux[c];
@@ -1101,6 +1373,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         part[fl.lv_in + tid] = 0.5f * s;
     }
     MAIN_SYNC();
+#endif
     // (3) metrics: nll (lane 0 of the first warp of each half) and the summary KL (pooling threads with part == 0)
     red[tid] = (lt < L * 8 && (lt & 7) == 0) ? a_skl : 0.f;
     red[NMAIN + tid] = (lt == 0) ? a_nll : 0.f;
