@@ -1224,7 +1224,11 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int r = tid - 6 * NQ2 + e * (NMAIN - 6 * NQ2);  // 84 threads, rows r and r + 84 of 120
+#if V3_OUTER == 16
+                if (r < 3 * H && (r < H || r >= 2 * H)) {   // column 40 of dW0 is covered by the tensor-core tiles
+#else
                 if (r < 3 * H) {
+#endif
                     const float* g = r < 2 * H ? g1T + (r < H ? r : r - H) * RP : g2T + (r - 2 * H) * RP;
                     float s0 = 0.f, s1 = 0.f;
                     if (r >= H && r < 2 * H) {
