@@ -41,7 +41,7 @@ enum { V3_M = 0, V3_VAR = 20, V3_SIM = 40, V3_SIV = 60, V3_VS = 80, V3_S = 100, 
 // record layout: s'[40] r1[40] r2[40] g_a1[40] g_a2[40] | dlvs[40] g_r[2] live right behind G2 in the record only
 enum { R_SP = 0, R_R1 = 40, R_R2 = 80, R_G1 = 120, R_G2 = 160, R_DLVS = 200, R_GR = 240 };
 // shared constants (floats, one copy)
-enum { C3_ELVH = 0, C3_LVS = 40, C3_NSC = 80, C3_TOTAL = 144 };
+enum { C3_ELVH = 0, C3_LVS = 40, C3_NSC = 80, C3_KLC = 144 /* exp(lv) - lv - 1 */, C3_TOTAL = 184 };
 
 struct Smem3 {
     int RP, xT, h1T, h2T, fT, g2T, g1T, W0T, b0, W1T, b1, W2T, b2, W2n, W1n, W0n, V0, V1, V2, cb, consts, small, prod, total;
@@ -547,6 +547,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         const float lv = __ldg(th + fl.lv_sum + tid);
         cst[C3_LVS + tid] = lv;
         cst[C3_ELVH + tid] = expf(__fdiv_rn(lv, 2.0f));
+        cst[C3_KLC + tid] = expf(lv) - lv - 1.0f;   // the parameter part of the summary KL term (:515-520)
     }
     if (tid < F) cst[C3_NSC + tid] = expf(__fdiv_rn(__ldg(th + fl.lv_in + tid), 2.0f));
     // the 4 pad rows of every feature row are never read (row GEMMs and outer products stop at 2T)
@@ -874,10 +875,9 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
                 const float sds = sqrtf(__fadd_rn(fabsf(vs), 1e-5f));                           // :430
                 sv[V3_M + c] = mean; sv[V3_VAR + c] = var; sv[V3_SIM + c] = sim; sv[V3_SIV + c] = siv; sv[V3_VS + c] = vs;
                 sv[V3_S + c] = mus; sv[V3_S + L + c] = sds;
-                const float lv0 = cst[C3_LVS + c], lv1 = cst[C3_LVS + L + c];
                 sv[V3_SP + c] = __fadd_rn(mus, __fmul_rn(sv[V3_ESN + c], cst[C3_ELVH + c]));
                 sv[V3_SP + L + c] = __fadd_rn(sds, __fmul_rn(sv[V3_ESN + L + c], cst[C3_ELVH + L + c]));
-                if (act) a_skl += 0.5f * (mus * mus + expf(lv0) - lv0 - 1.0f) + 0.5f * (sds * sds + expf(lv1) - lv1 - 1.0f);
+                if (act) a_skl += 0.5f * (mus * mus + cst[C3_KLC + c]) + 0.5f * (sds * sds + cst[C3_KLC + L + c]);
             }
         }
         MAIN_SYNC();
@@ -984,8 +984,10 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
         if (lt == 0 && act && !prm.saliency) { rec[R_GR] = gr0; rec[R_GR + 1] = gr1; }
         MAIN_SYNC();
         TL3(16);
-        if (lt < L) {
-            const int c = lt;
+        // ---- S8: g_f in place over f (each half its own system): g_f[t] = g_m / n + g_v 2 (f_t - m) / (n - 1), the two
+        // coefficients recomputed per item from the pooled statistics (cheaper than a 20-thread phase and its barrier) ----
+        for (int i = lt; i < L * NQ; i += HALF3) {
+            const int c = i / NQ, q = i - c * NQ;
             const float gmus = sv[V3_GS + c], gsds = sv[V3_GS + L + c];
             const float vs = sv[V3_VS + c], sds = sv[V3_S + L + c], var = sv[V3_VAR + c];
             const float sgn = vs > 0.f ? 1.0f : (vs < 0.f ? -1.0f : 0.f);
@@ -993,16 +995,10 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
             const float e1 = sv[V3_E12 + c], e2 = sv[V3_E12 + L + c];
             const float gv = gmus * e1 / (2.0f * Tf * sv[V3_SIM + c]) +
                              gvs * (1.0f + e2 * (2.0f * var) / (Tm1 * sv[V3_SIV + c]));
-            sv[V3_GM + c] = act ? gmus / Tf : 0.f;        // coefficient of 1
-            sv[V3_GV + c] = act ? 2.0f * gv / Tm1 : 0.f;  // coefficient of (f - m)
-        }
-        MAIN_SYNC();
-        TL3(17);
-        // ---- S8: g_f in place over f (each half its own system); b2 gradient = column sums of g_f ----
-        for (int i = lt; i < L * NQ; i += HALF3) {
-            const int c = i / NQ, q = i - c * NQ;
+            const float A = act ? gmus / Tf : 0.f;        // coefficient of 1
+            const float Bc = act ? 2.0f * gv / Tm1 : 0.f;  // coefficient of (f - m)
             float4* p = reinterpret_cast<float4*>(fT + c * RP + half * T + 4 * q);
-            const float m = sv[V3_M + c], A = sv[V3_GM + c], Bc = sv[V3_GV + c];
+            const float m = sv[V3_M + c];
             float4 f = *p;
             f.x = fmaf(Bc, f.x - m, A); f.y = fmaf(Bc, f.y - m, A); f.z = fmaf(Bc, f.z - m, A); f.w = fmaf(Bc, f.w - m, A);
             *p = f;
