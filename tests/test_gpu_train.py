@@ -362,3 +362,25 @@ def test_full_size_step_properties(dev, monkeypatch):
             assert float((res[v][0][s] - res["v3"][0][s]).abs().max()) <= 5e-5 * scale, (v, s)
         np.testing.assert_allclose(res[v][1][:, :5].cpu().numpy(), res["v3"][1][:, :5].cpu().numpy(), rtol=2e-5)
     assert not torch.equal(res["v3"][0][0], res["v3"][0][1])
+
+
+def test_repeated_steps_are_bit_identical(dev, train_variant):
+    """compute-sanitizer is not available on the pool: a race between the producer warps, the pipeline warps, the
+    TMEM stash and the L2 scratch hand-off would show as run-to-run differences.  40 repetitions of the same step
+    (odd batch, three seeds, several tiles per CTA) must agree bit for bit, gradients and metrics."""
+    lib = _lib.load()
+    S, B, N = 3, 613, 700
+    m = make_swag_model(17, dev)
+    cfg = m.config(100)
+    x = torch.from_numpy(synth.make_systems(N, seed=91)).to(dev)
+    y = torch.from_numpy(synth.make_labels(N, seed=91)).to(dev)
+    theta0 = m.w_avg[None].repeat(S, 1).contiguous()
+    gen = torch.Generator(device=dev); gen.manual_seed(3)
+    idx = torch.stack([torch.randperm(N, device=dev, generator=gen)[:B] for _ in range(S)]).to(torch.int32).contiguous()
+    hp = TrainHParams(lr=1e-4, momentum=0.9, weight_decay=1e-14, clip_norm=758.3, beta_in=1e-5, beta_out=1e-3,
+                      first_step=1, apply_update=0)
+    g0, met0 = _step(lib, cfg, hp, S, theta0.clone(), None, x, y, idx, B, None, 8, 2, dev)
+    assert bool(torch.isfinite(g0).all())
+    for rep in range(40):
+        g, met = _step(lib, cfg, hp, S, theta0.clone(), None, x, y, idx, B, None, 8, 2, dev)
+        assert torch.equal(g, g0) and torch.equal(met, met0), (train_variant, rep)
