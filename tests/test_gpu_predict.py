@@ -213,6 +213,22 @@ def test_unit_chunked_launches_equal_single_launch(dev, monkeypatch):
     assert torch.equal(ref_sm, ref_um.permute(1, 0, 2))
 
 
+def test_repeated_predictions_are_bit_identical(dev):
+    """The tensor-core kernel hands tiles between epilogue, MMA-issuing and tail warps through mbarriers, named barriers
+    and a weight ring; compute-sanitizer is not available on the pool, so a race would have to show here: 30 repetitions
+    of a multi-tile, multi-unit launch (ragged last tile) agree bit for bit, for both output layouts."""
+    ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(3, dev)], device=dev)
+    N, S_ = 1523, 37
+    x = torch.from_numpy(synth.make_systems(N, seed=29)).to(dev)
+    _, thp = ens.sample_thetas(S_, 12)
+    ref = ens.predict(x, S_, seed=12, thp=thp)
+    ref_sm = ens.predict(x, S_, seed=12, thp=thp, system_major=True)
+    assert bool(torch.isfinite(ref).all()) and torch.equal(ref_sm, ref.permute(1, 0, 2))
+    for rep in range(30):
+        assert torch.equal(ens.predict(x, S_, seed=12, thp=thp), ref), rep
+    assert torch.equal(ens.predict(x, S_, seed=12, thp=thp, system_major=True), ref_sm)
+
+
 def test_edge_cases(dev):
     m = make_swag_model(0, dev)
     m.load(m.w_avg.clone())
