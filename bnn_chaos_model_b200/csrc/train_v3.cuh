@@ -259,7 +259,9 @@ __device__ __forceinline__ void outer_mma(const float* __restrict__ Ms, const fl
 // products.  Measured (4 seeds x 2000): 0.754 ms vs 1.115 ms per step -- for the row GEMMs the 3xTF32 tile rate of the
 // legacy tensor path (three 8-cycle MMAs per 16 x 8 x 8 = 1.33 x the FP32 FMA rate, 0.85 of it left after padding
 // 200 x 41 / 20 to tile multiples) does not beat FFMA2 tiles that already run from registers, and every layer pays
-// two splits per operand word; the outer products win because their operand traffic drops 8-fold.
+// two splits per operand word; the outer products win because their operand traffic drops 8-fold.  Also tried for the row
+// GEMMs: 8 rows x 8 columns per thread (4.0 FMA per loaded word instead of 2.7; 125 threads = one warp per scheduler):
+// 0.91 ms -- a single warp per scheduler cannot cover its own LDS latency.
 #ifndef V3_GEMM
 #define V3_GEMM 0
 #endif
