@@ -105,13 +105,19 @@ SIGNATURES = {
     "bnn_sample_instability": (
         C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_float, C.c_int32, c_f32p, C.c_void_p]),
     "bnn_summarize_instability": (C.c_int, [c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
+    "bnn_saliency": (C.c_int, [_CFG, C.c_int32, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_uint64, c_f32p, c_f32p, c_f32p,
+                               C.c_void_p, C.c_void_p]),
+}
+
+# diagnostics declared in include/bnnchaos_diag.h (probes / timers; not part of the product ABI)
+DIAG_SIGNATURES = {
     "bnn_ffma_peak": (C.c_int, [C.c_int32, C.c_int64, c_f32p, C.POINTER(C.c_int64), C.c_void_p]),
     "bnn_tc_probe": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bnn_tc_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bnn_train_timeline": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int32]),
     "bnn_mma_sync_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_f32p, C.c_void_p]),
-    "bnn_saliency": (C.c_int, [_CFG, C.c_int32, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_uint64, c_f32p, c_f32p, c_f32p,
-                               C.c_void_p, C.c_void_p]),
+    "bnn_tc_probe_ss": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_void_p]),
 }
 
 _lib = None
@@ -133,7 +139,7 @@ def load():
             "This package has no CPU fallback."
         )
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(DIAG_SIGNATURES.items()):
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
@@ -155,6 +161,29 @@ def ptr(t):
     if t is None:
         return None
     assert t.is_contiguous(), "libbnnchaos needs contiguous tensors"
+    return t.data_ptr()
+
+
+def dev_ptr(t, device, name, dtype=None):
+    """Pointer of a tensor the kernels will dereference ON `device`: raises BnnChaosError unless the tensor lives on
+    exactly that device, is contiguous and has the expected dtype (default float32) -- a tensor on another GPU would
+    otherwise be read through a foreign address, a float64 / int64 tensor as fp32 words."""
+    import torch
+
+    if t is None:
+        return None
+    dtype = torch.float32 if dtype is None else dtype
+    device = torch.device(device)
+    if not t.is_cuda:
+        require_cuda(t, name)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if t.device != device:
+        raise BnnChaosError(f"{name} is on {t.device} but the launch device is {device}: move it first")
+    if t.dtype != dtype:
+        raise BnnChaosError(f"{name} has dtype {t.dtype}; the kernels read {dtype}")
+    if not t.is_contiguous():
+        raise BnnChaosError(f"{name} must be contiguous")
     return t.data_ptr()
 
 

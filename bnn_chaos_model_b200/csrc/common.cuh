@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "../../include/bnnchaos.h"
+#include "../../include/bnnchaos_diag.h"
 
 namespace bnn {
 

@@ -69,6 +69,81 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// SS probe: D[j][k] = sum_r G[r][j] * Hm[r][k] (the weight-gradient GEMM of the training step: the contraction runs over
+// the time-step ROWS) with BOTH operands in shared memory in the canonical K-major no-swizzle layout with K = rows:
+// [row quad][feature][4 rows] fp32, feature pitch 16 B (one core matrix = 8 features x 4 rows), 8-feature groups 128 B
+// apart (SBO), row quads `pitch` features apart (LBO).  M = 128: feature rows beyond MJ read whatever follows in shared
+// memory (their D lanes are garbage and ignored), likewise N beyond NK.  bias_round: operands are stored as
+// bits + 0x1000, so that the tensor core's truncation of the 13 low mantissa bits rounds to nearest.  two_batches: the
+// k-steps are issued in two halves with a commit + wait in between (accumulation across commits).
+__global__ void __launch_bounds__(128) tc_probe_ss_kernel(const float* __restrict__ G, const float* __restrict__ Hm,
+                                                          float* __restrict__ D, int R, int MJ, int NK, int N,
+                                                          int bias_round, int two_batches) {
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int NQ = R / 4, PG = MJ | 1, PH = NK | 1;
+    float* ga = sm;
+    float* hb = sm + NQ * PG * 4;
+    float* tail = hb + NQ * PH * 4;
+    if (warp == 0) {
+        tmem_alloc(&tmem_base_s, 256);
+        tmem_relinquish();
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init_fence();
+    }
+    const uint32_t add = bias_round ? 0x1000u : 0u;
+    for (int i = tid; i < NQ * PG * 4; i += 128) ga[i] = 0.f;
+    for (int i = tid; i < NQ * PH * 4; i += 128) hb[i] = 0.f;
+    for (int i = tid; i < 1024; i += 128) tail[i] = 3.0e30f;   // what the out-of-range feature rows of the last quad read
+    __syncthreads();
+    for (int i = tid; i < R * MJ; i += 128) {
+        const int r = i / MJ, j = i - r * MJ;
+        ga[((r >> 2) * PG + j) * 4 + (r & 3)] = __uint_as_float(__float_as_uint(G[i]) + add);
+    }
+    for (int i = tid; i < R * NK; i += 128) {
+        const int r = i / NK, k = i - r * NK;
+        hb[((r >> 2) * PH + k) * 4 + (r & 3)] = __uint_as_float(__float_as_uint(Hm[i]) + add);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int KS = R / 8, half = two_batches ? KS / 2 : KS;
+    uint32_t par = 0;
+    for (int batch = 0; batch < (two_batches ? 2 : 1); ++batch) {
+        if (tid == 0) {
+            const uint32_t idesc = idesc_tf32(128, N);
+            const int k0 = batch ? half : 0, k1 = batch ? KS : half;
+            for (int ks = k0; ks < k1; ++ks) {
+                const uint64_t ad = smem_desc_kmajor(smem_u32(ga) + (uint32_t)ks * 2u * PG * 16u, (uint32_t)PG * 16u, 128u);
+                const uint64_t bd = smem_desc_kmajor(smem_u32(hb) + (uint32_t)ks * 2u * PH * 16u, (uint32_t)PH * 16u, 128u);
+                mma_tf32_ss(tmem, ad, bd, idesc, ks > 0);
+            }
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, par);
+        par ^= 1;
+        __syncthreads();
+    }
+    tc_fence_after();
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int c = 0; c < N; c += 8) {
+        uint32_t v[8];
+        tmem_ld8(tmem + lane_base + c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) D[tid * N + c + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // Timing probe: `reps` x (K/8) dependent tcgen05.mma (same D) issued back to back by one thread;
 // out[0] = cycles from first issue to commit completion, out[1] = cycles spent issuing.
 __global__ void __launch_bounds__(128) tc_time_kernel(int K, int N, int reps, int from_smem, long long* out) {
@@ -143,6 +218,22 @@ extern "C" int bnn_tc_time(int32_t K, int32_t N, int32_t reps, int32_t from_smem
     const size_t smem = (size_t)(N + 128) * K * 4;
     cudaFuncSetAttribute(tc_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     tc_time_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(K, N, reps, from_smem, d_out);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+extern "C" int bnn_tc_probe_ss(const float* d_G, const float* d_H, float* d_D, int32_t R, int32_t MJ, int32_t NK, int32_t N,
+                               int32_t bias_round, int32_t two_batches, void* stream) {
+    using namespace bnn;
+    int rc = check_device();
+    if (rc != BNN_OK) return rc;
+    BNN_REQUIRE(d_G && d_H && d_D, BNN_E_ARG, "bnn_tc_probe_ss: null pointer");
+    BNN_REQUIRE(R % 8 == 0 && R >= 8 && R <= 128 && MJ >= 1 && MJ <= 128 && NK >= 1 && NK <= N && N % 16 == 0 && N >= 16 &&
+                    N <= 256, BNN_E_ARG, "bnn_tc_probe_ss: need R%%8==0 (8..128), MJ<=128, NK<=N, N%%16==0 (16..256)");
+    const size_t smem = ((size_t)(R / 4) * ((MJ | 1) + (NK | 1)) * 4 + 1024) * sizeof(float);
+    BNN_REQUIRE(smem <= 200 * 1024, BNN_E_ARG, "bnn_tc_probe_ss: operands do not fit in shared memory");
+    cudaFuncSetAttribute(tc_probe_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    tc_probe_ss_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_G, d_H, d_D, R, MJ, NK, N, bias_round, two_batches);
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }

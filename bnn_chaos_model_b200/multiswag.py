@@ -111,10 +111,11 @@ class MultiSWAG:
             um = None
             if unit_model is not None:
                 um = torch.as_tensor(unit_model, dtype=torch.int32, device=self.device).contiguous()
+            dp = lambda t, name, dt=None: _lib.dev_ptr(t, self.device, name, dt)
             _lib.check(
                 lib.bnn_swag_sample(cfg, _lib.ptr(self.w_avg), _lib.ptr(self.w2_avg), _lib.ptr(self.pre_D), M, self.K,
-                                    _lib.ptr(um), U, unit_offset, max(int(samples_per_model), 1), float(scale),
-                                    int(seed), _lib.ptr(z1), _lib.ptr(z2), _lib.ptr(theta), _lib.ptr(thp),
+                                    dp(um, "unit_model", torch.int32), U, unit_offset, max(int(samples_per_model), 1),
+                                    float(scale), int(seed), dp(z1, "z1"), dp(z2, "z2"), _lib.ptr(theta), _lib.ptr(thp),
                                     _lib.current_stream_ptr()),
                 "bnn_swag_sample",
             )
@@ -135,7 +136,8 @@ class MultiSWAG:
             if N == 0:  # an empty shard (fewer system groups than ranks)
                 return out
             _lib.check(
-                lib.bnn_predict(cfg, _lib.ptr(x), N, _lib.ptr(thp), U, None, None, int(seed), 0, int(system_offset),
+                lib.bnn_predict(cfg, _lib.dev_ptr(x, self.device, "x"), N, _lib.dev_ptr(thp, self.device, "thp"), U, None,
+                                None, int(seed), 0, int(system_offset),
                                 int(system_major), _lib.ptr(out), None, None, _lib.current_stream_ptr()),
                 "bnn_predict",
             )
@@ -257,12 +259,28 @@ class MultiSWAG:
         return model.forward_swag_fast(X_sample, scale=0.5)
 
     def predict_trios(self, X: torch.Tensor, samples: int, seed: int = 0, scale: float = 0.5):
-        """5-planet style input (figures/multiswag_5_planet.py:280-298): X [N, n_trios, T, F]
-        (already normalised) -> [samples*M?]..."""
+        """5-planet style input (figures/multiswag_5_planet.py:204,280-298): X [N, n_trios, T, F], already normalised with
+        ssX like :280-283, is flattened to [N*n_trios, T, F] (:287) and EVERY (model, weight sample) unit evaluates
+        all trio rows in one launch: returns [M*samples, N, n_trios, 2] -- the reference's ``time`` array (:294-298)
+        with its first axis running over all M*samples units instead of `samples` random (model, chunk) picks.
+        Philox draws are keyed on (unit, trio row), so shards of systems reproduce the full result."""
         N, R = X.shape[0], X.shape[1]
         flat = X.reshape(N * R, X.shape[2], X.shape[3])
         out = self.predict(flat, samples, seed, scale)  # [U, N*R, 2]
         return out.reshape(out.shape[0], N, R, 2)
+
+    def sample_trios(self, X: torch.Tensor, samples: int, chunks: int = 10):
+        """The reference's 5-planet loop verbatim (figures/multiswag_5_planet.py:294-298): per weight sample, the
+        flattened trio rows are cut into ``chunks`` pieces and each piece goes through ``sample_full_swag`` (a random
+        ensemble member from numpy's global RNG, torch draws in forward_swag_fast's order).  Returns
+        [samples, N, n_trios, 2].  Drop-in semantics; ``predict_trios`` is the batched form."""
+        N, R = X.shape[0], X.shape[1]
+        flat = X.reshape(N * R, X.shape[2], X.shape[3])
+        time = torch.cat([
+            torch.cat([self.sample_full_swag(Xpart).detach() for Xpart in torch.chunk(flat, chunks=chunks)])[None]
+            for _ in range(samples)
+        ], dim=0)
+        return time.reshape(samples, N, R, 2)
 
 
 def load_ensemble(paths: Sequence[str], device=None) -> MultiSWAG:

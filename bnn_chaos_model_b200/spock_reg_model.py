@@ -52,6 +52,12 @@ class AttributeDict(dict):
         self[key] = val
 
 
+class ScheduleFinished(ValueError):
+    """The one-cycle schedule was stepped past its total (the reference raises a plain ValueError, :137-139, which
+    find_minima.py:79-82 catches to end the run): a ValueError subclass, so reference-style ``except ValueError`` still
+    works, while our trainers catch exactly this and let every other ValueError propagate."""
+
+
 def one_cycle_lr_momentum(step_num, max_lr, total_steps, pct_start=0.3, div_factor=25.0, final_div_factor=1e4,
                           base_momentum=0.85, max_momentum=0.95, anneal_strategy="cos"):
     """(lr, momentum) of the reference's one-cycle schedule at optimizer step ``step_num`` (:131-158): up from
@@ -59,7 +65,7 @@ def one_cycle_lr_momentum(step_num, max_lr, total_steps, pct_start=0.3, div_fact
     over the rest, momentum moving the opposite way.  Past ``total_steps`` it raises ValueError like :137-139 --
     find_minima.py relies on that to end the run (find_minima.py:79-82)."""
     if step_num > total_steps:
-        raise ValueError("Tried to step {} times. The specified number of total steps is {}".format(step_num + 1, total_steps))
+        raise ScheduleFinished("Tried to step {} times. The specified number of total steps is {}".format(step_num + 1, total_steps))
     size_up = float(pct_start * total_steps) - 1
     size_down = float(total_steps - size_up) - 1
     lr0 = max_lr / div_factor
@@ -278,9 +284,10 @@ class VarModel(nn.Module):
         U, B = thp.shape[0], x.shape[0]
         out = torch.empty((B, U, 2) if system_major else (U, B, 2), device=x.device, dtype=torch.float32)
         summ = torch.empty((U, B, 2 * self.hparams["latent"]), device=x.device) if want_summary else None
+        dp = lambda t, name: _lib.dev_ptr(t, x.device, name)
         _lib.check(
-            lib.bnn_predict(cfg, _lib.ptr(x), B, _lib.ptr(thp), U, _lib.ptr(eps), _lib.ptr(eps_sum), 0, 0, 0,
-                            int(system_major), _lib.ptr(out), _lib.ptr(summ), None, _lib.current_stream_ptr()),
+            lib.bnn_predict(cfg, _lib.ptr(x), B, dp(thp, "packed weights"), U, dp(eps, "eps"), dp(eps_sum, "eps_sum"), 0,
+                            0, 0, int(system_major), _lib.ptr(out), _lib.ptr(summ), None, _lib.current_stream_ptr()),
             "bnn_predict",
         )
         return out, summ
@@ -649,15 +656,51 @@ class _SafeUnpickler(pickle.Unpickler):
         raise pickle.UnpicklingError(f"global {module}.{name} is not allowed in a SWAG checkpoint")
 
 
+def _safe_load(f, **kw):
+    return _SafeUnpickler(f, **kw).load()
+
+
+def _safe_loads(b, **kw):
+    return _SafeUnpickler(io.BytesIO(b), **kw).load()
+
+
 class _SafePickleModule:
+    """pickle_module for torch.load: EVERY entry point goes through the allow-listed unpickler (torch's legacy,
+    non-zip loader calls pickle_module.load() directly on the magic number / protocol / sys_info records)."""
+
     __name__ = "bnn_safe_pickle"
     Unpickler = _SafeUnpickler
-    load = staticmethod(pickle.load)
-    loads = staticmethod(pickle.loads)
+    load = staticmethod(_safe_load)
+    loads = staticmethod(_safe_loads)
     dump = staticmethod(pickle.dump)
     dumps = staticmethod(pickle.dumps)
     HIGHEST_PROTOCOL = pickle.HIGHEST_PROTOCOL
     UnpicklingError = pickle.UnpicklingError
+
+
+class _ScalerUnpickler(pickle.Unpickler):
+    """``*_ssX.pkl`` (spock_reg_model.py:958-963): a pickled sklearn StandardScaler -- the class itself plus the numpy
+    array / scalar reconstructors, nothing else."""
+
+    _ALLOWED = {
+        ("sklearn.preprocessing._data", "StandardScaler"), ("sklearn.preprocessing.data", "StandardScaler"),
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+        ("numpy", "ndarray"), ("numpy", "dtype"),
+    }
+
+    def find_class(self, module, name):
+        if (module, name) not in self._ALLOWED:
+            raise pickle.UnpicklingError(f"global {module}.{name} is not allowed in a StandardScaler pickle")
+        if name == "StandardScaler":
+            from sklearn.preprocessing import StandardScaler
+
+            return StandardScaler
+        import importlib
+
+        if module.startswith("numpy.core"):
+            module = module.replace("numpy.core", "numpy._core") if hasattr(np, "_core") else module
+        return getattr(importlib.import_module(module), name)
 
 
 def fixed_v50_scaler():
@@ -685,7 +728,7 @@ def load_swag(path):
         ssX_file = str(path)[:-4] + "_ssX.pkl"
         try:
             with open(ssX_file, "rb") as f:
-                swag_model.ssX = pickle.load(f)
+                swag_model.ssX = _ScalerUnpickler(f).load()
         except FileNotFoundError:
             print(f"ssX file not found! {ssX_file}")
     return swag_model

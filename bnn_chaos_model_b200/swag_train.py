@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import BnnChaosError, TrainHParams
 from .multiswag import shard_range
-from .spock_reg_model import SWAGModel, VarModel, one_cycle_lr_momentum
+from .spock_reg_model import ScheduleFinished, SWAGModel, VarModel, one_cycle_lr_momentum
 
 
 def seeds_of_rank(n_seeds: int, rank: int, world: int):
@@ -31,8 +31,17 @@ def seeds_of_rank(n_seeds: int, rank: int, world: int):
 
 
 class MultiSeedSWAGTrainer:
+    """Arguments beyond the data: ``swa_start`` -- the moment-collection gate (default hparams['swa_start'], the value
+    :808 reads); ``noisy_val`` -- validate with the input / summary noise on, the reference's
+    default (hparams['noisy_val'] = True, :787-799; default here: the first model's hparams); ``lr_milestone`` -- apply the
+    reference's ``MultiStepLR([swa_params['swa_start']], swa_recording_lr_factor)`` (:709-720) per optimizer step.  The
+    reference registers both of its schedulers with 'interval': 'steps'; its pre-training run ENDS through the one-cycle
+    scheduler's ValueError (find_minima.py:79-82), so in the reference's Lightning version such schedulers do step every
+    optimizer step -- both trainers here follow that reading (pass ``lr_milestone=False`` for a constant swa_lr)."""
+
     def __init__(self, models: Sequence[SWAGModel], X_train, y_train, X_val=None, y_val=None, batch_size=2000,
-                 device=None, seed=0, swa_start: Optional[int] = None, noisy_val: bool = False):
+                 device=None, seed=0, swa_start: Optional[int] = None, noisy_val: Optional[bool] = None,
+                 lr_milestone: bool = True):
         if len(models) == 0:
             raise ValueError("no seed models")
         self.models: List[SWAGModel] = list(models)
@@ -52,9 +61,11 @@ class MultiSeedSWAGTrainer:
         self.yv = None if y_val is None else y_val.to(dev).contiguous().float()
         self.batch_size = int(batch_size)
         self.seed = int(seed)
-        self.noisy_val = noisy_val
-        if noisy_val:
-            raise NotImplementedError("batched validation is noise-free (bnn_eval_loss); use SWAGModel.validation_step")
+        self.noisy_val = bool(m0.hparams.get("noisy_val", True) if noisy_val is None else noisy_val)
+        self.test_len = int(getattr(m0, "test_len", 8740))   # :392; validation losses are divided by it (:789)
+        sp = getattr(m0, "swa_params", None) or {}
+        self.lr_milestone = int(sp["swa_start"]) if (lr_milestone and "swa_start" in sp) else None
+        self.lr_factor = float(sp.get("swa_recording_lr_factor", 0.5))
         self.swa_start = int(m0.hparams["swa_start"] if swa_start is None else swa_start)  # :808 reads hparams
         self.theta = torch.stack([m._flat().detach().float() for m in self.models]).to(dev).contiguous()  # [S,d]
         self.momentum = torch.zeros_like(self.theta)
@@ -69,6 +80,7 @@ class MultiSeedSWAGTrainer:
         self.current_epoch = 0
         self.first_step = True
         self._ws = None
+        self._ws_val = None
         self._gen = torch.Generator(device=dev)
         self._gen.manual_seed(self.seed)
         self.lr = float(m0.swa_params["swa_lr"])
@@ -79,7 +91,7 @@ class MultiSeedSWAGTrainer:
     def train_step(self, batch_index: Optional[torch.Tensor], B: int, lr: Optional[float] = None):
         lib = _lib.load()
         cfg = self.models[0].config(self.X.shape[1])
-        hp = TrainHParams(lr=self.lr if lr is None else float(lr), first_step=int(self.first_step), apply_update=1,
+        hp = TrainHParams(lr=self.step_lr() if lr is None else float(lr), first_step=int(self.first_step), apply_update=1,
                           **self.step_hparams())
         with torch.cuda.device(self.device):
             nbytes = lib.bnn_train_workspace_bytes(cfg, B, self.S)
@@ -94,6 +106,14 @@ class MultiSeedSWAGTrainer:
             )
         self.first_step = False
         self.global_step += 1
+
+    def step_lr(self, step: Optional[int] = None) -> float:
+        """Learning rate of optimizer step ``step`` (default: the coming one): swa_lr, times swa_recording_lr_factor from
+        step swa_params['swa_start'] on (torch MultiStepLR stepped once per optimizer step, :709-720)."""
+        g = self.global_step if step is None else int(step)
+        if self.lr_milestone is not None and g >= self.lr_milestone:
+            return self.lr * self.lr_factor
+        return self.lr
 
     def step_hparams(self):
         """momentum, weight decay, clip and KL weights of the coming step (constant in the SWAG phase, :722-732)."""
@@ -116,24 +136,43 @@ class MultiSeedSWAGTrainer:
 
     # ------------------------------------------------------------------ validation + moment collection
     def validation_losses(self):
-        """(val_loss[S], swa_loss[S]) = lossfnc(noisy_val=False) summed over the validation set, per system
-        normalised by its size like :789; evaluated at theta and at w_avg in one launch."""
+        """(val_loss[S], swa_loss[S]): the reference's validation_step (:787-799) over the whole validation set --
+        lossfnc(X, y, noisy_val=self.noisy_val) summed over the systems and divided by ``test_len`` (8740, :789), at the
+        current weights and at w_avg (the current weights where nothing has been collected yet), in one launch.
+        noisy_val=False: K2 + the per-unit NLL sum (bnn_eval_loss; eps1, eps2 from Philox).  noisy_val=True: the
+        training kernel's noisy forward without update (bnn_train_step, apply_update=0: input noise, eps1, eps2 and
+        summary noise from Philox keyed on (seed ^ 0x5EED; unit, system, epoch)); metrics[:, 0] * B is the summed loss."""
         lib = _lib.load()
         m0 = self.models[0]
         cfg = m0.config(self.Xv.shape[1])
         have_avg = bool((self.n_models > 0).all())
-        thetas = torch.cat([self.theta, self.w_avg]) if have_avg else self.theta
-        thp = m0._packed(cfg, thetas)
-        U, B = thp.shape[0], self.Xv.shape[0]
+        thetas = (torch.cat([self.theta, self.w_avg]) if have_avg else self.theta).contiguous()
+        U, B = thetas.shape[0], self.Xv.shape[0]
         with torch.cuda.device(self.device):
-            out = torch.empty((U, B, 2), device=self.device)
-            loss = torch.empty(U, device=self.device)
-            _lib.check(
-                lib.bnn_eval_loss(cfg, _lib.ptr(self.Xv), _lib.ptr(self.yv), B, _lib.ptr(thp), U, None,
-                                  self.seed ^ 0x5EED, _lib.ptr(out), _lib.ptr(loss), None, _lib.current_stream_ptr()),
-                "bnn_eval_loss",
-            )
-        loss = loss / B
+            if self.noisy_val:
+                hp = TrainHParams(lr=0.0, momentum=0.0, weight_decay=0.0, clip_norm=float("inf"), beta_in=0.0, beta_out=0.0,
+                                  first_step=1, apply_update=0)
+                nbytes = lib.bnn_train_workspace_bytes(cfg, B, U)
+                if self._ws_val is None or self._ws_val.numel() * 4 < nbytes:
+                    self._ws_val = torch.empty((nbytes + 3) // 4, device=self.device, dtype=torch.float32)
+                met = torch.empty((U, 8), device=self.device)
+                _lib.check(
+                    lib.bnn_train_step(cfg, hp, U, _lib.ptr(thetas), None, _lib.ptr(self.Xv), _lib.ptr(self.yv), None, B,
+                                       None, None, None, self.seed ^ 0x5EED, self.current_epoch, None, _lib.ptr(met),
+                                       _lib.ptr(self._ws_val), _lib.current_stream_ptr()),
+                    "bnn_train_step (noisy validation)",
+                )
+                loss = met[:, 0] * float(B)
+            else:
+                thp = m0._packed(cfg, thetas)
+                out = torch.empty((U, B, 2), device=self.device)
+                loss = torch.empty(U, device=self.device)
+                _lib.check(
+                    lib.bnn_eval_loss(cfg, _lib.ptr(self.Xv), _lib.ptr(self.yv), B, _lib.ptr(thp), U, None,
+                                      self.seed ^ 0x5EED, _lib.ptr(out), _lib.ptr(loss), None, _lib.current_stream_ptr()),
+                    "bnn_eval_loss",
+                )
+        loss = loss / float(self.test_len)
         return (loss[: self.S], loss[self.S:] if have_avg else loss[: self.S])
 
     def collect(self):
@@ -198,13 +237,13 @@ class MultiSeedPretrainer(MultiSeedSWAGTrainer):
     """
 
     def __init__(self, models: Sequence[VarModel], X_train, y_train, X_val=None, y_val=None, batch_size=None,
-                 device=None, seed=0):
+                 device=None, seed=0, noisy_val: Optional[bool] = None):
         m0 = models[0]
         for m in models:  # the SWAG bookkeeping of the base class reads these; unused here
             if not hasattr(m, "K"):
                 m.K, m.c, m.swa_params = 1, 1, {"swa_lr": m.lr}
         super().__init__(models, X_train, y_train, X_val, y_val, batch_size=batch_size or m0.batch_size, device=device,
-                         seed=seed, swa_start=1 << 62)
+                         seed=seed, swa_start=1 << 62, noisy_val=noisy_val, lr_milestone=False)
         self.steps = int(m0.steps)
         self.max_lr = float(m0.lr)
         self.total_sched = int(0.9 * self.steps)
@@ -219,13 +258,21 @@ class MultiSeedPretrainer(MultiSeedSWAGTrainer):
         f = min([1, (g / self.steps) / 0.3])
         return lr, mom, f * self.hp["beta_in"], f * self.hp["beta_out"]
 
+    def step_lr(self, step: Optional[int] = None) -> float:
+        """Learning rate of optimizer step ``step`` (default: the coming one): swa_lr, times swa_recording_lr_factor from
+        step swa_params['swa_start'] on (torch MultiStepLR stepped once per optimizer step, :709-720)."""
+        g = self.global_step if step is None else int(step)
+        if self.lr_milestone is not None and g >= self.lr_milestone:
+            return self.lr * self.lr_factor
+        return self.lr
+
     def step_hparams(self):
         _, mom, b_in, b_out = self.schedule()
         return dict(self.hp, momentum=mom, beta_in=b_in, beta_out=b_out)
 
     def train_step(self, batch_index, B, lr=None):
         if lr is None:
-            lr = self.schedule()[0]  # raises ValueError past the schedule's end, like scheduler.step() does
+            lr = self.schedule()[0]  # raises ScheduleFinished (a ValueError) past the schedule's end, like scheduler.step()
         super().train_step(batch_index, B, lr)
 
     def fit(self, epochs: Optional[int] = None, validate: bool = True, check_nan_every: int = 1):
@@ -236,7 +283,7 @@ class MultiSeedPretrainer(MultiSeedSWAGTrainer):
         for _ in range(epochs):
             try:
                 self.train_epoch()
-            except ValueError:
+            except ScheduleFinished:   # only the schedule's own end-of-run signal; any other ValueError propagates
                 self.finished = True
             entry = {"epoch": self.current_epoch, "global_step": self.global_step}
             if not self.finished and validate and self.Xv is not None:

@@ -34,3 +34,41 @@ def test_tcgen05_tf32_gemm_matches(K, N):
     err0, scale = run_probe(K, N, 0)
     print(f"K={K} N={N}: err={err0:.3e} scale={scale:.2f}")
     assert err0 < 1e-5 * scale, err0
+
+
+def rn_tf32(x):
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("R,MJ,NK,N,bias_round,two", [
+    (104, 40, 41, 48, 1, 0),    # dW1-shaped: g_a2^T [h1 | 1], round-to-nearest by the +0x1000 bias
+    (104, 20, 41, 48, 1, 1),    # dW2-shaped, accumulated across two commits
+    (104, 40, 73, 80, 1, 0),    # dW0-shaped: g_a1^T [x' | n(live) | 1]
+    (104, 40, 83, 96, 1, 1),
+    (104, 40, 41, 48, 0, 0),    # raw fp32 operands: the tensor core truncates the 13 low mantissa bits
+    (8, 5, 3, 16, 1, 0),
+])
+def test_tcgen05_ss_row_contraction(R, MJ, NK, N, bias_round, two):
+    """The training kernel's weight-gradient GEMM: both operands in shared memory, contraction over the rows, M = 128
+    with surplus feature rows reading neighbouring data (their lanes are ignored)."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(R * 1000 + MJ)
+    G = torch.randn(R, MJ, generator=g)
+    Hm = torch.randn(R, NK, generator=g).abs()
+    D = torch.full((128, N), float("nan"), device=dev)
+    Gd, Hd = G.to(dev).contiguous(), Hm.to(dev).contiguous()
+    _lib.check(lib.bnn_tc_probe_ss(_lib.ptr(Gd), _lib.ptr(Hd), _lib.ptr(D), R, MJ, NK, N, bias_round, two,
+                                   _lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    rnd = rn_tf32 if bias_round else tf32_exact
+    ref = (rnd(G).double().T @ rnd(Hm).double()).float()
+    got = D.cpu()[:MJ, :NK]
+    err = float((got - ref).abs().max())
+    scale = float(ref.abs().max())
+    print(f"R={R} MJ={MJ} NK={NK} N={N} bias={bias_round} two={two}: err={err:.3e} scale={scale:.2f}")
+    assert err < 2e-6 * scale * max(1.0, (R / 8) ** 0.5), err
+    # and the single-pass tf32 product is within the stated 1-term tolerance of the exact fp32 product
+    exact = (G.double().T @ Hm.double()).float()
+    if bias_round:
+        assert float((got - exact).abs().max()) < 2e-3 * scale

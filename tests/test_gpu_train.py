@@ -384,3 +384,40 @@ def test_repeated_steps_are_bit_identical(dev, train_variant):
     for rep in range(40):
         g, met = _step(lib, cfg, hp, S, theta0.clone(), None, x, y, idx, B, None, 8, 2, dev)
         assert torch.equal(g, g0) and torch.equal(met, met0), (train_variant, rep)
+
+
+def test_trainer_noisy_validation_and_lr_milestone_vs_oracle(dev):
+    """MultiSeedSWAGTrainer.validation_losses with the reference's default noisy_val=True (:787-799): loss at the current
+    weights and at w_avg, / test_len, against the oracle's noisy forward fed the Philox draws of the launch; and the
+    MultiStepLR milestone (:709-720) as a per-step learning rate."""
+    lib = _lib.load()
+    models = [make_swag_model(s, dev) for s in (0, 17)]
+    for m in models:
+        m.load(m.w_avg.clone())
+        m.init_params({"K": 3, "c": 1, "swa_lr": 1e-4, "swa_start": 3, "swa_recording_lr_factor": 0.5})
+        m.hparams["swa_start"] = 0
+    N = 90
+    X = torch.from_numpy(synth.make_systems(N, seed=63)); y = torch.from_numpy(synth.make_labels(N, seed=63))
+    assert not MultiSeedSWAGTrainer(models, X[:60], y[:60], batch_size=30, device=dev).noisy_val   # v50 hparams: noisy_val False
+    tr = MultiSeedSWAGTrainer(models, X[:60], y[:60], X[60:], y[60:], batch_size=30, device=dev, seed=6, noisy_val=True)
+    assert tr.noisy_val and tr.test_len == 8740
+    assert [tr.step_lr(g) for g in (0, 2, 3, 4)] == [1e-4, 1e-4, 5e-5, 5e-5]   # torch MultiStepLR([3], 0.5), stepped per step
+    assert MultiSeedSWAGTrainer(models, X[:60], y[:60], batch_size=30, device=dev, lr_milestone=False).step_lr(100) == 1e-4
+    tr.fit(2, validate=False)          # two epochs: moments exist, theta != w_avg
+    assert int(tr.n_models[0]) == 2
+    v, s = tr.validation_losses()
+    spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
+    cfg = models[0].config(100)
+    B, U = 30, 4
+    e_in = torch.empty((U, B, 100, 41), device=dev); e12 = torch.empty((U, B, 40), device=dev); e_sum = torch.empty((U, B, 40), device=dev)
+    _lib.check(lib.bnn_train_noise(cfg, U, B, tr.seed ^ 0x5EED, tr.current_epoch, _lib.ptr(e_in), _lib.ptr(e12), _lib.ptr(e_sum), None))
+    thetas = torch.cat([tr.theta, tr.w_avg]).cpu()
+    got = torch.cat([v, s]).cpu()
+    for u in range(U):
+        out, _ = R.forward(spec, thetas[u], X[60:], True, e_in[u].cpu(), e12[u, :, :20].cpu(), e12[u, :, 20:].cpu(), e_sum[u].cpu())
+        want = float(R.lossfnc_per_system(out, y[60:]).sum()) / 8740
+        assert float(got[u]) == pytest.approx(want, rel=1e-5), u
+    # noise-free variant: same normalisation
+    tr.noisy_val = False
+    v0, s0 = tr.validation_losses()
+    assert bool(torch.isfinite(v0).all()) and not torch.equal(v0, v)

@@ -16,8 +16,11 @@ HEADER = os.path.join(ROOT, "include", "bnnchaos.h")
 LIB = os.path.join(ROOT, "bnn_chaos_model_b200", "libbnnchaos.so")
 
 
-def declared_symbols():
-    txt = open(HEADER).read()
+DIAG_HEADER = os.path.join(ROOT, "include", "bnnchaos_diag.h")
+
+
+def declared_symbols(header=HEADER):
+    txt = open(header).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(bnn_[a-z0-9_]+)\s*\(", txt)))
 
@@ -35,6 +38,11 @@ def test_library_exports_every_declared_symbol():
     from bnn_chaos_model_b200 import _lib
 
     assert sorted(_lib.SIGNATURES) == syms  # the ctypes table covers the whole header
+    diag = declared_symbols(DIAG_HEADER)  # probes / timers live in their own header, outside the product ABI
+    assert not set(diag) & set(syms)
+    for s in diag:
+        assert hasattr(lib, s), f"{s} declared in include/bnnchaos_diag.h but not exported"
+    assert sorted(_lib.DIAG_SIGNATURES) == diag
     assert _lib.load().bnn_abi_version() == 1
 
 
@@ -107,6 +115,48 @@ def test_unsafe_pickle_rejected(tmp_path):
     torch.save({"hparams": Evil()}, path)
     with pytest.raises(pickle.UnpicklingError):
         S.load_swag(path)
+
+
+def test_unsafe_legacy_pickle_and_scaler_rejected(tmp_path):
+    """torch's legacy (non-zip) loader calls pickle_module.load() on the leading records before it builds
+    an Unpickler, and *_ssX.pkl was read with plain pickle.load: both must go through an allow-list, and the payload
+    must never run."""
+    import pickle
+
+    from bnn_chaos_model_b200 import spock_reg_model as S
+
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, (f"touch {marker}",))
+
+    legacy = tmp_path / "legacy_v50_0_output.pkl"
+    with open(legacy, "wb") as f:  # a legacy-format torch file starts with a pickled magic number
+        pickle.dump(Evil(), f, protocol=2)
+        pickle.dump(1001, f, protocol=2)
+    with pytest.raises(pickle.UnpicklingError):
+        S.load_swag(str(legacy))
+    assert not marker.exists()
+    # a genuine checkpoint whose scaler side-file is malicious (non-'v50' path -> the ssX file is read)
+    st = swag_stats(0)
+    m = S.SWAGModel(st["hparams"]).init_params(st["swa_params"])
+    m.w_avg, m.w2_avg, m.pre_D = (torch.from_numpy(st[k]) for k in ("w_avg", "w2_avg", "pre_D"))
+    good = tmp_path / "x_output.pkl"
+    S.save_swag(m, str(good))
+    with open(str(good)[:-4] + "_ssX.pkl", "wb") as f:
+        pickle.dump(Evil(), f)
+    with pytest.raises(pickle.UnpicklingError):
+        S.load_swag(str(good))
+    assert not marker.exists()
+    # and a real StandardScaler pickle still loads
+    from sklearn.preprocessing import StandardScaler
+
+    ss = StandardScaler().fit(np.arange(12.0).reshape(4, 3))
+    with open(str(good)[:-4] + "_ssX.pkl", "wb") as f:
+        pickle.dump(ss, f)
+    m2 = S.load_swag(str(good))
+    assert np.allclose(m2.ssX.mean_, ss.mean_) and np.allclose(m2.ssX.scale_, ss.scale_)
 
 
 def test_philox_known_answers():
