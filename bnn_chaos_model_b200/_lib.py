@@ -116,6 +116,7 @@ DIAG_SIGNATURES = {
     "bnn_tc_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bnn_train_timeline": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int32]),
     "bnn_mma_sync_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_f32p, C.c_void_p]),
+    "bnn_set_train_variant": (C.c_int, [C.c_int32]),
     "bnn_tc_probe_ss": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
 }

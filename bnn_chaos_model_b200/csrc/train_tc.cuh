@@ -268,7 +268,7 @@ __device__ __forceinline__ void slot_sync(int slot) { named_sync(3 + slot, 128);
 
 __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params prm) {
     using namespace tcx;
-    extern __shared__ __align__(128) float sm[];
+    extern __shared__ __align__(16) float sm[];
     const SmemTC L_(prm.zero_mask);
     const FlatLayout fl(F);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
         int next_acc2 = 0, next_acc1 = 0, next_acc0 = 0;   // tile whose weight-gradient MMAs come next, per accumulator
         for (;;) {
             bool any_active = false, progressed = false;
-#pragma unroll 1
+#pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
                 const int k = kk[s];
                 if (k >= n_k) continue;
@@ -587,8 +587,8 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             }
             slot_sync(slot);
             // ---- pooling per latent column: two-pass mean / unbiased variance (:418-419), sampled summary statistics ----
-            if (lt < L * 4) {
-                const int c = lt >> 2, part = lt & 3;
+            if (quad < 3) {   // 80 pooling threads (column c, 4 parts); the branch is warp-uniform for the shuffles
+                const int c = min(lt >> 2, L - 1), part = lt & 3;
                 float4 v[7];
 #pragma unroll
                 for (int i = 0; i < 7; ++i)
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                     }
                 m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
                 m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
-                if (part == 0) {
+                if (part == 0 && lt < L * 4) {
                     const float sd = sqrtf(__fdiv_rn(m2, Tm1));
                     const float var = __fmul_rn(sd, sd);
                     const float sim = sqrtf(__fdiv_rn(var, Tf));                                   // :422
@@ -717,21 +717,23 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                     cB = 2.0f * gv / Tm1;
                     cM = sv[V3_M + c];
                 }
-                uint32_t hi[24], lo[24];
+                uint32_t hi0[16], lo0[16], hi1[8], lo1[8];
 #pragma unroll
                 for (int c = 0; c < L; ++c) {
                     const float A = __shfl_sync(0xffffffffu, cA, c), Bc = __shfl_sync(0xffffffffu, cB, c), m = __shfl_sync(0xffffffffu, cM, c);
                     const float g = live ? fmaf(Bc, f[c] - m, A) : 0.f;
-                    uint32_t bz;
-                    split3(g, hi[c], lo[c], bz);
+                    uint32_t bz, h_, l_;
+                    split3(g, h_, l_, bz);
+                    if (c < 16) { hi0[c < 16 ? c : 0] = h_; lo0[c < 16 ? c : 0] = l_; }
+                    else { hi1[c >= 16 ? c - 16 : 0] = h_; lo1[c >= 16 ? c - 16 : 0] = l_; }
                     if (stored) gfa[(rq * PGF + c) * 4 + rr] = __uint_as_float(live ? bz : 0u);
                 }
 #pragma unroll
-                for (int c = L; c < 24; ++c) { hi[c] = 0u; lo[c] = 0u; }
-                tmem_st16(tl + TM_AHI, *reinterpret_cast<uint32_t(*)[16]>(&hi[0]));
-                tmem_st8(tl + TM_AHI + 16, *reinterpret_cast<uint32_t(*)[8]>(&hi[16]));
-                tmem_st16(tl + TM_ALO, *reinterpret_cast<uint32_t(*)[16]>(&lo[0]));
-                tmem_st8(tl + TM_ALO + 16, *reinterpret_cast<uint32_t(*)[8]>(&lo[16]));
+                for (int c = L - 16; c < 8; ++c) { hi1[c] = 0u; lo1[c] = 0u; }
+                tmem_st16(tl + TM_AHI, hi0);
+                tmem_st8(tl + TM_AHI + 16, hi1);
+                tmem_st16(tl + TM_ALO, lo0);
+                tmem_st8(tl + TM_ALO + 16, lo1);
             }
             publish();
             // ---- P6: g_a2 = (g_f W2) . [h2 > 0] -> A and over h2 ----
@@ -754,8 +756,9 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
     float* part = prm.partial + ((int64_t)sidx * prm.n_cta + blockIdx.x) * (fl.d + DPAD);
     float* red = sm;   // the activation areas are dead
     // (1) feature matrices, biases, E: lanes 0..39 of the accumulators (row warps 0 and 1 of slot 0 own those lanes)
-    if (warp < 2 && (warp == 0 || lane < 8)) {
+    if (warp < 2) {   // tcgen05.ld is warp-collective: every lane loads, lanes j >= 40 store nothing
         const int j = warp * 32 + lane;
+        const bool jv = j < H;
         const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
         const int N0 = L_.N0;
         for (int c0 = 0; c0 < N0; c0 += 8) {
@@ -766,6 +769,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             for (int i = 0; i < 8; ++i) {
                 const int c = c0 + i;
                 const float a = __uint_as_float(v[i]);
+                if (!jv) continue;
                 if (c < F) {
                     part[fl.W0 + j * F + c] = a;
                     if (lidx[c] < 0) red[j * 48 + c] = __ldg(th + fl.W0 + j * F + c) * a;   // zeroed column: n = x', E = dW0
@@ -785,11 +789,12 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = c0 + i;
+                if (!jv) continue;
                 if (c < H) part[fl.W1 + j * H + c] = __uint_as_float(v[i]);
                 else if (c == H) part[fl.b1 + j] = __uint_as_float(v[i]);
             }
         }
-        if (j < L) {
+        if (warp == 0) {
             for (int c0 = 0; c0 < 48; c0 += 8) {
                 uint32_t v[8];
                 tmem_ld8(ta + TM_ACC2 + c0, v);
@@ -797,6 +802,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int c = c0 + i;
+                    if (j >= L) continue;
                     if (c < H) part[fl.W2 + j * H + c] = __uint_as_float(v[i]);
                     else if (c == H) part[fl.b2 + j] = __uint_as_float(v[i]);
                 }

@@ -47,6 +47,11 @@ int bnn_train_timeline(unsigned long long* host_out, int32_t n);
 int bnn_tc_probe_ss(const float* d_G, const float* d_H, float* d_D, int32_t R, int32_t MJ, int32_t NK, int32_t N,
                     int32_t bias_round, int32_t two_batches, void* stream);
 
+/* Diagnostic: force the kernel behind bnn_train_step / bnn_train_noise for this process: 0 = automatic (the tensor-core
+ * kernel where its shared-memory plan fits, else the FP32 FFMA kernel), 1 = tensor-core, 2 = FP32 FFMA.  The default is
+ * read once from the environment variable BNN_TRAIN_VARIANT (tc | v3). */
+int bnn_set_train_variant(int32_t variant);
+
 #ifdef __cplusplus
 }
 #endif
