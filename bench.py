@@ -2,7 +2,8 @@
 """bench.py -- headline benchmark of the MultiSWAG posterior-predictive hot path.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
-    python bench.py --impl reference ...                     (CPU arm: the oracle port)
+    python bench.py --impl reference ...                     (CPU arm: the unmodified reference from baseline/_ref,
+                                                              else the oracle port)
 
 A STEP is one pass of the hot path over one batch of synthetic input: sample S weight vectors
 from the SWAG posterior (K1) and evaluate all S x N_sys (system x weight-sample) pairs with the
@@ -108,6 +109,41 @@ def cpu_oracle_arm(steps, warmup, n_sys=10000, n_samp=4):
                       f"oracle/restatement.py on torch CPU fp32, {steps} steps)"}, dt
 
 
+def cpu_reference_arm(steps, warmup, n_sys=10000, n_samp=4):
+    """The UNMODIFIED reference (baseline/_ref/spock_reg_model.py, staged by __graft_entry__.build(); imported under the
+    three sys.modules stubs of oracle/ref_shim.py: pytorch_lightning, torch._six, matplotlib) on the host cores: per
+    weight sample one ``SWAGModel.forward_swag_fast(x, scale=0.5)`` -- its own sample_weights (dense d x d diagonal,
+    spock_reg_model.py:815-838) + masks + forward -- on 10,000 synthetic systems.  Returns None when the files are absent."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_root, "spock_reg_model.py")):
+        return None
+    os.environ["BNN_REFERENCE_ROOT"] = ref_root
+    from bnn_chaos_model_b200 import synth
+    from oracle import ref_shim
+
+    ref_shim.REFERENCE_ROOT = ref_root
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = ref_shim.load_reference_swag(ref_shim.pretrained_path(0))
+    model.eval()
+    x = torch.from_numpy(synth.make_systems(n_sys, seed=1))
+
+    def step():
+        for _ in range(n_samp):
+            model.forward_swag_fast(x, scale=0.5).detach()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n_sys * n_samp / dt, "unit": "evals/s", "cores": cores, "kind": "reference",
+            "sample": f"{n_sys} systems x {n_samp} weight samples per step: the unmodified reference's "
+                      f"SWAGModel.forward_swag_fast incl. its sample_weights (baseline/_ref, torch {torch.__version__} CPU "
+                      f"fp32, {steps} steps)"}, dt
+
+
 def cpu_train_arm(B=2000, steps=2):
     """One SWAG-phase training step (noisy forward + loss + KL + autograd backward + clip + SGD) of the oracle
     port on the host cores, same batch shape as BASELINE configs[3]."""
@@ -141,6 +177,127 @@ def cpu_train_arm(B=2000, steps=2):
     dt = (time.perf_counter() - t0) / steps
     return {"value": 1.0 / dt, "unit": "seed-steps/s", "cores": cores, "kind": "port",
             "sample": f"{steps} steps of 1 seed, batch {B} x 100 x 41 (oracle/restatement.py training_loss + autograd + SGD)"}
+
+
+def tf32_peak_tflops(dev):
+    """Measured dense TF32 tensor-pipe peak of this GPU: cuBLAS fp32 GEMM with TF32 allowed, 8192^3, best of 5."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((8192, 8192), device=dev)
+        b = torch.randn((8192, 8192), device=dev)
+        best = 0.0
+        for i in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c = a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            if i:
+                best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        del a, b, c
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return best
+
+
+def make_ensemble(dev, n_models):
+    """n_models SWAG posteriors on `dev`: the three shipped v50 statistics of tests/golden (seeds 0, 3, 17) cycled over
+    the model slots (the Philox units of equal statistics still differ)."""
+    from bnn_chaos_model_b200 import spock_reg_model as S
+    from bnn_chaos_model_b200.multiswag import MultiSWAG
+
+    models = []
+    for i in range(n_models):
+        z, hp, sp = load_stats((0, 3, 17)[i % 3])
+        m = S.SWAGModel(hp).init_params(sp).to(dev)
+        m.w_avg, m.w2_avg, m.pre_D = (torch.from_numpy(z[k]).to(dev) for k in ("w_avg", "w2_avg", "pre_D"))
+        models.append(m)
+    return MultiSWAG(models, device=dev)
+
+
+def config3_arm(dev, rank, world, total_systems, n_models=30, samples=2000):
+    """BASELINE configs[2]: MultiSWAG 30 seeds x 2000 weight samples x 100k systems, STRONG-scaled: the systems are
+    block-partitioned over the ranks, every rank evaluates all 60,000 units on its shard and reduces them to the
+    per-system posterior summary on the device; the path's single all_gather then moves [N, 8] (not [N, 60000, 2])."""
+    import torch.distributed as dist
+
+    from bnn_chaos_model_b200 import synth
+    from bnn_chaos_model_b200.multiswag import shard_range
+
+    ens = make_ensemble(dev, n_models)
+    g = ens.system_granule(100)
+    lo, hi = shard_range(total_systems, rank, world, g)
+    base = torch.from_numpy(synth.make_systems(2500, seed=77)).to(dev)
+    x = base.repeat((hi - lo + 2499) // 2500, 1, 1)[: hi - lo].contiguous()   # distinct Philox draws per (unit, system) anyway
+    del base
+    torch.cuda.reset_peak_memory_stats(dev)
+    m0 = torch.cuda.memory_allocated(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st = ens.posterior_summary_sharded(x, total_systems, samples, n_trios=1, seed=5)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    evals = n_models * samples * total_systems
+    assert st.shape == (total_systems, 8) and bool(torch.isfinite(st).all())
+    return {"metric": "MultiSWAG (system x weight-sample) evals/s", "value": evals / (ms * 1e-3), "unit": "evals/s",
+            "scaling": "strong", "ms": ms, "models": n_models, "samples_per_model": samples, "systems_total": total_systems,
+            "systems_this_rank": hi - lo, "evals": evals, "output": f"[{total_systems}, 8] posterior summary, all_gather of "
+            f"{total_systems * 32} bytes", "peak_extra_memory_GB": (torch.cuda.max_memory_allocated(dev) - m0) / 1e9,
+            "data": "synthetic systems (2,500 distinct, tiled); the three shipped v50 SWAG statistics cycled over 30 model slots"}
+
+
+def config5_arm(dev, rank, world, systems_per_rank, samples_per_model=34):
+    """BASELINE configs[4]: 5-planet sliding-window inference (multiswag_5_planet.py: every adjacent trio), WEAK-scaled:
+    systems_per_rank five-planet systems per GPU, raw time series -> input packing (K6) -> 3 models x 34 weight samples
+    over the 3 trios (K1 + K2) -> sampled instability times, min over trios, per-system summary (K7) -> all_gather [N, 8]."""
+    import torch.distributed as dist
+
+    from bnn_chaos_model_b200 import synth
+    from bnn_chaos_model_b200.inputs import pack_trios
+    from bnn_chaos_model_b200.multiswag import gather_system_shards
+
+    ens = make_ensemble(dev, 3)
+    Rt, N = 3, systems_per_rank
+    base = torch.from_numpy(synth.raw_systems(3000, seed=8 + rank)).to(dev)
+    raw = base.repeat((N * Rt + 2999) // 3000, 1, 1)[: N * Rt]
+    ts = raw[:, :, :26].contiguous().reshape(N, Rt, 100, 26)
+    msr = raw[:, 0, 26:29].contiguous().reshape(N, Rt, 3)
+    del raw, base
+
+    def run(seed):
+        x = pack_trios(ts, msr)
+        st = ens.posterior_summary(x, samples_per_model, n_trios=Rt, seed=seed, system_offset=rank * N)
+        if world > 1:
+            st = gather_system_shards(st, N * world)
+        return st
+
+    run(0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st = run(1)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    U = 3 * samples_per_model
+    assert st.shape == (N * world, 8) and bool(torch.isfinite(st).all())
+    return {"metric": "5-planet systems/s (raw series -> [N, 8] posterior summary)", "value": N * world / (ms * 1e-3),
+            "unit": "systems/s", "scaling": "weak", "ms": ms, "systems_per_gpu": N, "trios": Rt, "units": U,
+            "evals_per_s": N * world * Rt * U / (ms * 1e-3),
+            "data": "synthetic raw 3-planet series (3,000 distinct, tiled) as the trios of 5-planet systems"}
 
 
 def gpu_train_arm(dev, n_seeds=4, B=2000, n_data=8000, iters=10):
@@ -186,8 +343,12 @@ def gpu_train_arm(dev, n_seeds=4, B=2000, n_data=8000, iters=10):
     assert bool((met[:, 6] == 0).all()) and bool(torch.isfinite(met).all())
     return {"value": n_seeds / (ms * 1e-3), "unit": "seed-steps/s", "n_seeds": n_seeds, "batch": B, "ms_per_step": ms,
             "gpu_launches_per_step": 4, "data": "synthetic, 8000 resident systems, per-seed index batches, Philox noise",
+            "kernel": "train_tc_kernel (tcgen05 kind::tf32: 3xTF32 forward, 2-term activation-gradient and single-pass "
+                      "round-to-nearest weight-gradient GEMMs)",
             "roofline": {"bound": "fp32_fma", "achieved": tf, "peak": FP32_PEAK_NOMINAL, "unit": "TFLOP/s",
-                         "frac": tf / FP32_PEAK_NOMINAL, "flop_per_seed_step": 3 * 814_560 * B}}
+                         "frac": tf / FP32_PEAK_NOMINAL, "flop_per_seed_step": 3 * 814_560 * B,
+                         "note": "algorithmic FLOPs (3 x the dense forward) over the FP32 CUDA-core peak, north_star's "
+                                 "roofline for this path; the GEMMs run on the tensor pipe"}}
 
 
 def ncu_traffic_bytes():
@@ -209,7 +370,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, dt = cpu_oracle_arm(args.steps, args.warmup)
+    got = cpu_reference_arm(args.steps, args.warmup)   # the unmodified reference when it is staged, else the oracle port
+    cb, dt = got if got is not None else cpu_oracle_arm(args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "MultiSWAG (system x weight-sample) evals/s", "value": cb["value"],
         "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -338,14 +500,34 @@ def run_ours(args):
         train["ms_per_step"] = float(tt[0])
         train["n_seeds"] *= world
         train["value"] = train["n_seeds"] / (train["ms_per_step"] * 1e-3)
-        train["roofline"]["note"] = "per-GPU fraction; value is the aggregate over ranks"
+        train["roofline"]["note"] += "; per-GPU fraction, value is the aggregate over ranks"
+    train30 = None
+    if not args.no_train:
+        # BASELINE configs[3] as stated: 30 seeds in parallel across the GPUs of the box (strong scaling): rank r trains
+        # seeds_of_rank(30, r, world) -- 4,4,4,4,4,4,3,3 at 8 GPUs, all 30 on one GPU at N = 1
+        from bnn_chaos_model_b200.swag_train import seeds_of_rank
+
+        mine = seeds_of_rank(30, rank, world)
+        t30 = gpu_train_arm(dev, n_seeds=max(1, len(mine)))
+        tt = torch.tensor([t30["ms_per_step"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        train30 = {"value": 30 / (float(tt[0]) * 1e-3), "unit": "seed-steps/s", "n_seeds": 30, "scaling": "strong",
+                   "seeds_this_rank": len(mine), "ms_per_step": float(tt[0]), "batch": 2000,
+                   "roofline_frac_this_rank": t30["roofline"]["frac"]}
+    extras = {}
+    if not args.no_extra:
+        extras["config3"] = config3_arm(dev, rank, world, args.config3_systems)
+        extras["config5"] = config5_arm(dev, rank, world, args.config5_systems)
+    tf32_peak = tf32_peak_tflops(dev)
 
     if rank == 0:
         evals = n_sys * n_samp * world
         achieved = FLOP_PER_EVAL_V50 * n_sys * n_samp / (k_ms * 1e-3) / 1e12
         cb = None
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_oracle_arm(3, 1)
+            got = cpu_reference_arm(3, 1)
+            cb, _ = got if got is not None else cpu_oracle_arm(3, 1)
         line = {
             "metric": "MultiSWAG (system x weight-sample) evals/s", "value": evals / (ms * 1e-3), "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -360,10 +542,16 @@ def run_ours(args):
                     "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": e2e_ms},
             "gpu_launches": 3 * args.steps,
             "clocks": clk,
-            "roofline": {"bound": "fp32_fma", "kernel": "predict (K2)", "achieved": achieved,
-                         "peak": FP32_PEAK_NOMINAL, "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_NOMINAL,
-                         "peak_source": "148 SM x 128 lanes x 2 x clocks.max.sm 1965 MHz (MEASURED_PEAKS.json sm_max_mhz); "
-                                        "no fp32 figure in MEASURED_PEAKS.json",
+            "roofline": {"bound": "tensor", "kernel": "predict (K2, tcgen05 kind::tf32, 3xTF32)", "achieved": achieved,
+                         "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+                         "frac_tensor": achieved / tf32_peak, "frac_fp32": achieved / FP32_PEAK_NOMINAL,
+                         "fp32_peak": FP32_PEAK_NOMINAL,
+                         "executed_tflops": 3.96 * achieved, "frac_tensor_executed": 3.96 * achieved / tf32_peak,
+                         "peak_source": "tensor: cuBLAS TF32 GEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no TF32 "
+                                        "figure; bf16_tflops / 2 is the nominal ratio); fp32: 148 SM x 128 lanes x 2 x "
+                                        "clocks.max.sm 1965 MHz (MEASURED_PEAKS.json sm_max_mhz). achieved = ALGORITHMIC "
+                                        "fp32 FLOPs / kernel time; the kernel executes 3.96 x as many tf32 MACs (three split "
+                                        "terms x padding K 31->32, N 40->48 / 20->32, rows 500->512)",
                          "measured_ffma_peak_tflops": ffma, "kernel_ms": k_ms,
                          "flop_per_eval": FLOP_PER_EVAL_V50, "traffic": ncu_traffic_bytes(),
                          "traffic_source": "profiles/r1_predict_tc4n4_ncu.txt (ncu --set full, same workload, per launch); "
@@ -372,6 +560,8 @@ def run_ours(args):
                                  "feature MLP as 3xTF32 on tcgen05 (tensor pipe active 33 %, profiles/)"},
             "cpu_baseline": cb,
             "train": train,
+            "train_30_seeds": train30,
+            **extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -388,6 +578,9 @@ def main():
     ap.add_argument("--samples", type=int, default=N_SAMP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the BASELINE configs[2] / configs[4] sections")
+    ap.add_argument("--config3-systems", type=int, default=100_000, help="total systems of the configs[2] section")
+    ap.add_argument("--config5-systems", type=int, default=125_000, help="5-planet systems per GPU of the configs[4] section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -35,12 +35,12 @@
 // B = 2000, against the 2e-4 tolerance of tests/test_gpu_train.py (the hardware's own truncation would be biased:
 // 8e-5).  tools/dw_precision.py reproduces the study on the CPU.
 //
-// Warp roles (13 warps, 416 threads, one CTA per SM):
+// Warp roles (16 warps, 512 threads, one CTA per SM):
 //   0..7   row warps: slot = w / 4, TMEM lane quadrant = w % 4
 //   8      issuer: the only thread that issues tcgen05.mma (one in-order stream: the three weight-gradient
 //          accumulators are shared by both slots and are updated in strict tile order, so a step is bit-reproducible)
 //          and the bulk copies (cp.async.bulk) of the input images
-//   9..12  producers: draw the Philox input noise up to three tiles ahead and write the tile's IMAGE -- exactly the
+//   9..15  producers: draw the Philox input noise up to four tiles ahead and write the tile's IMAGE -- exactly the
 //          bytes of the slot's shared-memory input area: [row quad][x''(41) | n''(live) | 1][4 rows], eps1 | eps2,
 //          summary noise, labels -- into an L2-resident ring; one 30 kB bulk copy brings it in when the slot is free.
 // Tensor memory (512 columns): slot s: A_hi [144 s, +48) A_lo [+48, +96) D [+96, +144); acc0 [288, 288 + N0) =
@@ -59,9 +59,9 @@ constexpr int PHH = 41;                  // features per quad of the h1 / h2 arr
 constexpr int PGF = 21;                  // features per quad of the f / g_f array (20 + 1 pad: odd pitch, conflict-free)
 constexpr int SMALLF = 96;               // tail of an image: eps1|eps2 [40], summary noise [40], labels [2], pad
 constexpr int IM_E12 = 0, IM_ESN = 40, IM_Y = 80;
-constexpr int NST = 3;                   // depth of the L2 image ring
+constexpr int NST = 4;                   // depth of the L2 image ring
 constexpr int NSLOT = 2;
-constexpr int W_ISSUE = 8, W_PROD = 9, NWARP = 13, NTHR_TC = NWARP * 32, NPRODT = 128;
+constexpr int W_ISSUE = 8, W_PROD = 9, NWARP = 16, NTHR_TC = NWARP * 32, NPRODT = 224;   // 512 threads: 128 registers each
 constexpr int TM_AHI = 0, TM_ALO = 48, TM_D = 96, TM_SLOT = 144, TM_ACC0 = 288, TM_ACC1 = 384, TM_ACC2 = 432;
 constexpr int SVF = 512;                 // head scratch per slot (layout: the V3_* enum of train_v3.cuh)
 // B-operand shapes (canonical K-major chunks [k/4][n][4]; only the real n rows are stored, the MMA's surplus rows
@@ -72,11 +72,13 @@ enum Phase { PH_X = 0, PH_L1, PH_L2, PH_L3, PH_B2, PH_B1, PH_DW0, PH_END };
 
 struct Bars {
     uint64_t a_ready[NSLOT];   // 128 row threads: operands of the slot's next phase are in place
+    uint64_t a_ready0[NSLOT];  // the same for layer 1 of the slot's NEXT tile: its stage does not wait for the issuer to have
+                               // consumed the previous tile's last a_ready phase, and an mbarrier can only be one phase ahead
     uint64_t d_ready[NSLOT];   // tcgen05.commit of the slot's phase
     uint64_t x_free[NSLOT];    // tcgen05.commit of the slot's last phase: its shared-memory areas may be overwritten
-    uint64_t x_full[NSLOT];    // bulk copy of the slot's image landed
+    uint64_t x_full[NSLOT];    // bulk copy of the slot's image landed (the issuer waits for it before the last phase)
     uint64_t img_full[NST];    // producers finished the image of ring stage i
-    uint64_t img_free[NST];    // the image of ring stage i has been copied out
+    uint64_t img_free[NST];    // ring stage i has been read by the slot's 128 row threads AND copied out by the bulk copy
     uint32_t tmem_base, pad;
 };
 
@@ -140,6 +142,20 @@ __device__ __forceinline__ void issue_ts3(uint32_t d, uint32_t ahi, uint32_t alo
         for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, alo + 8 * ks, dh + ks * step, idesc, ks > 0);
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dl + ks * step, idesc, true);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dh + ks * step, idesc, true);
+    }
+    __syncwarp();
+}
+// D = A_hi (W_lo + W_hi): the activation-gradient GEMMs, A rounded to nearest (one operand word), W split
+template <int N, int KS>
+__device__ __forceinline__ void issue_ts2(uint32_t d, uint32_t ahi, uint32_t bh_addr, uint32_t bl_addr, uint32_t chunk_bytes) {
+    constexpr uint32_t idesc = idesc_tf32(128, N);
+    const uint64_t dh = smem_desc_kmajor(bh_addr, chunk_bytes, 128u), dl = smem_desc_kmajor(bl_addr, chunk_bytes, 128u);
+    const uint64_t step = (uint64_t)(2u * chunk_bytes) >> 4;
+    if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dl + ks * step, idesc, ks > 0);
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dh + ks * step, idesc, true);
     }
@@ -262,7 +278,80 @@ __device__ __forceinline__ void produce_rest(const ProdTC& a, float* __restrict_
     }
 }
 
+// ---- row-thread epilogues, NC consecutive columns of this thread's row -------------------------------------------
+// hidden layer: v = relu(d + bias) -> A (tf32 hi, fp32 lo) and the biased word (bits + 0x1000) into arow[col * 4]
+template <int NC>
+__device__ __forceinline__ void hidden_cols(const uint32_t (&d)[NC], const float* __restrict__ bl, float* __restrict__ arow,
+                                            bool stored, uint32_t t_hi, uint32_t t_lo) {
+    uint32_t hi[NC], lo[NC];
+#pragma unroll
+    for (int g4 = 0; g4 < NC / 4; ++g4) {
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bl + 4 * g4);
+        const u64 v01 = add2(pack2(__uint_as_float(d[4 * g4]), __uint_as_float(d[4 * g4 + 1])), b.x);
+        const u64 v23 = add2(pack2(__uint_as_float(d[4 * g4 + 2]), __uint_as_float(d[4 * g4 + 3])), b.y);
+        float v[4];
+        unpack2(v01, v[0], v[1]);
+        unpack2(v23, v[2], v[3]);
+        uint32_t hb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = relu_nan(v[u]);
+            const uint32_t bz = rn_bias(v[u]);
+            hb[u] = bz & 0xFFFFE000u;
+            hi[4 * g4 + u] = hb[u];
+            if (stored) arow[(4 * g4 + u) * 4] = __uint_as_float(bz);
+        }
+        const u64 l01 = sub2(pack2(v[0], v[1]), pack2(__uint_as_float(hb[0]), __uint_as_float(hb[1])));
+        const u64 l23 = sub2(pack2(v[2], v[3]), pack2(__uint_as_float(hb[2]), __uint_as_float(hb[3])));
+        float l[4];
+        unpack2(l01, l[0], l[1]);
+        unpack2(l23, l[2], l[3]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) lo[4 * g4 + u] = __float_as_uint(l[u]);
+    }
+    if constexpr (NC == 16) {
+        tmem_st16(t_hi, hi);
+        tmem_st16(t_lo, lo);
+    } else {
+        tmem_st8(t_hi, hi);
+        tmem_st8(t_lo, lo);
+    }
+}
+// activation gradient: g = d . [h > 0] (h's biased word sits in arow[col * 4]; +0 is 0x1000) -> the biased word of g over
+// it, and (TM) the rounded g as the A operand of the next activation-gradient GEMM (single word: 2-term product)
+template <int NC, bool TM>
+__device__ __forceinline__ void grad_cols(const uint32_t (&d)[NC], float* __restrict__ arow, bool stored, uint32_t t_hi) {
+    uint32_t hi[NC];
+    uint32_t hw[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) hw[j] = stored ? __float_as_uint(arow[j * 4]) : 0u;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const uint32_t g = hw[j] > 0x1000u ? d[j] : 0u;
+        const uint32_t bz = g + 0x1000u;
+        hi[j] = bz & 0xFFFFE000u;
+        if (stored) arow[j * 4] = __uint_as_float(bz);
+    }
+    if constexpr (TM) {
+        if constexpr (NC == 16) tmem_st16(t_hi, hi);
+        else tmem_st8(t_hi, hi);
+    }
+}
+
 __device__ __forceinline__ void slot_sync(int slot) { named_sync(3 + slot, 128); }
+
+// per-role cycle stamps of CTA (0, 0) (make train_timeline; read back with bnn_train_timeline): row thread 0 -> slots
+// 0..12 (x wait | stage | D wait, epilogue x 2 | D wait | pooling + head | g_f | D wait | g_a2 | D wait | g_a1), issuer ->
+// 13 (loop) 14 (inside issue) , producer thread 0 -> 16 (work) 17 (waiting for a free ring stage)
+#ifdef BNN_TRAIN_TIMELINE
+#define TCT_DECL long long tct_prev = tl_clock(); unsigned long long tct[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define TCT(i) do { if (tid == 0) { const long long t_ = tl_clock(); tct[i] += (unsigned long long)(t_ - tct_prev); tct_prev = t_; } } while (0)
+#define TCT_FLUSH do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) for (int i_ = 0; i_ < 13; ++i_) g_train_tl[i_] = tct[i_]; } while (0)
+#else
+#define TCT_DECL do { } while (0)
+#define TCT(i) do { } while (0)
+#define TCT_FLUSH do { } while (0)
+#endif
 
 }  // namespace tcx
 
@@ -334,11 +423,12 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
     if (tid == 0) {
         for (int s = 0; s < NSLOT; ++s) {
             mbar_init(&bars->a_ready[s], 128);
+            mbar_init(&bars->a_ready0[s], 128);
             mbar_init(&bars->d_ready[s], 1);
             mbar_init(&bars->x_free[s], 1);
             mbar_init(&bars->x_full[s], 1);
         }
-        for (int s = 0; s < NST; ++s) { mbar_init(&bars->img_full[s], NPRODT); mbar_init(&bars->img_free[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&bars->img_full[s], NPRODT); mbar_init(&bars->img_free[s], 128 + 1); }
         mbar_init_fence();
     }
     if (warp == 0) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
@@ -365,9 +455,18 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
         // Producers: the images of tiles 0, 1, 2, ... into the L2 ring, up to NST tiles ahead
         // =================================================================================================
         const int p = tid - W_PROD * 32;
+#ifdef BNN_TRAIN_TIMELINE
+        long long tp_wait = 0, tp_work = 0;
+#endif
         for (int k = 0; k < n_k; ++k) {
             const int st = k % NST;
+#ifdef BNN_TRAIN_TIMELINE
+            const long long tp0 = tl_clock();
+#endif
             if (k >= NST) mbar_wait_backoff(&bars->img_free[st], (uint32_t)((k / NST - 1) & 1), 200);
+#ifdef BNN_TRAIN_TIMELINE
+            const long long tp1 = tl_clock();
+#endif
             const int b = (int)blockIdx.x + k * (int)gridDim.x;
             ProdTC a;
             a.X = prm.X; a.eps_in = prm.eps_in; a.Y = prm.Y; a.eps12 = prm.eps12; a.eps_sum = prm.eps_sum;
@@ -376,13 +475,26 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             a.row = prm.batch_index ? prm.batch_index[a.sb] : b;
             a.b = b; a.step = (int)prm.step; a.PX = PX; a.NL = NL;
             float* img = ring + (int64_t)st * L_.img_floats;
+            {   // pull the rows of the tile after next into L2 (129 lines of 128 B per system)
+                const int b2 = b + 2 * (int)gridDim.x;
+                if (b2 < prm.B && p < 129) {   // (NPRODT >= 129)
+                    const int64_t sb2 = (int64_t)sidx * prm.B + b2;
+                    const int64_t r2 = prm.batch_index ? (int64_t)prm.batch_index[sb2] : (int64_t)b2;
+                    const char* p2 = reinterpret_cast<const char*>(prm.X + r2 * T * F) + 128 * p;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
+                }
+            }
             produce_rest(a, img, p);
-            produce_items<4>(a, img, p);
-            produce_items<4>(a, img, p + 4 * NPRODT);
-            produce_items<1>(a, img, p + 8 * NPRODT);   // 1025 = 8 * 128 + 1 items
+            produce_items<5>(a, img, p);   // 1025 items over 224 threads
             __threadfence();                            // the image is read back by the bulk-copy engine through L2
             mbar_arrive(&bars->img_full[st]);
+#ifdef BNN_TRAIN_TIMELINE
+            tp_wait += tp1 - tp0; tp_work += tl_clock() - tp1;
+#endif
         }
+#ifdef BNN_TRAIN_TIMELINE
+        if (p == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_train_tl[16] = tp_work; g_train_tl[17] = tp_wait; }
+#endif
     } else if (warp == W_ISSUE) {
         // =================================================================================================
         // Issuer: bulk copies of the images and every tcgen05.mma of the CTA, in one in-order stream
@@ -390,9 +502,14 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
         const uint32_t sbase = smem_u32(sm);
         const uint32_t idesc48 = idesc_tf32(128, 48), idesc0 = idesc_tf32(128, L_.N0);
         int kk[NSLOT], ph[NSLOT];
-        uint32_t par_a[NSLOT], par_xf[NSLOT];
-        for (int s = 0; s < NSLOT; ++s) { kk[s] = s; ph[s] = PH_X; par_a[s] = 0; par_xf[s] = 0; }
+        uint32_t par_a[NSLOT], par_a0[NSLOT], par_xf[NSLOT], par_xl[NSLOT];
+        bool x_issued[NSLOT];   // the bulk copy of the slot's current tile has been issued
+        for (int s = 0; s < NSLOT; ++s) { kk[s] = s; ph[s] = PH_L1; par_a[s] = 0; par_a0[s] = 0; par_xf[s] = 0; par_xl[s] = 0; x_issued[s] = false; }
         int next_acc2 = 0, next_acc1 = 0, next_acc0 = 0;   // tile whose weight-gradient MMAs come next, per accumulator
+#ifdef BNN_TRAIN_TIMELINE
+        const long long ti0 = tl_clock();
+        long long ti_issue = 0;
+#endif
         for (;;) {
             bool any_active = false, progressed = false;
 #pragma unroll
@@ -401,27 +518,40 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 if (k >= n_k) continue;
                 any_active = true;
                 const uint32_t ts = tmem + (uint32_t)(s * TM_SLOT);
-                if (ph[s] == PH_X) {
-                    if (k >= NSLOT && !mbar_test(&bars->x_free[s], par_xf[s])) continue;   // dW0 of the slot's previous tile
+                if (!x_issued[s]) {
+                    // the image of tile k -> the slot's input area, as soon as the weight-gradient MMAs of the slot's previous
+                    // tile (its last readers) have completed and the producers have finished the image; off the row
+                    // threads' critical path: they stage x' straight from the L2 ring
                     const int st = k % NST;
-                    if (!mbar_test(&bars->img_full[st], (uint32_t)((k / NST) & 1))) continue;
-                    if (k >= NSLOT) par_xf[s] ^= 1;
-                    if (lane == 0) {
-                        asm volatile("fence.proxy.async;" ::: "memory");   // producers' generic-proxy writes -> bulk-copy engine
-                        mbar_arrive_expect_tx(&bars->x_full[s], img_bytes);
-                        bulk_g2s(sm + L_.xa[s], ring + (int64_t)st * L_.img_floats, img_bytes, &bars->x_full[s]);
+                    if ((k < NSLOT || mbar_test(&bars->x_free[s], par_xf[s])) && mbar_test(&bars->img_full[st], (uint32_t)((k / NST) & 1))) {
+                        if (k >= NSLOT) par_xf[s] ^= 1;
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async;" ::: "memory");   // producers' generic-proxy writes -> bulk-copy engine
+                            mbar_arrive_expect_tx(&bars->x_full[s], img_bytes);
+                            bulk_g2s(sm + L_.xa[s], ring + (int64_t)st * L_.img_floats, img_bytes, &bars->x_full[s]);
+                        }
+                        __syncwarp();
+                        x_issued[s] = true;
+                        progressed = true;
                     }
-                    __syncwarp();
-                    ph[s] = PH_L1;
-                    progressed = true;
-                    continue;
+                }
+                if (ph[s] == PH_DW0) {
+                    if (!x_issued[s] || !mbar_test(&bars->x_full[s], par_xl[s])) continue;   // [x' | n | 1] must have landed
                 }
                 if (ph[s] == PH_B2 && next_acc2 != k) continue;
                 if (ph[s] == PH_B1 && next_acc1 != k) continue;
                 if (ph[s] == PH_DW0 && next_acc0 != k) continue;
-                if (!mbar_test(&bars->a_ready[s], par_a[s])) continue;
-                par_a[s] ^= 1;
+                if (ph[s] == PH_L1) {
+                    if (!mbar_test(&bars->a_ready0[s], par_a0[s])) continue;
+                    par_a0[s] ^= 1;
+                } else {
+                    if (!mbar_test(&bars->a_ready[s], par_a[s])) continue;
+                    par_a[s] ^= 1;
+                }
                 tc_fence_after();
+#ifdef BNN_TRAIN_TIMELINE
+                const long long ti1 = tl_clock();
+#endif
                 const uint32_t d = ts + TM_D, ahi = ts + TM_AHI, alo = ts + TM_ALO;
                 switch (ph[s]) {
                     case PH_L1: issue_ts3<48, 6>(d, ahi, alo, sbase + 4u * L_.B1h, sbase + 4u * L_.B1l, H * 16u); break;
@@ -429,27 +559,35 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                     case PH_L3: issue_ts3<32, 5>(d, ahi, alo, sbase + 4u * L_.B3h, sbase + 4u * L_.B3l, L * 16u); break;
                     case PH_B2:
                         issue_ss_rows(tmem + TM_ACC2, sbase + 4u * L_.gf[s], PGF, sbase + 4u * L_.h2[s], PHH, idesc48, k == 0);
-                        issue_ts3<48, 3>(d, ahi, alo, sbase + 4u * L_.W2Th, sbase + 4u * L_.W2Tl, H * 16u);
+                        issue_ts2<48, 3>(d, ahi, sbase + 4u * L_.W2Th, sbase + 4u * L_.W2Tl, H * 16u);
                         ++next_acc2;
                         break;
                     case PH_B1:
                         issue_ss_rows(tmem + TM_ACC1, sbase + 4u * L_.h2[s], PHH, sbase + 4u * L_.h1[s], PHH, idesc48, k == 0);
-                        issue_ts3<48, 5>(d, ahi, alo, sbase + 4u * L_.W1Th, sbase + 4u * L_.W1Tl, H * 16u);
+                        issue_ts2<48, 5>(d, ahi, sbase + 4u * L_.W1Th, sbase + 4u * L_.W1Tl, H * 16u);
                         ++next_acc1;
                         break;
                     default:
+                        par_xl[s] ^= 1;
+                        if (lane == 0) mbar_arrive(&bars->img_free[k % NST]);   // the bulk copy has read the ring stage
                         issue_ss_rows(tmem + TM_ACC0, sbase + 4u * L_.h1[s], PHH, sbase + 4u * L_.xa[s], (uint32_t)PX, idesc0, k == 0);
                         ++next_acc0;
                         break;
                 }
                 if (elect_one_sync()) mma_commit(ph[s] == PH_DW0 ? &bars->x_free[s] : &bars->d_ready[s]);
                 __syncwarp();
-                if (++ph[s] == PH_END) { ph[s] = PH_X; kk[s] = k + NSLOT; }
+                if (++ph[s] == PH_END) { ph[s] = PH_L1; kk[s] = k + NSLOT; x_issued[s] = false; }
                 progressed = true;
+#ifdef BNN_TRAIN_TIMELINE
+                ti_issue += tl_clock() - ti1;
+#endif
             }
             if (!any_active) break;
-            if (!progressed) __nanosleep(40);
+            if (!progressed) __nanosleep(20);
         }
+#ifdef BNN_TRAIN_TIMELINE
+        if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_train_tl[13] = tl_clock() - ti0; g_train_tl[14] = ti_issue; }
+#endif
         // every MMA of the CTA has completed once the last commit of each slot has arrived
         for (int s = 0; s < NSLOT; ++s) {
             const int n_s = (n_k - s + NSLOT - 1) / NSLOT;   // tiles of slot s
@@ -469,11 +607,10 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
         float* h2a = sm + L_.h2[slot];
         float* gfa = sm + L_.gf[slot];
         float* sv = sm + L_.sv[slot];
-        const float* small = xa + NQ * PX * 4;
         const int rq = (r >> 2), rr = r & 3;
         const float* bias = sm + L_.bias;
         const float Tf = (float)T, Tm1 = (float)(T - 1);
-        uint32_t pd = 0, px = 0;
+        uint32_t pd = 0;
 
         auto wait_d = [&]() {
             if (quad == 0) {
@@ -487,91 +624,96 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             tc_fence_after();
         };
         // operands of the next phase are written: TMEM stores complete, shared-memory stores visible to the tensor core
-        auto publish = [&]() {
+        auto publish = [&](bool layer1 = false) {
             tc_wait_st();
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(&bars->a_ready[slot]);
+            mbar_arrive(layer1 ? &bars->a_ready0[slot] : &bars->a_ready[slot]);
         };
-        // D[0..NC) + bias -> ReLU -> A (hi / lo) and the biased word into act[row quad][col][row % 4]
         auto hidden_epilogue = [&](const float* bl, float* act) {
-#pragma unroll
-            for (int c0 = 0; c0 < H; c0 += 8) {
-                uint32_t d[8], hi[8], lo[8];
-                tmem_ld8(tl + TM_D + c0, d);
-                tc_wait_ld();
-                const float4 b0 = *reinterpret_cast<const float4*>(bl + c0), b1 = *reinterpret_cast<const float4*>(bl + c0 + 4);
-                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float v = live ? relu_nan(__uint_as_float(d[j]) + bv[j]) : 0.f;
-                    uint32_t bz;
-                    split3(v, hi[j], lo[j], bz);
-                    if (stored) act[(rq * PHH + c0 + j) * 4 + rr] = __uint_as_float(live ? bz : 0u);
-                }
-                tmem_st8(tl + TM_AHI + c0, hi);
-                tmem_st8(tl + TM_ALO + c0, lo);
-            }
+            uint32_t d0[16], d1[16], d2[8];
+            tmem_ld16(tl + TM_D, d0);
+            tmem_ld16(tl + TM_D + 16, d1);
+            tmem_ld8(tl + TM_D + 32, d2);
+            tc_wait_ld();
+            float* arow = act + rq * PHH * 4 + rr;
+            hidden_cols<16>(d0, bl, arow, stored, tl + TM_AHI, tl + TM_ALO);
+            hidden_cols<16>(d1, bl + 16, arow + 64, stored, tl + TM_AHI + 16, tl + TM_ALO + 16);
+            hidden_cols<8>(d2, bl + 32, arow + 128, stored, tl + TM_AHI + 32, tl + TM_ALO + 32);
         };
-        // D . [h > 0] -> g: A (hi / lo, when a row GEMM follows) and the biased word over h in place
-        auto grad_epilogue = [&](float* act, bool to_tmem) {
-#pragma unroll
-            for (int c0 = 0; c0 < H; c0 += 8) {
-                uint32_t d[8], hi[8], lo[8];
-                tmem_ld8(tl + TM_D + c0, d);
-                tc_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float* p = act + (rq * PHH + c0 + j) * 4 + rr;
-                    const uint32_t hb = stored ? __float_as_uint(*p) : 0u;
-                    const float g = (live && hb > 0x1000u) ? __uint_as_float(d[j]) : 0.f;   // h > 0 (biased word of +0 is 0x1000)
-                    uint32_t bz;
-                    split3(g, hi[j], lo[j], bz);
-                    if (stored) *p = __uint_as_float(live ? bz : 0u);
-                }
-                if (to_tmem) {
-                    tmem_st8(tl + TM_AHI + c0, hi);
-                    tmem_st8(tl + TM_ALO + c0, lo);
-                }
-            }
+        auto grad_epilogue_tm = [&](float* act) {
+            uint32_t d0[16], d1[16], d2[8];
+            tmem_ld16(tl + TM_D, d0);
+            tmem_ld16(tl + TM_D + 16, d1);
+            tmem_ld8(tl + TM_D + 32, d2);
+            tc_wait_ld();
+            float* arow = act + rq * PHH * 4 + rr;
+            grad_cols<16, true>(d0, arow, stored, tl + TM_AHI);
+            grad_cols<16, true>(d1, arow + 64, stored, tl + TM_AHI + 16);
+            grad_cols<8, true>(d2, arow + 128, stored, tl + TM_AHI + 32);
+        };
+        auto grad_epilogue_sm = [&](float* act) {
+            uint32_t d0[16], d1[16], d2[8];
+            tmem_ld16(tl + TM_D, d0);
+            tmem_ld16(tl + TM_D + 16, d1);
+            tmem_ld8(tl + TM_D + 32, d2);
+            tc_wait_ld();
+            float* arow = act + rq * PHH * 4 + rr;
+            grad_cols<16, false>(d0, arow, stored, 0u);
+            grad_cols<16, false>(d1, arow + 64, stored, 0u);
+            grad_cols<8, false>(d2, arow + 128, stored, 0u);
         };
 
+        TCT_DECL;
         for (int k = slot; k < n_k; k += NSLOT) {
             const int b = (int)blockIdx.x + k * (int)gridDim.x;
             const int64_t sb = (int64_t)sidx * prm.B + b;
-            // ---- P0: the image has landed -> x' exact -> A of layer 1 (48 columns, 41 real) ----
-            if (lane == 0) mbar_wait_backoff(&bars->x_full[slot], px, 40);
-            px ^= 1;
+            // ---- P0: the producers have finished the image -> x'' straight from the L2 ring (ld.global.cg: the stage is
+            // rewritten every NST tiles, L1 must not serve it) -> exact x' -> A of layer 1 (48 columns, 41 real) ----
+            const int st = k % NST;
+            const float* img = ring + (int64_t)st * L_.img_floats;
+            if (lane == 0) mbar_wait_backoff(&bars->img_full[st], (uint32_t)((k / NST) & 1), 40);
             __syncwarp();
-            if (lt == 0) mbar_arrive(&bars->img_free[k % NST]);
+            TCT(0);
+            {
+                uint32_t xw[48];
+                const float* xr = img + rq * PX * 4 + rr;
 #pragma unroll
-            for (int c0 = 0; c0 < 48; c0 += 8) {
-                uint32_t hi[8], lo[8];
+                for (int c = 0; c < F; ++c) xw[c] = live ? __float_as_uint(__ldcg(xr + c * 4)) : 0x1000u;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = c0 + j;
-                    uint32_t h_ = 0u, l_ = 0u;
-                    if (c < F && live) {
-                        const uint32_t bz = __float_as_uint(xa[(rq * PX + c) * 4 + rr]);
-                        const float xp = __uint_as_float(bz - 0x1000u);
-                        h_ = bz & 0xFFFFE000u;
-                        l_ = __float_as_uint(xp - __uint_as_float(h_));
+                for (int c = F; c < 48; ++c) xw[c] = 0x1000u;
+                if (lt < 21)   // eps1 | eps2, summary noise, labels: 82 floats, contiguous in the image and in the scratch
+                    *reinterpret_cast<float4*>(sv + V3_E12 + 4 * lt) = __ldcg(reinterpret_cast<const float4*>(img + NQ * PX * 4) + lt);
+#pragma unroll
+                for (int c0 = 0; c0 < 48; c0 += 16) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t bz = xw[c0 + j];
+                        hi[j] = bz & 0xFFFFE000u;
+                        lo[j] = __float_as_uint(__uint_as_float(bz - 0x1000u) - __uint_as_float(hi[j]));
                     }
-                    hi[j] = h_; lo[j] = l_;
+                    tmem_st16(tl + TM_AHI + c0, hi);
+                    tmem_st16(tl + TM_ALO + c0, lo);
                 }
-                tmem_st8(tl + TM_AHI + c0, hi);
-                tmem_st8(tl + TM_ALO + c0, lo);
             }
-            publish();
+            mbar_arrive(&bars->img_free[st]);   // this thread's part of the image is in registers / tensor memory
+            publish(true);
+            TCT(1);
             // ---- P1, P2: hidden layers ----
             wait_d();
+            TCT(2);
             hidden_epilogue(bias, h1a);
             publish();
+            TCT(3);
             wait_d();
+            TCT(4);
             hidden_epilogue(bias + 48, h2a);
             publish();
+            TCT(5);
             // ---- P3: latent rows f = D + b2 -> registers and shared memory (the pooling reads columns) ----
             wait_d();
+            TCT(6);
             float f[L];
             {
                 uint32_t d0[16], d1[8];
@@ -614,33 +756,38 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                     const float var = __fmul_rn(sd, sd);
                     const float sim = sqrtf(__fdiv_rn(var, Tf));                                   // :422
                     const float siv = sqrtf(__fdiv_rn(__fmul_rn(2.0f, __fmul_rn(var, var)), Tm1));   // :423
-                    const float e1 = small[IM_E12 + c], e2 = small[IM_E12 + L + c];
+                    const float e1 = sv[V3_E12 + c], e2 = sv[V3_E12 + L + c];
                     const float mus = __fadd_rn(__fmul_rn(e1, sim), mean);                          // :426
                     const float vs = __fadd_rn(__fmul_rn(e2, siv), var);                            // :427
                     const float sds = sqrtf(__fadd_rn(fabsf(vs), 1e-5f));                           // :430
                     sv[V3_M + c] = mean; sv[V3_VAR + c] = var; sv[V3_SIM + c] = sim; sv[V3_SIV + c] = siv; sv[V3_VS + c] = vs;
                     sv[V3_S + c] = mus; sv[V3_S + L + c] = sds;
-                    sv[V3_SP + c] = __fadd_rn(mus, __fmul_rn(small[IM_ESN + c], cst[C3_ELVH + c]));
-                    sv[V3_SP + L + c] = __fadd_rn(sds, __fmul_rn(small[IM_ESN + L + c], cst[C3_ELVH + L + c]));
+                    sv[V3_SP + c] = __fadd_rn(mus, __fmul_rn(sv[V3_ESN + c], cst[C3_ELVH + c]));
+                    sv[V3_SP + L + c] = __fadd_rn(sds, __fmul_rn(sv[V3_ESN + L + c], cst[C3_ELVH + L + c]));
                     a_skl += 0.5f * (mus * mus + cst[C3_KLC + c]) + 0.5f * (sds * sds + cst[C3_KLC + L + c]);
                 }
             }
             slot_sync(slot);
             // ---- regress_nn forward: 10 outputs per warp, three 14 / 13 / 13-term partial sums per output ----
-            const int hj = quad * 10 + (lane % 10), hpart = lane / 10;   // lanes 30, 31 idle
-            const int hk0 = hpart == 0 ? 0 : (hpart == 1 ? 14 : 27), hk1 = hpart == 0 ? 14 : (hpart == 1 ? 27 : 40);
+            const int hj = quad * 10 + (lane % 10), hpart = min(lane / 10, 2);   // lanes 30, 31 shadow part 2 (results unused)
             {
                 float a = 0.f;
-                if (lane < 30)
-                    for (int kx = hk0; kx < hk1; ++kx) a = fmaf(sv[V3_SP + kx], V0s[hj * S2 + kx], a);
+#pragma unroll
+                for (int i = 0; i < 14; ++i) {
+                    const int kx = hpart + 3 * i;
+                    if (kx < S2) a = fmaf(sv[V3_SP + kx], V0s[hj * S2 + kx], a);
+                }
                 const float a1 = __shfl_down_sync(0xffffffffu, a, 10), a2 = __shfl_down_sync(0xffffffffu, a, 20);
                 if (lane < 10) sv[V3_R1 + hj] = relu_nan((a + a1) + a2 + cbs[hj]);
             }
             slot_sync(slot);
             {
                 float a = 0.f;
-                if (lane < 30)
-                    for (int kx = hk0; kx < hk1; ++kx) a = fmaf(sv[V3_R1 + kx], V1s[hj * H + kx], a);
+#pragma unroll
+                for (int i = 0; i < 14; ++i) {
+                    const int kx = hpart + 3 * i;
+                    if (kx < H) a = fmaf(sv[V3_R1 + kx], V1s[hj * H + kx], a);
+                }
                 const float a1 = __shfl_down_sync(0xffffffffu, a, 10), a2 = __shfl_down_sync(0xffffffffu, a, 20);
                 if (lane < 10) sv[V3_R2 + hj] = relu_nan((a + a1) + a2 + cbs[H + hj]);
             }
@@ -661,7 +808,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 const float mu = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, __fadd_rn(t0, 1.0f)), __fsub_rn(prm.hc.hi_mu, prm.hc.lo_mu)), prm.hc.lo_mu);
                 const float sd = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, __fadd_rn(t1, 1.0f)), __fsub_rn(prm.hc.hi_sd, prm.hc.lo_sd)), prm.hc.lo_sd);
                 float l = 0.f, dm = 0.f, ds = 0.f;
-                if (lane < 2) nll_terms(mu, sd, small[IM_Y + lane], l, dm, ds);
+                if (lane < 2) nll_terms(mu, sd, sv[V3_Y + lane], l, dm, ds);
                 const float l1 = __shfl_sync(0xffffffffu, l, 1), dm1 = __shfl_sync(0xffffffffu, dm, 1), ds1 = __shfl_sync(0xffffffffu, ds, 1);
                 if (lane == 0) {
                     a_nll += -(l + l1);
@@ -679,8 +826,11 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             slot_sync(slot);
             {   // g_a1h[k] = (sum_j g_a2h[j] V1[j][k]) . [r1 > 0]
                 float a = 0.f;
-                if (lane < 30)
-                    for (int j = hk0; j < hk1; ++j) a = fmaf(sv[V3_G2 + j], V1s[j * H + hj], a);
+#pragma unroll
+                for (int i = 0; i < 14; ++i) {
+                    const int j = hpart + 3 * i;
+                    if (j < H) a = fmaf(sv[V3_G2 + j], V1s[j * H + hj], a);
+                }
                 const float a1 = __shfl_down_sync(0xffffffffu, a, 10), a2 = __shfl_down_sync(0xffffffffu, a, 20);
                 if (lane < 10) sv[V3_G1 + hj] = sv[V3_R1 + hj] > 0.f ? (a + a1) + a2 : 0.f;
             }
@@ -688,12 +838,15 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             float* rec = prm.head_rec + sb * REC;
             {   // g_s'[k] = sum_j g_a1h[j] V0[j][k]; summary-noise log-variance gradient; KL gradient of s
                 float a = 0.f;
-                if (lane < 30)
-                    for (int j = hk0; j < hk1; ++j) a = fmaf(sv[V3_G1 + j], V0s[j * S2 + hj], a);
+#pragma unroll
+                for (int i = 0; i < 14; ++i) {
+                    const int j = hpart + 3 * i;
+                    if (j < H) a = fmaf(sv[V3_G1 + j], V0s[j * S2 + hj], a);
+                }
                 const float a1 = __shfl_down_sync(0xffffffffu, a, 10), a2 = __shfl_down_sync(0xffffffffu, a, 20);
                 if (lane < 10) {
                     const float g = (a + a1) + a2;
-                    rec[R_DLVS + hj] = g * (0.5f * (small[IM_ESN + hj] * cst[C3_ELVH + hj]));   // ds'/dlv = eps e^{lv/2} / 2
+                    rec[R_DLVS + hj] = g * (0.5f * (sv[V3_ESN + hj] * cst[C3_ELVH + hj]));   // ds'/dlv = eps e^{lv/2} / 2
                     sv[V3_GS + hj] = g + prm.beta_out * sv[V3_S + hj];
                 }
                 // the record of the deferred head outer products: s', r1, r2, g_a1h, g_a2h (complete since the last barrier)
@@ -701,6 +854,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 if (lt == 0) { rec[R_GR] = gr0; rec[R_GR + 1] = gr1; }
             }
             slot_sync(slot);
+            TCT(7);
             // ---- P5: g_f[t] = g_m / n + g_v 2 (f_t - m) / (n - 1); lanes 0..19 of every warp hold their column's coefficients ----
             {
                 float cA = 0.f, cB = 0.f, cM = 0.f;
@@ -710,41 +864,44 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                     const float vs = sv[V3_VS + c], sds = sv[V3_S + L + c], var = sv[V3_VAR + c];
                     const float sgn = vs > 0.f ? 1.0f : (vs < 0.f ? -1.0f : 0.f);
                     const float gvs = gsds * sgn / (2.0f * sds);
-                    const float e1 = small[IM_E12 + c], e2 = small[IM_E12 + L + c];
+                    const float e1 = sv[V3_E12 + c], e2 = sv[V3_E12 + L + c];
                     const float gv = gmus * e1 / (2.0f * Tf * sv[V3_SIM + c]) +
                                      gvs * (1.0f + e2 * (2.0f * var) / (Tm1 * sv[V3_SIV + c]));
                     cA = gmus / Tf;
                     cB = 2.0f * gv / Tm1;
                     cM = sv[V3_M + c];
                 }
-                uint32_t hi0[16], lo0[16], hi1[8], lo1[8];
+                uint32_t hi0[16], hi1[8];
 #pragma unroll
                 for (int c = 0; c < L; ++c) {
                     const float A = __shfl_sync(0xffffffffu, cA, c), Bc = __shfl_sync(0xffffffffu, cB, c), m = __shfl_sync(0xffffffffu, cM, c);
-                    const float g = live ? fmaf(Bc, f[c] - m, A) : 0.f;
-                    uint32_t bz, h_, l_;
-                    split3(g, h_, l_, bz);
-                    if (c < 16) { hi0[c < 16 ? c : 0] = h_; lo0[c < 16 ? c : 0] = l_; }
-                    else { hi1[c >= 16 ? c - 16 : 0] = h_; lo1[c >= 16 ? c - 16 : 0] = l_; }
+                    const float g = live ? fmaf(Bc, f[c] - m, A) : 0.f;   // rows >= T: exact zeros (they ARE rows of the contraction)
+                    const uint32_t bz = rn_bias(g), h_ = bz & 0xFFFFE000u;
+                    if (c < 16) hi0[c < 16 ? c : 0] = h_;
+                    else hi1[c >= 16 ? c - 16 : 0] = h_;
                     if (stored) gfa[(rq * PGF + c) * 4 + rr] = __uint_as_float(live ? bz : 0u);
                 }
 #pragma unroll
-                for (int c = L - 16; c < 8; ++c) { hi1[c] = 0u; lo1[c] = 0u; }
+                for (int c = L - 16; c < 8; ++c) hi1[c] = 0u;
                 tmem_st16(tl + TM_AHI, hi0);
                 tmem_st8(tl + TM_AHI + 16, hi1);
-                tmem_st16(tl + TM_ALO, lo0);
-                tmem_st8(tl + TM_ALO + 16, lo1);
             }
             publish();
+            TCT(8);
             // ---- P6: g_a2 = (g_f W2) . [h2 > 0] -> A and over h2 ----
             wait_d();
-            grad_epilogue(h2a, true);
+            TCT(9);
+            grad_epilogue_tm(h2a);
             publish();
+            TCT(10);
             // ---- P7: g_a1 = (g_a2 W1) . [h1 > 0] -> over h1; the issuer then adds g_a1^T [x' | n | 1] ----
             wait_d();
-            grad_epilogue(h1a, false);
+            TCT(11);
+            grad_epilogue_sm(h1a);
             publish();
+            TCT(12);
         }
+        TCT_FLUSH;
     }
 
     // =====================================================================================================

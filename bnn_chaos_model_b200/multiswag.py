@@ -219,15 +219,43 @@ class MultiSWAG:
         return out_host
 
     def posterior_summary(self, x: torch.Tensor, samples_per_model: int, n_trios: int = 1, seed: int = 0,
-                          scale: float = 0.5, system_offset: int = 0):
+                          scale: float = 0.5, system_offset: int = 0, max_block_bytes: int = 1 << 30):
         """Predict + post-process on the device: x [N*n_trios, T, F] (rows = system*n_trios + trio, the
         reshape(-1, 100, 41) of multiswag_5_planet.py:287) -> [N, 8] per-system statistics
         (``posterior.STAT_NAMES``) of the sampled instability time, min over trios (figures/main_figures.py:
-        167-277, figures/multiswag_5_planet.py:306-481).  Only [N, 8] ever leaves the GPU."""
+        167-277, figures/multiswag_5_planet.py:306-481).  Only [N, 8] ever leaves the GPU, and the [rows, U, 2]
+        prediction block (+ the [rows, U] sampled times) never exists as a whole: systems are walked in chunks of at
+        most ``max_block_bytes`` of predictions (12 bytes per (row, unit)), cut at multiples of the kernel's system
+        granule -- the Philox draws are keyed on global (unit, row) indices, so the result does not depend on the
+        chunking (BASELINE configs[2]: 12,500 systems x 60,000 units per GPU would be 9 GB in one piece)."""
+        import math
+
         from . import posterior
 
-        pred = self.predict(x, samples_per_model, seed, scale, system_offset=system_offset * n_trios, system_major=True)
-        return posterior.posterior_summary(pred, n_trios, seed, row_offset=system_offset * n_trios)
+        rows = x.shape[0]
+        if rows % n_trios:
+            raise ValueError(f"{rows} rows are not a multiple of {n_trios} trios")
+        N = rows // n_trios
+        with torch.cuda.device(self.device):
+            _, thp = self.sample_thetas(samples_per_model, seed, scale)
+            U = thp.shape[0]
+            g = self.system_granule(x.shape[1])
+            gs = g // math.gcd(g, n_trios)                      # systems per chunk boundary such that rows stay aligned
+            per = max(1, int(max_block_bytes // (12 * U * n_trios)))
+            per = max(gs, per // gs * gs)
+            if per >= N:
+                pred = self.predict(x, samples_per_model, seed, scale, system_offset=system_offset * n_trios,
+                                    system_major=True, thp=thp)
+                return posterior.posterior_summary(pred, n_trios, seed, row_offset=system_offset * n_trios)
+            out = torch.empty((N, 8), device=self.device)
+            for lo in range(0, N, per):
+                hi = min(lo + per, N)
+                row0 = (system_offset + lo) * n_trios
+                pred = self.predict(x[lo * n_trios:hi * n_trios], samples_per_model, seed, scale, system_offset=row0,
+                                    system_major=True, thp=thp)
+                out[lo:hi] = posterior.posterior_summary(pred, n_trios, seed, row_offset=row0)
+                del pred
+        return out
 
     def posterior_summary_sharded(self, x_local: torch.Tensor, n_total: int, samples_per_model: int, n_trios: int = 1,
                                   seed: int = 0, scale: float = 0.5, group=None):

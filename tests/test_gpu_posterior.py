@@ -117,3 +117,21 @@ def test_ensemble_posterior_summary_end_to_end(dev):
     ref = R.posterior_stats(pred[..., 0], pred)
     np.testing.assert_allclose(full[:, 6].cpu().numpy(), ref["median_mu"], rtol=2e-6)
     np.testing.assert_allclose(full[:, 7].cpu().numpy(), ref["median_std"], rtol=2e-6)
+
+
+def test_posterior_summary_chunking_is_invisible(dev):
+    """posterior_summary walks the systems in chunks so that [rows, U, 2] never exists as a whole (BASELINE configs[2]:
+    9 GB per GPU otherwise); the chunk size must not show in the result, bit for bit, for 1 and 3 trios."""
+    from conftest import make_swag_model
+    from bnn_chaos_model_b200 import synth
+    from bnn_chaos_model_b200.multiswag import MultiSWAG
+
+    ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(17, dev)], device=dev)
+    x = torch.from_numpy(synth.make_systems(3 * 47, seed=33)).to(dev)
+    for n_trios, N in ((1, 141), (3, 47)):
+        S_ = 20
+        full = ens.posterior_summary(x, S_, n_trios=n_trios, seed=5, system_offset=10)
+        assert full.shape == (N, 8)
+        for budget in (12 * 40 * n_trios * 5, 12 * 40 * n_trios * 17, 12 * 40 * n_trios * 46):   # 5, 15, 45 systems per chunk
+            got = ens.posterior_summary(x, S_, n_trios=n_trios, seed=5, system_offset=10, max_block_bytes=budget)
+            assert torch.equal(got, full), (n_trios, budget)

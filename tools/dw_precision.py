@@ -25,7 +25,11 @@ def mm3(a, b):  # a[M,K] @ b[K,N], 3xTF32
     ah, al = split(a); bh, bl = split(b)
     return (al.double()@bh.double() + ah.double()@bl.double() + ah.double()@bh.double()).float()
 
-MODE = {'dw': '2term'}
+def mm2(a, b):  # a rounded to nearest tf32 (single), b split: a_hi b_lo + a_hi b_hi
+    ah = rn_tf32(a); bh, bl = split(b)
+    return (ah.double()@bl.double() + ah.double()@bh.double()).float()
+
+MODE = {'dw': '2term', 'bwd': '3term'}
 class TCLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, b):
@@ -37,7 +41,7 @@ class TCLinear(torch.autograd.Function):
     def backward(ctx, g):
         x, W = ctx.saved_tensors
         g2 = g.reshape(-1, g.shape[-1]); x2 = x.reshape(-1, x.shape[-1])
-        gx = mm3(g2, W).reshape(x.shape)
+        gx = (mm2(g2, W) if MODE.get('bwd') == '2term' else mm3(g2, W)).reshape(x.shape)
         gh, gl = split(g2)
         if MODE['dw'] == '2term':
             xh = rn_tf32(x2)
@@ -85,8 +89,8 @@ for step in range(3):
     gref = torch.from_numpy(z[f'grad_ref_{step}'])
     l0, g0 = grad_with(spec, th, x, y, e_in, e12[:, :20], e12[:, 20:], es, False)
     print(f"step {step}: fp32 restatement vs golden: {float((g0-gref).abs().max()/gref.abs().max()):.2e}  loss {l0} vs {float(z[f'loss_ref_{step}'])}")
-    for mode in ('3term', '2term', 'trunc2', '1term'):
-        MODE['dw'] = mode
+    for mode in ('3term', '2term', 'trunc2', '1term', '1term+bwd2'):
+        MODE['dw'] = mode.split('+')[0]; MODE['bwd'] = '2term' if '+' in mode else '3term'
         l1, g1 = grad_with(spec, th, x, y, e_in, e12[:, :20], e12[:, 20:], es, True)
         print(f"   {mode}: grad err/max {float((g1-gref).abs().max()/gref.abs().max()):.2e}  loss rel {abs(l1-l0)/abs(l0):.2e}")
 # B = 2000
@@ -96,7 +100,7 @@ g = torch.Generator().manual_seed(1)
 e_in = torch.randn(x.shape, generator=g); e12 = torch.randn((B, 40), generator=g); es = torch.randn((B, 40), generator=g)
 theta = torch.from_numpy(st['w_avg'])
 l0, g0 = grad_with(spec, theta.double() if False else theta, x, y, e_in, e12[:, :20], e12[:, 20:], es, False)
-for mode in ('3term', '2term', 'trunc2', '1term'):
-    MODE['dw'] = mode
+for mode in ('3term', '2term', 'trunc2', '1term', '1term+bwd2'):
+    MODE['dw'] = mode.split('+')[0]; MODE['bwd'] = '2term' if '+' in mode else '3term'
     l1, g1 = grad_with(spec, theta, x, y, e_in, e12[:, :20], e12[:, 20:], es, True)
     print(f"B=2000 {mode}: grad err/max {float((g1-g0).abs().max()/g0.abs().max()):.2e}  loss rel {abs(l1-l0)/abs(l0):.2e}")

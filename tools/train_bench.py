@@ -43,8 +43,14 @@ print(json.dumps({"n_seeds": n_seeds, "B": B, "ms_per_step": round(ms, 4), "seed
 tl = (ctypes.c_ulonglong * 24)()
 _lib.check(lib.bnn_train_timeline(tl, 24))
 if any(tl):
-    names = ["stage", "S0 load", "L1 fwd", "L2 fwd", "L3 fwd", "head tail (g_f)", "B1 g_a2", "B2 g_a1", "outer", "g_x+sums", "epilogue",
-             "pool", "head V0", "head V1", "head V2+nll", "bwd V1", "bwd V0+rec", "gm/gv", "producer: work", "producer: wait for free scratch", "p20", "p21", "p22", "p23"]
-    tot = float(sum(tl[:18]))
-    print(json.dumps({"timeline_cycles_cta0_last_step": {n: int(v) for n, v in zip(names, tl)},
-                      "share": {n: round(v / tot, 3) for n, v in zip(names, tl)}}))
+    if lib.bnn_set_train_variant and os.environ.get("BNN_TRAIN_VARIANT", "tc") != "v3":
+        names = ["wait x image", "stage x -> A", "wait D1", "epilogue h1", "wait D2", "epilogue h2", "wait D3", "f + pool + head",
+                 "g_f", "wait D(g_a2)", "epilogue g_a2", "wait D(g_a1)", "epilogue g_a1", "issuer: loop", "issuer: inside issue",
+                 "-", "producer: work", "producer: wait for a free ring stage"] + ["-"] * 6
+        tot = float(sum(tl[:13]))
+    else:
+        names = ["stage", "S0 load", "L1 fwd", "L2 fwd", "L3 fwd", "head tail (g_f)", "B1 g_a2", "B2 g_a1", "outer", "g_x+sums", "epilogue",
+                 "pool", "head V0", "head V1", "head V2+nll", "bwd V1", "bwd V0+rec", "gm/gv", "producer: work", "producer: wait for free scratch", "p20", "p21", "p22", "p23"]
+        tot = float(sum(tl[:18]))
+    print(json.dumps({"timeline_cycles_cta0_last_step": {n: int(v) for n, v in zip(names, tl) if n != "-"},
+                      "share_of_row_thread_0": {n: round(v / tot, 3) for n, v in zip(names, tl) if n != "-"}}))
