@@ -236,6 +236,14 @@ static bool use_tc(const bnn_model_config* cfg) {
     return tcx::SmemTC(cfg->zero_mask).fits();
 }
 
+// per-CTA input-tile scratch in the workspace: v3's two parities of (x' | n | small inputs), or the tensor-core kernel's
+// ring of NST images
+static size_t scratch_floats_per_cta(const bnn_model_config* cfg) {
+    const size_t v3 = (size_t)8 * cfg->n_features * cfg->n_times + 2 * XSM;
+    const size_t tc = (size_t)tcx::NST * (tcx::NQ * 97 * 4 + tcx::SMALLF);
+    return v3 > tc ? v3 : tc;
+}
+
 static int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -268,7 +276,7 @@ size_t bnn_train_workspace_bytes(const bnn_model_config* cfg, int64_t B, int32_t
     // partial | grad | sq | pad | head records (v3)
     return ((size_t)n_seeds * n_cta * DP + (size_t)n_seeds * DP + (size_t)n_seeds * nb + 64 +
             (size_t)n_seeds * B * train::REC + 4 +
-            (size_t)n_seeds * n_cta * (8 * cfg->n_features * cfg->n_times + 2 * train::XSM)) * sizeof(float);
+            (size_t)n_seeds * n_cta * train::scratch_floats_per_cta(cfg)) * sizeof(float);
 }
 
 int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int32_t n_seeds, float* d_theta,

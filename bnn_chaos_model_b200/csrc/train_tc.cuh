@@ -59,9 +59,9 @@ constexpr int PHH = 41;                  // features per quad of the h1 / h2 arr
 constexpr int PGF = 21;                  // features per quad of the f / g_f array (20 + 1 pad: odd pitch, conflict-free)
 constexpr int SMALLF = 96;               // tail of an image: eps1|eps2 [40], summary noise [40], labels [2], pad
 constexpr int IM_E12 = 0, IM_ESN = 40, IM_Y = 80;
-constexpr int NST = 4;                   // depth of the L2 image ring
+constexpr int NST = 8;                   // depth of the L2 image ring
 constexpr int NSLOT = 2;
-constexpr int W_ISSUE = 8, W_PROD = 9, NWARP = 16, NTHR_TC = NWARP * 32, NPRODT = 224;   // 512 threads: 128 registers each
+constexpr int W_ISSUE = 8, W_PROD = 10, NPW = 6, NWARP = 16, NTHR_TC = NWARP * 32;   // 512 threads: 128 registers each
 constexpr int TM_AHI = 0, TM_ALO = 48, TM_D = 96, TM_SLOT = 144, TM_ACC0 = 288, TM_ACC1 = 384, TM_ACC2 = 432;
 constexpr int SVF = 512;                 // head scratch per slot (layout: the V3_* enum of train_v3.cuh)
 // B-operand shapes (canonical K-major chunks [k/4][n][4]; only the real n rows are stored, the MMA's surplus rows
@@ -79,7 +79,8 @@ struct Bars {
     uint64_t x_full[NSLOT];    // bulk copy of the slot's image landed (the issuer waits for it before the last phase)
     uint64_t img_full[NST];    // producers finished the image of ring stage i
     uint64_t img_free[NST];    // ring stage i has been read by the slot's 128 row threads AND copied out by the bulk copy
-    uint32_t tmem_base, pad;
+    uint32_t tmem_base;
+    int turn[3];               // tile whose weight-gradient MMAs may be issued next into acc0 / acc1 / acc2 (two issuers)
 };
 
 struct SmemTC {
@@ -182,14 +183,14 @@ struct ProdTC {
 
 // items (row quad q < 25, feature c): 4 normals (Philox block q * F + c, box_muller_fast) for rows 4q..4q+3 of column c
 template <int NR>
-__device__ __forceinline__ void produce_items(const ProdTC& a, float* __restrict__ img, int first) {
+__device__ __forceinline__ void produce_items(const ProdTC& a, float* __restrict__ img, int first, int stride) {
     float xv[NR][4], ev[NR][4];
     uint4 ctr[NR];
     int qs[NR], cs[NR];
     bool ok[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-        const int id0 = first + NPRODT * k;
+        const int id0 = first + stride * k;
         ok[k] = id0 < RQ * F;
         const int id = ok[k] ? id0 : RQ * F - 1;
         const int q = id / F, c = id - q * F;
@@ -249,7 +250,7 @@ __device__ __forceinline__ void produce_items(const ProdTC& a, float* __restrict
     }
 }
 
-__device__ __forceinline__ void produce_rest(const ProdTC& a, float* __restrict__ img, int p) {
+__device__ __forceinline__ void produce_rest(const ProdTC& a, float* __restrict__ img, int p, int NPRODT) {
     // ones column (and the pad column when PX is padded) of the 25 data quads, the whole pad quad, the small inputs
     const int c1 = F + a.NL;
     for (int i = p; i < RQ * (a.PX - c1); i += NPRODT) {
@@ -270,11 +271,11 @@ __device__ __forceinline__ void produce_rest(const ProdTC& a, float* __restrict_
         }
         reinterpret_cast<float4*>(sm_out + IM_E12)[p] = e;
         reinterpret_cast<float4*>(sm_out + IM_ESN)[p] = c;
-    } else if (p == 32) {
+    } else if (p == 10) {
         float2 y = __ldg(reinterpret_cast<const float2*>(a.Y) + a.row);
         *reinterpret_cast<float4*>(sm_out + IM_Y) = make_float4(y.x, y.y, 0.f, 0.f);
-    } else if (p >= 33 && p < 36) {
-        *reinterpret_cast<float4*>(sm_out + IM_Y + 4 * (p - 32)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (p >= 11 && p < 14) {
+        *reinterpret_cast<float4*>(sm_out + IM_Y + 4 * (p - 10)) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -341,12 +342,13 @@ __device__ __forceinline__ void grad_cols(const uint32_t (&d)[NC], float* __rest
 __device__ __forceinline__ void slot_sync(int slot) { named_sync(3 + slot, 128); }
 
 // per-role cycle stamps of CTA (0, 0) (make train_timeline; read back with bnn_train_timeline): row thread 0 -> slots
-// 0..12 (x wait | stage | D wait, epilogue x 2 | D wait | pooling + head | g_f | D wait | g_a2 | D wait | g_a1), issuer ->
-// 13 (loop) 14 (inside issue) , producer thread 0 -> 16 (work) 17 (waiting for a free ring stage)
+// 0..12 (x wait | stage | D wait, epilogue x 2 | D wait | head: last phase | g_f | D wait | g_a2 | D wait | g_a1) and 13..18
+// (head: f store | pooling | V0 | V1 | output + NLL | V1^T), issuer of slot 0 -> 20 (loop) 21 (inside issue), producer
+// warp 0 -> 22 (work) 23 (waiting for a free ring stage)
 #ifdef BNN_TRAIN_TIMELINE
-#define TCT_DECL long long tct_prev = tl_clock(); unsigned long long tct[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define TCT_DECL long long tct_prev = tl_clock(); unsigned long long tct[19] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define TCT(i) do { if (tid == 0) { const long long t_ = tl_clock(); tct[i] += (unsigned long long)(t_ - tct_prev); tct_prev = t_; } } while (0)
-#define TCT_FLUSH do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) for (int i_ = 0; i_ < 13; ++i_) g_train_tl[i_] = tct[i_]; } while (0)
+#define TCT_FLUSH do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) for (int i_ = 0; i_ < 19; ++i_) g_train_tl[i_] = tct[i_]; } while (0)
 #else
 #define TCT_DECL do { } while (0)
 #define TCT(i) do { } while (0)
@@ -428,7 +430,8 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             mbar_init(&bars->x_free[s], 1);
             mbar_init(&bars->x_full[s], 1);
         }
-        for (int s = 0; s < NST; ++s) { mbar_init(&bars->img_full[s], NPRODT); mbar_init(&bars->img_free[s], 128 + 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&bars->img_full[s], 32); mbar_init(&bars->img_free[s], 128 + 1); }
+        bars->turn[0] = bars->turn[1] = bars->turn[2] = 0;
         mbar_init_fence();
     }
     if (warp == 0) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
@@ -452,13 +455,14 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
 
     if (warp >= W_PROD) {
         // =================================================================================================
-        // Producers: the images of tiles 0, 1, 2, ... into the L2 ring, up to NST tiles ahead
+        // Producers: warp w draws the images of tiles w, w + NPW, ... ALONE (the work is latency-bound -- Philox chains,
+        // DRAM loads of the rows -- so six independent tile streams beat six warps sharing one tile), up to NST tiles ahead
         // =================================================================================================
-        const int p = tid - W_PROD * 32;
+        const int pw = warp - W_PROD;
 #ifdef BNN_TRAIN_TIMELINE
         long long tp_wait = 0, tp_work = 0;
 #endif
-        for (int k = 0; k < n_k; ++k) {
+        for (int k = pw; k < n_k; k += NPW) {
             const int st = k % NST;
 #ifdef BNN_TRAIN_TIMELINE
             const long long tp0 = tl_clock();
@@ -475,17 +479,20 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             a.row = prm.batch_index ? prm.batch_index[a.sb] : b;
             a.b = b; a.step = (int)prm.step; a.PX = PX; a.NL = NL;
             float* img = ring + (int64_t)st * L_.img_floats;
-            {   // pull the rows of the tile after next into L2 (129 lines of 128 B per system)
-                const int b2 = b + 2 * (int)gridDim.x;
-                if (b2 < prm.B && p < 129) {   // (NPRODT >= 129)
+            {   // pull the rows of this warp's next tile into L2 (129 lines of 128 B per system)
+                const int b2 = b + NPW * (int)gridDim.x;
+                if (b2 < prm.B) {
                     const int64_t sb2 = (int64_t)sidx * prm.B + b2;
                     const int64_t r2 = prm.batch_index ? (int64_t)prm.batch_index[sb2] : (int64_t)b2;
-                    const char* p2 = reinterpret_cast<const char*>(prm.X + r2 * T * F) + 128 * p;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
+                    for (int ln = lane; ln < 129; ln += 32) {
+                        const char* p2 = reinterpret_cast<const char*>(prm.X + r2 * T * F) + 128 * ln;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p2));
+                    }
                 }
             }
-            produce_rest(a, img, p);
-            produce_items<5>(a, img, p);   // 1025 items over 224 threads
+            produce_rest(a, img, lane, 32);
+#pragma unroll 1
+            for (int i0 = 0; i0 < RQ * F; i0 += 4 * 32) produce_items<4>(a, img, i0 + lane, 32);   // 1025 items, 4 per lane per round
             __threadfence();                            // the image is read back by the bulk-copy engine through L2
             mbar_arrive(&bars->img_full[st]);
 #ifdef BNN_TRAIN_TIMELINE
@@ -493,103 +500,93 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
 #endif
         }
 #ifdef BNN_TRAIN_TIMELINE
-        if (p == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_train_tl[16] = tp_work; g_train_tl[17] = tp_wait; }
+        if (pw == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_train_tl[22] = tp_work; g_train_tl[23] = tp_wait; }
 #endif
-    } else if (warp == W_ISSUE) {
+    } else if (warp >= W_ISSUE) {
         // =================================================================================================
-        // Issuer: bulk copies of the images and every tcgen05.mma of the CTA, in one in-order stream
+        // Issuers: warp W_ISSUE + s issues every tcgen05.mma and the image bulk copy of slot s, in the slot's program order.
+        // The three weight-gradient accumulators are shared by the slots: their MMAs take turns in strict tile order
+        // (turn[] in shared memory, handed over with tcgen05 fences), so a step is bit-reproducible.
         // =================================================================================================
+        const int s = warp - W_ISSUE;
         const uint32_t sbase = smem_u32(sm);
         const uint32_t idesc48 = idesc_tf32(128, 48), idesc0 = idesc_tf32(128, L_.N0);
-        int kk[NSLOT], ph[NSLOT];
-        uint32_t par_a[NSLOT], par_a0[NSLOT], par_xf[NSLOT], par_xl[NSLOT];
-        bool x_issued[NSLOT];   // the bulk copy of the slot's current tile has been issued
-        for (int s = 0; s < NSLOT; ++s) { kk[s] = s; ph[s] = PH_L1; par_a[s] = 0; par_a0[s] = 0; par_xf[s] = 0; par_xl[s] = 0; x_issued[s] = false; }
-        int next_acc2 = 0, next_acc1 = 0, next_acc0 = 0;   // tile whose weight-gradient MMAs come next, per accumulator
+        const uint32_t ts = tmem + (uint32_t)(s * TM_SLOT);
+        const uint32_t d = ts + TM_D, ahi = ts + TM_AHI, alo = ts + TM_ALO;
+        uint32_t pa = 0, pa0 = 0, pxf = 0, pxl = 0;
+        volatile int* turn = bars->turn;
+        auto take_turn = [&](int acc, int k) {
+            while (turn[acc] != k) __nanosleep(20);
+            __syncwarp();
+            tc_fence_after();
+        };
+        auto pass_turn = [&](int acc, int k) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); turn[acc] = k + 1; }
+        };
+        auto commit = [&](uint64_t* bar) {
+            if (elect_one_sync()) mma_commit(bar);
+            __syncwarp();
+        };
 #ifdef BNN_TRAIN_TIMELINE
         const long long ti0 = tl_clock();
         long long ti_issue = 0;
+#define TI_BEGIN const long long ti1_ = tl_clock()
+#define TI_END ti_issue += tl_clock() - ti1_
+#else
+#define TI_BEGIN do { } while (0)
+#define TI_END do { } while (0)
 #endif
-        for (;;) {
-            bool any_active = false, progressed = false;
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
-                const int k = kk[s];
-                if (k >= n_k) continue;
-                any_active = true;
-                const uint32_t ts = tmem + (uint32_t)(s * TM_SLOT);
-                if (!x_issued[s]) {
-                    // the image of tile k -> the slot's input area, as soon as the weight-gradient MMAs of the slot's previous
-                    // tile (its last readers) have completed and the producers have finished the image; off the row
-                    // threads' critical path: they stage x' straight from the L2 ring
-                    const int st = k % NST;
-                    if ((k < NSLOT || mbar_test(&bars->x_free[s], par_xf[s])) && mbar_test(&bars->img_full[st], (uint32_t)((k / NST) & 1))) {
-                        if (k >= NSLOT) par_xf[s] ^= 1;
-                        if (lane == 0) {
-                            asm volatile("fence.proxy.async;" ::: "memory");   // producers' generic-proxy writes -> bulk-copy engine
-                            mbar_arrive_expect_tx(&bars->x_full[s], img_bytes);
-                            bulk_g2s(sm + L_.xa[s], ring + (int64_t)st * L_.img_floats, img_bytes, &bars->x_full[s]);
-                        }
-                        __syncwarp();
-                        x_issued[s] = true;
-                        progressed = true;
-                    }
-                }
-                if (ph[s] == PH_DW0) {
-                    if (!x_issued[s] || !mbar_test(&bars->x_full[s], par_xl[s])) continue;   // [x' | n | 1] must have landed
-                }
-                if (ph[s] == PH_B2 && next_acc2 != k) continue;
-                if (ph[s] == PH_B1 && next_acc1 != k) continue;
-                if (ph[s] == PH_DW0 && next_acc0 != k) continue;
-                if (ph[s] == PH_L1) {
-                    if (!mbar_test(&bars->a_ready0[s], par_a0[s])) continue;
-                    par_a0[s] ^= 1;
-                } else {
-                    if (!mbar_test(&bars->a_ready[s], par_a[s])) continue;
-                    par_a[s] ^= 1;
-                }
-                tc_fence_after();
-#ifdef BNN_TRAIN_TIMELINE
-                const long long ti1 = tl_clock();
-#endif
-                const uint32_t d = ts + TM_D, ahi = ts + TM_AHI, alo = ts + TM_ALO;
-                switch (ph[s]) {
-                    case PH_L1: issue_ts3<48, 6>(d, ahi, alo, sbase + 4u * L_.B1h, sbase + 4u * L_.B1l, H * 16u); break;
-                    case PH_L2: issue_ts3<48, 5>(d, ahi, alo, sbase + 4u * L_.B2h, sbase + 4u * L_.B2l, H * 16u); break;
-                    case PH_L3: issue_ts3<32, 5>(d, ahi, alo, sbase + 4u * L_.B3h, sbase + 4u * L_.B3l, L * 16u); break;
-                    case PH_B2:
-                        issue_ss_rows(tmem + TM_ACC2, sbase + 4u * L_.gf[s], PGF, sbase + 4u * L_.h2[s], PHH, idesc48, k == 0);
-                        issue_ts2<48, 3>(d, ahi, sbase + 4u * L_.W2Th, sbase + 4u * L_.W2Tl, H * 16u);
-                        ++next_acc2;
-                        break;
-                    case PH_B1:
-                        issue_ss_rows(tmem + TM_ACC1, sbase + 4u * L_.h2[s], PHH, sbase + 4u * L_.h1[s], PHH, idesc48, k == 0);
-                        issue_ts2<48, 5>(d, ahi, sbase + 4u * L_.W1Th, sbase + 4u * L_.W1Tl, H * 16u);
-                        ++next_acc1;
-                        break;
-                    default:
-                        par_xl[s] ^= 1;
-                        if (lane == 0) mbar_arrive(&bars->img_free[k % NST]);   // the bulk copy has read the ring stage
-                        issue_ss_rows(tmem + TM_ACC0, sbase + 4u * L_.h1[s], PHH, sbase + 4u * L_.xa[s], (uint32_t)PX, idesc0, k == 0);
-                        ++next_acc0;
-                        break;
-                }
-                if (elect_one_sync()) mma_commit(ph[s] == PH_DW0 ? &bars->x_free[s] : &bars->d_ready[s]);
-                __syncwarp();
-                if (++ph[s] == PH_END) { ph[s] = PH_L1; kk[s] = k + NSLOT; x_issued[s] = false; }
-                progressed = true;
-#ifdef BNN_TRAIN_TIMELINE
-                ti_issue += tl_clock() - ti1;
-#endif
+        for (int k = s; k < n_k; k += NSLOT) {
+            const int st = k % NST;
+            // the image of tile k -> the slot's input area (read only by the last phase): needs the weight-gradient MMAs of
+            // the slot's previous tile (its last readers) complete and the image produced
+            if (k >= NSLOT) { mbar_wait_backoff(&bars->x_free[s], pxf, 20); pxf ^= 1; }
+            mbar_wait_backoff(&bars->img_full[st], (uint32_t)((k / NST) & 1), 20);
+            if (lane == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");   // producers' generic-proxy writes -> bulk-copy engine
+                mbar_arrive_expect_tx(&bars->x_full[s], img_bytes);
+                bulk_g2s(sm + L_.xa[s], ring + (int64_t)st * L_.img_floats, img_bytes, &bars->x_full[s]);
             }
-            if (!any_active) break;
-            if (!progressed) __nanosleep(20);
+            __syncwarp();
+            mbar_wait_backoff(&bars->a_ready0[s], pa0, 20); pa0 ^= 1;
+            tc_fence_after();
+            { TI_BEGIN; issue_ts3<48, 6>(d, ahi, alo, sbase + 4u * L_.B1h, sbase + 4u * L_.B1l, H * 16u); commit(&bars->d_ready[s]); TI_END; }
+            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            tc_fence_after();
+            { TI_BEGIN; issue_ts3<48, 5>(d, ahi, alo, sbase + 4u * L_.B2h, sbase + 4u * L_.B2l, H * 16u); commit(&bars->d_ready[s]); TI_END; }
+            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            tc_fence_after();
+            { TI_BEGIN; issue_ts3<32, 5>(d, ahi, alo, sbase + 4u * L_.B3h, sbase + 4u * L_.B3l, L * 16u); commit(&bars->d_ready[s]); TI_END; }
+            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            tc_fence_after();
+            issue_ts2<48, 3>(d, ahi, sbase + 4u * L_.W2Th, sbase + 4u * L_.W2Tl, H * 16u);   // g_a2 first: it gates the row threads
+            take_turn(2, k);
+            { TI_BEGIN; issue_ss_rows(tmem + TM_ACC2, sbase + 4u * L_.gf[s], PGF, sbase + 4u * L_.h2[s], PHH, idesc48, k == 0); TI_END; }
+            commit(&bars->d_ready[s]);
+            pass_turn(2, k);
+            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            tc_fence_after();
+            issue_ts2<48, 5>(d, ahi, sbase + 4u * L_.W1Th, sbase + 4u * L_.W1Tl, H * 16u);
+            take_turn(1, k);
+            { TI_BEGIN; issue_ss_rows(tmem + TM_ACC1, sbase + 4u * L_.h2[s], PHH, sbase + 4u * L_.h1[s], PHH, idesc48, k == 0); TI_END; }
+            commit(&bars->d_ready[s]);
+            pass_turn(1, k);
+            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            mbar_wait_backoff(&bars->x_full[s], pxl, 20); pxl ^= 1;      // [x' | n | 1] has landed
+            if (lane == 0) mbar_arrive(&bars->img_free[st]);              // ... so the ring stage is free (with the 128 row threads)
+            tc_fence_after();
+            take_turn(0, k);
+            { TI_BEGIN; issue_ss_rows(tmem + TM_ACC0, sbase + 4u * L_.h1[s], PHH, sbase + 4u * L_.xa[s], (uint32_t)PX, idesc0, k == 0); TI_END; }
+            commit(&bars->x_free[s]);
+            pass_turn(0, k);
         }
 #ifdef BNN_TRAIN_TIMELINE
-        if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_train_tl[13] = tl_clock() - ti0; g_train_tl[14] = ti_issue; }
+        if (s == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) { g_train_tl[20] = tl_clock() - ti0; g_train_tl[21] = ti_issue; }
 #endif
-        // every MMA of the CTA has completed once the last commit of each slot has arrived
-        for (int s = 0; s < NSLOT; ++s) {
+        // every MMA of the slot has completed once its last commit has arrived
+        {
             const int n_s = (n_k - s + NSLOT - 1) / NSLOT;   // tiles of slot s
             if (n_s > 0) mbar_wait_backoff(&bars->x_free[s], (uint32_t)((n_s - 1) & 1), 100);
         }
@@ -728,6 +725,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 }
             }
             slot_sync(slot);
+            TCT(13);
             // ---- pooling per latent column: two-pass mean / unbiased variance (:418-419), sampled summary statistics ----
             if (quad < 3) {   // 80 pooling threads (column c, 4 parts); the branch is warp-uniform for the shuffles
                 const int c = min(lt >> 2, L - 1), part = lt & 3;
@@ -768,6 +766,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 }
             }
             slot_sync(slot);
+            TCT(14);
             // ---- regress_nn forward: 10 outputs per warp, three 14 / 13 / 13-term partial sums per output ----
             const int hj = quad * 10 + (lane % 10), hpart = min(lane / 10, 2);   // lanes 30, 31 shadow part 2 (results unused)
             {
@@ -781,6 +780,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 if (lane < 10) sv[V3_R1 + hj] = relu_nan((a + a1) + a2 + cbs[hj]);
             }
             slot_sync(slot);
+            TCT(15);
             {
                 float a = 0.f;
 #pragma unroll
@@ -792,6 +792,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 if (lane < 10) sv[V3_R2 + hj] = relu_nan((a + a1) + a2 + cbs[H + hj]);
             }
             slot_sync(slot);
+            TCT(16);
             // ---- output layer, soft clamp, truncated-normal NLL and its gradient (one warp), V2 backward ----
             float gr0 = 0.f, gr1 = 0.f;
             if (quad == 0) {
@@ -824,6 +825,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 }
             }
             slot_sync(slot);
+            TCT(17);
             {   // g_a1h[k] = (sum_j g_a2h[j] V1[j][k]) . [r1 > 0]
                 float a = 0.f;
 #pragma unroll
@@ -835,6 +837,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 if (lane < 10) sv[V3_G1 + hj] = sv[V3_R1 + hj] > 0.f ? (a + a1) + a2 : 0.f;
             }
             slot_sync(slot);
+            TCT(18);
             float* rec = prm.head_rec + sb * REC;
             {   // g_s'[k] = sum_j g_a1h[j] V0[j][k]; summary-noise log-variance gradient; KL gradient of s
                 float a = 0.f;

@@ -44,10 +44,11 @@ tl = (ctypes.c_ulonglong * 24)()
 _lib.check(lib.bnn_train_timeline(tl, 24))
 if any(tl):
     if lib.bnn_set_train_variant and os.environ.get("BNN_TRAIN_VARIANT", "tc") != "v3":
-        names = ["wait x image", "stage x -> A", "wait D1", "epilogue h1", "wait D2", "epilogue h2", "wait D3", "f + pool + head",
-                 "g_f", "wait D(g_a2)", "epilogue g_a2", "wait D(g_a1)", "epilogue g_a1", "issuer: loop", "issuer: inside issue",
-                 "-", "producer: work", "producer: wait for a free ring stage"] + ["-"] * 6
-        tot = float(sum(tl[:13]))
+        names = ["wait x image", "stage x -> A", "wait D1", "epilogue h1", "wait D2", "epilogue h2", "wait D3", "head: V0^T + record",
+                 "g_f", "wait D(g_a2)", "epilogue g_a2", "wait D(g_a1)", "epilogue g_a1", "head: f store", "head: pooling", "head: V0",
+                 "head: V1", "head: output + NLL", "head: V1^T", "-", "issuer 0: loop", "issuer 0: inside issue",
+                 "producer warp 0: work", "producer warp 0: wait for a free ring stage"]
+        tot = float(sum(tl[:19]))
     else:
         names = ["stage", "S0 load", "L1 fwd", "L2 fwd", "L3 fwd", "head tail (g_f)", "B1 g_a2", "B2 g_a1", "outer", "g_x+sums", "epilogue",
                  "pool", "head V0", "head V1", "head V2+nll", "bwd V1", "bwd V0+rec", "gm/gv", "producer: work", "producer: wait for free scratch", "p20", "p21", "p22", "p23"]
