@@ -240,7 +240,7 @@ static bool use_tc(const bnn_model_config* cfg) {
 // ring of NST images
 static size_t scratch_floats_per_cta(const bnn_model_config* cfg) {
     const size_t v3 = (size_t)8 * cfg->n_features * cfg->n_times + 2 * XSM;
-    const size_t tc = (size_t)tcx::NST * (tcx::NQ * 97 * 4 + tcx::SMALLF);
+    const size_t tc = (size_t)tcx::NST * (tcx::NQ * 97 * 4 + tcx::SMALLF + tcx::XG * 4 * tcx::NQ * 4);
     return v3 > tc ? v3 : tc;
 }
 

@@ -61,6 +61,7 @@ constexpr int SMALLF = 96;               // tail of an image: eps1|eps2 [40], su
 constexpr int IM_E12 = 0, IM_ESN = 40, IM_Y = 80;
 constexpr int NST = 8;                   // depth of the L2 image ring
 constexpr int NSLOT = 2;
+constexpr int XG = 11;                   // 4-column groups of x (44 columns, 41 real)
 constexpr int W_ISSUE = 8, W_PROD = 10, NPW = 6, NWARP = 16, NTHR_TC = NWARP * 32;   // 512 threads: 128 registers each
 constexpr int TM_AHI = 0, TM_ALO = 48, TM_D = 96, TM_SLOT = 144, TM_ACC0 = 288, TM_ACC1 = 384, TM_ACC2 = 432;
 constexpr int SVF = 512;                 // head scratch per slot (layout: the V3_* enum of train_v3.cuh)
@@ -84,7 +85,7 @@ struct Bars {
 };
 
 struct SmemTC {
-    int NL, PX, N0, img_floats;
+    int NL, PX, N0, img_floats, stage_floats;
     int xa[NSLOT], h1[NSLOT], h2[NSLOT], gf[NSLOT], sv[NSLOT];
     int B1h, B1l, B2h, B2l, B3h, B3l, W2Th, W2Tl, W1Th, W1Tl, bias, V0, V1, V2, cb, consts, lidx, bars, total;
     __host__ __device__ SmemTC(uint64_t zero_mask) {
@@ -92,7 +93,9 @@ struct SmemTC {
         for (int c = 0; c < F; ++c) NL += ((zero_mask >> c) & 1ull) ? 0 : 1;
         PX = (F + NL + 1) | 1;                       // x'' | n''(live) | ones (| pad): odd pitch, conflict-free
         N0 = (F + NL + 1 + 15) & ~15;
-        img_floats = NQ * PX * 4 + SMALLF;
+        img_floats = NQ * PX * 4 + SMALLF;            // what the bulk copy brings into the slot's input area
+        stage_floats = img_floats + XG * 4 * NQ * 4;  // + x'' once more as [4-column group][row][4]: the row threads' own
+                                                      //   stage reads (11 fully coalesced 16-byte loads per thread)
         int o = 0;
         for (int s = 0; s < NSLOT; ++s) {
             xa[s] = o; o += img_floats;
@@ -178,7 +181,7 @@ __device__ __forceinline__ void issue_ss_rows(uint32_t acc, uint32_t a_addr, uin
 struct ProdTC {
     const float* X; const float* eps_in; const float* Y; const float* eps12; const float* eps_sum;
     const float* nsc; const int* lidx;
-    uint64_t key, zero_mask; int64_t sb; int row, b, step, PX, NL;
+    uint64_t key, zero_mask; int64_t sb; int row, b, step, PX, NL, rm_off;   // rm_off: float offset of the [group][row][4] copy
 };
 
 // items (row quad q < 25, feature c): 4 normals (Philox block q * F + c, box_muller_fast) for rows 4q..4q+3 of column c
@@ -245,6 +248,9 @@ __device__ __forceinline__ void produce_items(const ProdTC& a, float* __restrict
         }
         float* dst = img + (qs[k] * a.PX + c) * 4;
         *reinterpret_cast<uint4*>(dst) = make_uint4(xb[0], xb[1], xb[2], xb[3]);
+        uint32_t* rm = reinterpret_cast<uint32_t*>(img) + a.rm_off + (((c >> 2) * (4 * NQ) + 4 * qs[k]) * 4 + (c & 3));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rm[4 * u] = xb[u];
         const int li = a.lidx[c];
         if (li >= 0) *reinterpret_cast<uint4*>(img + (qs[k] * a.PX + li) * 4) = make_uint4(nb[0], nb[1], nb[2], nb[3]);
     }
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             mbar_init(&bars->x_free[s], 1);
             mbar_init(&bars->x_full[s], 1);
         }
-        for (int s = 0; s < NST; ++s) { mbar_init(&bars->img_full[s], 32); mbar_init(&bars->img_free[s], 128 + 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&bars->img_full[s], 96); mbar_init(&bars->img_free[s], 128 + 1); }
         bars->turn[0] = bars->turn[1] = bars->turn[2] = 0;
         mbar_init_fence();
     }
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     const uint64_t key = seed_key(prm.seed, sidx);
-    float* ring = prm.xprod + ((int64_t)sidx * prm.n_cta + blockIdx.x) * (int64_t)(NST * L_.img_floats);
+    float* ring = prm.xprod + ((int64_t)sidx * prm.n_cta + blockIdx.x) * (int64_t)(NST * L_.stage_floats);
     const uint32_t img_bytes = (uint32_t)L_.img_floats * 4u;
 
     float a_nll = 0.f, a_skl = 0.f;   // row threads: metric partial sums (lane 0 of the slot's warp 0 / the 20 pooling leaders)
@@ -462,7 +468,13 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
 #ifdef BNN_TRAIN_TIMELINE
         long long tp_wait = 0, tp_work = 0;
 #endif
-        for (int k = pw; k < n_k; k += NPW) {
+        // tiles 0 and 1 (the first tile of each slot) are drawn by three warps each, so that the pipeline starts after a
+        // third of a warp's tile time; from tile 2 on every warp has its own stream: pw + 2, pw + 2 + NPW, ...
+        for (int it = -1;; ++it) {
+            const bool coop = it < 0;
+            const int k = coop ? pw / 3 : NSLOT + pw + it * NPW;
+            if (k >= n_k) { if (coop) continue; else break; }
+            const int p0 = coop ? (pw % 3) * 32 + lane : lane, pstride = coop ? 96 : 32;
             const int st = k % NST;
 #ifdef BNN_TRAIN_TIMELINE
             const long long tp0 = tl_clock();
@@ -477,10 +489,10 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             a.nsc = cst + C3_NSC; a.lidx = lidx; a.key = key; a.zero_mask = prm.zero_mask;
             a.sb = (int64_t)sidx * prm.B + b;
             a.row = prm.batch_index ? prm.batch_index[a.sb] : b;
-            a.b = b; a.step = (int)prm.step; a.PX = PX; a.NL = NL;
-            float* img = ring + (int64_t)st * L_.img_floats;
+            a.b = b; a.step = (int)prm.step; a.PX = PX; a.NL = NL; a.rm_off = L_.img_floats;
+            float* img = ring + (int64_t)st * L_.stage_floats;
             {   // pull the rows of this warp's next tile into L2 (129 lines of 128 B per system)
-                const int b2 = b + NPW * (int)gridDim.x;
+                const int b2 = ((int)blockIdx.x) + (coop ? NSLOT + pw : k + NPW) * (int)gridDim.x;
                 if (b2 < prm.B) {
                     const int64_t sb2 = (int64_t)sidx * prm.B + b2;
                     const int64_t r2 = prm.batch_index ? (int64_t)prm.batch_index[sb2] : (int64_t)b2;
@@ -490,11 +502,11 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                     }
                 }
             }
-            produce_rest(a, img, lane, 32);
+            produce_rest(a, img, p0, pstride);
 #pragma unroll 1
-            for (int i0 = 0; i0 < RQ * F; i0 += 4 * 32) produce_items<4>(a, img, i0 + lane, 32);   // 1025 items, 4 per lane per round
+            for (int i0 = 0; i0 < RQ * F; i0 += 4 * pstride) produce_items<4>(a, img, i0 + p0, pstride);   // 1025 items
             __threadfence();                            // the image is read back by the bulk-copy engine through L2
-            mbar_arrive(&bars->img_full[st]);
+            mbar_arrive_n(&bars->img_full[st], coop ? 1u : 3u);   // 96 arrivals complete a stage: 3 warps, or one warp x 3
 #ifdef BNN_TRAIN_TIMELINE
             tp_wait += tp1 - tp0; tp_work += tl_clock() - tp1;
 #endif
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             if (lane == 0) {
                 asm volatile("fence.proxy.async;" ::: "memory");   // producers' generic-proxy writes -> bulk-copy engine
                 mbar_arrive_expect_tx(&bars->x_full[s], img_bytes);
-                bulk_g2s(sm + L_.xa[s], ring + (int64_t)st * L_.img_floats, img_bytes, &bars->x_full[s]);
+                bulk_g2s(sm + L_.xa[s], ring + (int64_t)st * L_.stage_floats, img_bytes, &bars->x_full[s]);
             }
             __syncwarp();
             mbar_wait_backoff(&bars->a_ready0[s], pa0, 20); pa0 ^= 1;
@@ -649,36 +661,45 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
             grad_cols<16, true>(d1, arow + 64, stored, tl + TM_AHI + 16);
             grad_cols<8, true>(d2, arow + 128, stored, tl + TM_AHI + 32);
         };
-        auto grad_epilogue_sm = [&](float* act) {
-            uint32_t d0[16], d1[16], d2[8];
-            tmem_ld16(tl + TM_D, d0);
-            tmem_ld16(tl + TM_D + 16, d1);
-            tmem_ld8(tl + TM_D + 32, d2);
-            tc_wait_ld();
+        auto grad_epilogue_sm = [&](float* act) {   // chunk by chunk: the prefetched x'' words (41 registers) are live across it
             float* arow = act + rq * PHH * 4 + rr;
-            grad_cols<16, false>(d0, arow, stored, 0u);
-            grad_cols<16, false>(d1, arow + 64, stored, 0u);
-            grad_cols<8, false>(d2, arow + 128, stored, 0u);
+            {
+                uint32_t d0[16];
+                tmem_ld16(tl + TM_D, d0);
+                tc_wait_ld();
+                grad_cols<16, false>(d0, arow, stored, 0u);
+            }
+            {
+                uint32_t d1[16];
+                tmem_ld16(tl + TM_D + 16, d1);
+                tc_wait_ld();
+                grad_cols<16, false>(d1, arow + 64, stored, 0u);
+            }
+            {
+                uint32_t d2[8];
+                tmem_ld8(tl + TM_D + 32, d2);
+                tc_wait_ld();
+                grad_cols<8, false>(d2, arow + 128, stored, 0u);
+            }
         };
 
         TCT_DECL;
         for (int k = slot; k < n_k; k += NSLOT) {
             const int b = (int)blockIdx.x + k * (int)gridDim.x;
             const int64_t sb = (int64_t)sidx * prm.B + b;
-            // ---- P0: the producers have finished the image -> x'' straight from the L2 ring (ld.global.cg: the stage is
-            // rewritten every NST tiles, L1 must not serve it) -> exact x' -> A of layer 1 (48 columns, 41 real) ----
+            // ---- P0: the producers have finished the image -> this row's x'' straight from the L2 ring (11 coalesced 16-byte
+            // ld.global.cg: the stage is rewritten every NST tiles, L1 must not serve it) -> exact x' -> A of layer 1 (48
+            // columns, 41 real; rows >= T and the K padding are zeros); the tile's small inputs -> head scratch ----
             const int st = k % NST;
-            const float* img = ring + (int64_t)st * L_.img_floats;
+            const float* img = ring + (int64_t)st * L_.stage_floats;
             if (lane == 0) mbar_wait_backoff(&bars->img_full[st], (uint32_t)((k / NST) & 1), 40);
             __syncwarp();
             TCT(0);
             {
-                uint32_t xw[48];
-                const float* xr = img + rq * PX * 4 + rr;
+                uint4 xg[XG];
+                const uint4* xr = reinterpret_cast<const uint4*>(img + L_.img_floats) + min(r, 4 * NQ - 1);
 #pragma unroll
-                for (int c = 0; c < F; ++c) xw[c] = live ? __float_as_uint(__ldcg(xr + c * 4)) : 0x1000u;
-#pragma unroll
-                for (int c = F; c < 48; ++c) xw[c] = 0x1000u;
+                for (int g = 0; g < XG; ++g) xg[g] = __ldcg(xr + g * (4 * NQ));
                 if (lt < 21)   // eps1 | eps2, summary noise, labels: 82 floats, contiguous in the image and in the scratch
                     *reinterpret_cast<float4*>(sv + V3_E12 + 4 * lt) = __ldcg(reinterpret_cast<const float4*>(img + NQ * PX * 4) + lt);
 #pragma unroll
@@ -686,7 +707,9 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const uint32_t bz = xw[c0 + j];
+                        const int c = c0 + j, g = c < 44 ? c >> 2 : 0;
+                        const uint32_t w = (c & 3) == 0 ? xg[g].x : ((c & 3) == 1 ? xg[g].y : ((c & 3) == 2 ? xg[g].z : xg[g].w));
+                        const uint32_t bz = (c < F && live) ? w : 0x1000u;
                         hi[j] = bz & 0xFFFFE000u;
                         lo[j] = __float_as_uint(__uint_as_float(bz - 0x1000u) - __uint_as_float(hi[j]));
                     }
