@@ -117,6 +117,9 @@ DIAG_SIGNATURES = {
     "bnn_train_timeline": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int32]),
     "bnn_mma_sync_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_f32p, C.c_void_p]),
     "bnn_set_train_variant": (C.c_int, [C.c_int32]),
+    "bnn_set_summary_variant": (C.c_int, [C.c_int32]),
+    "bnn_set_predict_variant": (C.c_int, [C.c_int32]),
+    "bnn_set_predict_unit_chunk": (C.c_int, [C.c_int64]),
     "bnn_tc_probe_ss": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
 }

@@ -348,6 +348,22 @@ int bnn_sample_instability(const float* d_pred, int64_t n_rows, int64_t n_units,
     return BNN_OK;
 }
 
+// 0 = automatic (shared-memory sort while it fits, else radix select), 1 = radix select; process-wide diagnostic override
+// (bnn_set_summary_variant), default read once from BNN_SUMMARY_VARIANT = select
+static int g_summary_variant = -1;
+static int summary_variant() {
+    if (g_summary_variant < 0) {
+        const char* force = getenv("BNN_SUMMARY_VARIANT");
+        g_summary_variant = (force && !strcmp(force, "select")) ? 1 : 0;
+    }
+    return g_summary_variant;
+}
+int bnn_set_summary_variant(int32_t variant) {
+    BNN_REQUIRE(variant == 0 || variant == 1, BNN_E_ARG, "bnn_set_summary_variant: 0 = auto, 1 = radix select");
+    g_summary_variant = variant;
+    return BNN_OK;
+}
+
 int bnn_summarize_instability(const float* d_t, const float* d_pred, int64_t n_systems, int32_t n_trios, int32_t n_units,
                               float* d_stats, void* stream) {
     using namespace bnn;
@@ -360,8 +376,7 @@ int bnn_summarize_instability(const float* d_t, const float* d_pred, int64_t n_s
     const int threads = 512;
     const size_t smem = (size_t)(n_pow2 + threads) * sizeof(float);
     BNN_REQUIRE(n_systems < (1ll << 31), BNN_E_ARG, "bnn_summarize_instability: too many systems for one launch");
-    const char* force = getenv("BNN_SUMMARY_VARIANT");  // sort | select (tests cross-check the two)
-    const bool use_select = (force && !strcmp(force, "select")) || smem > 200 * 1024;
+    const bool use_select = summary_variant() == 1 || smem > 200 * 1024;   // 1: forced (tests cross-check the two)
     if (use_select) {
         // more weight samples than the shared-memory sort holds (30 models x 2000 samples = 60000 at BASELINE config 3):
         // exact order statistics by radix select, nothing is stored

@@ -262,10 +262,43 @@ extern "C" {
 
 size_t bnn_predict_workspace_bytes(const bnn_model_config*, int64_t, int64_t) { return 0; }
 
-// true when bnn_predict runs the tensor-core kernel for this config (no BNN_PREDICT_VARIANT override)
+// Kernel selection.  Default (0): the tensor-core kernel (tcgen05, 3xTF32) when T = 100 and at most 32 live input columns,
+// else the FP32 FFMA2 kernels (v2: warp-specialised with a TMA weight ring, when its tile fits in shared memory; else
+// v1).  A process-wide override for tests / tools: bnn_set_predict_variant() (diagnostic header), initialised ONCE from
+// the environment variable BNN_PREDICT_VARIANT = tc | v2 | v1; likewise the unit chunk (BNN_PREDICT_UNIT_CHUNK).
+enum { PV_AUTO = 0, PV_TC = 1, PV_V2 = 2, PV_V1 = 3 };
+static int g_predict_variant = -1;
+static long long g_unit_chunk = -1;
+static int predict_variant() {
+    if (g_predict_variant < 0) {
+        const char* f = getenv("BNN_PREDICT_VARIANT");
+        g_predict_variant = !f ? PV_AUTO : (!strncmp(f, "tc", 2) ? PV_TC : (!strncmp(f, "v2", 2) ? PV_V2 : (!strcmp(f, "v1") ? PV_V1 : PV_AUTO)));
+    }
+    return g_predict_variant;
+}
+static long long predict_unit_chunk() {
+    if (g_unit_chunk < 0) {
+        const char* uc = getenv("BNN_PREDICT_UNIT_CHUNK");
+        g_unit_chunk = uc ? strtoll(uc, nullptr, 10) : 0;
+        if (g_unit_chunk < 0) g_unit_chunk = 0;
+    }
+    return g_unit_chunk;
+}
+int bnn_set_predict_variant(int32_t variant) {
+    BNN_REQUIRE(variant >= 0 && variant <= 3, BNN_E_ARG, "bnn_set_predict_variant: 0 = auto, 1 = tensor-core, 2 = FFMA v2, 3 = FFMA v1");
+    g_predict_variant = variant;
+    return BNN_OK;
+}
+int bnn_set_predict_unit_chunk(int64_t units) {
+    BNN_REQUIRE(units >= 0, BNN_E_ARG, "bnn_set_predict_unit_chunk: units per launch, 0 = default (1024)");
+    g_unit_chunk = units;
+    return BNN_OK;
+}
+
+// true when bnn_predict runs the tensor-core kernel for this config
 static bool tc_selected(const bnn_model_config* cfg, int kin) {
-    const char* force = getenv("BNN_PREDICT_VARIANT");
-    if (force && strncmp(force, "tc", 2) != 0) return false;
+    const int v = predict_variant();
+    if (v != PV_AUTO && v != PV_TC) return false;
     return cfg->n_times == bnn::tc::T_FIXED && kin <= bnn::TC_K1;
 }
 
@@ -309,19 +342,27 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     for (int c = 0; c < MAXF; ++c) prm.cm.inv[c] = -1;
     for (int k = 0; k < lc.n; ++k) prm.cm.inv[(int)lc.col[k]] = (int8_t)k;
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
-    {
-        const char* dbgp = getenv("BNN_TC_TIMELINE_PTR");  // device pointer (decimal) to 8*512 int64, debugging only
+    prm.dbg = nullptr;
+#ifdef BNN_TC_TIMELINE
+    {   // diagnostic build only (make TIMELINE=1): device pointer (decimal) to 8*512 int64 of clock stamps
+        const char* dbgp = getenv("BNN_TC_TIMELINE_PTR");
         prm.dbg = dbgp ? reinterpret_cast<long long*>(strtoull(dbgp, nullptr, 10)) : nullptr;
     }
+#endif
     // Units are processed in chunks whose weights stay resident in L2: every system tile streams the weights of all
     // units of a launch (~52 kB per unit: tensor-core operands + head), so with 60,000 units (BASELINE configs[2]) one
     // launch would pull 3 GB per tile from HBM; per chunk only x is re-read (16.4 kB per system).  Results do not
-    // depend on the chunking (Philox is keyed on the global unit index).  BNN_PREDICT_UNIT_CHUNK overrides (tests).
-    int64_t unit_chunk = 1024;
-    if (const char* uc = getenv("BNN_PREDICT_UNIT_CHUNK")) unit_chunk = strtoll(uc, nullptr, 10);
+    // depend on the chunking (Philox is keyed on the global unit index).  bnn_set_predict_unit_chunk overrides (tests).
+    int64_t unit_chunk = predict_unit_chunk() > 0 ? predict_unit_chunk() : 1024;
     if (unit_chunk < 1 || n_units <= unit_chunk + unit_chunk / 2) unit_chunk = n_units;
     const PredictParams prm_all = prm;
     const int L2_ = 2 * L;
+    int n_sms = 148;
+    {
+        int dev = 0;
+        BNN_CUDA(cudaGetDevice(&dev));
+        BNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
     for (int64_t u0 = 0; u0 < n_units; u0 += unit_chunk) {
     const int64_t n_units_launch = n_units - u0 < unit_chunk ? n_units - u0 : unit_chunk;
     prm = prm_all;
@@ -336,25 +377,15 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     // split units over CTAs only when the tiles alone cannot fill the GPU twice
     const int64_t tiles = (n_systems + SYS_TILE - 1) / SYS_TILE;
     int64_t chunks = 1;
-    if (tiles < 2 * 148) chunks = (2 * 148 + tiles - 1) / tiles;
+    if (tiles < 2 * n_sms) chunks = (2 * n_sms + tiles - 1) / tiles;
     if (chunks > n_units_launch) chunks = n_units_launch;
     prm.units_per_cta = (int)((n_units_launch + chunks - 1) / chunks);
-    // variant selection: tensor cores (tcgen05, 3xTF32; 4 TMEM slots, 4 tail warps) when T = 100 and at most 31
-    // live input columns; else the FFMA2 kernels: v2 (warp-specialised, TMA ring) when its tile fits in shared
-    // memory, else v1.  BNN_PREDICT_VARIANT=tc4n4|tc4n3|tc3n4|tc2n4|v1|v2c8|v2c12|v2c16 forces one (benchmarks /
-    // cross-checks).
-    const char* force = getenv("BNN_PREDICT_VARIANT");
+    const int force = predict_variant();
     const int T = cfg->n_times;
     cudaStream_t st = (cudaStream_t)stream;
     auto fits = [&](int nc) { return v2_smem_bytes(prm.kin, prm.F, T, nc) <= 227 * 1024; };
-    if (tc::tc_fits(prm, T) && (!force || !strncmp(force, "tc", 2))) {
-        if (force && !strcmp(force, "tc4n3")) rc_launch = tc::launch_tc<4, 3>(prm, st);
-        else if (force && !strcmp(force, "tc3n4")) rc_launch = tc::launch_tc<3, 4>(prm, st);
-        else if (force && !strcmp(force, "tc2n4")) rc_launch = tc::launch_tc<2, 4>(prm, st);
-        else rc_launch = tc::launch_tc<4, 4>(prm, st);
-    } else if (force && !strcmp(force, "v1")) rc_launch = launch_v1<8>(prm, T, st);
-    else if (force && !strcmp(force, "v2c8") && fits(8)) rc_launch = launch_v2<8>(prm, T, st);
-    else if (force && !strcmp(force, "v2c16") && fits(16)) rc_launch = launch_v2<16>(prm, T, st);
+    if (tc::tc_fits(prm, T) && (force == PV_AUTO || force == PV_TC)) rc_launch = tc::launch_tc<4, 4>(prm, st);
+    else if (force == PV_V1) rc_launch = launch_v1<8>(prm, T, st);
     else if (fits(12)) rc_launch = launch_v2<12>(prm, T, st);
     else if (fits(8)) rc_launch = launch_v2<8>(prm, T, st);
     else rc_launch = launch_v1<8>(prm, T, st);

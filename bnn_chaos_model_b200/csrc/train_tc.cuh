@@ -562,30 +562,30 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
                 bulk_g2s(sm + L_.xa[s], ring + (int64_t)st * L_.stage_floats, img_bytes, &bars->x_full[s]);
             }
             __syncwarp();
-            mbar_wait_backoff(&bars->a_ready0[s], pa0, 20); pa0 ^= 1;
+            mbar_wait(&bars->a_ready0[s], pa0); pa0 ^= 1;
             tc_fence_after();
             { TI_BEGIN; issue_ts3<48, 6>(d, ahi, alo, sbase + 4u * L_.B1h, sbase + 4u * L_.B1l, H * 16u); commit(&bars->d_ready[s]); TI_END; }
-            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            mbar_wait(&bars->a_ready[s], pa); pa ^= 1;
             tc_fence_after();
             { TI_BEGIN; issue_ts3<48, 5>(d, ahi, alo, sbase + 4u * L_.B2h, sbase + 4u * L_.B2l, H * 16u); commit(&bars->d_ready[s]); TI_END; }
-            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            mbar_wait(&bars->a_ready[s], pa); pa ^= 1;
             tc_fence_after();
             { TI_BEGIN; issue_ts3<32, 5>(d, ahi, alo, sbase + 4u * L_.B3h, sbase + 4u * L_.B3l, L * 16u); commit(&bars->d_ready[s]); TI_END; }
-            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            mbar_wait(&bars->a_ready[s], pa); pa ^= 1;
             tc_fence_after();
             issue_ts2<48, 3>(d, ahi, sbase + 4u * L_.W2Th, sbase + 4u * L_.W2Tl, H * 16u);   // g_a2 first: it gates the row threads
             take_turn(2, k);
             { TI_BEGIN; issue_ss_rows(tmem + TM_ACC2, sbase + 4u * L_.gf[s], PGF, sbase + 4u * L_.h2[s], PHH, idesc48, k == 0); TI_END; }
             commit(&bars->d_ready[s]);
             pass_turn(2, k);
-            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            mbar_wait(&bars->a_ready[s], pa); pa ^= 1;
             tc_fence_after();
             issue_ts2<48, 5>(d, ahi, sbase + 4u * L_.W1Th, sbase + 4u * L_.W1Tl, H * 16u);
             take_turn(1, k);
             { TI_BEGIN; issue_ss_rows(tmem + TM_ACC1, sbase + 4u * L_.h2[s], PHH, sbase + 4u * L_.h1[s], PHH, idesc48, k == 0); TI_END; }
             commit(&bars->d_ready[s]);
             pass_turn(1, k);
-            mbar_wait_backoff(&bars->a_ready[s], pa, 20); pa ^= 1;
+            mbar_wait(&bars->a_ready[s], pa); pa ^= 1;
             mbar_wait_backoff(&bars->x_full[s], pxl, 20); pxl ^= 1;      // [x' | n | 1] has landed
             if (lane == 0) mbar_arrive(&bars->img_free[st]);              // ... so the ring stage is free (with the 128 row threads)
             tc_fence_after();
@@ -622,11 +622,8 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
         uint32_t pd = 0;
 
         auto wait_d = [&]() {
-            if (quad == 0) {
-                if (!mbar_test(&bars->d_ready[slot], pd)) {
-                    __nanosleep(100);
-                    mbar_wait_backoff(&bars->d_ready[slot], pd, 20);
-                }
+            if (quad == 0) {   // try_wait suspends the warp in hardware until the phase completes: no polling granularity
+                mbar_wait(&bars->d_ready[slot], pd);
                 pd ^= 1;
             }
             named_sync(1 + slot, 128);

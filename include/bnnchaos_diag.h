@@ -47,6 +47,16 @@ int bnn_train_timeline(unsigned long long* host_out, int32_t n);
 int bnn_tc_probe_ss(const float* d_G, const float* d_H, float* d_D, int32_t R, int32_t MJ, int32_t NK, int32_t N,
                     int32_t bias_round, int32_t two_batches, void* stream);
 
+/* Diagnostic: force the kernel behind bnn_predict for this process: 0 = automatic (tensor cores when T = 100 and at most 32
+ * live columns, else FP32 FFMA2), 1 = tensor-core, 2 = FFMA2 v2 (warp-specialised), 3 = FFMA2 v1 (synchronous).  Default:
+ * read once from BNN_PREDICT_VARIANT (tc | v2 | v1).  bnn_set_predict_unit_chunk: units per launch of bnn_predict's
+ * L2-sized unit chunks (0 = default 1024; the results do not depend on it). */
+int bnn_set_predict_variant(int32_t variant);
+int bnn_set_predict_unit_chunk(int64_t units);
+
+/* Diagnostic: 1 forces the radix-select path of bnn_summarize_instability (default 0: shared-memory sort while it fits). */
+int bnn_set_summary_variant(int32_t variant);
+
 /* Diagnostic: force the kernel behind bnn_train_step / bnn_train_noise for this process: 0 = automatic (the tensor-core
  * kernel where its shared-memory plan fits, else the FP32 FFMA kernel), 1 = tensor-core, 2 = FP32 FFMA.  The default is
  * read once from the environment variable BNN_TRAIN_VARIANT (tc | v3). */

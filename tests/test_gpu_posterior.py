@@ -30,7 +30,7 @@ def test_summary_statistics_vs_numpy(dev, N, Rt, U):
         np.testing.assert_allclose(got[:, i], ref[name], rtol=2e-6, err_msg=name)
 
 
-def test_radix_select_summary_for_many_weight_samples(dev, monkeypatch):
+def test_radix_select_summary_for_many_weight_samples(dev):
     """U = 60000 (30 models x 2000 samples, BASELINE config 3) exceeds the shared-memory sort: exact radix select.
     Also cross-checked against the sort path at a size both support, with ties, negatives and a NaN."""
     N, Rt, U = 2, 2, 60000
@@ -46,8 +46,13 @@ def test_radix_select_summary_for_many_weight_samples(dev, monkeypatch):
     pred = np.stack([np.round(rng.uniform(4, 12, (3, U)), 1), rng.uniform(0.5, 6, (3, U))], -1).astype(np.float32)
     pred[1, 5, 0] = np.nan
     a = summarize_instability(torch.from_numpy(t).to(dev), torch.from_numpy(pred).to(dev), 1)
-    monkeypatch.setenv("BNN_SUMMARY_VARIANT", "select")
-    b = summarize_instability(torch.from_numpy(t).to(dev), torch.from_numpy(pred).to(dev), 1)
+    from bnn_chaos_model_b200 import _lib
+
+    _lib.check(_lib.load().bnn_set_summary_variant(1))   # force the radix select (diagnostic switch)
+    try:
+        b = summarize_instability(torch.from_numpy(t).to(dev), torch.from_numpy(pred).to(dev), 1)
+    finally:
+        _lib.check(_lib.load().bnn_set_summary_variant(0))
     assert torch.equal(a[:, 1:], b[:, 1:]) and torch.allclose(a[:, 0], b[:, 0], rtol=1e-6)
 
 

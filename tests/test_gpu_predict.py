@@ -13,6 +13,20 @@ from oracle import restatement as R
 pytestmark = pytest.mark.gpu
 SEEDS = (0, 3, 17)
 TOL = 1e-5
+PV = {"auto": 0, "tc": 1, "v2": 2, "v1": 3}   # bnn_set_predict_variant (include/bnnchaos_diag.h)
+
+
+@pytest.fixture
+def predict_variant():
+    """Process-wide diagnostic override of the predictive kernel, reset to automatic after the test."""
+    lib = _lib.load()
+
+    def set_(name):
+        _lib.check(lib.bnn_set_predict_variant(PV[name]))
+
+    yield set_
+    _lib.check(lib.bnn_set_predict_variant(0))
+    _lib.check(lib.bnn_set_predict_unit_chunk(0))
 
 
 @pytest.fixture(scope="module")
@@ -184,7 +198,7 @@ def test_sharded_equals_single_bitwise(dev):
         assert torch.equal(got, full.permute(1, 0, 2))
 
 
-def test_unit_chunked_launches_equal_single_launch(dev, monkeypatch):
+def test_unit_chunked_launches_equal_single_launch(dev, predict_variant):
     """bnn_predict walks many units in L2-sized chunks (60,000 units at BASELINE configs[2]); the chunking must not show
     in the results: both output layouts, the explicit-eps path and the summary output, bit for bit."""
     ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(3, dev), make_swag_model(17, dev)], device=dev)
@@ -204,8 +218,8 @@ def test_unit_chunked_launches_equal_single_launch(dev, monkeypatch):
         torch.cuda.synchronize()
         return out, summ
     ref_e, ref_s = explicit()
-    for chunk in ("4", "5", "13"):
-        monkeypatch.setenv("BNN_PREDICT_UNIT_CHUNK", chunk)
+    for chunk in (4, 5, 13):
+        _lib.check(lib.bnn_set_predict_unit_chunk(chunk))
         assert torch.equal(ens.predict(x, S_, seed=6, thp=thp), ref_um), chunk
         assert torch.equal(ens.predict(x, S_, seed=6, thp=thp, system_major=True), ref_sm), chunk
         o, sm_ = explicit()
@@ -294,30 +308,28 @@ def test_full_size_properties(dev):
         assert rel_err(a[u, idx].cpu(), ref) < TOL
 
 
-def test_kernel_variants_agree_bitwise(dev, monkeypatch):
-    """The synchronous kernel (v1) and the warp-specialised TMA/mbarrier kernel (v2, any consumer
-    count) share the arithmetic order: outputs must be identical, also on ragged sizes and when an
-    item's unit range is split into chunks."""
+def test_kernel_variants_agree_bitwise(dev, predict_variant):
+    """The synchronous kernel (v1) and the warp-specialised TMA/mbarrier kernel (v2) share the arithmetic order:
+    outputs must be identical, also on ragged sizes and when an item's unit range is split into chunks."""
     ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(3, dev)], device=dev)
     for N, S_ in ((13, 3), (203, 40), (1200, 70)):
         x = torch.from_numpy(synth.make_systems(N, seed=N)).to(dev)
         _, thp = ens.sample_thetas(S_, seed=N)
         outs = {}
-        for v in ("v1", "v2c8", "v2c12", "v2c16"):
-            monkeypatch.setenv("BNN_PREDICT_VARIANT", v)
+        for v in ("v1", "v2"):
+            predict_variant(v)
             outs[v] = ens.predict(x, S_, seed=N, thp=thp)
         torch.cuda.synchronize()
-        for v in ("v2c8", "v2c12", "v2c16"):
-            assert torch.equal(outs[v], outs["v1"]), (v, N, S_)
+        assert torch.equal(outs["v2"], outs["v1"]), (N, S_)
 
 
-TC_VARIANTS = ("tc4n4", "tc4n3", "tc3n4", "tc2n4")
+TC_VARIANTS = ("tc",)
 
 
-@pytest.mark.parametrize("variant", TC_VARIANTS)
-def test_tensor_core_variants_vs_reference_golden(gold_predict, dev, monkeypatch, variant):
-    """tcgen05 3xTF32 kernels: same golden theta / eps / systems as the FFMA path, same 1e-5 tolerance."""
-    monkeypatch.setenv("BNN_PREDICT_VARIANT", variant)
+@pytest.mark.parametrize("variant", TC_VARIANTS + ("v2", "v1"))
+def test_every_kernel_vs_reference_golden(gold_predict, dev, predict_variant, variant):
+    """The tcgen05 3xTF32 kernel and both FFMA kernels: same golden theta / eps / systems, same 1e-5 tolerance."""
+    predict_variant(variant)
     for seed in SEEDS:
         m = make_swag_model(seed, dev)
         cfg = m.config()
@@ -329,7 +341,7 @@ def test_tensor_core_variants_vs_reference_golden(gold_predict, dev, monkeypatch
         assert rel_err(out.cpu(), ref) < TOL, (variant, seed)
 
 
-def test_tensor_core_variants_vs_fp32_kernel(dev, monkeypatch):
+def test_tensor_core_variants_vs_fp32_kernel(dev, predict_variant):
     """Ragged sizes, unit chunking, many units per CTA (exercises the record ring back-pressure and the weight
     ring) and a NaN-poisoned system: every tc variant against the FFMA kernel, which is pinned to the oracle."""
     ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(3, dev)], device=dev)
@@ -338,12 +350,12 @@ def test_tensor_core_variants_vs_fp32_kernel(dev, monkeypatch):
         xh[N // 2, 7, 3] = float("nan")  # zeroed column: poisons that system only
         x = torch.from_numpy(xh).to(dev)
         _, thp = ens.sample_thetas(S_, seed=N)
-        monkeypatch.setenv("BNN_PREDICT_VARIANT", "v1")
+        predict_variant("v1")
         want = ens.predict(x, S_, seed=N, thp=thp)
         ok = torch.isfinite(want[:, :, 0])
         assert not bool(ok[:, N // 2].any()) and bool(ok[:, : N // 2].all())
         for v in TC_VARIANTS:
-            monkeypatch.setenv("BNN_PREDICT_VARIANT", v)
+            predict_variant(v)
             for rep in range(2):  # twice: races show up as run-to-run differences
                 got = ens.predict(x, S_, seed=N, thp=thp)
                 assert bool(torch.isnan(got[:, N // 2]).all()), (v, N)

@@ -236,17 +236,21 @@ def test_full_size_gradient_vs_oracle_autograd(dev):
         assert float((a - b).abs().max()) <= 3e-4 * float(b.abs().max()) + 1e-7, name
 
 
-def test_tensor_core_accuracy_at_config2_size(dev, monkeypatch):
+def test_tensor_core_accuracy_at_config2_size(dev):
     """1e7 evaluations (BASELINE configs[1]: 10,000 systems x 1,000 weight samples): the default (tensor-core, 3xTF32)
     kernel against the FP32 FFMA kernel, which is pinned to the oracle -- every (mu, std) within 1e-5 relative."""
     ens = MultiSWAG([make_swag_model(0, dev)], device=dev)
     N, S_ = 10000, 1000
     x = torch.from_numpy(synth.make_systems(N, seed=108)).to(dev)
     _, thp = ens.sample_thetas(S_, seed=5)
+    lib = _lib.load()
     got = ens.predict(x, S_, seed=5, thp=thp)
-    monkeypatch.setenv("BNN_PREDICT_VARIANT", "v2c12")
-    want = ens.predict(x, S_, seed=5, thp=thp)
-    torch.cuda.synchronize()
+    _lib.check(lib.bnn_set_predict_variant(2))   # FFMA2 v2
+    try:
+        want = ens.predict(x, S_, seed=5, thp=thp)
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.bnn_set_predict_variant(0))
     rel = ((got - want).abs() / want.abs()).amax(dim=(1, 2))
     worst = float(rel.max())
     print(f"tensor-core vs FFMA over {N * S_:.0e} evals: max rel err {worst:.2e}, median of per-unit max {float(rel.median()):.2e}")
