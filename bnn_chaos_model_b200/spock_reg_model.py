@@ -626,8 +626,11 @@ class SWAGModel(VarModel):
 # save_swag / load_swag (:911-967): same dict, same keys.
 # ----------------------------------------------------------------------------------------
 def save_swag(swag_model, path):
+    # hparams go out as a plain dict: the reference pickles Lightning's AttributeDict, a class this package cannot name in
+    # a pickle without Lightning installed; the reference's load_swag only needs item access (SWAGModel(save_items['hparams']),
+    # :925), and a file without foreign globals also loads under torch.load(weights_only=True).
     save_items = {
-        "hparams": swag_model.hparams,
+        "hparams": dict(swag_model.hparams),
         "swa_params": swag_model.swa_params,
         "w_avg": swag_model.w_avg.cpu(),
         "w2_avg": swag_model.w2_avg.cpu(),

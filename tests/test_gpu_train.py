@@ -1,6 +1,11 @@
 """GPU parity of the fused SWAG training step (K4), the validation loss and the multi-seed trainer, through the
 C ABI.  Tolerances: logged losses 1e-5 relative; gradient 2e-4 of the gradient's max-norm (fp32 sums over
-B*T rows in a different order than autograd); theta after a step 1e-6; gradient norm 1e-5."""
+B*T rows in a different order than autograd); gradient norm 1e-5; theta after a step 1e-6 relative + 1e-7 absolute
+on the FP32 kernel.  The tensor-core kernel's weight-gradient GEMMs are single-pass TF32 on round-to-nearest operands:
+their unbiased rounding noise falls as 1 / sqrt(B T), so at the SMALL batches of these tests (B = 20..64, where
+automatic selection runs the FP32 kernel) theta after a step is held to 1e-6 relative + 2e-6 absolute and the
+input_noise_logvar block (a difference of large terms) to 2e-3 of its own max; at the reference's B = 2000
+(tests/test_gpu_surface.py::test_full_size_gradient_vs_oracle_autograd) the tight tolerances hold for it too."""
 import ctypes
 
 import numpy as np
@@ -51,7 +56,7 @@ def train_variant(request):
     _lib.check(lib.bnn_set_train_variant(0))
 
 
-def test_train_steps_vs_reference_golden(gold_train, dev):
+def test_train_steps_vs_reference_golden(gold_train, dev, train_variant):
     """Three SGD-momentum steps of the reference (autograd + clip_grad_norm_ + torch.optim.SGD) with all four
     noise tensors fixed: logged scalars, full gradient, gradient norm and theta after every step."""
     g = gold_train
@@ -79,10 +84,11 @@ def test_train_steps_vs_reference_golden(gold_train, dev):
         assert float(met[0, 1]) * B == pytest.approx(float(g[f"loss_ref_{s}"]), rel=1e-5)
         assert float(met[0, 4]) == pytest.approx(float(g[f"gradnorm_ref_{s}"]), rel=1e-5)
         assert float(met[0, 6]) == 0.0
-        np.testing.assert_allclose(theta[0].cpu().numpy(), g[f"theta_ref_{s}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(theta[0].cpu().numpy(), g[f"theta_ref_{s}"], rtol=1e-6,
+                                   atol=2e-6 if train_variant == "tc" else 1e-7)
 
 
-def test_gradient_by_parameter_group(gold_train, dev):
+def test_gradient_by_parameter_group(gold_train, dev, train_variant):
     """Every parameter tensor's gradient on its own scale (a wrong small block would hide under a global max-norm)."""
     g = gold_train
     lib = _lib.load()
@@ -104,10 +110,11 @@ def test_gradient_by_parameter_group(gold_train, dev):
     for name, (off, shp) in spec.offsets().items():
         n = int(np.prod(shp))
         a, b = got[off:off + n], ref[off:off + n]
-        assert np.abs(a - b).max() <= 3e-4 * np.abs(b).max() + 1e-7, name
+        tol = 2e-3 if (train_variant == "tc" and name == "input_noise_logvar") else 3e-4
+        assert np.abs(a - b).max() <= tol * np.abs(b).max() + 1e-7, name
 
 
-def test_training_step_dropin_backward_and_optimizer(dev):
+def test_training_step_dropin_backward_and_optimizer(dev, train_variant):
     """SWAGModel.training_step with torch draws in the reference's order; loss.backward() installs the fused
     gradient, clip_grad_norm_ + the SGD of configure_optimizers() then match the oracle's step."""
     m = make_swag_model(3, dev)
@@ -138,7 +145,7 @@ def test_training_step_dropin_backward_and_optimizer(dev):
     assert float(gn) == pytest.approx(float(gref.norm()), rel=1e-4)
     th1, _, _ = R.clip_and_sgd_step(theta0, gref, None, m.swa_params["swa_lr"], m.hparams["momentum"],
                                     m.hparams["weight_decay"], clip, True)
-    np.testing.assert_allclose(m.flatten().cpu().numpy(), th1.numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(m.flatten().cpu().numpy(), th1.numpy(), rtol=1e-6, atol=2e-6 if train_variant == "tc" else 1e-7)
 
 
 def test_philox_noise_and_multi_seed_batches(dev):
@@ -247,7 +254,7 @@ def test_multi_seed_trainer_collects_reference_moments(dev):
     assert seeds_of_rank(30, 0, 8) == [0, 1, 2, 3] and seeds_of_rank(30, 7, 8) == [27, 28, 29]
 
 
-def test_multi_seed_pretrainer_vs_oracle_schedule(dev):
+def test_multi_seed_pretrainer_vs_oracle_schedule(dev, train_variant):
     """find_minima.py phase: fused steps under the custom one-cycle schedule (lr AND momentum per step) and the KL
     annealing, for two seeds at once; replayed step by step on the oracle (autograd + clip + SGD) with the Philox draws
     the kernel made; ends at the schedule's ValueError and restores the best-validation weights."""
@@ -287,7 +294,8 @@ def test_multi_seed_pretrainer_vs_oracle_schedule(dev):
                                            e_sum[i].cpu(), beta_in=b_in, beta_out=b_out)
                 (gr,) = torch.autograd.grad(total, th)
                 th_o[i], buf_o[i], _ = R.clip_and_sgd_step(th_o[i], gr, buf_o[i], lr, mom, 1e-14, 0.1 * d, g == 0)
-                np.testing.assert_allclose(tr.theta[i].cpu().numpy(), th_o[i].numpy(), rtol=1e-5, atol=2e-6)
+                np.testing.assert_allclose(tr.theta[i].cpu().numpy(), th_o[i].numpy(), rtol=1e-5,
+                                           atol=2e-5 if train_variant == "tc" else 2e-6)   # B = 20, lr up to 1e-3
                 th_o[i] = tr.theta[i].cpu().clone()   # no drift: every step is compared from the same start
                 buf_o[i] = tr.momentum[i].cpu().clone()
             n_checked += 1
