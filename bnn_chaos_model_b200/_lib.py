@@ -191,6 +191,26 @@ def dev_ptr(t, device, name, dtype=None):
     return t.data_ptr()
 
 
+class nvtx:
+    """NVTX range around a launch group (K1 sample / K2 predict / K4 train step / K6 pack / K7 posterior), visible in
+    nsys / ncu timelines.  A no-op costing two host calls when no profiler is attached."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        import torch
+
+        torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 def current_stream_ptr():
     import torch
 

@@ -19,6 +19,9 @@ struct PredictParams {
     const float* eps_sum; // [U,N,2L] or null (noisy forward)
     float* summary;       // [U,N,2L] or null
     float* out;           // [U,N,2] or [N,U,2]
+#ifdef BNN_TC_TIMELINE
+    long long* dbg;       // timeline buffer of the diagnostic build (tools/tc_timeline.py)
+#endif
     int64_t N, U;
     int64_t unit_offset, system_offset;
     int64_t out_unit_stride, out_sys_stride;  // in floats
@@ -27,7 +30,6 @@ struct PredictParams {
     int units_per_cta;
     HeadConsts hc;
     ColMap cm;
-    long long* dbg;  // optional timeline buffer (tools/tc_timeline.py), normally null
 };
 
 // ---------------------------------------------------------------------------------------
@@ -342,7 +344,6 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     for (int c = 0; c < MAXF; ++c) prm.cm.inv[c] = -1;
     for (int k = 0; k < lc.n; ++k) prm.cm.inv[(int)lc.col[k]] = (int8_t)k;
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
-    prm.dbg = nullptr;
 #ifdef BNN_TC_TIMELINE
     {   // diagnostic build only (make TIMELINE=1): device pointer (decimal) to 8*512 int64 of clock stamps
         const char* dbgp = getenv("BNN_TC_TIMELINE_PTR");
@@ -384,7 +385,7 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     const int T = cfg->n_times;
     cudaStream_t st = (cudaStream_t)stream;
     auto fits = [&](int nc) { return v2_smem_bytes(prm.kin, prm.F, T, nc) <= 227 * 1024; };
-    if (tc::tc_fits(prm, T) && (force == PV_AUTO || force == PV_TC)) rc_launch = tc::launch_tc<4, 4>(prm, st);
+    if (tc::tc_fits(prm, T) && (force == PV_AUTO || force == PV_TC)) rc_launch = tc::launch_tc<2>(prm, st);
     else if (force == PV_V1) rc_launch = launch_v1<8>(prm, T, st);
     else if (fits(12)) rc_launch = launch_v2<12>(prm, T, st);
     else if (fits(8)) rc_launch = launch_v2<8>(prm, T, st);

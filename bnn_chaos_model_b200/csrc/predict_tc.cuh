@@ -38,16 +38,21 @@ constexpr int ROWS = SYS * T_FIXED;
 constexpr int TM_AHI = 0, TM_ALO = 40, TM_D = 80, TM_SLOT = 128;  // TMEM columns of one slot
 constexpr int N_BLOCKS = MT * 4;  // 32-row blocks per tile
 constexpr int REC_FLOATS = N_BLOCKS * 2 * L * 2;  // [block][segment][col][mean, M2]
-constexpr int FB_FLOATS = 32 * L;                 // per epilogue warp
+constexpr int FB_PITCH = 12;                     // latent rows staged for the pooling: 32 rows x 12 columns per epilogue warp
+constexpr int FB_FLOATS = 32 * FB_PITCH;
 constexpr int TAIL_SCRATCH = 640;                // sA[5*41] + sB[5*41] + eS[5*40] floats per tail warp
-constexpr int MAX_NT = 4;
+constexpr int HEAD_FLOATS = S2 * HP + HP + H * HP + HP + 2 * H + 4 + S2;  // PackedLayout V0p .. lv_sum: one contiguous block
+constexpr int NREC = 4;                          // depth of the block-record ring (units the epilogue may run ahead of the tails)
+constexpr int N_SLOT = 4;                        // TMEM slots = jobs in flight (2 per team)
 
 struct Bars {
     uint64_t w_full[2];                                // B operands of unit i landed in ring slot i & 1
-    uint64_t unit_done[MAX_NT], rec_free[MAX_NT];      // record ring slot i % NT: written by the epilogue / read by the tail
-    uint64_t d_ready[4];                               // tcgen05.commit of the slot's current layer
+    uint64_t unit_done[NREC], rec_free[NREC];          // record ring slot i % NREC: written by the epilogue / read by the tail
+    uint64_t d_ready[N_SLOT];                          // tcgen05.commit of the slot's current layer
+    uint64_t a_ready[N_SLOT];                          // the team's 8 epilogue warps: A of the slot's next layer is in place
+    uint64_t h_full[4];                                // tail warp t: the head block of its next unit landed in its buffer
     uint32_t tmem_base;
-    uint32_t pad;
+    int next_item;                                     // dynamic work distribution: the item this CTA runs next
 };
 
 // The 4 records of system p (T = 100, 5 systems per tile, 32-row blocks): record index (block*2 + segment) and
@@ -106,66 +111,53 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
     __syncthreads();
 }
 
-// hi/lo split of 8 values and store to the A_hi / A_lo columns of this thread's TMEM lane.
-// hi = v rounded to nearest tf32 (|lo| <= 2^-12 |v|), lo = v - hi exactly.
-__device__ __forceinline__ void split_store8(const float (&v)[8], uint32_t t_hi, uint32_t t_lo) {
-    uint32_t h[8], l[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        // round to nearest tf32, ties away (= cvt.rna.tf32.f32 for every finite input; Inf / NaN are preserved):
-        // two integer instructions instead of the 5-instruction cvt expansion
-        const uint32_t hb = (__float_as_uint(v[j]) + 0x1000u) & 0xFFFFE000u;
-        h[j] = hb;
-        l[j] = __float_as_uint(v[j] - __uint_as_float(hb));
+// (d + bias) -> ReLU -> hi/lo of 4 consecutive columns; bias: 16-byte aligned shared memory, same for every lane.
+// hi = v rounded to nearest tf32 (two integer instructions), lo = v - hi exactly.
+template <bool EPI>
+__device__ __forceinline__ void split_group4(const uint32_t* __restrict__ d, const float* __restrict__ bias,
+                                             uint32_t* __restrict__ h, uint32_t* __restrict__ l) {
+    // packed fp32x2 adds (Blackwell FADD2): one issue slot for two bias adds / two lo = v - hi subtractions
+    u64 v01 = pack2(__uint_as_float(d[0]), __uint_as_float(d[1]));
+    u64 v23 = pack2(__uint_as_float(d[2]), __uint_as_float(d[3]));
+    if (EPI) {
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bias);
+        v01 = add2(v01, b.x);
+        v23 = add2(v23, b.y);
     }
-    tmem_st8(t_hi, h);
-    tmem_st8(t_lo, l);
+    float v[4];
+    unpack2(v01, v[0], v[1]);
+    unpack2(v23, v[2], v[3]);
+    uint32_t hb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (EPI) v[u] = relu_nan(v[u]);
+        hb[u] = (__float_as_uint(v[u]) + 0x1000u) & 0xFFFFE000u;
+        h[u] = hb[u];
+    }
+    const u64 l01 = sub2(pack2(v[0], v[1]), pack2(__uint_as_float(hb[0]), __uint_as_float(hb[1])));
+    const u64 l23 = sub2(pack2(v[2], v[3]), pack2(__uint_as_float(hb[2]), __uint_as_float(hb[3])));
+    float lo[4];
+    unpack2(l01, lo[0], lo[1]);
+    unpack2(l23, lo[2], lo[3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) l[u] = __float_as_uint(lo[u]);
 }
-
-// (d + bias) -> ReLU -> hi/lo, 16 (8) consecutive columns; bias: 16-byte aligned shared memory, same for every lane
 template <bool EPI>
 __device__ __forceinline__ void split_store16(const uint32_t (&d)[16], const float* __restrict__ bias, uint32_t t_hi,
                                               uint32_t t_lo) {
     uint32_t h[16], l[16];
 #pragma unroll
-    for (int g4 = 0; g4 < 4; ++g4) {
-        // packed fp32x2 adds (Blackwell FADD2): one issue slot for two bias adds / two lo = v - hi subtractions
-        u64 v01 = pack2(__uint_as_float(d[4 * g4]), __uint_as_float(d[4 * g4 + 1]));
-        u64 v23 = pack2(__uint_as_float(d[4 * g4 + 2]), __uint_as_float(d[4 * g4 + 3]));
-        if (EPI) {
-            const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bias + 4 * g4);
-            v01 = add2(v01, b.x);
-            v23 = add2(v23, b.y);
-        }
-        float v[4];
-        unpack2(v01, v[0], v[1]);
-        unpack2(v23, v[2], v[3]);
-        uint32_t hb[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (EPI) v[u] = relu_nan(v[u]);
-            hb[u] = (__float_as_uint(v[u]) + 0x1000u) & 0xFFFFE000u;
-            h[4 * g4 + u] = hb[u];
-        }
-        const u64 l01 = sub2(pack2(v[0], v[1]), pack2(__uint_as_float(hb[0]), __uint_as_float(hb[1])));
-        const u64 l23 = sub2(pack2(v[2], v[3]), pack2(__uint_as_float(hb[2]), __uint_as_float(hb[3])));
-        float lo[4];
-        unpack2(l01, lo[0], lo[1]);
-        unpack2(l23, lo[2], lo[3]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) l[4 * g4 + u] = __float_as_uint(lo[u]);
-    }
+    for (int g4 = 0; g4 < 4; ++g4) split_group4<EPI>(&d[4 * g4], bias + 4 * g4, &h[4 * g4], &l[4 * g4]);
     tmem_st16(t_hi, h);
     tmem_st16(t_lo, l);
 }
-__device__ __forceinline__ void split_store8_bias(const uint32_t (&d)[8], const float* __restrict__ bias, uint32_t t_hi,
-                                                  uint32_t t_lo) {
-    float v[8];
-    const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = relu_nan(__uint_as_float(d[k]) + bv[k]);
-    split_store8(v, t_hi, t_lo);
+template <bool EPI>
+__device__ __forceinline__ void split_store4(const uint32_t (&d)[4], const float* __restrict__ bias, uint32_t t_hi,
+                                             uint32_t t_lo) {
+    uint32_t h[4], l[4];
+    split_group4<EPI>(d, bias, h, l);
+    tmem_st4(t_hi, h);
+    tmem_st4(t_lo, l);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -201,41 +193,34 @@ __device__ __forceinline__ void issue_layer(uint32_t ts, uint32_t bh_addr, uint3
 
 // ---------------------------------------------------------------------------------------
 // Tail of one unit from the per-block records (one warp; lane = p*4+q, p = system slot, q = 10 hidden / 5 latent
-// columns).  thp: this unit's packed weights in GLOBAL memory (13 KB of head weights, read once through L2 with
-// 8 k-steps of loads in flight); scratch: TAIL_SCRATCH floats of warp-private shared memory.
+// columns).  hw: this unit's head block (PackedLayout V0p .. lv_sum, HEAD_FLOATS floats) in SHARED memory -- the tail
+// warp prefetches it with one bulk copy while it waits for the unit's records; read through L2 (round 1) the 40 + 40
+// dependent weight rows made the tail the longest chain of the kernel.  scratch: TAIL_SCRATCH floats, warp-private.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void head_layer_g(const float* __restrict__ sin_, const float* __restrict__ wg,
-                                             const float* __restrict__ bg, int p, int q, float* __restrict__ sout) {
+__device__ __forceinline__ void head_layer_s(const float* __restrict__ sin_, const float* __restrict__ ws,
+                                             const float* __restrict__ bs, int p, int q, float* __restrict__ sout) {
     float acc[10];
-    const float* bq = bg + q * GC;
+    const float* bq = bs + q * GC;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) acc[i] = __ldg(bq + i);
-    const float* wq = wg + q * GC;
-#pragma unroll 1
-    for (int k0 = 0; k0 < H; k0 += 8) {
-        float4 a[8], b[8];
-        float2 c[8];
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            a[kk] = __ldg(reinterpret_cast<const float4*>(wq + (k0 + kk) * HP));
-            b[kk] = __ldg(reinterpret_cast<const float4*>(wq + (k0 + kk) * HP + 4));
-            c[kk] = __ldg(reinterpret_cast<const float2*>(wq + (k0 + kk) * HP + 8));
-        }
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            const float sv = sin_[p * 41 + k0 + kk];
-            acc[0] = fmaf(sv, a[kk].x, acc[0]); acc[1] = fmaf(sv, a[kk].y, acc[1]);
-            acc[2] = fmaf(sv, a[kk].z, acc[2]); acc[3] = fmaf(sv, a[kk].w, acc[3]);
-            acc[4] = fmaf(sv, b[kk].x, acc[4]); acc[5] = fmaf(sv, b[kk].y, acc[5]);
-            acc[6] = fmaf(sv, b[kk].z, acc[6]); acc[7] = fmaf(sv, b[kk].w, acc[7]);
-            acc[8] = fmaf(sv, c[kk].x, acc[8]); acc[9] = fmaf(sv, c[kk].y, acc[9]);
-        }
+    for (int i = 0; i < 10; ++i) acc[i] = bq[i];
+    const float* wq = ws + q * GC;
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(wq + k * HP);
+        const float4 b = *reinterpret_cast<const float4*>(wq + k * HP + 4);
+        const float2 c = *reinterpret_cast<const float2*>(wq + k * HP + 8);
+        const float sv = sin_[p * 41 + k];
+        acc[0] = fmaf(sv, a.x, acc[0]); acc[1] = fmaf(sv, a.y, acc[1]);
+        acc[2] = fmaf(sv, a.z, acc[2]); acc[3] = fmaf(sv, a.w, acc[3]);
+        acc[4] = fmaf(sv, b.x, acc[4]); acc[5] = fmaf(sv, b.y, acc[5]);
+        acc[6] = fmaf(sv, b.z, acc[6]); acc[7] = fmaf(sv, b.w, acc[7]);
+        acc[8] = fmaf(sv, c.x, acc[8]); acc[9] = fmaf(sv, c.y, acc[9]);
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) sout[p * 41 + q * 10 + i] = relu_nan(acc[i]);
 }
 
-__device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, const float* __restrict__ thp,
+__device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, const float* __restrict__ hw,
                                              const PackedLayout& pl, const float* __restrict__ eps_u,
                                              const float* __restrict__ eps_sum_u, float* __restrict__ summary_u,
                                              uint64_t seed, uint32_t gunit, int64_t gsys0, int64_t n0, int n_valid,
@@ -254,6 +239,7 @@ __device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, cons
             eS[idx] = (s < n_valid) ? __ldg(eps_u + (n0 + s) * S2 + j) : 0.f;
         }
     } else {
+#pragma unroll 1
         for (int b = lane; b < SYS * (S2 / 4); b += 32) {
             const int s = b / (S2 / 4), blk = b % (S2 / 4);
             const float4 n4 = philox_normal4(seed, STREAM_EPS, gunit, (uint32_t)(gsys0 + s), (uint32_t)blk);
@@ -264,7 +250,9 @@ __device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, cons
 
     const SysRec sr = sys_records(p);
     const float Tf = (float)T_FIXED, Tm1 = (float)(T_FIXED - 1);
-#pragma unroll
+    // (code size matters here: the tail is a few thousand instructions that two warps walk once per unit, next to 16
+    // epilogue warps whose loop has to stay in the 32 KB instruction cache -- the loops below are deliberately not unrolled)
+#pragma unroll 1
     for (int i = 0; i < 5; ++i) {
         const int col = q * 5 + i;
         float2 r[4];
@@ -294,8 +282,8 @@ __device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, cons
             if (eps_sum_u) {
                 const float e0 = __ldg(eps_sum_u + (n0 + p) * S2 + col);
                 const float e1 = __ldg(eps_sum_u + (n0 + p) * S2 + L + col);
-                s_mu = __fadd_rn(s_mu, __fmul_rn(e0, expf(__fdiv_rn(__ldg(thp + pl.lv_sum + col), 2.0f))));
-                s_sd = __fadd_rn(s_sd, __fmul_rn(e1, expf(__fdiv_rn(__ldg(thp + pl.lv_sum + L + col), 2.0f))));
+                s_mu = __fadd_rn(s_mu, __fmul_rn(e0, expf(__fdiv_rn(hw[pl.lv_sum - pl.V0p + col], 2.0f))));
+                s_sd = __fadd_rn(s_sd, __fmul_rn(e1, expf(__fdiv_rn(hw[pl.lv_sum - pl.V0p + L + col], 2.0f))));
             }
         }
         if (live) {
@@ -304,25 +292,26 @@ __device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, cons
         }
     }
     __syncwarp();
-    if (live) head_layer_g(sA, thp + pl.V0p, thp + pl.c0p, p, q, sB);
-    __syncwarp();
-    if (live) head_layer_g(sB, thp + pl.V1p, thp + pl.c1p, p, q, sA);
-    __syncwarp();
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+        if (live) head_layer_s(layer ? sB : sA, hw + (layer ? pl.V1p - pl.V0p : 0), hw + (layer ? pl.c1p : pl.c0p) - pl.V0p, p, q, layer ? sA : sB);
+        __syncwarp();
+    }
     float o0 = 0.f, o1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const int k = q * 10 + i;
         const float r = sA[p * 41 + k];
-        o0 = fmaf(r, __ldg(thp + pl.V2 + k), o0);
-        o1 = fmaf(r, __ldg(thp + pl.V2 + H + k), o1);
+        o0 = fmaf(r, hw[pl.V2 - pl.V0p + k], o0);
+        o1 = fmaf(r, hw[pl.V2 - pl.V0p + H + k], o1);
     }
     o0 += __shfl_xor_sync(0xffffffffu, o0, 1);
     o1 += __shfl_xor_sync(0xffffffffu, o1, 1);
     o0 += __shfl_xor_sync(0xffffffffu, o0, 2);
     o1 += __shfl_xor_sync(0xffffffffu, o1, 2);
     if (q == 0 && live && p < n_valid) {
-        o0 += __ldg(thp + pl.c2);
-        o1 += __ldg(thp + pl.c2 + 1);
+        o0 += hw[pl.c2 - pl.V0p];
+        o1 += hw[pl.c2 - pl.V0p + 1];
         float2 o = make_float2(soft_clamp_dev(o0, hc.lo_mu, hc.hi_mu), soft_clamp_dev(o1, hc.lo_sd, hc.hi_sd));
         *reinterpret_cast<float2*>(out_unit + (n0 + p) * out_sys_stride) = o;
     }

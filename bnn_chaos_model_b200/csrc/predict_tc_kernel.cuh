@@ -6,74 +6,80 @@ namespace bnn {
 namespace tc {
 
 // timeline probe (tools/tc_timeline.py): role-major [8][512] int64 of clock64() stamps, CTA 0 lane 0 only.  Compiled in
-// only with -DBNN_TC_TIMELINE (make TIMELINE=1): the stamps cost registers in the hot loops (13 % of the kernel time
-// when they were always compiled).
+// only with -DBNN_TC_TIMELINE (make TIMELINE=1): the stamps cost registers in the hot loops.
 #ifdef BNN_TC_TIMELINE
-#define TC_STAMP_CTR(ctr, role, code)                                                                 \
+#define TC_STAMP(role, code)                                                                          \
     do {                                                                                             \
-        if (prm.dbg && blockIdx.x == 0 && lane == 0 && ctr < 511) {                                   \
-            prm.dbg[(role) * 512 + 1 + ctr] = ((long long)(code) << 48) | (clock64() & 0xFFFFFFFFFFFFll); \
-            prm.dbg[(role) * 512] = ++ctr;                                                            \
+        if (prm.dbg && blockIdx.x == 0 && lane == 0 && dbg_n < 511) {                                 \
+            prm.dbg[(role) * 512 + 1 + dbg_n] = ((long long)(code) << 48) | (clock64() & 0xFFFFFFFFFFFFll); \
+            prm.dbg[(role) * 512] = ++dbg_n;                                                          \
         }                                                                                            \
     } while (0)
-#define TC_STAMP(role, code) TC_STAMP_CTR(dbg_n, role, code)
-// own counter: the MMA-issue stamps (role 7) come from the warp that also stamps role 0
-#define TC_STAMP_M(role, code) TC_STAMP_CTR(dbg_m, role, code)
 #else
 #define TC_STAMP(role, code) do { } while (0)
-#define TC_STAMP_M(role, code) do { } while (0)
 #endif
 
-constexpr int BAR_A = 1, BAR_D = 5;  // named barrier ids: A-ready / D-ready of TMEM slot s are BAR_A + s / BAR_D + s
 constexpr int B_FLOATS = 2 * (TC_K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3) + TC_BIAS;  // hi + lo B operands + biases
 constexpr int B_BYTES = B_FLOATS * 4;
 constexpr int O_B1H = 0, O_B1L = O_B1H + TC_K1 * TC_N * 4, O_B2H = O_B1L + TC_K1 * TC_N * 4,
               O_B2L = O_B2H + TC_K2 * TC_N * 4, O_B3H = O_B2L + TC_K2 * TC_N * 4, O_B3L = O_B3H + TC_K2 * TC_N3 * 4,
               O_BIAS = O_B3L + TC_K2 * TC_N3 * 4;  // byte offsets inside a ring slot
 
-template <int NSLOT, int NT>
+constexpr int N_TEAM = 2;              // epilogue teams; team t owns TMEM slots 2t and 2t+1 and the M tiles t and t+2
+constexpr int EW = 8 * N_TEAM;         // epilogue warps
+constexpr int NISS = N_SLOT;           // MMA-issuing warps (one per TMEM slot)
+constexpr int HC = 20;                 // hidden columns per epilogue warp (the two warps of a lane quadrant split 40)
+
+template <int NT>
 struct SmemPlan {
     // byte offsets inside dynamic shared memory
     static constexpr int xs = 0;                                   // ROWS*32 floats
     static constexpr int ring = xs + ROWS * 32 * 4;                // 2 slots of B operands + biases
-    static constexpr int fb = ring + 2 * B_BYTES;                  // per epilogue warp: 32 rows x 20 latent columns
-    static constexpr int rec = fb + NSLOT * 4 * FB_FLOATS * 4;     // NT slots of block records
-    static constexpr int scratch = rec + NT * REC_FLOATS * 4;      // per tail warp
-    static constexpr int bars = scratch + NT * TAIL_SCRATCH * 4;
+    static constexpr int fb = ring + 2 * B_BYTES;                  // per epilogue warp: 32 rows x 12 latent columns
+    static constexpr int rec = fb + EW * FB_FLOATS * 4;            // NREC slots of block records
+    static constexpr int scratch = rec + NREC * REC_FLOATS * 4;    // per tail warp
+    static constexpr int head = (scratch + NT * TAIL_SCRATCH * 4 + 127) & ~127;  // per tail warp: head block of its unit
+    static constexpr int head_bytes = (HEAD_FLOATS * 4 + 127) & ~127;
+    static constexpr int bars = head + NT * head_bytes;
     static constexpr int total = bars + (int)sizeof(Bars);
 };
 
-// Warp roles:
-//   [0, 4*NSLOT)             epilogue warps (slot = w / 4, TMEM lane quadrant = w % 4); the quadrant-0 warp of a slot
-//                            issues that slot's MMAs; slot 0's also refills the B-operand ring (it polls unit_done
-//                            without blocking at its own synchronisation points)
-//   [4*NSLOT, 4*NSLOT + NT)  tail warps (unit i -> warp i % NT), on the highest warp ids: the issue arbiter favours
-//                            high ids (B300_MICROARCH.md), and the tails are 10 % of the instructions but their latency
-//                            gates the record ring
-// 640 threads at NSLOT = 4, NT = 4 -> 96 registers per thread.
-template <int NSLOT, int NT>
-__global__ void __launch_bounds__((((NT + 3) & ~3) + 4 * NSLOT) * 32, 1)
-predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) {
+// Warp roles (704 threads at NT = 2 -> 88 registers per thread):
+//   [0, 16)         epilogue warps: team = w / 8, half = (w / 4) % 2, TMEM lane quadrant = w % 4 (thread = tile row).  A team
+//                   works on TWO jobs at a time -- (unit i, M tile team) in slot 2*team and (unit i, M tile team + 2) in slot
+//                   2*team + 1 -- and alternates between them phase by phase, so that the tensor pipe runs one slot's layer
+//                   while the team's CUDA cores run the other slot's epilogue; the two warps of a quadrant split the
+//                   columns of a phase (hidden 20 + 20, x 16 + 16, latent 10 + 10).  With one job per 4 warps (round 1)
+//                   a warp idled through its slot's MMAs: a third of its time, 2.6 of 4 warps per scheduler active.
+//   [16, 20)        issuer warps: issuer s issues every tcgen05.mma of TMEM slot s (it sleeps on the slot's "A ready"
+//                   mbarrier); issuer 0 also refills the B-operand ring.  One issuer per slot, not per team: a thread
+//                   issues one N = 48 MMA per 44 cycles while the pipe takes two threads' MMAs at one per 33
+//   [20, 20 + NT)   tail warps (unit i -> warp i % NT), on the highest warp ids: the issue arbiter favours high ids
+//                   (B300_MICROARCH.md), and the tails are 10 % of the instructions but their latency gates the record ring
+template <int NT>
+__global__ void __launch_bounds__((EW + NISS + NT) * 32, 1)
+predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, unsigned int* __restrict__ item_counter) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
-    static_assert(NT >= 2 && NT <= MAX_NT && NSLOT <= 4 && MT >= NSLOT && NSLOT * TM_SLOT <= 512, "role layout");
+    static_assert(NT >= 1 && NT <= NREC && MT == 2 * N_TEAM && N_SLOT == 2 * N_TEAM && N_SLOT * TM_SLOT <= 512, "role layout");
     const PackedLayout pl(prm.kin, prm.F);
-    using Plan = SmemPlan<NSLOT, NT>;
+    using Plan = SmemPlan<NT>;
     float* xs = reinterpret_cast<float*>(smem_tc + Plan::xs);
     float* ring = reinterpret_cast<float*>(smem_tc + Plan::ring);
     float* fb = reinterpret_cast<float*>(smem_tc + Plan::fb);
     float* rec = reinterpret_cast<float*>(smem_tc + Plan::rec);
     float* scratch = reinterpret_cast<float*>(smem_tc + Plan::scratch);
+    static_assert(HEAD_FLOATS % 4 == 0, "bulk copies move multiples of 16 bytes");
     Bars* bars = reinterpret_cast<Bars*>(smem_tc + Plan::bars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = n_tiles * chunks;
+    constexpr int W_ISS = EW, W_TAIL = EW + NISS;
 #ifdef BNN_TC_TIMELINE
-    int dbg_n = 0, dbg_m = 0;
+    int dbg_n = 0;
 #endif
 
-    constexpr int W_EPI = 0, W_TAIL = 4 * NSLOT;  // tails sit on the highest warp ids: the issue arbiter favours them
     // ---- one-time setup: TMEM allocation ----
-    if (warp == W_EPI) {
+    if (warp == 0) {
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
@@ -82,109 +88,113 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // items (system tile, unit chunk) are handed out dynamically: the first one is the CTA's index, the following come
+    // from a global counter
+    for (int item = blockIdx.x, first_item = 1; item < n_items; first_item = 0) {
         const int tile = item / chunks, chunk = item % chunks;
         const int64_t n0 = (int64_t)tile * SYS;
         const int n_valid = (int)min((int64_t)SYS, prm.N - n0);
         const int64_t u_begin = prm.U * chunk / chunks, u_end = prm.U * (chunk + 1) / chunks;
         const int n_units = (int)(u_end - u_begin);
-        const int n_jobs = n_units * MT;
 
         tc_fence_before();
         __syncthreads();  // previous item drained by every role
         if (threadIdx.x == 0) {
-            if (item != (int)blockIdx.x) {
+            bars->next_item = (int)(atomicAdd(item_counter, 1u) + gridDim.x);  // the item after this one
+            if (!first_item) {
                 for (int s = 0; s < 2; ++s) mbar_inval(&bars->w_full[s]);
-                for (int s = 0; s < NT; ++s) { mbar_inval(&bars->unit_done[s]); mbar_inval(&bars->rec_free[s]); }
-                for (int s = 0; s < NSLOT; ++s) mbar_inval(&bars->d_ready[s]);
+                for (int s = 0; s < NREC; ++s) { mbar_inval(&bars->unit_done[s]); mbar_inval(&bars->rec_free[s]); }
+                for (int s = 0; s < N_SLOT; ++s) { mbar_inval(&bars->d_ready[s]); mbar_inval(&bars->a_ready[s]); }
+                for (int s = 0; s < NT; ++s) mbar_inval(&bars->h_full[s]);
             }
+            for (int s = 0; s < NT; ++s) mbar_init(&bars->h_full[s], 1);
             for (int s = 0; s < 2; ++s) mbar_init(&bars->w_full[s], 1);
-            for (int s = 0; s < NT; ++s) {
-                mbar_init(&bars->unit_done[s], MT * 4);  // 4 epilogue warps per job, MT jobs per unit
-                mbar_init(&bars->rec_free[s], 1);        // the tail warp of the slot
+            for (int s = 0; s < NREC; ++s) {
+                mbar_init(&bars->unit_done[s], EW * 2);  // every epilogue warp pools two jobs per unit
+                mbar_init(&bars->rec_free[s], 1);        // the tail warp of the unit
             }
-            for (int s = 0; s < NSLOT; ++s) mbar_init(&bars->d_ready[s], 1);  // tcgen05.commit
+            for (int s = 0; s < N_SLOT; ++s) {
+                mbar_init(&bars->d_ready[s], 1);  // tcgen05.commit
+                mbar_init(&bars->a_ready[s], 8);  // one lane of each of the team's warps
+            }
             mbar_init_fence();
         }
         load_x_tile_tc(prm.X, n0, n_valid, prm.F, prm.kin, prm.cm, xs, reinterpret_cast<int*>(fb));
         __syncthreads();
         tc_fence_after();
 
-        if (warp >= W_TAIL && warp < W_TAIL + NT) {
+        if (warp >= W_TAIL) {
             // ---------------- tail warps ----------------
             const int tw = warp - W_TAIL;
             float* my_scratch = scratch + tw * TAIL_SCRATCH;
+            float* my_head = reinterpret_cast<float*>(smem_tc + Plan::head + tw * Plan::head_bytes);
+            // head block (regress_nn weights, 16 kB) of this warp's next unit: one bulk copy, issued as soon as the
+            // buffer is free, so that it lands while the warp waits for the unit's records
+            auto fetch_head = [&](int i) {
+                if (lane == 0 && i < n_units) {
+                    fence_proxy_async_smem();  // the generic-proxy reads of the previous unit are ordered before the copy
+                    mbar_arrive_expect_tx(&bars->h_full[tw], (uint32_t)(HEAD_FLOATS * 4));
+                    bulk_g2s(my_head, prm.thp + (u_begin + i) * pl.P + pl.V0p, (uint32_t)(HEAD_FLOATS * 4), &bars->h_full[tw]);
+                }
+            };
+            fetch_head(tw);
+            uint32_t ph = 0;
             for (int i = tw; i < n_units; i += NT) {
-                TC_STAMP(4 + (tw & 1), 1);
-                mbar_wait_backoff(&bars->unit_done[tw], (uint32_t)((i / NT) & 1), 400);  // all 16 block records of unit i
-                TC_STAMP(4 + (tw & 1), 2);
+                const int rs = i % NREC;
+                mbar_wait_backoff(&bars->unit_done[rs], (uint32_t)((i / NREC) & 1), 400);  // all 16 block records of unit i
+                mbar_wait(&bars->h_full[tw], ph);
+                ph ^= 1;
                 const int64_t u = u_begin + i;
                 const float* eps_u = prm.eps ? prm.eps + u * prm.N * S2 : nullptr;
                 const float* eps_sum_u = prm.eps_sum ? prm.eps_sum + u * prm.N * S2 : nullptr;
                 float* summary_u = prm.summary ? prm.summary + u * prm.N * S2 : nullptr;
-                tail_unit_tc(rec + tw * REC_FLOATS, prm.thp + u * pl.P, pl, eps_u, eps_sum_u, summary_u, prm.seed,
+                tail_unit_tc(rec + rs * REC_FLOATS, my_head, pl, eps_u, eps_sum_u, summary_u, prm.seed,
                              (uint32_t)(prm.unit_offset + u), prm.system_offset + n0, n0, n_valid, prm.hc, my_scratch,
                              prm.out + u * prm.out_unit_stride, prm.out_sys_stride);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->rec_free[tw]);  // the record slot may take unit i + NT
-                TC_STAMP(4 + (tw & 1), 3);
+                if (lane == 0) mbar_arrive(&bars->rec_free[rs]);  // the record slot may take unit i + NREC
+                fetch_head(i + NT);
             }
-        } else if (warp < W_TAIL) {
-            // ---------------- epilogue warps (quadrant 0 also issues the MMAs of its slot) ----------------
-            const int slot = (warp - W_EPI) >> 2, quad = warp & 3;
-            const uint32_t ts = tmem + slot * TM_SLOT;                     // slot base (lane 0)
-            const uint32_t tl = ts + ((uint32_t)(quad * 32) << 16);        // this warp's lane quadrant
-            float* my_fb = fb + (warp - W_EPI) * FB_FLOATS;
+        } else if (warp >= W_ISS) {
+            // ---------------- issuer warps: every tcgen05.mma of the team's two slots; ring refill ----------------
+            const int slot = warp - W_ISS;
             const uint32_t ring_addr = smem_u32(ring);
-            uint32_t pd = 0;
-            int pend_i = -1, pend_m = 0;  // job whose latent rows sit in my_fb and still have to be pooled
-
-            // pooled (mean, M2) records of one 32-row block, two-pass per segment like torch.mean / torch.std;
-            // runs in the shadow of the next job's layer-1 MMAs
-            auto pool_block = [&](int pi, int pm) {
-                const int rs = pi % NT;
-                if (pi >= NT) mbar_wait_backoff(&bars->rec_free[rs], (uint32_t)((pi / NT - 1) & 1), 100);  // tail of unit pi-NT done
-                if (quad == 0 && slot < 3) TC_STAMP(slot, 21);
-                if (lane < L) {
-                    const int b = pm * 4 + quad;
-                    int sysA, split, nvalid;
-                    block_geom(b, sysA, split, nvalid);
-                    float* rb = rec + rs * REC_FLOATS + (b * 2) * L * 2 + lane * 2;
-                    const int e0 = min(split, nvalid);
-                    const float* col = my_fb + lane;
-                    float s = 0.f;
-#pragma unroll 8
-                    for (int r = 0; r < e0; ++r) s += col[r * L];
-                    float mean = s / (float)max(e0, 1), m2 = 0.f;
-#pragma unroll 8
-                    for (int r = 0; r < e0; ++r) { const float dlt = col[r * L] - mean; m2 = fmaf(dlt, dlt, m2); }
-                    rb[0] = mean;
-                    rb[1] = m2;
-                    if (nvalid > split) {
-                        s = 0.f;
-#pragma unroll 8
-                        for (int r = split; r < nvalid; ++r) s += col[r * L];
-                        mean = s / (float)(nvalid - split);
-                        m2 = 0.f;
-#pragma unroll 8
-                        for (int r = split; r < nvalid; ++r) { const float dlt = col[r * L] - mean; m2 = fmaf(dlt, dlt, m2); }
-                        rb[L * 2] = mean;
-                        rb[L * 2 + 1] = m2;
+            uint32_t pa = 0;  // parity of a_ready[slot]
+            // B operands + biases of unit i -> ring slot i & 1, free once every block record of unit i-2 is written
+            // (all its MMAs and bias reads are done).  Issued by one lane of issuer 0 whenever it passes.
+            int next_load = 0;
+            auto refill = [&]() {
+                if (slot == 0 && lane == 0) {
+                    while (next_load < n_units &&
+                           (next_load < 2 ||
+                            mbar_test(&bars->unit_done[(next_load - 2) % NREC], (uint32_t)(((next_load - 2) / NREC) & 1)))) {
+                        mbar_arrive_expect_tx(&bars->w_full[next_load & 1], (uint32_t)B_BYTES);
+                        bulk_g2s(ring + (size_t)(next_load & 1) * B_FLOATS, prm.thp + (u_begin + next_load) * pl.P + pl.B1h,
+                                 (uint32_t)B_BYTES, &bars->w_full[next_load & 1]);
+                        ++next_load;
                     }
                 }
                 __syncwarp();
-                if (quad == 0 && slot < 3) TC_STAMP(slot, 22);
-                if (lane == 0) mbar_arrive(&bars->unit_done[rs]);
             };
-            // A of the slot is complete (named barrier over the slot's 4 warps); quadrant 0 issues the layer and the commit
-            auto issue = [&](int layer, int ws) {
-                named_sync(BAR_A + slot, 128);
-                if (quad == 0) {
+            refill();
+#pragma unroll 1
+            for (int i = 0; i < n_units; ++i) {
+                const int ws = i & 1;
+                // every issuer visits every unit in order, so its view of w_full[ws] never skips a phase
+                while (!mbar_test(&bars->w_full[ws], (uint32_t)((i >> 1) & 1))) {
+                    refill();
+                    __nanosleep(40);
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int layer = 0; layer < 3; ++layer) {
+                    mbar_wait(&bars->a_ready[slot], pa);
+                    pa ^= 1u;
                     tc_fence_after();
+                    TC_STAMP(2 + slot, 10 * layer + 1);
                     uint32_t wb = ring_addr + (uint32_t)ws * (uint32_t)B_BYTES;
-                    uint32_t tsv = ts;
+                    uint32_t tsv = tmem + slot * TM_SLOT;
                     asm volatile("" : "+r"(wb), "+r"(tsv));  // keep the descriptors out of loop-invariant hoisting
-                    if (slot == 0) TC_STAMP_M(7, layer);
                     if (layer == 0)
                         issue_layer<TC_N, TC_K1 / 8>(tsv, wb + O_B1H, wb + O_B1L);
                     else if (layer == 1)
@@ -193,152 +203,192 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks) 
                         issue_layer<TC_N3, TC_K2 / 8>(tsv, wb + O_B3H, wb + O_B3L);
                     if (elect_one_sync()) mma_commit(&bars->d_ready[slot]);
                     __syncwarp();
-                    if (slot == 0) TC_STAMP_M(7, 100 + layer);
-                }
-            };
-            // D of the slot is complete: quadrant 0 polls the commit barrier, the other three sleep on the named barrier
-            auto wait_d = [&]() {
-                if (quad == 0) {
-                    // a layer's MMAs take >= 0.3 us behind the other slots' queues: one long nap, then short ones
-                    if (!mbar_test(&bars->d_ready[slot], pd)) {
-                        __nanosleep(120);
-                        mbar_wait_backoff(&bars->d_ready[slot], pd, 20);
-                    }
-                    pd ^= 1;
-                }
-                named_sync(BAR_D + slot, 128);
-                tc_fence_after();
-            };
-
-            // B operands + biases of unit i -> ring slot i & 1, free once every block record of unit i-2 is written
-            // (all its MMAs and bias reads are done).  Issued by one lane of slot 0's quadrant-0 warp whenever it passes.
-            int next_load = 0;
-            auto refill = [&]() {
-                if (slot == 0 && quad == 0 && lane == 0) {
-                    while (next_load < n_units &&
-                           (next_load < 2 || mbar_test(&bars->unit_done[(next_load - 2) % NT], (uint32_t)(((next_load - 2) / NT) & 1)))) {
-                        mbar_arrive_expect_tx(&bars->w_full[next_load & 1], (uint32_t)B_BYTES);
-                        bulk_g2s(ring + (size_t)(next_load & 1) * B_FLOATS, prm.thp + (u_begin + next_load) * pl.P + pl.B1h,
-                                 (uint32_t)B_BYTES, &bars->w_full[next_load & 1]);
-                        ++next_load;
-                    }
-                }
-            };
-            refill();
-
-            int seen_unit = -1;
-            for (int j = slot; j < n_jobs; j += NSLOT) {
-                const int i = j / MT, m = j % MT, ws = i & 1;
-                const int R = m * 128 + quad * 32 + lane;  // tile row of this thread
-                const float* bias = ring + (size_t)ws * B_FLOATS + O_BIAS / 4;
-                // ---- stage x -> A (hi / lo, 32 columns each) ----
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[16];
-                    if (R < ROWS) {
-#pragma unroll
-                        for (int g4 = 0; g4 < 4; ++g4) {
-                            const float4 a = *reinterpret_cast<const float4*>(xs + R * 32 + (((4 * c + g4) ^ (R & 7)) << 2));
-                            v[4 * g4] = __float_as_uint(a.x); v[4 * g4 + 1] = __float_as_uint(a.y);
-                            v[4 * g4 + 2] = __float_as_uint(a.z); v[4 * g4 + 3] = __float_as_uint(a.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) v[k] = 0u;
-                    }
-                    split_store16<false>(v, nullptr, tl + TM_AHI + 16 * c, tl + TM_ALO + 16 * c);
-                }
-                tc_wait_st();
-                tc_fence_before();
-                if (quad == 0 && slot < 3) TC_STAMP(slot, 1);
-                if (quad == 0 && i != seen_unit) {
-                    // a slot visits every unit (MT >= NSLOT), in order, so its view of w_full[ws] never skips a phase
-                    while (!mbar_test(&bars->w_full[ws], (i >> 1) & 1)) {
-                        refill();
-                        __nanosleep(20);
-                    }
-                    __syncwarp();
-                    seen_unit = i;
-                }
-                issue(0, ws);
-                refill();
-
-                // ---- pool the previous job's block while the tensor pipe works on layer 1 ----
-                if (pend_i >= 0) pool_block(pend_i, pend_m);
-                if (quad == 0 && slot < 3) TC_STAMP(slot, 2);
-
-                // ---- layers 1 and 2: D + bias -> ReLU -> hi/lo -> A ----
-#pragma unroll 1
-                for (int layer = 0; layer < 2; ++layer) {
-                    wait_d();
-                    if (quad == 0 && slot < 3) TC_STAMP(slot, 3 + 2 * layer);
-                    const float* bl = bias + layer * TC_N;
-                    uint32_t d0[16], d1[16], d2[8];
-                    tmem_ld16(tl + TM_D, d0);
-                    tmem_ld16(tl + TM_D + 16, d1);
-                    tmem_ld8(tl + TM_D + 32, d2);
-                    tc_wait_ld();
-                    split_store16<true>(d0, bl, tl + TM_AHI, tl + TM_ALO);
-                    split_store16<true>(d1, bl + 16, tl + TM_AHI + 16, tl + TM_ALO + 16);
-                    split_store8_bias(d2, bl + 32, tl + TM_AHI + 32, tl + TM_ALO + 32);
-                    tc_wait_st();
-                    tc_fence_before();
-                    if (quad == 0 && slot < 3) TC_STAMP(slot, 4 + 2 * layer);
-                    issue(layer + 1, ws);
+                    TC_STAMP(2 + slot, 10 * layer + 2);
                     refill();
                 }
+            }
+        } else {
+            // ---------------- epilogue warps ----------------
+            const int team = warp >> 3, half = (warp >> 2) & 1, quad = warp & 3;
+            const uint32_t tq = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * team * TM_SLOT);  // slot s: + s * TM_SLOT
+            float* my_fb = fb + warp * FB_FLOATS;
+            uint32_t pd = 0;  // bit s: parity of d_ready[2 * team + s]
 
-                // ---- layer 3: D + bias (20 latent columns) -> my_fb (pooled after the next job's x is staged) ----
-                wait_d();
-                if (quad == 0 && slot < 3) TC_STAMP(slot, 7);
-                {
-                    uint32_t d0[16], d1[8];
-                    tmem_ld16(tl + TM_D, d0);
-                    tmem_ld8(tl + TM_D + 16, d1);
-                    tc_wait_ld();
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + 2 * TC_N);
-                    float4* dst = reinterpret_cast<float4*>(my_fb + lane * L);
+            auto wait_d = [&](int s) {
+                mbar_wait(&bars->d_ready[2 * team + s], (pd >> s) & 1u);
+                pd ^= 1u << s;
+                tc_fence_after();
+            };
+            // A of the slot's next layer is written: TMEM stores complete, then one arrival per warp on the issuer's barrier
+            auto publish = [&](int s) {
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_ready[2 * team + s]);
+            };
+            // layer 3 of (unit pi, M tile m): D + bias -> this warp's latent columns [8 half, 8 half + 12) of its 32 rows
+            auto latent_to_fb = [&](int s, int pi) {
+                const uint32_t tl = tq + s * TM_SLOT;
+                const float* b3 = ring + (size_t)(pi & 1) * B_FLOATS + O_BIAS / 4 + 2 * TC_N + 8 * half;
+                uint32_t d0[8], d1[4];
+                tmem_ld8(tl + TM_D + 8 * half, d0);
+                tmem_ld4(tl + TM_D + 8 * half + 8, d1);
+                tc_wait_ld();
+                const float4* b4 = reinterpret_cast<const float4*>(b3);
+                float4* dst = reinterpret_cast<float4*>(my_fb + lane * FB_PITCH);
 #pragma unroll
-                    for (int g4 = 0; g4 < 5; ++g4) {
-                        const float4 b = b4[g4];
-                        const uint32_t* dd = g4 < 4 ? &d0[4 * g4] : &d1[0];
-                        dst[g4] = make_float4(__uint_as_float(dd[0]) + b.x, __uint_as_float(dd[1]) + b.y,
-                                              __uint_as_float(dd[2]) + b.z, __uint_as_float(dd[3]) + b.w);
-                    }
+                for (int g4 = 0; g4 < 3; ++g4) {
+                    const float4 b = b4[g4];
+                    const uint32_t* dd = g4 < 2 ? &d0[4 * g4] : &d1[0];
+                    dst[g4] = make_float4(__uint_as_float(dd[0]) + b.x, __uint_as_float(dd[1]) + b.y,
+                                          __uint_as_float(dd[2]) + b.z, __uint_as_float(dd[3]) + b.w);
                 }
                 __syncwarp();
-                if (quad == 0 && slot < 3) TC_STAMP(slot, 8);
-                pend_i = i;
-                pend_m = m;
+            };
+            // pooled (mean, M2) records of this warp's 10 latent columns of one 32-row block, two-pass per segment like
+            // torch.mean / torch.std.  lane = (row group g = lane / 10: rows [11 g, 11 g + 11), column c = lane % 10); the
+            // three partial sums of a column meet through shuffles.  Runs in the shadow of the slot's layer-1 MMAs.
+            auto pool_block = [&](int pi, int m) {
+                const int rs = pi % NREC;
+                if (pi >= NREC) mbar_wait_backoff(&bars->rec_free[rs], (uint32_t)((pi / NREC - 1) & 1), 100);  // tail of unit pi-NREC done
+                const int b = m * 4 + quad;
+                int sysA, split, nvalid;
+                block_geom(b, sysA, split, nvalid);
+                const int g = min(lane / 10, 2), c = lane - 10 * (lane / 10), base = 11 * g;
+                const int src = lane % 10;                     // lanes src, src + 10, src + 20 hold column c's partial sums
+                const float* col = my_fb + 2 * half + c + base * FB_PITCH;
+                float v[11];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) v[k] = lane < 30 ? col[k * FB_PITCH] : 0.f;
+                v[10] = lane < 20 ? col[10 * FB_PITCH] : 0.f;  // rows 10 / 21; group 2 has 10 rows
+                auto gather3 = [&](float x) {
+                    return __shfl_sync(0xffffffffu, x, src) + __shfl_sync(0xffffffffu, x, src + 10) + __shfl_sync(0xffffffffu, x, src + 20);
+                };
+                float* rb = rec + rs * REC_FLOATS + ((b * 2) * L + 10 * half + c) * 2;
+                if (split == 32 && nvalid == 32) {
+                    // 11 of the 16 blocks hold 32 rows of one system: no row predicates (rows past the group are exact zeros
+                    // in the sum and are left out of M2 by the group's row count)
+                    float s0 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) s0 += v[k];
+                    const float mean0 = gather3(s0) * 0.03125f;
+                    float q0 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) { const float d0 = v[k] - mean0; q0 = fmaf(d0, d0, q0); }
+                    if (lane < 20) { const float d0 = v[10] - mean0; q0 = fmaf(d0, d0, q0); }
+                    q0 = gather3(q0);
+                    if (lane < 10) { rb[0] = mean0; rb[1] = q0; }
+                } else {
+                    const int e0 = min(split, nvalid);
+                    const bool two = nvalid > split;               // the block holds rows of two systems (warp-uniform)
+                    const int t0 = (lane < 30 ? e0 : 0) - base, t1 = split - base, t2 = (lane < 30 ? nvalid : 0) - base;
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) {
+                        if (k < t0) s0 += v[k];
+                        if (two && k >= t1 && k < t2) s1 += v[k];
+                    }
+                    const float mean0 = gather3(s0) / (float)max(e0, 1);
+                    const float mean1 = two ? gather3(s1) / (float)(nvalid - split) : 0.f;
+                    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) {
+                        const float d0 = v[k] - mean0, d1 = v[k] - mean1;
+                        if (k < t0) q0 = fmaf(d0, d0, q0);
+                        if (two && k >= t1 && k < t2) q1 = fmaf(d1, d1, q1);
+                    }
+                    q0 = gather3(q0);
+                    if (two) q1 = gather3(q1);
+                    if (lane < 10) { rb[0] = mean0; rb[1] = q0; }
+                    if (two && lane >= 10 && lane < 20) { rb[L * 2] = mean1; rb[L * 2 + 1] = q1; }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->unit_done[rs]);
+            };
+
+#pragma unroll 1
+            for (int i = 0; i <= n_units; ++i) {
+                // ---- phase 0 of both slots: latent rows of the previous unit -> fb, x -> A (layer 1 starts), pooling ----
+#pragma unroll 1
+                for (int s = 0; s < 2; ++s) {
+                    const int m = team + 2 * s;
+                    const uint32_t tl = tq + s * TM_SLOT;
+                    if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 1);
+                    if (i > 0) {
+                        wait_d(s);
+                        if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 2);
+                        latent_to_fb(s, i - 1);
+                    }
+                    if (i < n_units) {
+                        const int R = m * 128 + quad * 32 + lane;  // tile row of this thread
+                        uint32_t v[16];
+                        if (R < ROWS) {
+#pragma unroll
+                            for (int g4 = 0; g4 < 4; ++g4) {
+                                const float4 a = *reinterpret_cast<const float4*>(xs + R * 32 + (((4 * half + g4) ^ (R & 7)) << 2));
+                                v[4 * g4] = __float_as_uint(a.x); v[4 * g4 + 1] = __float_as_uint(a.y);
+                                v[4 * g4 + 2] = __float_as_uint(a.z); v[4 * g4 + 3] = __float_as_uint(a.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) v[k] = 0u;
+                        }
+                        split_store16<false>(v, nullptr, tl + TM_AHI + 16 * half, tl + TM_ALO + 16 * half);
+                        publish(s);
+                        if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 3);
+                    }
+                    if (i > 0) pool_block(i - 1, m);
+                    if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 4);
+                }
+                if (i == n_units) break;
+                // ---- layers 1 and 2 of both slots: D + bias -> ReLU -> hi/lo -> A ----
+                const float* bias = ring + (size_t)(i & 1) * B_FLOATS + O_BIAS / 4 + HC * half;
+#pragma unroll 1
+                for (int layer = 0; layer < 2; ++layer) {
+#pragma unroll 1
+                    for (int s = 0; s < 2; ++s) {
+                        const uint32_t tl = tq + s * TM_SLOT + HC * half;
+                        const float* bl = bias + layer * TC_N;
+                        if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 10 * (layer + 1) + 1);
+                        wait_d(s);
+                        if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 10 * (layer + 1) + 2);
+                        uint32_t d0[16], d1[4];
+                        tmem_ld16(tl + TM_D, d0);
+                        tmem_ld4(tl + TM_D + 16, d1);
+                        tc_wait_ld();
+                        split_store16<true>(d0, bl, tl + TM_AHI, tl + TM_ALO);
+                        split_store4<true>(d1, bl + 16, tl + TM_AHI + 16, tl + TM_ALO + 16);
+                        publish(s);
+                        if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 10 * (layer + 1) + 3);
+                    }
+                }
             }
-            if (pend_i >= 0) pool_block(pend_i, pend_m);
         }
+        item = bars->next_item;  // written by thread 0 before the barriers of the x-tile load: visible to every thread
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == W_EPI) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int NSLOT, int NT>
+template <int NT>
 static int launch_tc(const PredictParams& prm, cudaStream_t st) {
-    constexpr size_t smem = (size_t)SmemPlan<NSLOT, NT>::total;
+    constexpr size_t smem = (size_t)SmemPlan<NT>::total;
     static_assert(smem <= 227 * 1024, "tensor-core tile does not fit in shared memory");
-    constexpr int threads = (((NT + 3) & ~3) + 4 * NSLOT) * 32;
+    constexpr int threads = (EW + NISS + NT) * 32;
     static PerDeviceOnce attr_done;
     if (attr_done.need()) {
-        BNN_CUDA(cudaFuncSetAttribute(predict_tc_kernel<NSLOT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BNN_CUDA(cudaFuncSetAttribute(predict_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    int n_sms = 0;
-    {
-        int dev = 0;
-        BNN_CUDA(cudaGetDevice(&dev));
-        BNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int n_sms = 0, dev = 0;
+    BNN_CUDA(cudaGetDevice(&dev));
+    BNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = (prm.N + SYS - 1) / SYS;
     BNN_REQUIRE(tiles < (1ll << 24), BNN_E_ARG, "too many system tiles for one launch (%lld)", (long long)tiles);
-    // Split each tile's units into `chunks` items so that the item count is close to a multiple of the SM count
-    // (static round-robin over persistent CTAs) while items stay long enough to amortise the x-tile load.
+    // Split each tile's units into `chunks` items so that the item count is close to a multiple of the SM count (items
+    // of one launch take the same time, so also a dynamic hand-out ends in a partial wave) while items stay long
+    // enough to amortise the x-tile load.
     int64_t max_chunks = prm.U >= 64 ? prm.U / 32 : 1;
     if (max_chunks > 64) max_chunks = 64;
     int best = 1;
@@ -351,7 +401,17 @@ static int launch_tc(const PredictParams& prm, cudaStream_t st) {
     }
     const int64_t items = tiles * best;
     const int grid = (int)(items < n_sms ? items : n_sms);
-    predict_tc_kernel<NSLOT, NT><<<grid, threads, smem, st>>>(prm, (int)tiles, best);
+    unsigned int* counter = nullptr;
+    {   // a zeroed work counter per launch, from a small per-device pool used round-robin (launches in flight on
+        // different streams never share one unless more than 64 are outstanding on the device)
+        static unsigned int* pool[64] = {nullptr};
+        static unsigned long long next = 0;
+        const int d = dev & 63;
+        if (!pool[d]) BNN_CUDA(cudaMalloc(&pool[d], 64 * sizeof(unsigned int)));
+        counter = pool[d] + (__atomic_fetch_add(&next, 1ull, __ATOMIC_RELAXED) & 63);
+        BNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    }
+    predict_tc_kernel<NT><<<grid, threads, smem, st>>>(prm, (int)tiles, best, counter);
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }

@@ -55,6 +55,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 
+// 4 / 2 consecutive columns per thread (column split of a slot between two warps of a lane quadrant)
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+}
+
 // ---- descriptors ------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major, no swizzle (canonical layout, units of 16 bytes:
 // ((8,n),2):((1,SBO),LBO) -- 8 rows of one core matrix are 16 B apart, 8-row groups SBO apart,

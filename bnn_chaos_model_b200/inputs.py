@@ -29,7 +29,7 @@ def data_setup_kernel(mass_array: torch.Tensor, cur_tseries: torch.Tensor, ssX=N
     scale = torch.as_tensor(np.asarray(SSX_SCALE if ssX is None else ssX.scale_), dtype=torch.float64, device=ts.device)
     N, T, _ = ts.shape
     x = torch.empty((N, T, 41), device=ts.device, dtype=torch.float32)
-    with torch.cuda.device(ts.device):
+    with torch.cuda.device(ts.device), _lib.nvtx("bnn:K6 pack_inputs"):
         _lib.check(lib.bnn_pack_inputs(_lib.ptr(ts), _lib.ptr(ms), _lib.ptr(mean), _lib.ptr(scale), N, T, _lib.ptr(x),
                                        _lib.current_stream_ptr()), "bnn_pack_inputs")
     return x

@@ -105,7 +105,7 @@ class MultiSWAG:
         M, d = self.w_avg.shape
         U = n_units if n_units is not None else M * samples_per_model
         P = lib.bnn_packed_param_count(cfg)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx("bnn:K1 swag_sample"):
             theta = torch.empty((U, d), device=self.device)
             thp = torch.empty((U, P), device=self.device)
             um = None
@@ -131,7 +131,7 @@ class MultiSWAG:
         if thp is None:
             _, thp = self.sample_thetas(samples_per_model, seed, scale)
         U, N = thp.shape[0], x.shape[0]
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx("bnn:K2 predict"):
             out = torch.empty((N, U, 2) if system_major else (U, N, 2), device=self.device)
             if N == 0:  # an empty shard (fewer system groups than ranks)
                 return out
@@ -144,11 +144,15 @@ class MultiSWAG:
         return out
 
     def predict_sharded(self, x_local: torch.Tensor, n_total: int, samples_per_model: int, seed: int = 0,
-                        scale: float = 0.5, group=None, gather: bool = True):
+                        scale: float = 0.5, group=None, gather: bool = True, overlap_chunks: int = 1):
         """Systems are block-partitioned over ranks (``shard_range``); every rank evaluates all
         units on its shard (system-major output, one contiguous send buffer) and ONE all_gather
         over NCCL assembles [N_total, M*S, 2].  No other collective: the path is embarrassingly
-        parallel."""
+        parallel.
+
+        ``overlap_chunks`` > 1 (equal shards only): the shard is evaluated in that many system chunks (cut at the
+        kernel's system granule: bit-identical) and the gather of chunk k runs on NCCL's stream under the predictive
+        kernel of chunk k+1 -- the collective is the same bytes in ``overlap_chunks`` pieces, hidden except for the last."""
         import torch.distributed as dist
 
         world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -156,10 +160,31 @@ class MultiSWAG:
         granule = self.system_granule(x_local.shape[1])
         lo, hi = shard_range(n_total, rank, world, granule)
         assert x_local.shape[0] == hi - lo, (x_local.shape, lo, hi)
-        local = self.predict(x_local, samples_per_model, seed, scale, system_offset=lo, system_major=True)
-        if not gather or world == 1:
-            return local
-        return gather_system_shards(local, n_total, group, granule)
+        n_loc = hi - lo
+        equal = all(shard_range(n_total, r, world, granule)[1] - shard_range(n_total, r, world, granule)[0] == n_loc
+                    for r in range(world))
+        if not gather or world == 1 or overlap_chunks <= 1 or not equal or n_loc < overlap_chunks * granule:
+            local = self.predict(x_local, samples_per_model, seed, scale, system_offset=lo, system_major=True)
+            if not gather or world == 1:
+                return local
+            return gather_system_shards(local, n_total, group, granule)
+        with torch.cuda.device(self.device):
+            _, thp = self.sample_thetas(samples_per_model, seed, scale)
+            U = thp.shape[0]
+            per = -(-n_loc // overlap_chunks)
+            per = -(-per // granule) * granule
+            bounds = [(a, min(a + per, n_loc)) for a in range(0, n_loc, per)]
+            full = torch.empty((world, n_loc, U, 2), device=self.device)
+            works, keep = [], []
+            for a, b in bounds:
+                part = self.predict(x_local[a:b], samples_per_model, seed, scale, system_offset=lo + a, system_major=True, thp=thp)
+                recv = torch.empty((world, b - a, U, 2), device=self.device)
+                works.append((dist.all_gather_into_tensor(recv.view(world * (b - a), U, 2), part, group=group, async_op=True), a, b, recv))
+                keep.append(part)
+            for w, a, b, recv in works:
+                w.wait()
+                full[:, a:b] = recv
+        return full.view(n_total, U, 2)
 
     def predict_host(self, x_host: torch.Tensor, samples_per_model: int, seed: int = 0, scale: float = 0.5,
                      out_host: Optional[torch.Tensor] = None, n_chunks=(0.04, 0.48, 0.48), system_offset: int = 0):

@@ -23,7 +23,7 @@ def sample_instability(pred: torch.Tensor, seed: int = 0, row_offset: int = 0, l
     t = torch.empty((rows, U), device=pred.device, dtype=torch.float32)
     if rows == 0:
         return t
-    with torch.cuda.device(pred.device):
+    with torch.cuda.device(pred.device), _lib.nvtx("bnn:K7 sample_instability"):
         _lib.check(lib.bnn_sample_instability(_lib.ptr(pred), rows, U, int(seed), int(row_offset), float(left), int(nsamp),
                                               _lib.ptr(t), _lib.current_stream_ptr()), "bnn_sample_instability")
     return t
@@ -41,7 +41,7 @@ def summarize_instability(t: torch.Tensor, pred: torch.Tensor, n_trios: int = 1)
     stats = torch.empty((N, 8), device=t.device, dtype=torch.float32)
     if N == 0:
         return stats
-    with torch.cuda.device(t.device):
+    with torch.cuda.device(t.device), _lib.nvtx("bnn:K7 summarize_instability"):
         _lib.check(lib.bnn_summarize_instability(_lib.ptr(t), _lib.ptr(pred), N, int(n_trios), U, _lib.ptr(stats),
                                                  _lib.current_stream_ptr()), "bnn_summarize_instability")
     return stats

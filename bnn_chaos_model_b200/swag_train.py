@@ -93,7 +93,7 @@ class MultiSeedSWAGTrainer:
         cfg = self.models[0].config(self.X.shape[1])
         hp = TrainHParams(lr=self.step_lr() if lr is None else float(lr), first_step=int(self.first_step), apply_update=1,
                           **self.step_hparams())
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx("bnn:K4 train_step"):
             nbytes = lib.bnn_train_workspace_bytes(cfg, B, self.S)
             if self._ws is None or self._ws.numel() * 4 < nbytes:
                 self._ws = torch.empty((nbytes + 3) // 4, device=self.device, dtype=torch.float32)
@@ -179,7 +179,7 @@ class MultiSeedSWAGTrainer:
         """aggregate_model (:763-785) for every seed."""
         lib = _lib.load()
         d = self.theta.shape[1]
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx("bnn:K5 swag_collect"):
             _lib.check(
                 lib.bnn_swag_collect(_lib.ptr(self.theta), d, self.S, self.K, _lib.ptr(self.w_avg), _lib.ptr(self.w2_avg),
                                      _lib.ptr(self.pre_D), _lib.ptr(self.n_models), _lib.ptr(self.n_cols),
