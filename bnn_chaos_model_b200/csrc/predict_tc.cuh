@@ -40,7 +40,7 @@ constexpr int N_BLOCKS = MT * 4;  // 32-row blocks per tile
 constexpr int REC_FLOATS = N_BLOCKS * 2 * L * 2;  // [block][segment][col][mean, M2]
 constexpr int FB_PITCH = 12;                     // latent rows staged for the pooling: 32 rows x 12 columns per epilogue warp
 constexpr int FB_FLOATS = 32 * FB_PITCH;
-constexpr int TAIL_SCRATCH = 640;                // sA[5*41] + sB[5*41] + eS[5*40] floats per tail warp
+constexpr int TAIL_SCRATCH = 4 * 208;            // per tail pair: eS[5*40] | sum[5*41] | sB[5*41] | sC[5*41] (208-float areas)
 constexpr int HEAD_FLOATS = S2 * HP + HP + H * HP + HP + 2 * H + 4 + S2;  // PackedLayout V0p .. lv_sum: one contiguous block
 constexpr int NREC = 4;                          // depth of the block-record ring (units the epilogue may run ahead of the tails)
 constexpr int N_SLOT = 4;                        // TMEM slots = jobs in flight (2 per team)
@@ -50,7 +50,8 @@ struct Bars {
     uint64_t unit_done[NREC], rec_free[NREC];          // record ring slot i % NREC: written by the epilogue / read by the tail
     uint64_t d_ready[N_SLOT];                          // tcgen05.commit of the slot's current layer
     uint64_t a_ready[N_SLOT];                          // the team's 8 epilogue warps: A of the slot's next layer is in place
-    uint64_t h_full[4];                                // tail warp t: the head block of its next unit landed in its buffer
+    uint64_t h_full[2];                                // head warp j: the head block of its next unit landed in its buffer
+    uint64_t sum_full[2], sum_free[2];                 // tail pair j: summary statistics written by the stats warp / consumed
     uint32_t tmem_base;
     int next_item;                                     // dynamic work distribution: the item this CTA runs next
 };
@@ -199,40 +200,41 @@ __device__ __forceinline__ void issue_layer(uint32_t ts, uint32_t bh_addr, uint3
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void head_layer_s(const float* __restrict__ sin_, const float* __restrict__ ws,
                                              const float* __restrict__ bs, int p, int q, float* __restrict__ sout) {
-    float acc[10];
+    // packed fp32x2 FMAs: 5 instead of 10 per k; (w[2j], w[2j+1]) pairs are adjacent in the padded row
+    u64 acc[5];
     const float* bq = bs + q * GC;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) acc[i] = bq[i];
+    for (int j = 0; j < 5; ++j) acc[j] = pack2(bq[2 * j], bq[2 * j + 1]);
     const float* wq = ws + q * GC;
 #pragma unroll 4
     for (int k = 0; k < H; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(wq + k * HP);
-        const float4 b = *reinterpret_cast<const float4*>(wq + k * HP + 4);
-        const float2 c = *reinterpret_cast<const float2*>(wq + k * HP + 8);
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(wq + k * HP);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(wq + k * HP + 4);
+        const u64 c = *reinterpret_cast<const u64*>(wq + k * HP + 8);
         const float sv = sin_[p * 41 + k];
-        acc[0] = fmaf(sv, a.x, acc[0]); acc[1] = fmaf(sv, a.y, acc[1]);
-        acc[2] = fmaf(sv, a.z, acc[2]); acc[3] = fmaf(sv, a.w, acc[3]);
-        acc[4] = fmaf(sv, b.x, acc[4]); acc[5] = fmaf(sv, b.y, acc[5]);
-        acc[6] = fmaf(sv, b.z, acc[6]); acc[7] = fmaf(sv, b.w, acc[7]);
-        acc[8] = fmaf(sv, c.x, acc[8]); acc[9] = fmaf(sv, c.y, acc[9]);
+        const u64 s2 = pack2(sv, sv);
+        acc[0] = fma2(s2, a.x, acc[0]);
+        acc[1] = fma2(s2, a.y, acc[1]);
+        acc[2] = fma2(s2, b.x, acc[2]);
+        acc[3] = fma2(s2, b.y, acc[3]);
+        acc[4] = fma2(s2, c, acc[4]);
     }
 #pragma unroll
-    for (int i = 0; i < 10; ++i) sout[p * 41 + q * 10 + i] = relu_nan(acc[i]);
+    for (int j = 0; j < 5; ++j) {
+        float lo, hi;
+        unpack2(acc[j], lo, hi);
+        sout[p * 41 + q * 10 + 2 * j] = relu_nan(lo);
+        sout[p * 41 + q * 10 + 2 * j + 1] = relu_nan(hi);
+    }
 }
 
-__device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, const float* __restrict__ hw,
-                                             const PackedLayout& pl, const float* __restrict__ eps_u,
-                                             const float* __restrict__ eps_sum_u, float* __restrict__ summary_u,
-                                             uint64_t seed, uint32_t gunit, int64_t gsys0, int64_t n0, int n_valid,
-                                             const HeadConsts& hc, float* __restrict__ scratch,
-                                             float* __restrict__ out_unit, int64_t out_sys_stride) {
+// ---- tail of one unit, in two stages run by two different warps (a "stats" warp and a "head" warp; lane = p*4+q,
+// p = system slot, q = 10 hidden / 5 latent columns) ----
+// Stage 1a: the unit's 5 x 40 standard normals for the sampled summary statistics (explicit eps, or Philox keyed on the
+// global unit / system index) -> eS.  Independent of the records: runs BEFORE the stats warp waits for them.
+__device__ __forceinline__ void tail_draw_eps(const float* __restrict__ eps_u, uint64_t seed, uint32_t gunit, int64_t gsys0,
+                                              int64_t n0, int n_valid, float* __restrict__ eS) {
     const int lane = threadIdx.x & 31;
-    const int p = min(lane >> 2, SYS - 1), q = lane & 3;  // lanes of p >= SYS shadow system SYS-1 (stores are masked)
-    const bool live = (lane >> 2) < SYS;
-    float* sA = scratch;
-    float* sB = scratch + SYS * 41;
-    float* eS = scratch + ((2 * SYS * 41 + 3) & ~3);  // float4 stores of the Philox draws: 16-byte aligned
-
     if (eps_u) {
         for (int idx = lane; idx < SYS * S2; idx += 32) {
             const int s = idx / S2, j = idx % S2;
@@ -247,12 +249,20 @@ __device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, cons
         }
     }
     __syncwarp();
+}
 
+// Stage 1b: merge the 4 block records of every system (exact two-level mean / M2), sampled summary statistics
+// (:416-430) -> sum[SYS][41] in shared memory.  lv_sum_g: the unit's summary_noise_logvar in GLOBAL memory (noisy forward).
+__device__ __forceinline__ void tail_stats(const float* __restrict__ rec, const float* __restrict__ eS,
+                                           const float* __restrict__ lv_sum_g, const float* __restrict__ eps_sum_u,
+                                           float* __restrict__ summary_u, int64_t n0, int n_valid, float* __restrict__ sum) {
+    const int lane = threadIdx.x & 31;
+    const int p = min(lane >> 2, SYS - 1), q = lane & 3;  // lanes of p >= SYS shadow system SYS-1 (stores are masked)
+    const bool live = (lane >> 2) < SYS;
     const SysRec sr = sys_records(p);
     const float Tf = (float)T_FIXED, Tm1 = (float)(T_FIXED - 1);
-    // (code size matters here: the tail is a few thousand instructions that two warps walk once per unit, next to 16
-    // epilogue warps whose loop has to stay in the 32 KB instruction cache -- the loops below are deliberately not unrolled)
-#pragma unroll 1
+    // unrolled: the five columns' sqrt / divide chains interleave
+#pragma unroll
     for (int i = 0; i < 5; ++i) {
         const int col = q * 5 + i;
         float2 r[4];
@@ -282,26 +292,38 @@ __device__ __forceinline__ void tail_unit_tc(const float* __restrict__ rec, cons
             if (eps_sum_u) {
                 const float e0 = __ldg(eps_sum_u + (n0 + p) * S2 + col);
                 const float e1 = __ldg(eps_sum_u + (n0 + p) * S2 + L + col);
-                s_mu = __fadd_rn(s_mu, __fmul_rn(e0, expf(__fdiv_rn(hw[pl.lv_sum - pl.V0p + col], 2.0f))));
-                s_sd = __fadd_rn(s_sd, __fmul_rn(e1, expf(__fdiv_rn(hw[pl.lv_sum - pl.V0p + L + col], 2.0f))));
+                s_mu = __fadd_rn(s_mu, __fmul_rn(e0, expf(__fdiv_rn(__ldg(lv_sum_g + col), 2.0f))));
+                s_sd = __fadd_rn(s_sd, __fmul_rn(e1, expf(__fdiv_rn(__ldg(lv_sum_g + L + col), 2.0f))));
             }
         }
         if (live) {
-            sA[p * 41 + col] = s_mu;
-            sA[p * 41 + L + col] = s_sd;
+            sum[p * 41 + col] = s_mu;
+            sum[p * 41 + L + col] = s_sd;
         }
     }
     __syncwarp();
-#pragma unroll 1
-    for (int layer = 0; layer < 2; ++layer) {
-        if (live) head_layer_s(layer ? sB : sA, hw + (layer ? pl.V1p - pl.V0p : 0), hw + (layer ? pl.c1p : pl.c0p) - pl.V0p, p, q, layer ? sA : sB);
-        __syncwarp();
-    }
+}
+
+// Stage 2: regress_nn + soft_clamp (:301-321, :432-442) from sum[SYS][41]; hw: the unit's head block in shared memory;
+// sB, sC: [SYS][41] scratch of the head warp.  `after_layer1()` runs once `sum` has been consumed.
+template <class F>
+__device__ __forceinline__ void tail_head(const float* __restrict__ sum, const float* __restrict__ hw, const PackedLayout& pl,
+                                          int64_t n0, int n_valid, const HeadConsts& hc, float* __restrict__ sB,
+                                          float* __restrict__ sC, float* __restrict__ out_unit, int64_t out_sys_stride,
+                                          F after_layer1) {
+    const int lane = threadIdx.x & 31;
+    const int p = min(lane >> 2, SYS - 1), q = lane & 3;
+    const bool live = (lane >> 2) < SYS;
+    if (live) head_layer_s(sum, hw, hw + pl.c0p - pl.V0p, p, q, sB);
+    __syncwarp();
+    after_layer1();
+    if (live) head_layer_s(sB, hw + pl.V1p - pl.V0p, hw + pl.c1p - pl.V0p, p, q, sC);
+    __syncwarp();
     float o0 = 0.f, o1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const int k = q * 10 + i;
-        const float r = sA[p * 41 + k];
+        const float r = sC[p * 41 + k];
         o0 = fmaf(r, hw[pl.V2 - pl.V0p + k], o0);
         o1 = fmaf(r, hw[pl.V2 - pl.V0p + H + k], o1);
     }
