@@ -113,35 +113,41 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
 }
 
 // (d + bias) -> ReLU -> hi/lo of 4 consecutive columns; bias: 16-byte aligned shared memory, same for every lane.
-// hi = v rounded to nearest tf32 (two integer instructions), lo = v - hi exactly.
+// hi = v rounded to the 11 significant bits of tf32, lo = v - hi exactly, on the FMA pipe with packed fp32x2 instructions:
+//   c = fma(v, 8192, v) = RN(8193 v);  hi = fma(v, -8192, c) = c - 8192 v (exact: Veltkamp's splitting with the exact
+//   product 8192 v in place of the rounded c - v, so every step is one FMA and no contraction can change a value);
+//   lo = v - hi (exact).  Three instructions per PAIR of values.  The integer form ((bits + 0x1000) & ~0x1fff: IADD3 +
+// LOP3 per value) kept the half-rate ALU pipe at 62 % of its peak -- the busiest pipe of the kernel, `math pipe throttle`
+// the top stall of the epilogue.  Inf becomes NaN (Inf - Inf), as it did in lo = v - hi before.
 template <bool EPI>
 __device__ __forceinline__ void split_group4(const uint32_t* __restrict__ d, const float* __restrict__ bias,
                                              uint32_t* __restrict__ h, uint32_t* __restrict__ l) {
-    // packed fp32x2 adds (Blackwell FADD2): one issue slot for two bias adds / two lo = v - hi subtractions
     u64 v01 = pack2(__uint_as_float(d[0]), __uint_as_float(d[1]));
     u64 v23 = pack2(__uint_as_float(d[2]), __uint_as_float(d[3]));
     if (EPI) {
         const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bias);
         v01 = add2(v01, b.x);
         v23 = add2(v23, b.y);
-    }
-    float v[4];
-    unpack2(v01, v[0], v[1]);
-    unpack2(v23, v[2], v[3]);
-    uint32_t hb[4];
+        float v[4];
+        unpack2(v01, v[0], v[1]);
+        unpack2(v23, v[2], v[3]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        if (EPI) v[u] = relu_nan(v[u]);
-        hb[u] = (__float_as_uint(v[u]) + 0x1000u) & 0xFFFFE000u;
-        h[u] = hb[u];
+        for (int u = 0; u < 4; ++u) v[u] = relu_nan(v[u]);
+        v01 = pack2(v[0], v[1]);
+        v23 = pack2(v[2], v[3]);
     }
-    const u64 l01 = sub2(pack2(v[0], v[1]), pack2(__uint_as_float(hb[0]), __uint_as_float(hb[1])));
-    const u64 l23 = sub2(pack2(v[2], v[3]), pack2(__uint_as_float(hb[2]), __uint_as_float(hb[3])));
-    float lo[4];
-    unpack2(l01, lo[0], lo[1]);
-    unpack2(l23, lo[2], lo[3]);
+    const u64 K = pack2(8192.0f, 8192.0f), Kn = pack2(-8192.0f, -8192.0f);
+    const u64 h01 = fma2(v01, Kn, fma2(v01, K, v01)), h23 = fma2(v23, Kn, fma2(v23, K, v23));
+    const u64 l01 = sub2(v01, h01), l23 = sub2(v23, h23);
+    float f[4];
+    unpack2(h01, f[0], f[1]);
+    unpack2(h23, f[2], f[3]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) l[u] = __float_as_uint(lo[u]);
+    for (int u = 0; u < 4; ++u) h[u] = __float_as_uint(f[u]);
+    unpack2(l01, f[0], f[1]);
+    unpack2(l23, f[2], f[3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) l[u] = __float_as_uint(f[u]);
 }
 template <bool EPI>
 __device__ __forceinline__ void split_store16(const uint32_t (&d)[16], const float* __restrict__ bias, uint32_t t_hi,

@@ -21,7 +21,7 @@ from oracle import restatement as R  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 U = int(sys.argv[2]) if len(sys.argv) > 2 else 500
-variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["v2c12", "tc4n4"]
+variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["v2", "tc"]
 dev = torch.device("cuda:0")
 z, hp, sp = load_stats(0)
 m = S.SWAGModel(hp).init_params(sp).to(dev)
@@ -51,7 +51,8 @@ rows = {}
 torch.backends.cuda.matmul.allow_tf32 = False
 rows["torch_fp32"] = torch_eval(torch.float32).double()
 for v in variants:
-    os.environ["BNN_PREDICT_VARIANT"] = v
+    from bnn_chaos_model_b200 import _lib
+    _lib.check(_lib.load().bnn_set_predict_variant({"auto": 0, "tc": 1, "v2": 2, "v1": 3}[v]))
     out, _ = m._predict(x, thp, eps, cfg=cfg)
     rows[v] = out.double()
 qs = torch.tensor([0.5, 0.99, 0.9999, 0.999999], device=dev, dtype=torch.float64)
