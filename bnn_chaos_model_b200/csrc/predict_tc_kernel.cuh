@@ -299,10 +299,11 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                     s0 += in0[i] ? pr : 0.f;
                     s1 += in1[i] ? pr : 0.f;
                 }
-                // (count reciprocals: the counts are 4, 8, ..., 32; a record's mean within 1 ulp of the quotient is all the
-                // exact two-level merge of the tail needs, and the divide was ~60 cycles on the warp's critical path)
-                const float mean0 = gather3(s0) * __frcp_rn((float)max(e0, 1));
-                const float mean1 = two ? gather3(s1) * __frcp_rn((float)(nvalid - split)) : 0.f;
+                // power-of-two counts (the 11 full blocks of 32 rows) multiply by the exact reciprocal: same value as the
+                // quotient without the ~60-cycle divide on the warp's critical path
+                const float S0 = gather3(s0);
+                const float mean0 = (e0 & (e0 - 1)) == 0 ? S0 * __frcp_rn((float)e0) : S0 / (float)e0;
+                const float mean1 = two ? gather3(s1) / (float)(nvalid - split) : 0.f;
                 float q0 = 0.f, q1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
