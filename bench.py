@@ -354,7 +354,7 @@ def gpu_train_arm(dev, n_seeds=4, B=2000, n_data=8000, iters=10):
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the predict kernel from the committed ncu --set full summary
     (profiles/), per launch of this same workload; None when the summary is absent."""
-    path = os.path.join(ROOT, "profiles", "r1_predict_tc4n4_ncu.txt")
+    path = os.path.join(ROOT, "profiles", "r2_predict_tc_ncu.txt")
     try:
         tot = 0.0
         for line in open(path):
@@ -417,7 +417,17 @@ def run_ours(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     k_ev = []  # (start, end) of the predict kernel alone, per timed step
 
+    pend = [None]
+
     def step(i, timed):
+        if world > 1:
+            # one launch for the shard; its predictions are gathered under the NEXT step's kernel -- copy-engine writes
+            # into the peers' symmetric-memory buffers (NCCL all_gather with --nccl-gather) -- and this call returns the
+            # completed result of the previous step; flush() below completes the last one inside the timed region
+            p = ens.predict_sharded(x, n_total, n_samp, seed=i, peer_push=not args.nccl_gather, defer=True)
+            out = pend[0].result() if pend[0] is not None else None
+            pend[0] = p
+            return out
         _, thp = ens.sample_thetas(n_samp, seed=i)  # K1 + pack (2 launches)
         if timed:
             a, b = ev(), ev()
@@ -426,8 +436,11 @@ def run_ours(args):
         if timed:
             b.record(stream)
             k_ev.append((a, b))
-        if world > 1:
-            out = gather_system_shards(out, n_total)
+        return out
+
+    def flush(out):
+        if pend[0] is not None:
+            out, pend[0] = pend[0].result(), None
         return out
 
     def sync():
@@ -437,6 +450,7 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step(i, False)
+    flush(None)
     sync()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -444,10 +458,21 @@ def run_ours(args):
     t0.record(stream)
     for i in range(args.steps):
         out = step(args.warmup + i, True)
+    out = flush(out)
     t1.record(stream)
     sync()
     clk = clocks.stop()
     ms = t0.elapsed_time(t1) / args.steps
+    if not k_ev:  # N > 1: the predictive kernel alone (whole shard, one launch), outside the timed region
+        _, thp = ens.sample_thetas(n_samp, seed=0)
+        for rep in range(3):
+            a, b = ev(), ev()
+            a.record(stream)
+            ens.predict(x, n_samp, seed=0, system_offset=lo, system_major=True, thp=thp)
+            b.record(stream)
+            if rep:
+                k_ev.append((a, b))
+        torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
     t = torch.tensor([ms, k_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -535,7 +560,10 @@ def run_ours(args):
             "config": {
                 "workload": f"BASELINE configs[1] per GPU: 1 SWAG model (v50 seed-0 statistics), {n_sys} synthetic "
                             f"3-planet systems x {n_samp} weight samples, T=100, F=41 (31 live columns)",
-                "systems_per_gpu": n_sys, "samples": n_samp, "parallelism": f"systems sharded x{world}, one all_gather",
+                "systems_per_gpu": n_sys, "samples": n_samp,
+                "parallelism": f"systems sharded x{world}, one gather of the predictions" + (
+                    "" if world == 1 else " that travels under the next step's kernel (" + (
+                        "NCCL all_gather" if args.nccl_gather else "copy-engine writes into the peers' symmetric-memory buffers") + ")"),
                 "l2": "inputs (164 MB x + 38 MB theta + 80 MB out per step) exceed the 126 MB L2; fresh theta every step",
             },
             "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": xh.numel() * 4,
@@ -554,10 +582,10 @@ def run_ours(args):
                                         "terms x padding K 31->32, N 40->48 / 20->32, rows 500->512)",
                          "measured_ffma_peak_tflops": ffma, "kernel_ms": k_ms,
                          "flop_per_eval": FLOP_PER_EVAL_V50, "traffic": ncu_traffic_bytes(),
-                         "traffic_source": "profiles/r1_predict_tc4n4_ncu.txt (ncu --set full, same workload, per launch); "
+                         "traffic_source": "profiles/r2_predict_tc_ncu.txt (ncu --set full, same workload, per launch); "
                                            "algorithmic HBM bytes per launch: 0.32e9",
                          "note": "north_star's roofline for this kernel is the FP32 CUDA-core FMA peak; the kernel runs the "
-                                 "feature MLP as 3xTF32 on tcgen05 (tensor pipe active 33 %, profiles/)"},
+                                 "feature MLP as 3xTF32 on tcgen05 (ncu: tensor pipe active 42 %, issue slots 70 %, profiles/r2_predict_tc_ncu.txt)"},
             "cpu_baseline": cb,
             "train": train,
             "train_30_seeds": train30,
@@ -578,6 +606,7 @@ def main():
     ap.add_argument("--samples", type=int, default=N_SAMP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather the prediction chunks with NCCL instead of peer-memory writes")
     ap.add_argument("--no-extra", action="store_true", help="skip the BASELINE configs[2] / configs[4] sections")
     ap.add_argument("--config3-systems", type=int, default=100_000, help="total systems of the configs[2] section")
     ap.add_argument("--config5-systems", type=int, default=125_000, help="5-planet systems per GPU of the configs[4] section")

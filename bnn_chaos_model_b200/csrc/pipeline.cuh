@@ -80,4 +80,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// global -> L2 prefetch of a contiguous run (no destination, no completion tracking): bytes a multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 }  // namespace bnn

@@ -59,6 +59,106 @@ def gather_system_shards(local: torch.Tensor, n_total: int, group=None, granule:
     return full
 
 
+class ChunkedSystemGather:
+    """The same collective as ``gather_system_shards`` (equal shards), issued in pieces: ``add(part, a, b)`` starts the
+    all_gather of the local systems [a, b) of every rank asynchronously (on the backend's own stream, so it runs under
+    whatever the caller launches next -- the predictive kernel of the following chunk); ``finish()`` waits for all
+    pieces and returns [world * n_local, ...].  The bytes on the wire are the same as for one all_gather."""
+
+    def __init__(self, n_local: int, tail, world: int, device, dtype=torch.float32, group=None):
+        self.full = torch.empty((world, n_local) + tuple(tail), device=device, dtype=dtype)
+        self.world, self.group, self.tail, self.pending = world, group, tuple(tail), []
+
+    def add(self, part: torch.Tensor, a: int, b: int):
+        import torch.distributed as dist
+
+        assert part.shape == (b - a,) + self.tail, (part.shape, a, b)
+        recv = torch.empty((self.world, b - a) + self.tail, device=part.device, dtype=part.dtype)
+        work = dist.all_gather_into_tensor(recv.view((self.world * (b - a),) + self.tail), part.contiguous(), group=self.group,
+                                           async_op=True)
+        self.pending.append((work, a, b, recv, part))   # `part` is kept alive until the collective has read it
+
+    def finish(self) -> torch.Tensor:
+        for work, a, b, recv, _ in self.pending:
+            work.wait()
+            self.full[:, a:b] = recv
+        self.pending = []
+        return self.full.view((self.full.shape[0] * self.full.shape[1],) + self.tail)
+
+
+class PeerPushGather:
+    """The gather as peer-memory writes over NVLink / NVSwitch instead of an NCCL kernel: the [world, n_local, ...]
+    result lives in a symmetric-memory buffer (``torch.distributed._symmetric_memory``: every rank maps every peer's
+    buffer), and ``add(part, a, b)`` copies the local systems [a, b) into slot [rank, a:b] of EVERY rank's buffer with
+    plain device-to-device copies on a side stream.  Those run on the copy engines, so they overlap a persistent
+    predictive kernel, which leaves no SM for an NCCL kernel to start on (one 768-thread CTA with 225 kB of shared
+    memory per SM).  ``finish()`` joins the side stream and runs the device-side barrier after which every peer's
+    writes into this rank's buffer are visible.  Two buffers alternate between gathers (``begin()`` picks the next one),
+    so a gather may be finished AFTER the next one has begun -- the previous batch's predictions travel under the next
+    batch's kernel -- and a returned tensor stays valid until the second ``begin()`` after its own."""
+
+    _cache = {}
+
+    def __init__(self, n_local: int, tail, world: int, rank: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank, self.tail = world, rank, tuple(tail)
+        grp = group if group is not None else dist.group.WORLD
+        self.bufs, self.hdls, self.peers = [], [], []
+        for _ in range(2):
+            buf = symm_mem.empty((world, n_local) + self.tail, device=device, dtype=torch.float32)
+            hdl = symm_mem.rendezvous(buf, group=grp)
+            self.bufs.append(buf)
+            self.hdls.append(hdl)
+            self.peers.append([hdl.get_buffer(r, buf.shape, buf.dtype) for r in range(world)])
+        self.stream = torch.cuda.Stream(device)
+        self.turn = 1
+
+    @classmethod
+    def get(cls, n_local, tail, world, rank, device, group=None):
+        key = (n_local, tuple(tail), world, rank, str(device), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(n_local, tail, world, rank, device, group)
+        return cls._cache[key]
+
+    def begin(self) -> int:
+        self.turn ^= 1
+        return self.turn
+
+    def add(self, part: torch.Tensor, a: int, b: int, turn: Optional[int] = None):
+        turn = self.turn if turn is None else turn
+        cur = torch.cuda.current_stream(part.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            for k in range(self.world):
+                r = (self.rank + k) % self.world          # own slot first, then the peers round-robin
+                self.peers[turn][r][self.rank, a:b].copy_(part, non_blocking=True)
+            part.record_stream(self.stream)
+
+    def finish(self, turn: Optional[int] = None) -> torch.Tensor:
+        turn = self.turn if turn is None else turn
+        cur = torch.cuda.current_stream(self.bufs[0].device)
+        cur.wait_stream(self.stream)
+        self.hdls[turn].barrier()
+        out = self.bufs[turn]
+        return out.view((out.shape[0] * out.shape[1],) + self.tail)
+
+
+class PendingGather:
+    """A gather that has been started; ``result()`` completes it (idempotent)."""
+
+    def __init__(self, fn):
+        self._fn, self._out = fn, None
+
+    def result(self) -> torch.Tensor:
+        if self._fn is not None:
+            self._out, self._fn = self._fn(), None
+        return self._out
+
+
 class MultiSWAG:
     """An ensemble of SWAG posteriors (the reference's ``swag_ensemble`` list) resident on one GPU."""
 
@@ -144,7 +244,8 @@ class MultiSWAG:
         return out
 
     def predict_sharded(self, x_local: torch.Tensor, n_total: int, samples_per_model: int, seed: int = 0,
-                        scale: float = 0.5, group=None, gather: bool = True, overlap_chunks: int = 1):
+                        scale: float = 0.5, group=None, gather: bool = True, overlap_chunks: int = 1,
+                        peer_push: bool = False, defer: bool = False):
         """Systems are block-partitioned over ranks (``shard_range``); every rank evaluates all
         units on its shard (system-major output, one contiguous send buffer) and ONE all_gather
         over NCCL assembles [N_total, M*S, 2].  No other collective: the path is embarrassingly
@@ -152,7 +253,12 @@ class MultiSWAG:
 
         ``overlap_chunks`` > 1 (equal shards only): the shard is evaluated in that many system chunks (cut at the
         kernel's system granule: bit-identical) and the gather of chunk k runs on NCCL's stream under the predictive
-        kernel of chunk k+1 -- the collective is the same bytes in ``overlap_chunks`` pieces, hidden except for the last."""
+        kernel of chunk k+1 -- the collective is the same bytes in ``overlap_chunks`` pieces, hidden except for the last.
+        ``peer_push``: move the pieces with copy-engine writes into the peers' symmetric-memory buffers (``PeerPushGather``)
+        instead of NCCL kernels, which cannot start while the persistent predictive kernel holds every SM; the returned
+        tensor is then a view of a buffer that is overwritten two calls later.
+        ``defer``: return a ``PendingGather`` whose ``result()`` the caller takes AFTER launching its next batch, so that
+        this batch's predictions travel under the next batch's kernel (with ``peer_push`` the copies need no SM)."""
         import torch.distributed as dist
 
         world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -163,28 +269,39 @@ class MultiSWAG:
         n_loc = hi - lo
         equal = all(shard_range(n_total, r, world, granule)[1] - shard_range(n_total, r, world, granule)[0] == n_loc
                     for r in range(world))
-        if not gather or world == 1 or overlap_chunks <= 1 or not equal or n_loc < overlap_chunks * granule:
+        chunked = (overlap_chunks > 1 or peer_push or defer) and equal and n_loc >= max(1, overlap_chunks) * granule
+        if not gather or world == 1 or not chunked:
             local = self.predict(x_local, samples_per_model, seed, scale, system_offset=lo, system_major=True)
             if not gather or world == 1:
-                return local
-            return gather_system_shards(local, n_total, group, granule)
+                return PendingGather(lambda: local) if defer else local
+            full = gather_system_shards(local, n_total, group, granule)
+            return PendingGather(lambda: full) if defer else full
+        overlap_chunks = max(1, overlap_chunks)
         with torch.cuda.device(self.device):
             _, thp = self.sample_thetas(samples_per_model, seed, scale)
-            U = thp.shape[0]
             per = -(-n_loc // overlap_chunks)
             per = -(-per // granule) * granule
-            bounds = [(a, min(a + per, n_loc)) for a in range(0, n_loc, per)]
-            full = torch.empty((world, n_loc, U, 2), device=self.device)
-            works, keep = [], []
-            for a, b in bounds:
+            gather, turn = None, None
+            if peer_push:
+                try:
+                    gather = PeerPushGather.get(n_loc, (thp.shape[0], 2), world, rank, self.device, group)
+                    turn = gather.begin()
+                except Exception as e:  # symmetric memory unavailable (driver / fabric): the NCCL pieces below
+                    import warnings
+
+                    warnings.warn(f"peer-memory gather unavailable ({type(e).__name__}: {e}); using NCCL all_gather pieces")
+                    gather = None
+            if gather is None:
+                gather = ChunkedSystemGather(n_loc, (thp.shape[0], 2), world, self.device, group=group)
+            for a in range(0, n_loc, per):
+                b = min(a + per, n_loc)
                 part = self.predict(x_local[a:b], samples_per_model, seed, scale, system_offset=lo + a, system_major=True, thp=thp)
-                recv = torch.empty((world, b - a, U, 2), device=self.device)
-                works.append((dist.all_gather_into_tensor(recv.view(world * (b - a), U, 2), part, group=group, async_op=True), a, b, recv))
-                keep.append(part)
-            for w, a, b, recv in works:
-                w.wait()
-                full[:, a:b] = recv
-        return full.view(n_total, U, 2)
+                if turn is None:
+                    gather.add(part, a, b)
+                else:
+                    gather.add(part, a, b, turn)
+            pending = PendingGather((lambda: gather.finish()) if turn is None else (lambda: gather.finish(turn)))
+            return pending if defer else pending.result()
 
     def predict_host(self, x_host: torch.Tensor, samples_per_model: int, seed: int = 0, scale: float = 0.5,
                      out_host: Optional[torch.Tensor] = None, n_chunks=(0.04, 0.48, 0.48), system_offset: int = 0):

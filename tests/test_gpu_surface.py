@@ -286,6 +286,21 @@ for N, S_ in ((60, 4), (43, 3)):          # equal shards, then a ragged split (p
     full = ens.predict_sharded(x[lo:hi].to(dev), N, S_, seed=9)
     single = ens.predict(x.to(dev), S_, seed=9, system_major=True)
     assert full.shape == (N, 2 * S_, 2) and torch.equal(full, single), (rank, N, "predict_sharded")
+    if N == 60:   # equal shards: the gather in pieces under the next chunk's kernel, NCCL and peer-memory writes, twice
+        for peer in (False, True, True):   # (the second peer-push call uses the other of its two buffers)
+            import warnings
+            with warnings.catch_warnings(record=True) as w:
+                warnings.simplefilter("always")
+                got = ens.predict_sharded(x[lo:hi].to(dev), N, S_, seed=9, overlap_chunks=3, peer_push=peer)
+            if peer and w:
+                print("peer-memory gather fell back to NCCL:", w[0].message)
+            assert got.shape == (N, 2 * S_, 2) and torch.equal(got, single), (rank, N, "overlapped gather", peer)
+        # deferred: batch k's predictions travel under batch k+1's kernel and are taken afterwards
+        single10 = ens.predict(x.to(dev), S_, seed=10, system_major=True)
+        for peer in (False, True):
+            p1 = ens.predict_sharded(x[lo:hi].to(dev), N, S_, seed=9, peer_push=peer, defer=True)
+            p2 = ens.predict_sharded(x[lo:hi].to(dev), N, S_, seed=10, peer_push=peer, defer=True)
+            assert torch.equal(p1.result(), single) and torch.equal(p2.result(), single10), (rank, "deferred gather", peer)
     # 5-planet style rows (3 trios per system): only [N, 8] is gathered
     Ns = N // 3
     import math

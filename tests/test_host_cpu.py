@@ -197,9 +197,16 @@ def test_shard_range_partitions():
 _GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, {root!r})
-from bnn_chaos_model_b200.multiswag import gather_system_shards, shard_range
+from bnn_chaos_model_b200.multiswag import ChunkedSystemGather, gather_system_shards, shard_range
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
+# the same gather in asynchronous pieces (what predict_sharded(overlap_chunks > 1) runs under the next chunk's kernel)
+n_loc, tail = 7, (3, 2)
+ref = torch.arange(2 * n_loc * 6, dtype=torch.float32).reshape(2 * n_loc, 3, 2)
+cg = ChunkedSystemGather(n_loc, tail, 2, torch.device("cpu"))
+for a, b in ((0, 3), (3, 6), (6, 7)):
+    cg.add(ref[rank * n_loc + a: rank * n_loc + b].clone(), a, b)
+assert torch.equal(cg.finish(), ref), rank
 for n_total, g in ((10, 1), (11, 1), (23, 5), (4, 5)):
     lo, hi = shard_range(n_total, rank, 2, g)
     full_ref = torch.arange(n_total * 3 * 2, dtype=torch.float32).reshape(n_total, 3, 2)
