@@ -60,7 +60,8 @@ constexpr int HP = 4 * GC;   // padded hidden row: 4 lane groups x 12
 constexpr int MAXF = 64;     // zero_mask is 64 bits wide
 constexpr int SYS_TILE = 8;  // systems per CTA tile
 // tensor-core path: padded GEMM shapes (N is a multiple of 16; the biases are added in the epilogue)
-constexpr int TC_K1 = 32;   // layer-1 K: up to 32 live inputs
+constexpr int TC_K1 = 32;   // layer-1 K: up to 32 live inputs (the v50 flag set has 31)
+constexpr int TC_K1W = 48;  // layer-1 K of the "wide" variant: 33..48 live inputs (all 41 columns: noisy forward, other flag sets)
 constexpr int TC_K2 = 40;   // layer-2/3 K: 40 hidden
 constexpr int TC_N = 48;    // layer-1/2 N: 40 hidden + 8 zero rows
 constexpr int TC_N3 = 32;   // layer-3 N: 20 latent + 12 zero rows
@@ -102,9 +103,9 @@ struct PackedLayout {
     int kin;  // live input columns
     int W0p, b0p, W1p, b1p, W2p, b2p, feat_floats;
     int V0p, c0p, V1p, c1p, V2, c2, lv_sum, lv_in;
-    // tensor-core section (only when kin <= 32): tf32 hi/lo splits of the feature weights as tcgen05 B
+    // tensor-core section (only when kin <= 48): tf32 hi/lo splits of the feature weights as tcgen05 B
     // operands, canonical K-major chunk layout [k/4][n][4], then the fp32 bias block.
-    int tc_ok, B1h, B1l, B2h, B2l, B3h, B3l, Bb, P;
+    int tc_ok, tc_k1, B1h, B1l, B2h, B2l, B3h, B3l, Bb, P;
     __host__ __device__ explicit PackedLayout(int kin_, int F_ = MAXF) : kin(kin_) {
         int o = 0;
         W0p = o; o += kin * HP;
@@ -122,9 +123,10 @@ struct PackedLayout {
         c2 = o; o += 4;
         lv_sum = o; o += S2;                 // summary_noise_logvar (noisy forward only)
         lv_in = o; o += (F_ + 3) & ~3;       // input_noise_logvar, all F columns
-        tc_ok = (kin <= TC_K1) ? 1 : 0;
-        B1h = o; o += tc_ok ? TC_K1 * TC_N * 1 : 0;     // [32/4][48][4]
-        B1l = o; o += tc_ok ? TC_K1 * TC_N * 1 : 0;
+        tc_ok = (kin <= TC_K1W) ? 1 : 0;
+        tc_k1 = kin <= TC_K1 ? TC_K1 : TC_K1W;
+        B1h = o; o += tc_ok ? tc_k1 * TC_N * 1 : 0;     // [K1/4][48][4]
+        B1l = o; o += tc_ok ? tc_k1 * TC_N * 1 : 0;
         B2h = o; o += tc_ok ? TC_K2 * TC_N : 0;          // [40/4][48][4]
         B2l = o; o += tc_ok ? TC_K2 * TC_N : 0;
         B3h = o; o += tc_ok ? TC_K2 * TC_N3 : 0;         // [40/4][32][4]

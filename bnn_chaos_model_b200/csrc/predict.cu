@@ -27,6 +27,7 @@ struct PredictParams {
     int64_t out_unit_stride, out_sys_stride;  // in floats
     uint64_t seed;
     int F, kin;
+    int8_t wide_col[16];  // tensor-core kernel, wide variant: X column of the live inputs 32..47 (-1: none)
     int units_per_cta;
     HeadConsts hc;
     ColMap cm;
@@ -264,7 +265,8 @@ extern "C" {
 
 size_t bnn_predict_workspace_bytes(const bnn_model_config*, int64_t, int64_t) { return 0; }
 
-// Kernel selection.  Default (0): the tensor-core kernel (tcgen05, 3xTF32) when T = 100 and at most 32 live input columns,
+// Kernel selection.  Default (0): the tensor-core kernel (tcgen05, 3xTF32) when T = 100 (at most 32 live input columns: one
+// layer-1 pass; 33..48, e.g. all 41 columns of the noisy forward: K = 40 + a second 8-column pass),
 // else the FP32 FFMA2 kernels (v2: warp-specialised with a TMA weight ring, when its tile fits in shared memory; else
 // v1).  A process-wide override for tests / tools: bnn_set_predict_variant() (diagnostic header), initialised ONCE from
 // the environment variable BNN_PREDICT_VARIANT = tc | v2 | v1; likewise the unit chunk (BNN_PREDICT_UNIT_CHUNK).
@@ -301,7 +303,7 @@ int bnn_set_predict_unit_chunk(int64_t units) {
 static bool tc_selected(const bnn_model_config* cfg, int kin) {
     const int v = predict_variant();
     if (v != PV_AUTO && v != PV_TC) return false;
-    return cfg->n_times == bnn::tc::T_FIXED && kin <= bnn::TC_K1;
+    return cfg->n_times == bnn::tc::T_FIXED && kin <= bnn::TC_K1W;
 }
 
 int32_t bnn_predict_system_granule(const bnn_model_config* cfg) {
@@ -343,6 +345,7 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     prm.kin = lc.n;
     for (int c = 0; c < MAXF; ++c) prm.cm.inv[c] = -1;
     for (int k = 0; k < lc.n; ++k) prm.cm.inv[(int)lc.col[k]] = (int8_t)k;
+    for (int j = 0; j < 16; ++j) prm.wide_col[j] = (32 + j < lc.n) ? lc.col[32 + j] : (int8_t)-1;
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
 #ifdef BNN_TC_TIMELINE
     {   // diagnostic build only (make TIMELINE=1): device pointer (decimal) to 8*512 int64 of clock stamps
@@ -385,7 +388,8 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     const int T = cfg->n_times;
     cudaStream_t st = (cudaStream_t)stream;
     auto fits = [&](int nc) { return v2_smem_bytes(prm.kin, prm.F, T, nc) <= 227 * 1024; };
-    if (tc::tc_fits(prm, T) && (force == PV_AUTO || force == PV_TC)) rc_launch = tc::launch_tc<2>(prm, st);
+    if (tc::tc_fits(prm, T) && (force == PV_AUTO || force == PV_TC))
+        rc_launch = prm.kin <= TC_K1 ? tc::launch_tc<2, false>(prm, st) : tc::launch_tc<2, true>(prm, st);
     else if (force == PV_V1) rc_launch = launch_v1<8>(prm, T, st);
     else if (fits(12)) rc_launch = launch_v2<12>(prm, T, st);
     else if (fits(8)) rc_launch = launch_v2<8>(prm, T, st);

@@ -42,7 +42,7 @@ constexpr int FB_PITCH = 12;                     // latent rows staged for the p
 constexpr int FB_FLOATS = 32 * FB_PITCH;
 constexpr int TAIL_SCRATCH = 4 * 208;            // per tail pair: eS[5*40] | sum[5*41] | sB[5*41] | sC[5*41] (208-float areas)
 constexpr int HEAD_FLOATS = S2 * HP + HP + H * HP + HP + 2 * H + 4 + S2;  // PackedLayout V0p .. lv_sum: one contiguous block
-constexpr int NREC = 4;                          // depth of the block-record ring (units the epilogue may run ahead of the tails)
+constexpr int NREC = 4;                          // depth of the block-record ring (units the epilogue may run ahead of the tails; 2 in the wide variant)
 constexpr int N_SLOT = 4;                        // TMEM slots = jobs in flight (2 per team)
 
 struct Bars {
@@ -99,10 +99,11 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
     auto put = [&](int idx, float v) {
         const int row = idx / F, c = idx - row * F;
         const int k = cm.inv[c];
-        if (k >= 0)
-            xs[xs_index(row, k)] = v;
-        else if (!isfinite(v))
+        if (k >= 0) {
+            if (k < 32) xs[xs_index(row, k)] = v;   // live columns 32.. (wide variant) are read from L2 by the stage
+        } else if (!isfinite(v)) {
             poison[row] = 1;
+        }
     };
     if ((total & 3) == 0 && ((n0 * (int64_t)T_FIXED * F) & 3) == 0) {
         // the tile is one contiguous, 16-byte aligned run of X: 16-byte loads, all of a thread's loads in flight before
@@ -181,6 +182,15 @@ __device__ __forceinline__ void split_store16(const uint32_t (&d)[16], const flo
     tmem_st16(t_lo, l);
 }
 template <bool EPI>
+__device__ __forceinline__ void split_store8(const uint32_t (&d)[8], const float* __restrict__ bias, uint32_t t_hi,
+                                             uint32_t t_lo) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int g4 = 0; g4 < 2; ++g4) split_group4<EPI>(&d[4 * g4], bias + 4 * g4, &h[4 * g4], &l[4 * g4]);
+    tmem_st8(t_hi, h);
+    tmem_st8(t_lo, l);
+}
+template <bool EPI>
 __device__ __forceinline__ void split_store4(const uint32_t (&d)[4], const float* __restrict__ bias, uint32_t t_hi,
                                              uint32_t t_lo) {
     uint32_t h[4], l[4];
@@ -198,11 +208,13 @@ __device__ __forceinline__ uint64_t bdesc(uint32_t base_addr, int N, int ks) {
     return smem_desc_kmajor(base_addr + (uint32_t)ks * 2u * chunk, chunk, 128u);
 }
 
-template <int N, int KS>
-__device__ __forceinline__ void issue_layer(uint32_t ts, uint32_t bh_addr, uint32_t bl_addr) {
+// K steps [KS0, KS1) of one layer; FIRST: the very first MMA overwrites D (no accumulate)
+template <int N, int KS0, int KS1, bool FIRST>
+__device__ __forceinline__ void issue_layer_part(uint32_t ts, uint32_t bh_addr, uint32_t bl_addr) {
     constexpr uint32_t idesc = idesc_tf32(128, N);
     const uint32_t d = ts + TM_D, ahi = ts + TM_AHI, alo = ts + TM_ALO;
-    // descriptors advance by two 16-byte K chunks (2*N*16 bytes -> 2*N in the 16-byte address field) per K = 8 step
+    // descriptors advance by two 16-byte K chunks (2*N*16 bytes -> 2*N in the 16-byte address field) per K = 8 step;
+    // A always starts at column 0 of the slot's A regions (a second pass restages its columns there)
     const uint64_t dh = bdesc(bh_addr, N, 0), dl = bdesc(bl_addr, N, 0);
     constexpr uint64_t step = 2ull * N;
     // called by a whole (converged) warp; one elected lane issues a_lo w_hi + a_hi w_lo + a_hi w_hi, the two
@@ -211,13 +223,17 @@ __device__ __forceinline__ void issue_layer(uint32_t ts, uint32_t bh_addr, uint3
     // accumulating the corrections after the main term, tools/accuracy_study.py)
     if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, alo + 8 * ks, dh + ks * step, idesc, ks > 0);
+        for (int ks = KS0; ks < KS1; ++ks) mma_tf32_ts(d, alo + 8 * (ks - KS0), dh + ks * step, idesc, !FIRST || ks > KS0);
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dl + ks * step, idesc, true);
+        for (int ks = KS0; ks < KS1; ++ks) mma_tf32_ts(d, ahi + 8 * (ks - KS0), dl + ks * step, idesc, true);
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, ahi + 8 * ks, dh + ks * step, idesc, true);
+        for (int ks = KS0; ks < KS1; ++ks) mma_tf32_ts(d, ahi + 8 * (ks - KS0), dh + ks * step, idesc, true);
     }
     __syncwarp();
+}
+template <int N, int KS>
+__device__ __forceinline__ void issue_layer(uint32_t ts, uint32_t bh_addr, uint32_t bl_addr) {
+    issue_layer_part<N, 0, KS, true>(ts, bh_addr, bl_addr);
 }
 
 // ---------------------------------------------------------------------------------------

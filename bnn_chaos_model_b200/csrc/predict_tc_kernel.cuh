@@ -19,25 +19,33 @@ namespace tc {
 #define TC_STAMP(role, code) do { } while (0)
 #endif
 
-constexpr int B_FLOATS = 2 * (TC_K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3) + TC_BIAS;  // hi + lo B operands + biases
-constexpr int B_BYTES = B_FLOATS * 4;
-constexpr int O_B1H = 0, O_B1L = O_B1H + TC_K1 * TC_N * 4, O_B2H = O_B1L + TC_K1 * TC_N * 4,
-              O_B2L = O_B2H + TC_K2 * TC_N * 4, O_B3H = O_B2L + TC_K2 * TC_N * 4, O_B3L = O_B3H + TC_K2 * TC_N3 * 4,
-              O_BIAS = O_B3L + TC_K2 * TC_N3 * 4;  // byte offsets inside a ring slot
+// One unit's ring slot: hi + lo B operands of the three layers + the bias block.  K1 = 32 (one layer-1 pass) or, in the
+// WIDE variant (33..48 live inputs), 48: a K = 40 pass over A's 40 columns, then a second pass of 8 restaged columns.
+template <bool WIDE>
+struct RingPlan {
+    static constexpr int K1 = WIDE ? TC_K1W : TC_K1;
+    static constexpr int B_FLOATS = 2 * (K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3) + TC_BIAS;
+    static constexpr int B_BYTES = B_FLOATS * 4;
+    static constexpr int O_B1H = 0, O_B1L = O_B1H + K1 * TC_N * 4, O_B2H = O_B1L + K1 * TC_N * 4,
+                         O_B2L = O_B2H + TC_K2 * TC_N * 4, O_B3H = O_B2L + TC_K2 * TC_N * 4,
+                         O_B3L = O_B3H + TC_K2 * TC_N3 * 4, O_BIAS = O_B3L + TC_K2 * TC_N3 * 4;  // byte offsets in a slot
+    static constexpr int NREC = WIDE ? 2 : tc::NREC;   // record-ring depth: the wide ring takes the shared memory of two slots
+};
 
 constexpr int N_TEAM = 2;              // epilogue teams; team t owns TMEM slots 2t and 2t+1 and the M tiles t and t+2
 constexpr int EW = 8 * N_TEAM;         // epilogue warps
 constexpr int NISS = N_SLOT;           // MMA-issuing warps (one per TMEM slot)
 constexpr int HC = 20;                 // hidden columns per epilogue warp (the two warps of a lane quadrant split 40)
 
-template <int NT>
+template <int NT, bool WIDE>
 struct SmemPlan {
+    using RG = RingPlan<WIDE>;
     // byte offsets inside dynamic shared memory
     static constexpr int xs = 0;                                   // ROWS*32 floats
     static constexpr int ring = xs + ROWS * 32 * 4;                // 2 slots of B operands + biases
-    static constexpr int fb = ring + 2 * B_BYTES;                  // per epilogue warp: 32 rows x 12 latent columns
+    static constexpr int fb = ring + 2 * RG::B_BYTES;                  // per epilogue warp: 32 rows x 12 latent columns
     static constexpr int rec = fb + EW * FB_FLOATS * 4;            // NREC slots of block records
-    static constexpr int scratch = rec + NREC * REC_FLOATS * 4;    // per tail warp
+    static constexpr int scratch = rec + RG::NREC * REC_FLOATS * 4;    // per tail warp
     static constexpr int head = (scratch + NT * TAIL_SCRATCH * 4 + 127) & ~127;  // per tail warp: head block of its unit
     static constexpr int head_bytes = (HEAD_FLOATS * 4 + 127) & ~127;
     static constexpr int bars = head + NT * head_bytes;
@@ -58,13 +66,16 @@ struct SmemPlan {
 //                   unit's block records and samples the summary statistics (then the record slot is free again); the head
 //                   warp runs regress_nn from its bulk-copied weight block.  The tails are 12 % of the instructions, but as
 //                   two warps they were the kernel's critical path (ncu: 100 % busy at 0.14 IPC behind 16 epilogue warps)
-template <int NT>
+template <int NT, bool WIDE>
 __global__ void __launch_bounds__((EW + NISS + 2 * NT) * 32, 1)
 predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, unsigned int* __restrict__ item_counter) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
-    static_assert(NT >= 1 && NT <= 2 && NT <= NREC && MT == 2 * N_TEAM && N_SLOT == 2 * N_TEAM && N_SLOT * TM_SLOT <= 512, "role layout");
+    static_assert(NT >= 1 && NT <= 2 && NT <= RingPlan<WIDE>::NREC && MT == 2 * N_TEAM && N_SLOT == 2 * N_TEAM && N_SLOT * TM_SLOT <= 512, "role layout");
     const PackedLayout pl(prm.kin, prm.F);
-    using Plan = SmemPlan<NT>;
+    using Plan = SmemPlan<NT, WIDE>;
+    using RG = RingPlan<WIDE>;
+    constexpr int NREC = RG::NREC, B_FLOATS = RG::B_FLOATS, B_BYTES = RG::B_BYTES, O_B1H = RG::O_B1H, O_B1L = RG::O_B1L,
+                  O_B2H = RG::O_B2H, O_B2L = RG::O_B2L, O_B3H = RG::O_B3H, O_B3L = RG::O_B3L, O_BIAS = RG::O_BIAS;
     float* xs = reinterpret_cast<float*>(smem_tc + Plan::xs);
     float* ring = reinterpret_cast<float*>(smem_tc + Plan::ring);
     float* fb = reinterpret_cast<float*>(smem_tc + Plan::fb);
@@ -220,9 +231,20 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                     uint32_t wb = ring_addr + (uint32_t)ws * (uint32_t)B_BYTES;
                     uint32_t tsv = tmem + slot * TM_SLOT;
                     asm volatile("" : "+r"(wb), "+r"(tsv));  // keep the descriptors out of loop-invariant hoisting
-                    if (layer == 0)
-                        issue_layer<TC_N, TC_K1 / 8>(tsv, wb + O_B1H, wb + O_B1L);
-                    else if (layer == 1)
+                    if (layer == 0) {
+                        if (WIDE) {
+                            // K = 40 over A's 40 columns, then (after the epilogue warps restaged 8 columns) K steps 5
+                            issue_layer_part<TC_N, 0, 5, true>(tsv, wb + O_B1H, wb + O_B1L);
+                            if (elect_one_sync()) mma_commit(&bars->d_ready[slot]);
+                            __syncwarp();
+                            mbar_wait(&bars->a_ready[slot], pa);
+                            pa ^= 1u;
+                            tc_fence_after();
+                            issue_layer_part<TC_N, 5, 6, false>(tsv, wb + O_B1H, wb + O_B1L);
+                        } else {
+                            issue_layer<TC_N, TC_K1 / 8>(tsv, wb + O_B1H, wb + O_B1L);
+                        }
+                    } else if (layer == 1)
                         issue_layer<TC_N, TC_K2 / 8>(tsv, wb + O_B2H, wb + O_B2L);
                     else
                         issue_layer<TC_N3, TC_K2 / 8>(tsv, wb + O_B3H, wb + O_B3L);
@@ -360,6 +382,27 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                             for (int k = 0; k < 16; ++k) v[k] = 0u;
                         }
                         split_store16<false>(v, nullptr, tl + TM_AHI + 16 * half, tl + TM_ALO + 16 * half);
+                        if (WIDE) {
+                            // live inputs 32..47 of this row from L2 (the x tile was just read by this CTA; they are the same
+                            // for every unit, but 16 more columns of shared memory do not exist): half 0 puts 32..39 behind the
+                            // 32 staged columns (first pass, K = 40); half 1 restages 40..47 into columns 0..7 once the first
+                            // pass has been read by the tensor core
+                            uint32_t w[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int c = prm.wide_col[8 * half + j];
+                                w[j] = (c >= 0 && R < n_valid * T_FIXED) ? __float_as_uint(__ldg(prm.X + (n0 * T_FIXED + R) * (int64_t)prm.F + c)) : 0u;
+                            }
+                            if (half == 0) {
+                                split_store8<false>(w, nullptr, tl + TM_AHI + 32, tl + TM_ALO + 32);
+                                publish(s);
+                                wait_d(s);
+                            } else {
+                                publish(s);
+                                wait_d(s);
+                                split_store8<false>(w, nullptr, tl + TM_AHI, tl + TM_ALO);
+                            }
+                        }
                         publish(s);
                         if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 3);
                     }
@@ -398,14 +441,14 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int NT>
+template <int NT, bool WIDE>
 static int launch_tc(const PredictParams& prm, cudaStream_t st) {
-    constexpr size_t smem = (size_t)SmemPlan<NT>::total;
+    constexpr size_t smem = (size_t)SmemPlan<NT, WIDE>::total;
     static_assert(smem <= 227 * 1024, "tensor-core tile does not fit in shared memory");
     constexpr int threads = (EW + NISS + 2 * NT) * 32;
     static PerDeviceOnce attr_done;
     if (attr_done.need()) {
-        BNN_CUDA(cudaFuncSetAttribute(predict_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BNN_CUDA(cudaFuncSetAttribute((predict_tc_kernel<NT, WIDE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     int n_sms = 0, dev = 0;
     BNN_CUDA(cudaGetDevice(&dev));
@@ -437,7 +480,7 @@ static int launch_tc(const PredictParams& prm, cudaStream_t st) {
         counter = pool[d] + (__atomic_fetch_add(&next, 1ull, __ATOMIC_RELAXED) & 63);
         BNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     }
-    predict_tc_kernel<NT><<<grid, threads, smem, st>>>(prm, (int)tiles, best, counter);
+    predict_tc_kernel<NT, WIDE><<<grid, threads, smem, st>>>(prm, (int)tiles, best, counter);
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }

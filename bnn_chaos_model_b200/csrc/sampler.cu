@@ -148,7 +148,7 @@ __global__ void pack_theta_kernel(const float* __restrict__ theta, int64_t n_uni
         int r, N, nreal, wsrc, kreal, ld;
         bool lo;
         if (i < pl.B2h) {
-            r = i - pl.B1h; N = TC_N; lo = r >= TC_K1 * TC_N; r -= lo ? TC_K1 * TC_N : 0;
+            r = i - pl.B1h; N = TC_N; lo = r >= pl.tc_k1 * TC_N; r -= lo ? pl.tc_k1 * TC_N : 0;
             nreal = H; kreal = pl.kin; wsrc = fl.W0; ld = fl.F;
         } else if (i < pl.B3h) {
             r = i - pl.B2h; N = TC_N; lo = r >= TC_K2 * TC_N; r -= lo ? TC_K2 * TC_N : 0;

@@ -362,6 +362,50 @@ def test_tensor_core_variants_vs_fp32_kernel(dev, predict_variant):
                 assert rel_err(got[ok], want[ok]) < TOL, (v, N, S_, rep)
 
 
+def test_wide_tensor_core_path_all_41_columns(dev, predict_variant):
+    """Flag sets with more than 32 live input columns (here include_mmr / nan / eplusminus = True: 40 live columns; the
+    noisy forward feeds all 41) run the WIDE tensor-core variant (layer 1 as K = 40 + a second 8-column
+    pass): selected by default, equal to the FFMA kernel within the tolerance on ragged sizes with many units per CTA,
+    a NaN system poisoned alone, and equal to the oracle on a small case."""
+    from bnn_chaos_model_b200 import spock_reg_model as S
+
+    models = []
+    for seed in (0, 3):
+        st = swag_stats(seed)
+        hp = dict(st["hparams"], include_mmr=True, include_nan=True, include_eplusminus=True)
+        m = S.SWAGModel(hp).init_params(st["swa_params"]).to(dev)
+        m.w_avg, m.w2_avg, m.pre_D = (torch.from_numpy(st[k]).to(dev) for k in ("w_avg", "w2_avg", "pre_D"))
+        models.append(m)
+    assert 41 - len(models[0].zero_columns()) > 32 and 36 not in models[0].zero_columns()   # (fix_megno still zeroes column 7)
+    ens = MultiSWAG(models, device=dev)
+    assert ens.system_granule() == 5          # = the tensor-core kernel's tile: it is what bnn_predict selects
+    for N, S_ in ((13, 3), (203, 40), (745, 33)):
+        xh = synth.make_systems(N, seed=100 + N)
+        xh[N // 2, 7, 36] = float("nan")      # a live column here: that system's outputs are NaN, nobody else's
+        x = torch.from_numpy(xh).to(dev)
+        _, thp = ens.sample_thetas(S_, seed=N)
+        predict_variant("v1")
+        want = ens.predict(x, S_, seed=N, thp=thp)
+        ok = torch.isfinite(want[:, :, 0])
+        assert not bool(ok[:, N // 2].any()) and bool(ok[:, : N // 2].all())
+        predict_variant("auto")
+        for rep in range(2):
+            got = ens.predict(x, S_, seed=N, thp=thp)
+            assert bool(torch.isnan(got[:, N // 2]).all()), N
+            assert rel_err(got[ok], want[ok]) < TOL, (N, S_, rep)
+    # against the oracle: the dense model's forward with explicit draws
+    m = models[0]
+    m.load(m.w_avg.clone())
+    spec = R.ModelSpec.from_hparams(m.hparams)
+    x = torch.from_numpy(synth.make_systems(23, seed=77))
+    torch.manual_seed(4)
+    out = m.forward(x.to(dev), noisy_val=False).cpu()
+    torch.manual_seed(4)
+    e1 = torch.randn((23, 20), device=dev).cpu(); e2 = torch.randn((23, 20), device=dev).cpu()
+    ref, _ = R.forward(spec, m.flatten().cpu(), x, False, None, e1, e2, None)
+    assert rel_err(out, ref) < TOL
+
+
 def test_predict_host_pipelined_equals_single_launch(dev):
     """Host-buffer entry with chunked H2D / compute / D2H overlap: bit-identical to one device-resident launch."""
     ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(17, dev)], device=dev)

@@ -13,11 +13,13 @@ from bench import FLOP_PER_EVAL_V50, load_stats  # noqa: E402
 from bnn_chaos_model_b200 import spock_reg_model as S, synth  # noqa: E402
 from bnn_chaos_model_b200.multiswag import MultiSWAG  # noqa: E402
 
-variants = sys.argv[1].split(",") if len(sys.argv) > 1 else ["v2c12", "tc4n4", "tc4n3", "tc3n4", "tc2n4"]
+variants = sys.argv[1].split(",") if len(sys.argv) > 1 else ["v2", "tc"]
 n_sys = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
 n_samp = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 dev = torch.device("cuda:0")
 z, hp, sp = load_stats(0)
+if len(sys.argv) > 4 and sys.argv[4] == "dense":   # all 41 input columns live (zero_mask == 0): the wide tensor-core variant
+    hp = dict(hp, include_mmr=True, include_nan=True, include_eplusminus=True)
 m = S.SWAGModel(hp).init_params(sp).to(dev)
 m.w_avg, m.w2_avg, m.pre_D = (torch.from_numpy(z[k]).to(dev) for k in ("w_avg", "w2_avg", "pre_D"))
 ens = MultiSWAG([m], device=dev)
@@ -25,7 +27,8 @@ x = torch.from_numpy(synth.make_systems(n_sys, seed=1)).to(dev)
 _, thp = ens.sample_thetas(n_samp, seed=1)
 ref = None
 for v in variants:
-    os.environ["BNN_PREDICT_VARIANT"] = v
+    from bnn_chaos_model_b200 import _lib
+    _lib.check(_lib.load().bnn_set_predict_variant({"auto": 0, "tc": 1, "v2": 2, "v1": 3}[v]))
     out = ens.predict(x, n_samp, seed=1, thp=thp)
     torch.cuda.synchronize()
     ts = []
