@@ -113,6 +113,7 @@ class PeerPushGather:
             self.hdls.append(hdl)
             self.peers.append([hdl.get_buffer(r, buf.shape, buf.dtype) for r in range(world)])
         self.stream = torch.cuda.Stream(device)
+        self.done = [None, None]   # per buffer: event after the last copy of its current gather
         self.turn = 1
 
     @classmethod
@@ -137,11 +138,14 @@ class PeerPushGather:
                 r = (self.rank + k) % self.world          # own slot first, then the peers round-robin
                 self.peers[turn][r][self.rank, a:b].copy_(part, non_blocking=True)
             part.record_stream(self.stream)
+            self.done[turn] = torch.cuda.Event()
+            self.done[turn].record(self.stream)
 
     def finish(self, turn: Optional[int] = None) -> torch.Tensor:
         turn = self.turn if turn is None else turn
         cur = torch.cuda.current_stream(self.bufs[0].device)
-        cur.wait_stream(self.stream)
+        if self.done[turn] is not None:
+            cur.wait_event(self.done[turn])   # THIS gather's copies only: a later gather's copies may still be in flight
         self.hdls[turn].barrier()
         out = self.bufs[turn]
         return out.view((out.shape[0] * out.shape[1],) + self.tail)
