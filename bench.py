@@ -37,19 +37,21 @@ def load_stats(seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  The query process is started
+    BEFORE the warm-up steps -- its start-up (NVML initialisation) stalls the GPU for a moment on some boxes and used to
+    land in the first timed steps -- and only the samples that arrive between mark_begin() and mark_end() are reported."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
                  str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -58,21 +60,40 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def wait_first(self, timeout=6.0):
+        """Block until the query process has delivered its first sample (its start-up is over)."""
+        t = time.time()
+        while self.proc and not self.rows and time.time() - t < timeout:
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 7]
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        rows = [r for t, r in ok if t0 <= t <= t1 + 0.25]
+        where = "timed region"
+        if not rows and ok:   # region shorter than the sampling period: the sample closest to it
+            rows = [min(ok, key=lambda tr: abs(tr[0] - 0.5 * (t0 + min(t1, t0 + 3600))))[1]]
+            where = "nearest sample to the timed region"
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].startswith("Active") for r in self.rows)]
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].startswith("Active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": where, "reasons": reasons}
 
 
 def cpu_oracle_arm(steps, warmup, n_sys=10000, n_samp=4):
@@ -448,12 +469,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    clocks.wait_first()
     for i in range(args.warmup):
         step(i, False)
     flush(None)
     sync()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark_begin()
     t0, t1 = ev(), ev()
     t0.record(stream)
     for i in range(args.steps):
@@ -461,6 +484,7 @@ def run_ours(args):
     out = flush(out)
     t1.record(stream)
     sync()
+    clocks.mark_end()
     clk = clocks.stop()
     ms = t0.elapsed_time(t1) / args.steps
     if not k_ev:  # N > 1: the predictive kernel alone (whole shard, one launch), outside the timed region
