@@ -105,29 +105,9 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
             poison[row] = 1;
         }
     };
-    if ((total & 3) == 0 && ((n0 * (int64_t)T_FIXED * F) & 3) == 0) {
-        // the tile is one contiguous, 16-byte aligned run of X: 16-byte loads, all of a thread's loads in flight before
-        // the first scatter (an item starts with this load; as scalar dependent rounds it was tens of microseconds of a
-        // cold HBM read per item)
-        const float4* src4 = reinterpret_cast<const float4*>(src);
-        const int nvec = total >> 2;
-        constexpr int MAXV = 4;
-        for (int v0 = threadIdx.x; v0 < nvec; v0 += MAXV * (int)blockDim.x) {
-            float4 q[MAXV];
-#pragma unroll
-            for (int j = 0; j < MAXV; ++j) {
-                const int v = v0 + j * (int)blockDim.x;
-                if (v < nvec) q[j] = __ldg(src4 + v);
-            }
-#pragma unroll
-            for (int j = 0; j < MAXV; ++j) {
-                const int v = v0 + j * (int)blockDim.x;
-                if (v < nvec) { put(4 * v, q[j].x); put(4 * v + 1, q[j].y); put(4 * v + 2, q[j].z); put(4 * v + 3, q[j].w); }
-            }
-        }
-    } else {
-        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) put(idx, __ldg(src + idx));
-    }
+    // (the tile was bulk-prefetched into L2 while the previous item ran, so these scalar rounds are L2 hits; a version with
+    // 16-byte loads and four scattered stores per thread measured 1.6 ms slower per 1e7-eval launch)
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) put(idx, __ldg(src + idx));
     __syncthreads();
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
         if (poison[r]) xs[xs_index(r, 0)] = __int_as_float(0x7fc00000);  // x - mask keeps NaN/Inf as NaN (:452-478)
