@@ -72,6 +72,11 @@ SIGNATURES = {
         [_CFG, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32,
          c_f32p, c_f32p, C.c_void_p, C.c_void_p],
     ),
+    "bnn_predict_strided": (
+        C.c_int,
+        [_CFG, c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64,
+         C.c_int64, c_f32p, c_f32p, C.c_void_p, C.c_void_p],
+    ),
     "bnn_add_input_noise": (C.c_int, [_CFG, c_f32p, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     "bnn_predict_instability": (C.c_int, [_CFG, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_void_p]),
     "bnn_multiswag_host_scratch_bytes": (C.c_size_t, [_CFG, C.c_int64, C.c_int64]),
@@ -116,6 +121,11 @@ DIAG_SIGNATURES = {
     "bnn_tc_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bnn_train_timeline": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int32]),
     "bnn_mma_sync_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_f32p, C.c_void_p]),
+    "bnn_swag_sample_unfused": (
+        C.c_int,
+        [_CFG, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, c_i32p, C.c_int64, C.c_int64, C.c_int32, C.c_float,
+         C.c_uint64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p],
+    ),
     "bnn_set_train_variant": (C.c_int, [C.c_int32]),
     "bnn_set_summary_variant": (C.c_int, [C.c_int32]),
     "bnn_set_predict_variant": (C.c_int, [C.c_int32]),

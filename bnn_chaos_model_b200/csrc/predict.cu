@@ -316,6 +316,15 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
                 int64_t n_units, const float* d_eps, const float* d_eps_sum, uint64_t seed, int64_t unit_offset,
                 int64_t system_offset, int32_t out_system_major, float* d_out, float* d_summary_out,
                 void* d_workspace, void* stream) {
+    return bnn_predict_strided(cfg, d_x, n_systems, d_theta_packed, n_units, d_eps, d_eps_sum, seed, unit_offset,
+                               system_offset, out_system_major ? 2 : n_systems * 2, out_system_major ? n_units * 2 : 2,
+                               d_out, d_summary_out, d_workspace, stream);
+}
+
+int bnn_predict_strided(const bnn_model_config* cfg, const float* d_x, int64_t n_systems, const float* d_theta_packed,
+                        int64_t n_units, const float* d_eps, const float* d_eps_sum, uint64_t seed, int64_t unit_offset,
+                        int64_t system_offset, int64_t out_unit_stride, int64_t out_system_stride, float* d_out,
+                        float* d_summary_out, void* d_workspace, void* stream) {
     using namespace bnn;
     (void)d_workspace;
     int rc = validate_config(cfg);
@@ -324,8 +333,11 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     BNN_REQUIRE(d_x && d_theta_packed && d_out, BNN_E_ARG, "bnn_predict: null pointer");
     BNN_REQUIRE(n_systems > 0 && n_units > 0, BNN_E_ARG, "bnn_predict: empty problem (N=%lld, U=%lld)",
                 (long long)n_systems, (long long)n_units);
-    BNN_REQUIRE(aligned16(d_theta_packed) && aligned16(d_out) && aligned16(d_x), BNN_E_ALIGN,
-                "bnn_predict: pointers must be 16-byte aligned");
+    BNN_REQUIRE(aligned16(d_theta_packed) && aligned16(d_x), BNN_E_ALIGN, "bnn_predict: pointers must be 16-byte aligned");
+    // every (mu, std) pair is one 8-byte store
+    BNN_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 7u) == 0 && out_unit_stride >= 2 && out_system_stride >= 2 &&
+                    out_unit_stride % 2 == 0 && out_system_stride % 2 == 0,
+                BNN_E_ALIGN, "bnn_predict: d_out must be 8-byte aligned and the output strides even (>= 2 floats)");
     PredictParams prm;
     prm.X = d_x;
     prm.thp = d_theta_packed;
@@ -337,8 +349,8 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
     prm.U = n_units;
     prm.unit_offset = unit_offset;
     prm.system_offset = system_offset;
-    prm.out_unit_stride = out_system_major ? 2 : n_systems * 2;
-    prm.out_sys_stride = out_system_major ? n_units * 2 : 2;
+    prm.out_unit_stride = out_unit_stride;
+    prm.out_sys_stride = out_system_stride;
     prm.seed = seed;
     prm.F = cfg->n_features;
     LiveCols lc = live_columns(cfg);

@@ -78,14 +78,14 @@ swag_sample_kernel(const float* __restrict__ w_avg, const float* __restrict__ w2
     }
 }
 
-// theta [U,d] (flatten order) -> theta_packed [U,P].  One thread per packed float.
-__global__ void pack_theta_kernel(const float* __restrict__ theta, int64_t n_units, FlatLayout fl, PackedLayout pl,
-                                  LiveCols lc, float* __restrict__ packed) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= n_units * pl.P) return;
-    const int64_t u = idx / pl.P;
-    const int i = (int)(idx % pl.P);
-    const float* th = theta + u * fl.d;
+// Where packed float i of a unit comes from: index into the flat (flatten()-order) vector and how it is transformed.
+enum PackKind : int { PK_ZERO = 0, PK_COPY = 1, PK_TF32_HI = 2, PK_TF32_LO = 3 };
+struct PackSrc {
+    int src;
+    int kind;
+};
+
+__device__ __forceinline__ PackSrc pack_source(int i, const FlatLayout& fl, const PackedLayout& pl, const LiveCols& lc) {
     int src = -1;
     auto grp = [](int c, int& q, int& ii) { q = c / GC; ii = c % GC; };
     int q, ii;
@@ -134,16 +134,12 @@ __global__ void pack_theta_kernel(const float* __restrict__ theta, int64_t n_uni
     } else if (i < pl.B1h) {
         int r = i - pl.lv_in;
         if (r < fl.F) src = fl.lv_in + r;
+    } else if (i >= pl.Bb) {  // fp32 bias block b0[48] | b1[48] | b2[32]
+        const int r = i - pl.Bb;
+        if (r < TC_N) { if (r < H) src = fl.b0 + r; }
+        else if (r < 2 * TC_N) { if (r - TC_N < H) src = fl.b1 + r - TC_N; }
+        else if (r - 2 * TC_N < L) src = fl.b2 + r - 2 * TC_N;
     } else {
-        if (i >= pl.Bb) {  // fp32 bias block b0[48] | b1[48] | b2[32]
-            const int r = i - pl.Bb;
-            float b = 0.f;
-            if (r < TC_N) { if (r < H) b = th[fl.b0 + r]; }
-            else if (r < 2 * TC_N) { if (r - TC_N < H) b = th[fl.b1 + r - TC_N]; }
-            else if (r - 2 * TC_N < L) b = th[fl.b2 + r - 2 * TC_N];
-            packed[idx] = b;
-            return;
-        }
         // tensor-core B operands: element (n, k) of a [N][K] matrix sits at ((k/4)*N + n)*4 + k%4
         int r, N, nreal, wsrc, kreal, ld;
         bool lo;
@@ -158,13 +154,168 @@ __global__ void pack_theta_kernel(const float* __restrict__ theta, int64_t n_uni
             nreal = L; kreal = H; wsrc = fl.W2; ld = H;
         }
         const int chunk = r / (N * 4), n = (r / 4) % N, k = chunk * 4 + (r & 3);
-        float w = 0.f;
-        if (n < nreal && k < kreal) w = th[wsrc + n * ld + ((wsrc == fl.W0) ? (int)lc.col[k] : k)];
-        const float hi = tf32_rna(w);
-        packed[idx] = lo ? tf32_rna(w - hi) : hi;  // lo pre-rounded: the tensor core would truncate it
-        return;
+        if (n < nreal && k < kreal)
+            return PackSrc{wsrc + n * ld + ((wsrc == fl.W0) ? (int)lc.col[k] : k), lo ? PK_TF32_LO : PK_TF32_HI};
+        return PackSrc{-1, PK_ZERO};
     }
-    packed[idx] = src >= 0 ? th[src] : 0.f;
+    return PackSrc{src, src >= 0 ? PK_COPY : PK_ZERO};
+}
+
+__device__ __forceinline__ float pack_value(const float* th, PackSrc ps) {
+    if (ps.kind == PK_ZERO) return 0.f;
+    const float w = th[ps.src];
+    if (ps.kind == PK_COPY) return w;
+    const float hi = tf32_rna(w);
+    return ps.kind == PK_TF32_HI ? hi : tf32_rna(w - hi);  // lo pre-rounded: the tensor core would truncate it
+}
+
+// theta [U,d] (flatten order) -> theta_packed [U,P].  One thread per packed float.
+__global__ void pack_theta_kernel(const float* __restrict__ theta, int64_t n_units, FlatLayout fl, PackedLayout pl,
+                                  LiveCols lc, float* __restrict__ packed) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n_units * pl.P) return;
+    const int64_t u = idx / pl.P;
+    const int i = (int)(idx % pl.P);
+    packed[idx] = pack_value(theta + u * fl.d, pack_source(i, fl, pl, lc));
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 fused: sample G units per CTA and write their packed layout directly (and the flat vector when asked).
+//   phase A: the CTA walks theta in chunks of 512 elements; the chunk's 512 x K block of pre_D is brought into shared
+//            memory once with coalesced 16-byte loads (the per-thread rows of the unfused kernel were 32 distinct
+//            lines per warp load: the L1 tag stage, not the arithmetic, set its 0.57 ms per 1000 units) and shared by
+//            the CTA's G units; thread (g, quad) draws one Philox block = 4 elements of unit g; theta lands in shared
+//            memory (30 kB per unit);
+//   phase B: packed index i -> flat source (pack_source, computed once per i) -> one coalesced store per unit.
+// Arithmetic identical to swag_sample_kernel + pack_theta_kernel (bit-equal results; tests/test_gpu_predict.py).
+// ---------------------------------------------------------------------------------------
+constexpr int SP_QUADS = 128;                     // element quads per chunk (one Philox block each)
+constexpr int SP_CHUNK = SP_QUADS * 4;            // 512 flat elements per chunk
+
+// floats per quad of pre_D rows in the shared-memory tile: 4 K + V with V = the widest vector K allows (4 | 2 | 1), so
+// that the stride between two lanes' quads is an odd number of V-float words: conflict-free V-wide reads
+static inline int sample_pack_vec(int K) { return (K & 3) == 0 ? 4 : ((K & 1) == 0 ? 2 : 1); }
+static inline size_t sample_pack_smem_bytes(int G, int d, int K) {
+    return ((size_t)G * ((d + 3) & ~3) + (size_t)SP_QUADS * (4 * K + sample_pack_vec(K)) + (size_t)G * MAXK) * sizeof(float);
+}
+
+template <int V> struct VecT;
+template <> struct VecT<4> { typedef float4 type; };
+template <> struct VecT<2> { typedef float2 type; };
+template <> struct VecT<1> { typedef float type; };
+
+template <int G, int V>
+__global__ void __launch_bounds__(SP_QUADS * G)
+swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict__ w2_avg,
+                        const float* __restrict__ pre_D, int d, int K, const int32_t* __restrict__ unit_model,
+                        int64_t unit_offset, int samples_per_model, int n_models, float c1, float scale, float c2div,
+                        uint64_t seed, const float* __restrict__ z1, const float* __restrict__ z2, int64_t n_units,
+                        float* __restrict__ theta, float* __restrict__ packed, FlatLayout fl, PackedLayout pl,
+                        LiveCols lc) {
+    typedef typename VecT<V>::type vec_t;
+    extern __shared__ __align__(16) float sp_smem[];
+    const int dpad = (d + 3) & ~3;
+    const int pitch = 4 * K + V;                  // floats per quad of pre_D rows
+    float* th_s = sp_smem;                        // [G][dpad]
+    float* tile = th_s + G * dpad;                // [SP_QUADS][pitch]
+    float* z2s = tile + SP_QUADS * pitch;         // [G][MAXK]
+    const int tid = threadIdx.x, g = tid / SP_QUADS, q = tid % SP_QUADS;
+    const int64_t u0 = (int64_t)blockIdx.x * G;
+    const int64_t u = u0 + g;
+    const bool live = u < n_units;
+    const int64_t gu = unit_offset + u;
+    auto model_of = [&](int64_t uu) {
+        int m = unit_model ? unit_model[uu] : (int)((unit_offset + uu) / samples_per_model);
+        return min(max(m, 0), n_models - 1);
+    };
+    const int m = live ? model_of(u) : 0;
+    // the units of one CTA normally share a model (consecutive units, samples_per_model of them per model)
+    bool same = true;
+#pragma unroll
+    for (int gg = 1; gg < G; ++gg)
+        if (u0 + gg < n_units && model_of(u0 + gg) != model_of(u0)) same = false;
+
+    if (live && q < (K + 3) / 4) {
+        float4 n4;
+        if (z2) {
+            const float* p = z2 + u * K + q * 4;
+            const int rem = K - q * 4;
+            n4.x = p[0];
+            n4.y = rem > 1 ? p[1] : 0.f;
+            n4.z = rem > 2 ? p[2] : 0.f;
+            n4.w = rem > 3 ? p[3] : 0.f;
+        } else {
+            n4 = philox_normal4(seed, STREAM_Z2, (uint32_t)gu, 0u, q);
+        }
+        float* zs = z2s + g * MAXK + q * 4;
+        zs[0] = n4.x; zs[1] = n4.y; zs[2] = n4.z; zs[3] = n4.w;
+    }
+
+    const float* wa = w_avg + (int64_t)m * d;
+    const float* w2a = w2_avg + (int64_t)m * d;
+    const int n_pass = same ? 1 : G;
+    const int qv = 4 * K / V;                     // V-float words per quad of rows
+    for (int jb = 0; jb < d; jb += SP_CHUNK) {
+        const int rows = min(SP_CHUNK, d - jb);
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int mt = same ? model_of(u0) : (u0 + pass < n_units ? model_of(u0 + pass) : 0);
+            // (mt d + jb) K floats from a 16-byte aligned base: V-float aligned because K is a multiple of V (jb K too)
+            const vec_t* src = reinterpret_cast<const vec_t*>(pre_D + ((int64_t)mt * d + jb) * K);
+            __syncthreads();                      // the previous chunk's readers are done with the tile
+            const int nv = rows * K / V;
+            for (int iv = tid; iv < nv; iv += SP_QUADS * G) {
+                const vec_t v = __ldg(src + iv);
+                const int qq = iv / qv, r = iv - qq * qv;
+                *reinterpret_cast<vec_t*>(tile + qq * pitch + r * V) = v;
+            }
+            __syncthreads();
+            const int j0 = jb + 4 * q;
+            if (live && j0 < d && (same || g == pass)) {
+                float zz[4];
+                if (z1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) zz[i] = (j0 + i < d) ? z1[u * (int64_t)d + j0 + i] : 0.f;
+                } else {
+                    float4 n4 = philox_normal4(seed, STREAM_Z1, (uint32_t)gu, 0u, (uint32_t)(j0 >> 2));
+                    zz[0] = n4.x; zz[1] = n4.y; zz[2] = n4.z; zz[3] = n4.w;
+                }
+                const float* zs = z2s + g * MAXK;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = j0 + i;
+                    if (j >= d) break;
+                    const float w = wa[j];
+                    // explicit _rn intrinsics: keep the reference's separate mul/sub/add roundings (no FMA contraction)
+                    const float sig = fabsf(__fsub_rn(w2a[j], __fmul_rn(w, w)));
+                    float th = __fadd_rn(w, __fmul_rn(__fmul_rn(c1, zz[i]), sqrtf(sig)));
+                    const float* row = tile + q * pitch + i * K;
+                    float dot = 0.f;   // k = 0 .. K-1 in order, like swag_sample_kernel
+                    for (int k = 0; k < K; k += V) {
+                        const vec_t rv = *reinterpret_cast<const vec_t*>(row + k);
+                        const float* r = reinterpret_cast<const float*>(&rv);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) dot = fmaf(__fsub_rn(r[e], w), zs[k + e], dot);
+                    }
+                    th = __fadd_rn(th, __fdiv_rn(__fmul_rn(scale, dot), c2div));
+                    th_s[g * dpad + j] = th;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n_live = (int)min((int64_t)G, n_units - u0);
+    if (theta) {
+        for (int gg = 0; gg < n_live; ++gg)
+            for (int j = tid; j < d; j += SP_QUADS * G) theta[(u0 + gg) * (int64_t)d + j] = th_s[gg * dpad + j];
+    }
+    if (packed) {
+        for (int i = tid; i < pl.P; i += SP_QUADS * G) {
+            const PackSrc ps = pack_source(i, fl, pl, lc);
+#pragma unroll
+            for (int gg = 0; gg < G; ++gg)
+                if (gg < n_live) packed[(u0 + gg) * (int64_t)pl.P + i] = pack_value(th_s + gg * dpad, ps);
+        }
+    }
 }
 
 int launch_pack_theta(const bnn_model_config* cfg, const float* d_theta, int64_t n_units, float* d_packed,
@@ -179,6 +330,45 @@ int launch_pack_theta(const bnn_model_config* cfg, const float* d_theta, int64_t
     pack_theta_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_theta, n_units, fl, pl, lc, d_packed);
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
+}
+
+struct SamplePackArgs {
+    const float *w_avg, *w2_avg, *pre_D;
+    int d, K;
+    const int32_t* unit_model;
+    int64_t unit_offset;
+    int samples_per_model, n_models;
+    float c1, scale, c2div;
+    uint64_t seed;
+    const float *z1, *z2;
+    int64_t n_units;
+    float *theta, *packed;
+};
+
+template <int G, int V>
+static int launch_sample_pack(const SamplePackArgs& a, const FlatLayout& fl, const PackedLayout& pl, const LiveCols& lc,
+                              cudaStream_t st) {
+    const size_t smem = sample_pack_smem_bytes(G, a.d, a.K);
+    static PerDeviceOnce attr_done;
+    if (attr_done.need())
+        BNN_CUDA(cudaFuncSetAttribute(swag_sample_pack_kernel<G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int64_t blocks = (a.n_units + G - 1) / G;
+    BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_swag_sample: too many units for one launch");
+    swag_sample_pack_kernel<G, V><<<(unsigned)blocks, SP_QUADS * G, smem, st>>>(
+        a.w_avg, a.w2_avg, a.pre_D, a.d, a.K, a.unit_model, a.unit_offset, a.samples_per_model, a.n_models, a.c1, a.scale,
+        a.c2div, a.seed, a.z1, a.z2, a.n_units, a.theta, a.packed, fl, pl, lc);
+    BNN_CUDA(cudaGetLastError());
+    return BNN_OK;
+}
+
+template <int G>
+static int launch_sample_pack_g(const SamplePackArgs& a, const FlatLayout& fl, const PackedLayout& pl, const LiveCols& lc,
+                                cudaStream_t st) {
+    switch (sample_pack_vec(a.K)) {
+        case 4: return launch_sample_pack<G, 4>(a, fl, pl, lc, st);
+        case 2: return launch_sample_pack<G, 2>(a, fl, pl, lc, st);
+        default: return launch_sample_pack<G, 1>(a, fl, pl, lc, st);
+    }
 }
 
 }  // namespace bnn
@@ -203,17 +393,60 @@ int bnn_swag_sample(const bnn_model_config* cfg, const float* d_w_avg, const flo
     if (rc != BNN_OK) return rc;
     if ((rc = check_device()) != BNN_OK) return rc;
     BNN_REQUIRE(d_w_avg && d_w2_avg && d_pre_D, BNN_E_ARG, "bnn_swag_sample: SWAG statistics pointer is NULL");
-    BNN_REQUIRE(d_theta, BNN_E_ARG, "bnn_swag_sample: d_theta is required (it also feeds the packed layout)");
+    BNN_REQUIRE(aligned16(d_pre_D), BNN_E_ALIGN, "bnn_swag_sample: d_pre_D must be 16-byte aligned");
+    BNN_REQUIRE(d_theta || d_theta_packed, BNN_E_ARG, "bnn_swag_sample: give d_theta, d_theta_packed or both");
     BNN_REQUIRE(n_models >= 1 && n_units >= 1, BNN_E_ARG, "bnn_swag_sample: n_models/n_units must be >= 1");
     // the reference fails in D @ z2 when pre_D has fewer than K columns (:835); K>=2 for sqrt(2(K-1))
     BNN_REQUIRE(K >= 2 && K <= MAXK, BNN_E_ARG, "bnn_swag_sample: K=%d out of [2,%d]", K, MAXK);
     BNN_REQUIRE((d_z1 == nullptr) == (d_z2 == nullptr), BNN_E_ARG, "bnn_swag_sample: give both z1 and z2 or neither");
     BNN_REQUIRE(d_unit_model || samples_per_model >= 1, BNN_E_ARG, "bnn_swag_sample: samples_per_model must be >= 1");
+    const FlatLayout fl(cfg->n_features);
+    const LiveCols lc = live_columns(cfg);
+    const PackedLayout pl(lc.n, cfg->n_features);
+    SamplePackArgs a;
+    a.w_avg = d_w_avg; a.w2_avg = d_w2_avg; a.pre_D = d_pre_D;
+    a.d = fl.d; a.K = K;
+    a.unit_model = d_unit_model; a.unit_offset = unit_offset;
+    a.samples_per_model = samples_per_model; a.n_models = n_models;
+    // scale * (1/np.sqrt(2.0)) is a double that torch casts to fp32 when it meets the fp32 tensor (:834)
+    a.c1 = (float)((double)scale * (1.0 / sqrt(2.0)));
+    a.scale = scale;
+    a.c2div = (float)sqrt(2.0 * (K - 1));
+    a.seed = seed; a.z1 = d_z1; a.z2 = d_z2; a.n_units = n_units; a.theta = d_theta; a.packed = d_theta_packed;
+    cudaStream_t st = (cudaStream_t)stream;
+    // G units per CTA share the pre_D tiles and the packed-index arithmetic: 4 when there are enough units to fill the
+    // GPU with such CTAs (and the tile fits), else one unit per CTA
+    int n_sms = 148;
+    {
+        int dev = 0;
+        BNN_CUDA(cudaGetDevice(&dev));
+        BNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    BNN_REQUIRE(sample_pack_smem_bytes(1, a.d, K) <= 227 * 1024, BNN_E_CONFIG,
+                "bnn_swag_sample: d=%d, K=%d exceed the shared-memory plan", a.d, K);
+    if (n_units >= 4ll * n_sms && sample_pack_smem_bytes(4, a.d, K) <= 227 * 1024)
+        return launch_sample_pack_g<4>(a, fl, pl, lc, st);
+    if (n_units >= 2ll * n_sms && sample_pack_smem_bytes(2, a.d, K) <= 227 * 1024)
+        return launch_sample_pack_g<2>(a, fl, pl, lc, st);
+    return launch_sample_pack_g<1>(a, fl, pl, lc, st);
+}
+
+/* The unfused K1 (one launch for theta, one for the packed layout): kept as the cross-check of the fused kernel. */
+int bnn_swag_sample_unfused(const bnn_model_config* cfg, const float* d_w_avg, const float* d_w2_avg,
+                            const float* d_pre_D, int32_t n_models, int32_t K, const int32_t* d_unit_model,
+                            int64_t n_units, int64_t unit_offset, int32_t samples_per_model, float scale, uint64_t seed,
+                            const float* d_z1, const float* d_z2, float* d_theta, float* d_theta_packed, void* stream) {
+    using namespace bnn;
+    int rc = validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    if ((rc = check_device()) != BNN_OK) return rc;
+    BNN_REQUIRE(d_w_avg && d_w2_avg && d_pre_D && d_theta, BNN_E_ARG, "bnn_swag_sample_unfused: null pointer");
+    BNN_REQUIRE(n_models >= 1 && n_units >= 1 && K >= 2 && K <= MAXK, BNN_E_ARG, "bnn_swag_sample_unfused: bad sizes");
+    BNN_REQUIRE((d_z1 == nullptr) == (d_z2 == nullptr), BNN_E_ARG, "bnn_swag_sample_unfused: give both z1 and z2 or neither");
     const int d = FlatLayout(cfg->n_features).d;
     const int bpu = (d + SAMPLER_THREADS * 4 - 1) / (SAMPLER_THREADS * 4);
     const int64_t blocks = n_units * bpu;
-    BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_swag_sample: too many units for one launch");
-    // scale * (1/np.sqrt(2.0)) is a double that torch casts to fp32 when it meets the fp32 tensor (:834)
+    BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_swag_sample_unfused: too many units for one launch");
     const float c1 = (float)((double)scale * (1.0 / sqrt(2.0)));
     const float c2div = (float)sqrt(2.0 * (K - 1));
     cudaStream_t st = (cudaStream_t)stream;

@@ -203,14 +203,16 @@ class MultiSWAG:
     # ------------------------------------------------------------------ batched path
     def sample_thetas(self, samples_per_model: int, seed: int, scale: float = 0.5, unit_model=None,
                       unit_offset: int = 0, n_units: Optional[int] = None, z1=None, z2=None, want_flat=True):
-        """(theta[U,d], theta_packed[U,P]).  Unit u = model*S + sample unless unit_model is given."""
+        """(theta[U,d], theta_packed[U,P]).  Unit u = model*S + sample unless unit_model is given; units
+        [unit_offset, unit_offset + n_units) of that numbering when a chunk is asked for (the Philox draws are keyed on
+        the global unit index).  ``want_flat=False``: only the packed layout is written (theta is None)."""
         lib = _lib.load()
         cfg = self.config()
         M, d = self.w_avg.shape
         U = n_units if n_units is not None else M * samples_per_model
         P = lib.bnn_packed_param_count(cfg)
         with torch.cuda.device(self.device), _lib.nvtx("bnn:K1 swag_sample"):
-            theta = torch.empty((U, d), device=self.device)
+            theta = torch.empty((U, d), device=self.device) if want_flat else None
             thp = torch.empty((U, P), device=self.device)
             um = None
             if unit_model is not None:
@@ -219,7 +221,8 @@ class MultiSWAG:
             _lib.check(
                 lib.bnn_swag_sample(cfg, _lib.ptr(self.w_avg), _lib.ptr(self.w2_avg), _lib.ptr(self.pre_D), M, self.K,
                                     dp(um, "unit_model", torch.int32), U, unit_offset, max(int(samples_per_model), 1),
-                                    float(scale), int(seed), dp(z1, "z1"), dp(z2, "z2"), _lib.ptr(theta), _lib.ptr(thp),
+                                    float(scale), int(seed), dp(z1, "z1"), dp(z2, "z2"),
+                                    _lib.ptr(theta) if want_flat else None, _lib.ptr(thp),
                                     _lib.current_stream_ptr()),
                 "bnn_swag_sample",
             )
@@ -233,7 +236,7 @@ class MultiSWAG:
         x = x.contiguous().float()
         cfg = self.config(x.shape[1])
         if thp is None:
-            _, thp = self.sample_thetas(samples_per_model, seed, scale)
+            _, thp = self.sample_thetas(samples_per_model, seed, scale, want_flat=False)
         U, N = thp.shape[0], x.shape[0]
         with torch.cuda.device(self.device), _lib.nvtx("bnn:K2 predict"):
             out = torch.empty((N, U, 2) if system_major else (U, N, 2), device=self.device)
@@ -282,7 +285,7 @@ class MultiSWAG:
             return PendingGather(lambda: full) if defer else full
         overlap_chunks = max(1, overlap_chunks)
         with torch.cuda.device(self.device):
-            _, thp = self.sample_thetas(samples_per_model, seed, scale)
+            _, thp = self.sample_thetas(samples_per_model, seed, scale, want_flat=False)
             per = -(-n_loc // overlap_chunks)
             per = -(-per // granule) * granule
             gather, turn = None, None
@@ -319,7 +322,7 @@ class MultiSWAG:
         x_host = x_host.contiguous().float()
         N = x_host.shape[0]
         with torch.cuda.device(self.device):
-            _, thp = self.sample_thetas(samples_per_model, seed, scale)
+            _, thp = self.sample_thetas(samples_per_model, seed, scale, want_flat=False)
             U = thp.shape[0]
             if out_host is None:
                 out_host = torch.empty((N, U, 2), dtype=torch.float32).pin_memory()
@@ -364,16 +367,40 @@ class MultiSWAG:
             main.synchronize()
         return out_host
 
+    def predict_into(self, x: torch.Tensor, thp: torch.Tensor, block: torch.Tensor, unit0: int, seed: int = 0,
+                     system_offset: int = 0):
+        """Predictions of the units in ``thp`` (global unit indices unit0 ...) for the systems x, written into columns
+        [unit0, unit0 + len(thp)) of the system-major ``block`` [N, U_total, 2] (``bnn_predict_strided``)."""
+        lib = _lib.load()
+        _lib.require_cuda(x, "x")
+        N, Uc, Ut = x.shape[0], thp.shape[0], block.shape[1]
+        assert block.shape[0] == N and block.shape[2] == 2 and block.is_contiguous() and unit0 + Uc <= Ut
+        if N == 0 or Uc == 0:
+            return block
+        with torch.cuda.device(self.device), _lib.nvtx("bnn:K2 predict"):
+            _lib.check(
+                lib.bnn_predict_strided(self.config(x.shape[1]), _lib.dev_ptr(x, self.device, "x"), N,
+                                        _lib.dev_ptr(thp, self.device, "thp"), Uc, None, None, int(seed), int(unit0),
+                                        int(system_offset), 2, 2 * Ut, block.data_ptr() + 8 * unit0, None, None,
+                                        _lib.current_stream_ptr()),
+                "bnn_predict_strided",
+            )
+        return block
+
     def posterior_summary(self, x: torch.Tensor, samples_per_model: int, n_trios: int = 1, seed: int = 0,
-                          scale: float = 0.5, system_offset: int = 0, max_block_bytes: int = 1 << 30):
+                          scale: float = 0.5, system_offset: int = 0, max_block_bytes: int = 640 << 20,
+                          unit_chunk: int = 2048):
         """Predict + post-process on the device: x [N*n_trios, T, F] (rows = system*n_trios + trio, the
         reshape(-1, 100, 41) of multiswag_5_planet.py:287) -> [N, 8] per-system statistics
         (``posterior.STAT_NAMES``) of the sampled instability time, min over trios (figures/main_figures.py:
-        167-277, figures/multiswag_5_planet.py:306-481).  Only [N, 8] ever leaves the GPU, and the [rows, U, 2]
-        prediction block (+ the [rows, U] sampled times) never exists as a whole: systems are walked in chunks of at
-        most ``max_block_bytes`` of predictions (12 bytes per (row, unit)), cut at multiples of the kernel's system
-        granule -- the Philox draws are keyed on global (unit, row) indices, so the result does not depend on the
-        chunking (BASELINE configs[2]: 12,500 systems x 60,000 units per GPU would be 9 GB in one piece)."""
+        167-277, figures/multiswag_5_planet.py:306-481).  Only [N, 8] ever leaves the GPU, and neither the [rows, U, 2]
+        prediction block (+ the [rows, U] sampled times) nor the weights of all U units ever exist as a whole: systems
+        are walked in chunks of at most ``max_block_bytes`` of predictions (12 bytes per (row, unit)), cut at multiples
+        of the kernel's system granule, and inside a system chunk the units in chunks of ``unit_chunk`` whose weights are
+        sampled on the spot (77 kB per unit; the sampler costs ~0.1 us per unit against ~6 us per unit and 1,000
+        systems of prediction).  Philox draws are keyed on global (unit, row) indices, so the result does not depend on
+        either chunking (BASELINE configs[2]: 12,500 systems x 60,000 units per GPU would be 9 GB of predictions and
+        4.6 GB of packed weights in one piece; peak here < 1 GB)."""
         import math
 
         from . import posterior
@@ -382,23 +409,31 @@ class MultiSWAG:
         if rows % n_trios:
             raise ValueError(f"{rows} rows are not a multiple of {n_trios} trios")
         N = rows // n_trios
+        U = self.n_models * samples_per_model
+        unit_chunk = max(1, int(unit_chunk))
         with torch.cuda.device(self.device):
-            _, thp = self.sample_thetas(samples_per_model, seed, scale)
-            U = thp.shape[0]
+            thp_all = None
+            if U <= unit_chunk + unit_chunk // 2:       # few units: sample once, reuse for every system chunk
+                _, thp_all = self.sample_thetas(samples_per_model, seed, scale, want_flat=False)
             g = self.system_granule(x.shape[1])
             gs = g // math.gcd(g, n_trios)                      # systems per chunk boundary such that rows stay aligned
             per = max(1, int(max_block_bytes // (12 * U * n_trios)))
             per = max(gs, per // gs * gs)
-            if per >= N:
-                pred = self.predict(x, samples_per_model, seed, scale, system_offset=system_offset * n_trios,
-                                    system_major=True, thp=thp)
-                return posterior.posterior_summary(pred, n_trios, seed, row_offset=system_offset * n_trios)
             out = torch.empty((N, 8), device=self.device)
             for lo in range(0, N, per):
                 hi = min(lo + per, N)
                 row0 = (system_offset + lo) * n_trios
-                pred = self.predict(x[lo * n_trios:hi * n_trios], samples_per_model, seed, scale, system_offset=row0,
-                                    system_major=True, thp=thp)
+                xs = x[lo * n_trios:hi * n_trios]
+                pred = torch.empty((xs.shape[0], U, 2), device=self.device)
+                if thp_all is not None:
+                    self.predict_into(xs, thp_all, pred, 0, seed, system_offset=row0)
+                else:
+                    for u0 in range(0, U, unit_chunk):
+                        u1 = min(u0 + unit_chunk, U)
+                        _, thp = self.sample_thetas(samples_per_model, seed, scale, unit_offset=u0, n_units=u1 - u0,
+                                                    want_flat=False)
+                        self.predict_into(xs, thp, pred, u0, seed, system_offset=row0)
+                        del thp
                 out[lo:hi] = posterior.posterior_summary(pred, n_trios, seed, row_offset=row0)
                 del pred
         return out

@@ -68,8 +68,9 @@ int64_t bnn_packed_param_count(const bnn_model_config* cfg);
  * Unit u uses model d_unit_model[u] (NULL: model = (unit_offset+u) / samples_per_model).
  * d_z1 [U,d] / d_z2 [U,K] explicit normal draws (the reference's randn((1,d)), randn((K,1))),
  * or both NULL: drawn in-kernel from Philox4x32-10 keyed on (seed; unit_offset+u, element).
- * Outputs (either may be NULL): d_theta [U,d] in flatten() order (what SWAGModel.load()
- * would install, :748-761) and d_theta_packed [U,P] in the layout bnn_predict consumes.
+ * Outputs (either may be NULL, not both): d_theta [U,d] in flatten() order (what SWAGModel.load()
+ * would install, :748-761) and d_theta_packed [U,P] in the layout bnn_predict consumes.  One fused
+ * launch: the packed layout is written from shared memory, theta never round-trips through HBM.
  * pre_D is [M,d,K] row-major, exactly the saved tensor (:917).
  */
 int bnn_swag_sample(const bnn_model_config* cfg, const float* d_w_avg, const float* d_w2_avg,
@@ -107,6 +108,14 @@ int bnn_predict(const bnn_model_config* cfg, const float* d_x, int64_t n_systems
                 const float* d_eps_sum, uint64_t seed, int64_t unit_offset, int64_t system_offset,
                 int32_t out_system_major, float* d_out, float* d_summary_out, void* d_workspace,
                 void* stream);
+/* The same with explicit output strides (in floats, even): the (mu, std) pair of (unit u, system n) of THIS call goes to
+ * d_out + u * out_unit_stride + n * out_system_stride.  Lets a caller fill a column block of a larger [N, U_total, 2]
+ * array from one chunk of units (weights sampled chunk by chunk: 60,000 units x 77 kB never exist at once). */
+int bnn_predict_strided(const bnn_model_config* cfg, const float* d_x, int64_t n_systems,
+                        const float* d_theta_packed, int64_t n_units, const float* d_eps,
+                        const float* d_eps_sum, uint64_t seed, int64_t unit_offset, int64_t system_offset,
+                        int64_t out_unit_stride, int64_t out_system_stride, float* d_out,
+                        float* d_summary_out, void* d_workspace, void* stream);
 
 /* VarModel.add_input_noise (:444-446) after the zero_* masks (:487-500):
  * x_noisy = x (zeroed columns set to 0) + eps_in * exp(input_noise_logvar/2).

@@ -10,6 +10,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "bnnchaos.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -46,6 +48,14 @@ int bnn_train_timeline(unsigned long long* host_out, int32_t n);
  * that the tensor core's truncation rounds to nearest tf32; two_batches: accumulate across two commits. */
 int bnn_tc_probe_ss(const float* d_G, const float* d_H, float* d_D, int32_t R, int32_t MJ, int32_t NK, int32_t N,
                     int32_t bias_round, int32_t two_batches, void* stream);
+
+/* Diagnostic: the unfused K1 -- swag_sample_kernel writes theta [U,d], pack_theta_kernel gathers it into the packed layout
+ * -- with bnn_swag_sample's arguments (d_theta required).  bnn_swag_sample itself runs the fused kernel, which must give
+ * bit-identical results (tests/test_gpu_predict.py). */
+int bnn_swag_sample_unfused(const bnn_model_config* cfg, const float* d_w_avg, const float* d_w2_avg,
+                            const float* d_pre_D, int32_t n_models, int32_t K, const int32_t* d_unit_model,
+                            int64_t n_units, int64_t unit_offset, int32_t samples_per_model, float scale, uint64_t seed,
+                            const float* d_z1, const float* d_z2, float* d_theta, float* d_theta_packed, void* stream);
 
 /* Diagnostic: force the kernel behind bnn_predict for this process: 0 = automatic (tensor cores when T = 100 and at most 32
  * live columns, else FP32 FFMA2), 1 = tensor-core, 2 = FFMA2 v2 (warp-specialised), 3 = FFMA2 v1 (synchronous).  Default:

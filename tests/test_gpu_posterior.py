@@ -140,3 +140,8 @@ def test_posterior_summary_chunking_is_invisible(dev):
         for budget in (12 * 40 * n_trios * 5, 12 * 40 * n_trios * 17, 12 * 40 * n_trios * 46):   # 5, 15, 45 systems per chunk
             got = ens.posterior_summary(x, S_, n_trios=n_trios, seed=5, system_offset=10, max_block_bytes=budget)
             assert torch.equal(got, full), (n_trios, budget)
+        # units walked in chunks too, their weights sampled per (system chunk, unit chunk)
+        for unit_chunk in (7, 16):
+            got = ens.posterior_summary(x, S_, n_trios=n_trios, seed=5, system_offset=10, unit_chunk=unit_chunk,
+                                        max_block_bytes=12 * 40 * n_trios * 17)
+            assert torch.equal(got, full), (n_trios, unit_chunk)

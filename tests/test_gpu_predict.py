@@ -77,6 +77,67 @@ def test_pack_theta_layout(gold_predict, dev):
     assert thp.shape[1] == _lib.load().bnn_packed_param_count(cfg)
 
 
+def _sample_both(ens, n_units, unit_offset, S_, seed, unit_model=None, z=None, want_flat=True):
+    """(theta, packed) of bnn_swag_sample (fused kernel) and of the unfused two-launch diagnostic entry."""
+    lib = _lib.load()
+    cfg = ens.config()
+    M, d = ens.w_avg.shape
+    P = lib.bnn_packed_param_count(cfg)
+    dev = ens.device
+    um = None if unit_model is None else torch.as_tensor(unit_model, dtype=torch.int32, device=dev)
+    z1, z2 = (None, None) if z is None else z
+    outs = []
+    for fn, flat in ((lib.bnn_swag_sample, want_flat), (lib.bnn_swag_sample_unfused, True)):
+        theta = torch.full((n_units, d), float("nan"), device=dev) if flat else None
+        thp = torch.full((n_units, P), float("nan"), device=dev)
+        _lib.check(fn(cfg, _lib.ptr(ens.w_avg), _lib.ptr(ens.w2_avg), _lib.ptr(ens.pre_D), M, ens.K, _lib.ptr(um), n_units,
+                      unit_offset, S_, 0.5, seed, _lib.ptr(z1), _lib.ptr(z2), _lib.ptr(theta), _lib.ptr(thp),
+                      _lib.current_stream_ptr()))
+        outs.append((theta, thp))
+    torch.cuda.synchronize()
+    return outs
+
+
+@pytest.mark.parametrize("n_units,unit_offset,S_", [(1, 0, 1), (7, 3, 2), (601, 5, 3), (1200, 0, 400), (333, 1000, 7)])
+def test_fused_sampler_equals_unfused_bitwise(dev, n_units, unit_offset, S_):
+    """bnn_swag_sample = ONE fused launch (pre_D tiles shared by the units of a CTA, packed layout written from shared
+    memory); it must reproduce the two-launch sampler + pack bit for bit: 1 / 2 / 4 units per CTA, ragged last CTA, CTAs
+    whose units straddle two models (S_ = 3, 7), unit chunks (unit_offset), Philox draws."""
+    ens = MultiSWAG([make_swag_model(s, dev) for s in SEEDS], device=dev)
+    (th_f, thp_f), (th_u, thp_u) = _sample_both(ens, n_units, unit_offset, S_, seed=11)
+    assert torch.equal(th_f, th_u)
+    assert torch.equal(thp_f, thp_u)          # also: no NaN fill left, every packed float is written
+    (none, thp_only), _ = _sample_both(ens, n_units, unit_offset, S_, seed=11, want_flat=False)
+    assert none is None and torch.equal(thp_only, thp_u)
+
+
+def test_fused_sampler_explicit_draws_and_unit_model(dev):
+    ens = MultiSWAG([make_swag_model(s, dev) for s in SEEDS], device=dev)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    U, d = 37, ens.w_avg.shape[1]
+    z = (torch.randn((U, d), generator=g).to(dev), torch.randn((U, ens.K), generator=g).to(dev))
+    um = torch.randint(0, 3, (U,), generator=g).tolist()
+    for unit_model, zz in ((um, None), (None, z), (um, z)):
+        (th_f, thp_f), (th_u, thp_u) = _sample_both(ens, U, 0, 13, seed=2, unit_model=unit_model, z=zz)
+        assert torch.equal(th_f, th_u) and torch.equal(thp_f, thp_u)
+
+
+def test_predict_strided_unit_chunks_fill_a_block(dev):
+    """bnn_predict_strided: units sampled and evaluated chunk by chunk into column blocks of one [N, U, 2] array equal
+    the one-shot system-major prediction bit for bit (Philox keyed on global unit / system indices)."""
+    ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(3, dev)], device=dev)
+    S_, N = 45, 35
+    x = torch.from_numpy(synth.make_systems(N, seed=8)).to(dev)
+    full = ens.predict(x, S_, seed=6, system_offset=20, system_major=True)
+    U = 2 * S_
+    block = torch.full((N, U, 2), float("nan"), device=dev)
+    for u0 in range(0, U, 32):
+        u1 = min(u0 + 32, U)
+        _, thp = ens.sample_thetas(S_, 6, unit_offset=u0, n_units=u1 - u0, want_flat=False)
+        ens.predict_into(x, thp, block, u0, seed=6, system_offset=20)
+    assert torch.equal(block, full)
+
+
 @pytest.mark.parametrize("seed", SEEDS)
 def test_predict_vs_reference_golden(gold_predict, dev, seed):
     """theta, eps and the 256 in-distribution systems of the reference-generated golden file."""
