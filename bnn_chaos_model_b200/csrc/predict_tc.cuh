@@ -35,6 +35,7 @@ constexpr int SYS = 5;            // systems per CTA tile
 constexpr int MT = 4;             // 128-row M tiles per tile (5 * 100 rows -> 512)
 constexpr int T_FIXED = 100;      // time steps (the tiling is specific to T = 100)
 constexpr int ROWS = SYS * T_FIXED;
+constexpr int XS_ROWS = MT * 128;   // rows of the shared-memory x tile: the 12 rows behind the tile stay zero (no row test in the stage)
 constexpr int TM_AHI = 0, TM_ALO = 40, TM_D = 80, TM_SLOT = 128;  // TMEM columns of one slot
 constexpr int N_BLOCKS = MT * 4;  // 32-row blocks per tile
 constexpr int REC_FLOATS = N_BLOCKS * 2 * L * 2;  // [block][segment][col][mean, M2]
@@ -75,6 +76,24 @@ __device__ __forceinline__ SysRec sys_records(int p) {
     return r;
 }
 
+// Pooling geometry of the 16 32-row blocks, fixed by T = 100 and 5 systems per tile: rows [0, e0) of block b belong to
+// one system, rows [e0, nvalid) (if any) to the next; n0 / n1 the two row counts as floats with their correctly rounded
+// reciprocals (mean = S / n as S * r corrected by one FMA pair).  In constant memory: the epilogue warps recomputed it
+// per (unit, block) with integer divisions -- 40 of the ~190 instructions of a pooling call.
+struct PoolGeom { int e0, nvalid; float n0, n1, rcp0, rcp1; int pad0, pad1; };
+constexpr PoolGeom pool_geom(int b) {
+    const int R0 = 32 * b, sysA = R0 / T_FIXED;
+    const int split = (T_FIXED * (sysA + 1) - R0) < 32 ? (T_FIXED * (sysA + 1) - R0) : 32;
+    const int nvalid = (ROWS - R0) < 32 ? (ROWS - R0) : 32;
+    const int e0 = split < nvalid ? split : nvalid;
+    const int n1 = nvalid > split ? nvalid - split : 1;
+    return PoolGeom{e0, nvalid, (float)e0, (float)n1, 1.0f / (float)e0, 1.0f / (float)n1, 0, 0};
+}
+__constant__ PoolGeom c_pool_geom[N_BLOCKS] = {
+    pool_geom(0), pool_geom(1), pool_geom(2), pool_geom(3), pool_geom(4), pool_geom(5), pool_geom(6), pool_geom(7),
+    pool_geom(8), pool_geom(9), pool_geom(10), pool_geom(11), pool_geom(12), pool_geom(13), pool_geom(14), pool_geom(15)};
+static_assert(N_BLOCKS == 16, "c_pool_geom lists 16 blocks");
+
 // block b covers tile rows [32b, 32b+32): rows of system sysA up to `split`, then system sysA+1
 __device__ __forceinline__ void block_geom(int b, int& sysA, int& split, int& nvalid) {
     const int R0 = 32 * b;
@@ -91,7 +110,7 @@ __device__ __forceinline__ int xs_index(int row, int c) { return row * 32 + ((((
 
 __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int64_t n0, int n_valid, int F, int kin,
                                                const ColMap& cm, float* __restrict__ xs, int* __restrict__ poison) {
-    for (int i = threadIdx.x; i < ROWS * 32; i += blockDim.x) xs[i] = 0.f;
+    for (int i = threadIdx.x; i < XS_ROWS * 32; i += blockDim.x) xs[i] = 0.f;
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) poison[r] = 0;
     __syncthreads();
     const float* src = X + n0 * (int64_t)T_FIXED * F;

@@ -41,8 +41,8 @@ template <int NT, bool WIDE>
 struct SmemPlan {
     using RG = RingPlan<WIDE>;
     // byte offsets inside dynamic shared memory
-    static constexpr int xs = 0;                                   // ROWS*32 floats
-    static constexpr int ring = xs + ROWS * 32 * 4;                // 2 slots of B operands + biases
+    static constexpr int xs = 0;                                   // XS_ROWS*32 floats
+    static constexpr int ring = xs + XS_ROWS * 32 * 4;             // 2 slots of B operands + biases
     static constexpr int fb = ring + 2 * RG::B_BYTES;                  // per epilogue warp: 32 rows x 12 latent columns
     static constexpr int rec = fb + EW * FB_FLOATS * 4;            // NREC slots of block records
     static constexpr int scratch = rec + RG::NREC * REC_FLOATS * 4;    // per tail warp
@@ -273,55 +273,49 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->a_ready[2 * team + s]);
             };
-            // layer 3 of (unit pi, M tile m): D + bias -> this warp's latent columns [8 half, 8 half + 12) of its 32 rows
-            auto latent_to_fb = [&](int s, int pi) {
+            // layer 3 of the slot's job: D -> this warp's latent columns [8 half, 8 half + 12) of its 32 rows (the bias is
+            // added to the pooled mean: the deviations do not see it)
+            auto latent_to_fb = [&](int s) {
                 const uint32_t tl = tq + s * TM_SLOT;
-                const float* b3 = ring + (size_t)(pi & 1) * B_FLOATS + O_BIAS / 4 + 2 * TC_N + 8 * half;
                 uint32_t d0[8], d1[4];
                 tmem_ld8(tl + TM_D + 8 * half, d0);
                 tmem_ld4(tl + TM_D + 8 * half + 8, d1);
                 tc_wait_ld();
-                const float4* b4 = reinterpret_cast<const float4*>(b3);
-                float4* dst = reinterpret_cast<float4*>(my_fb + lane * FB_PITCH);
-#pragma unroll
-                for (int g4 = 0; g4 < 3; ++g4) {
-                    const float4 b = b4[g4];
-                    const uint32_t* dd = g4 < 2 ? &d0[4 * g4] : &d1[0];
-                    dst[g4] = make_float4(__uint_as_float(dd[0]) + b.x, __uint_as_float(dd[1]) + b.y,
-                                          __uint_as_float(dd[2]) + b.z, __uint_as_float(dd[3]) + b.w);
-                }
+                uint4* dst = reinterpret_cast<uint4*>(my_fb + lane * FB_PITCH);
+                dst[0] = make_uint4(d0[0], d0[1], d0[2], d0[3]);
+                dst[1] = make_uint4(d0[4], d0[5], d0[6], d0[7]);
+                dst[2] = make_uint4(d1[0], d1[1], d1[2], d1[3]);
                 __syncwarp();
             };
             // pooled (mean, M2) records of this warp's 10 latent columns of one 32-row block, two-pass per segment like
             // torch.mean / torch.std.  Every boundary inside a block (the next system's first row at 4, 8, 12 or 16, the tile's
             // last row at 20) is a multiple of 4 rows, so a 4-row granule belongs to one segment: lane = (column c = lane % 10,
             // granules lane / 10 + {0, 3, 6}), one predicate per granule instead of per row, and the three lanes of a column
-            // meet through shuffles.  Runs in the shadow of the slot's layer-1 MMAs.
+            // meet through shuffles.  Runs in the shadow of the slot's layer-1 MMAs.  Lane constants (column pointer, first
+            // granule row) live in two registers, the block's geometry comes from constant memory.
+            const int pj3 = lane / 10, pc = lane - 10 * pj3;
+            const float* pool_col = my_fb + 2 * half + pc + 4 * min(pj3, 2) * FB_PITCH;
+            const int pool_r0 = lane < 30 ? 4 * pj3 : 64;     // rows of granule i: pool_r0 + 12 i ...; lanes 30, 31 idle
             auto pool_block = [&](int pi, int m) {
                 static_assert(T_FIXED % 4 == 0 && ROWS % 4 == 0, "4-row granules must not straddle systems");
                 const int rs = pi % NREC;
                 if (pi >= NREC) mbar_wait(&bars->rec_free[rs], (uint32_t)((pi / NREC - 1) & 1));  // tail of unit pi-NREC done (suspended wait:
                                                                                               // a polling loop here took 39 % of all issued instructions)
                 const int b = m * 4 + quad;
-                int sysA, split, nvalid;
-                block_geom(b, sysA, split, nvalid);
-                const int e0 = min(split, nvalid);
-                const bool two = nvalid > split;               // the block holds rows of two systems (warp-uniform)
-                const int j3 = lane / 10, c = lane - 10 * j3, src = c;
-                const float* col = my_fb + 2 * half + c;
+                const PoolGeom pg = c_pool_geom[b];
+                const bool two = pg.nvalid > pg.e0;            // the block holds rows of two systems (warp-uniform)
                 float v[3][4];
                 bool in0[3], in1[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const int r0 = 4 * (j3 + 3 * i);
-                    const bool ok = r0 < 32 && lane < 30;
-                    in0[i] = ok && r0 < e0;
-                    in1[i] = ok && r0 >= split && r0 < nvalid;
+                    const int r0 = pool_r0 + 12 * i;           // r0 >= 32 is beyond nvalid: both predicates false (the loads
+                    in0[i] = r0 < pg.e0;                       // then touch the next warp's rows; their values are dropped)
+                    in1[i] = !in0[i] && r0 < pg.nvalid;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) v[i][r] = ok ? col[(r0 + r) * FB_PITCH] : 0.f;
+                    for (int r = 0; r < 4; ++r) v[i][r] = pool_col[(12 * i + r) * FB_PITCH];
                 }
                 auto gather3 = [&](float x) {
-                    return __shfl_sync(0xffffffffu, x, src) + __shfl_sync(0xffffffffu, x, src + 10) + __shfl_sync(0xffffffffu, x, src + 20);
+                    return __shfl_sync(0xffffffffu, x, pc) + __shfl_sync(0xffffffffu, x, pc + 10) + __shfl_sync(0xffffffffu, x, pc + 20);
                 };
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -330,11 +324,14 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                     s0 += in0[i] ? pr : 0.f;
                     s1 += in1[i] ? pr : 0.f;
                 }
-                // power-of-two counts (the 11 full blocks of 32 rows) multiply by the exact reciprocal: same value as the
-                // quotient without the ~60-cycle divide on the warp's critical path
-                const float S0 = gather3(s0);
-                const float mean0 = (e0 & (e0 - 1)) == 0 ? S0 * __frcp_rn((float)e0) : S0 / (float)e0;
-                const float mean1 = two ? gather3(s1) / (float)(nvalid - split) : 0.f;
+                // S / n as S r corrected by the residual (r = the rounded reciprocal from the table): the correctly rounded
+                // quotient without the ~60-cycle divide sequence on the warp's critical path (exact for power-of-two counts)
+                auto div_n = [](float S, float n, float r) {
+                    const float q = S * r;
+                    return fmaf(fmaf(-n, q, S), r, q);
+                };
+                const float mean0 = div_n(gather3(s0), pg.n0, pg.rcp0);
+                const float mean1 = two ? div_n(gather3(s1), pg.n1, pg.rcp1) : 0.f;
                 float q0 = 0.f, q1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -347,9 +344,10 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                 }
                 q0 = gather3(q0);
                 if (two) q1 = gather3(q1);
-                float* rb = rec + rs * REC_FLOATS + ((b * 2) * L + 10 * half + c) * 2;
-                if (lane < 10) { rb[0] = mean0; rb[1] = q0; }
-                if (two && lane >= 10 && lane < 20) { rb[L * 2] = mean1; rb[L * 2 + 1] = q1; }
+                const float bias_c = ring[(size_t)(pi & 1) * B_FLOATS + O_BIAS / 4 + 2 * TC_N + 10 * half + pc];  // b2 of this column
+                float* rb = rec + rs * REC_FLOATS + ((b * 2) * L + 10 * half + pc) * 2;
+                if (lane < 10) *reinterpret_cast<float2*>(rb) = make_float2(mean0 + bias_c, q0);
+                if (two && lane >= 10 && lane < 20) *reinterpret_cast<float2*>(rb + L * 2) = make_float2(mean1 + bias_c, q1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->unit_done[rs]);
             };
@@ -365,21 +363,15 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                     if (i > 0) {
                         wait_d(s);
                         if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 2);
-                        latent_to_fb(s, i - 1);
+                        latent_to_fb(s);
                     }
                     if (i < n_units) {
-                        const int R = m * 128 + quad * 32 + lane;  // tile row of this thread
+                        const int R = m * 128 + quad * 32 + lane;  // tile row of this thread (rows 500..511 of xs are zero)
                         uint32_t v[16];
-                        if (R < ROWS) {
 #pragma unroll
-                            for (int g4 = 0; g4 < 4; ++g4) {
-                                const float4 a = *reinterpret_cast<const float4*>(xs + R * 32 + (((4 * half + g4) ^ (R & 7)) << 2));
-                                v[4 * g4] = __float_as_uint(a.x); v[4 * g4 + 1] = __float_as_uint(a.y);
-                                v[4 * g4 + 2] = __float_as_uint(a.z); v[4 * g4 + 3] = __float_as_uint(a.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) v[k] = 0u;
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(xs + R * 32 + (((4 * half + g4) ^ (lane & 7)) << 2));
+                            v[4 * g4] = a.x; v[4 * g4 + 1] = a.y; v[4 * g4 + 2] = a.z; v[4 * g4 + 3] = a.w;
                         }
                         split_store16<false>(v, nullptr, tl + TM_AHI + 16 * half, tl + TM_ALO + 16 * half);
                         if (WIDE) {
