@@ -105,7 +105,7 @@ struct PackedLayout {
     int V0p, c0p, V1p, c1p, V2, c2, lv_sum, lv_in;
     // tensor-core section (only when kin <= 48): tf32 hi/lo splits of the feature weights as tcgen05 B
     // operands, canonical K-major chunk layout [k/4][n][4], then the fp32 bias block.
-    int tc_ok, tc_k1, B1h, B1l, B2h, B2l, B3h, B3l, Bb, P;
+    int tc_ok, tc_k1, b1_f16, B1h, B1l, B2h, B2l, B3h, B3l, Bb, P;
     __host__ __device__ explicit PackedLayout(int kin_, int F_ = MAXF) : kin(kin_) {
         int o = 0;
         W0p = o; o += kin * HP;
@@ -125,8 +125,13 @@ struct PackedLayout {
         lv_in = o; o += (F_ + 3) & ~3;       // input_noise_logvar, all F columns
         tc_ok = (kin <= TC_K1W) ? 1 : 0;
         tc_k1 = kin <= TC_K1 ? TC_K1 : TC_K1W;
-        B1h = o; o += tc_ok ? tc_k1 * TC_N * 1 : 0;     // [K1/4][48][4]
-        B1l = o; o += tc_ok ? tc_k1 * TC_N * 1 : 0;
+        // layer 1 with at most 32 live inputs runs as kind::f16 (x is staged once per tile as fp16 hi / lo, see
+        // predict_tc.cuh): its B operands are fp16 hi / lo, [K1/8][48][8 halves], two halves per 32-bit word; the wide
+        // variant keeps tf32 operands [K1/4][48][4]
+        b1_f16 = (kin <= TC_K1) ? 1 : 0;
+        const int b1 = tc_ok ? (b1_f16 ? tc_k1 * TC_N / 2 : tc_k1 * TC_N) : 0;
+        B1h = o; o += b1;
+        B1l = o; o += b1;
         B2h = o; o += tc_ok ? TC_K2 * TC_N : 0;          // [40/4][48][4]
         B2l = o; o += tc_ok ? TC_K2 * TC_N : 0;
         B3h = o; o += tc_ok ? TC_K2 * TC_N3 : 0;         // [40/4][32][4]

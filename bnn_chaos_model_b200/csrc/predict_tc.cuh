@@ -25,6 +25,8 @@
 //       regress_nn with the fp32 head weights read through L2, store (mu, std); records live in an NT-deep ring
 //       (unit_done / rec_free barriers give the epilogue back-pressure when the tails fall behind).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "predict_device.cuh"
 #include "tc.cuh"
 
@@ -55,6 +57,8 @@ struct Bars {
     uint64_t sum_full[2], sum_free[2];                 // tail pair j: summary statistics written by the stats warp / consumed
     uint32_t tmem_base;
     int next_item;                                     // dynamic work distribution: the item this CTA runs next
+    unsigned int x_maxbits;                            // fp16 x tile: bits of the largest finite |x| of the tile
+    float x_scale;                                     // ... and the power of two that undoes the tile's down-scaling
 };
 
 // The 4 records of system p (T = 100, 5 systems per tile, 32-row blocks): record index (block*2 + segment) and
@@ -134,6 +138,72 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------
+// x tile for the fp16 layer 1 (at most 32 live inputs): the tile is split ONCE into fp16 hi = RN(x), lo = RN(x - hi)
+// -- 11 + 11 significant bits, the same as the tf32 split -- and written as the A operand of tcgen05.mma kind::f16 in
+// the canonical K-major no-swizzle layout [M tile][k / 8][128 rows][8 halves] (hi at byte 0, lo at byte 32768 of the
+// x area), which the tensor core reads straight from shared memory: no per-unit staging through registers and tensor
+// memory (16 values split + two tcgen05.st per thread, unit and slot before), and K = 16 per instruction.
+// fp16 range: lo below 2^-14 loses bits to gradual underflow (absolute error <= 2^-25 per input, ~1e-8 of a
+// pre-activation); a tile whose largest finite |x| reaches 2^15 is scaled down by a power of two and the layer-1
+// epilogue scales the accumulator back (*x_scale; 1 for in-distribution inputs), so large inputs stay finite like in
+// the fp32 reference.  NaN / Inf propagate (Inf: hi = Inf, lo = NaN).
+// ---------------------------------------------------------------------------------------
+constexpr int XH_BYTES = XS_ROWS * 32 * 2;   // bytes of the hi (and of the lo) array
+__device__ __forceinline__ int x16_offset(int row, int k) {   // byte offset of (row, k) inside the hi or lo array
+    return ((((row >> 7) * 4 + (k >> 3)) * 128 + (row & 127)) << 4) + ((k & 7) << 1);
+}
+__device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int64_t n0, int n_valid, int F,
+                                                const ColMap& cm, unsigned char* __restrict__ xs16,
+                                                int* __restrict__ poison, unsigned int* __restrict__ maxbits,
+                                                float* __restrict__ scale_out) {
+    for (int i = threadIdx.x; i < 2 * XH_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(xs16)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int r = threadIdx.x; r < ROWS; r += blockDim.x) poison[r] = 0;
+    if (threadIdx.x == 0) *maxbits = 0u;
+    __syncthreads();
+    const float* src = X + n0 * (int64_t)T_FIXED * F;
+    const int total = n_valid * T_FIXED * F;
+    // pass 1 (L2 hits: the tile was bulk-prefetched while the previous item ran): largest finite |x| of the live columns,
+    // non-finite values in zeroed columns
+    unsigned int mx = 0u;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const float v = __ldg(src + idx);
+        const int row = idx / F, c = idx - row * F;
+        const int k = cm.inv[c];
+        if (k >= 0) {
+            if (k < 32 && isfinite(v)) mx = max(mx, __float_as_uint(fabsf(v)));
+        } else if (!isfinite(v)) {
+            poison[row] = 1;
+        }
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxbits, mx);
+    __syncthreads();
+    const int e = (int)(*maxbits >> 23) - 127;
+    const int kk = e > 14 ? e - 14 : 0;                      // |x| 2^-kk < 2^15
+    const float down = __uint_as_float((uint32_t)(127 - kk) << 23);
+    if (threadIdx.x == 0) *scale_out = __uint_as_float((uint32_t)(127 + kk) << 23);
+    unsigned char* xh = xs16;
+    unsigned char* xl = xs16 + XH_BYTES;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const float v = __ldg(src + idx) * down;
+        const int row = idx / F, c = idx - row * F;
+        const int k = cm.inv[c];
+        if (k >= 0 && k < 32) {
+            const __half h = __float2half_rn(v);
+            const int off = x16_offset(row, k);
+            *reinterpret_cast<__half*>(xh + off) = h;
+            *reinterpret_cast<__half*>(xl + off) = __float2half_rn(v - __half2float(h));
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
+        if (poison[r]) *reinterpret_cast<unsigned short*>(xh + x16_offset(r, 0)) = 0x7e00u;  // x - mask keeps NaN/Inf as NaN (:452-478)
+    }
+    fence_proxy_async_smem();   // the tensor core reads the tile through the async proxy
+    __syncthreads();
+}
+
 // (d + bias) -> ReLU -> hi/lo of 4 consecutive columns; bias: 16-byte aligned shared memory, same for every lane.
 // hi = v rounded to the 11 significant bits of tf32, lo = v - hi exactly, on the FMA pipe with packed fp32x2 instructions:
 //   c = fma(v, 8192, v) = RN(8193 v);  hi = fma(v, -8192, c) = c - 8192 v (exact: Veltkamp's splitting with the exact
@@ -143,13 +213,14 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
 // the top stall of the epilogue.  Inf becomes NaN (Inf - Inf), as it did in lo = v - hi before.
 template <bool EPI>
 __device__ __forceinline__ void split_group4(const uint32_t* __restrict__ d, const float* __restrict__ bias,
-                                             uint32_t* __restrict__ h, uint32_t* __restrict__ l) {
+                                             uint32_t* __restrict__ h, uint32_t* __restrict__ l, u64 scale2 = 0x3f8000003f800000ull) {
     u64 v01 = pack2(__uint_as_float(d[0]), __uint_as_float(d[1]));
     u64 v23 = pack2(__uint_as_float(d[2]), __uint_as_float(d[3]));
     if (EPI) {
+        // d * scale + bias: scale = 1 (one rounding, the same value as d + bias) except in layer 1 of a down-scaled x tile
         const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bias);
-        v01 = add2(v01, b.x);
-        v23 = add2(v23, b.y);
+        v01 = fma2(v01, scale2, b.x);
+        v23 = fma2(v23, scale2, b.y);
         float v[4];
         unpack2(v01, v[0], v[1]);
         unpack2(v23, v[2], v[3]);
@@ -173,10 +244,10 @@ __device__ __forceinline__ void split_group4(const uint32_t* __restrict__ d, con
 }
 template <bool EPI>
 __device__ __forceinline__ void split_store16(const uint32_t (&d)[16], const float* __restrict__ bias, uint32_t t_hi,
-                                              uint32_t t_lo) {
+                                              uint32_t t_lo, u64 scale2 = 0x3f8000003f800000ull) {
     uint32_t h[16], l[16];
 #pragma unroll
-    for (int g4 = 0; g4 < 4; ++g4) split_group4<EPI>(&d[4 * g4], bias + 4 * g4, &h[4 * g4], &l[4 * g4]);
+    for (int g4 = 0; g4 < 4; ++g4) split_group4<EPI>(&d[4 * g4], bias + 4 * g4, &h[4 * g4], &l[4 * g4], scale2);
     tmem_st16(t_hi, h);
     tmem_st16(t_lo, l);
 }
@@ -191,9 +262,9 @@ __device__ __forceinline__ void split_store8(const uint32_t (&d)[8], const float
 }
 template <bool EPI>
 __device__ __forceinline__ void split_store4(const uint32_t (&d)[4], const float* __restrict__ bias, uint32_t t_hi,
-                                             uint32_t t_lo) {
+                                             uint32_t t_lo, u64 scale2 = 0x3f8000003f800000ull) {
     uint32_t h[4], l[4];
-    split_group4<EPI>(d, bias, h, l);
+    split_group4<EPI>(d, bias, h, l, scale2);
     tmem_st4(t_hi, h);
     tmem_st4(t_lo, l);
 }
@@ -230,6 +301,28 @@ __device__ __forceinline__ void issue_layer_part(uint32_t ts, uint32_t bh_addr, 
     }
     __syncwarp();
 }
+// Layer 1 as kind::f16 with BOTH operands in shared memory: A = the tile's fp16 hi / lo rows of M tile m (ah_addr /
+// al_addr: byte address of the M tile's first K chunk; chunks 2048 bytes apart), B = the unit's fp16 hi / lo W0.
+// K = 32 = two K = 16 steps per term; corrections first, like issue_layer_part.
+template <int N>
+__device__ __forceinline__ void issue_layer1_f16(uint32_t ts, uint32_t ah_addr, uint32_t al_addr, uint32_t bh_addr,
+                                                 uint32_t bl_addr) {
+    constexpr uint32_t idesc = idesc_f16(128, N);
+    const uint32_t d = ts + TM_D;
+    const uint64_t ah = smem_desc_kmajor(ah_addr, 2048u, 128u), al = smem_desc_kmajor(al_addr, 2048u, 128u);
+    const uint64_t bh = smem_desc_kmajor(bh_addr, (uint32_t)N * 16u, 128u), bl = smem_desc_kmajor(bl_addr, (uint32_t)N * 16u, 128u);
+    constexpr uint64_t astep = 2ull * 2048ull / 16ull, bstep = 2ull * N;   // two 16-byte K chunks per K = 16 step
+    if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < TC_K1 / 16; ++ks) mma_f16_ss(d, al + ks * astep, bh + ks * bstep, idesc, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < TC_K1 / 16; ++ks) mma_f16_ss(d, ah + ks * astep, bl + ks * bstep, idesc, true);
+#pragma unroll
+        for (int ks = 0; ks < TC_K1 / 16; ++ks) mma_f16_ss(d, ah + ks * astep, bh + ks * bstep, idesc, true);
+    }
+    __syncwarp();
+}
+
 template <int N, int KS>
 __device__ __forceinline__ void issue_layer(uint32_t ts, uint32_t bh_addr, uint32_t bl_addr) {
     issue_layer_part<N, 0, KS, true>(ts, bh_addr, bl_addr);

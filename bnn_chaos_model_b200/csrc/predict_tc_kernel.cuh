@@ -24,9 +24,10 @@ namespace tc {
 template <bool WIDE>
 struct RingPlan {
     static constexpr int K1 = WIDE ? TC_K1W : TC_K1;
-    static constexpr int B_FLOATS = 2 * (K1 * TC_N + TC_K2 * TC_N + TC_K2 * TC_N3) + TC_BIAS;
+    static constexpr int B1_BYTES = WIDE ? K1 * TC_N * 4 : K1 * TC_N * 2;   // tf32 (wide) or fp16 (kind::f16 layer 1) operands
+    static constexpr int B_FLOATS = 2 * (B1_BYTES / 4 + TC_K2 * TC_N + TC_K2 * TC_N3) + TC_BIAS;
     static constexpr int B_BYTES = B_FLOATS * 4;
-    static constexpr int O_B1H = 0, O_B1L = O_B1H + K1 * TC_N * 4, O_B2H = O_B1L + K1 * TC_N * 4,
+    static constexpr int O_B1H = 0, O_B1L = O_B1H + B1_BYTES, O_B2H = O_B1L + B1_BYTES,
                          O_B2L = O_B2H + TC_K2 * TC_N * 4, O_B3H = O_B2L + TC_K2 * TC_N * 4,
                          O_B3L = O_B3H + TC_K2 * TC_N3 * 4, O_BIAS = O_B3L + TC_K2 * TC_N3 * 4;  // byte offsets in a slot
     static constexpr int NREC = WIDE ? 2 : tc::NREC;   // record-ring depth: the wide ring takes the shared memory of two slots
@@ -141,7 +142,11 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
             }
             mbar_init_fence();
         }
-        load_x_tile_tc(prm.X, n0, n_valid, prm.F, prm.kin, prm.cm, xs, reinterpret_cast<int*>(fb));
+        if (WIDE)
+            load_x_tile_tc(prm.X, n0, n_valid, prm.F, prm.kin, prm.cm, xs, reinterpret_cast<int*>(fb));
+        else
+            load_x_tile_f16(prm.X, n0, n_valid, prm.F, prm.cm, smem_tc + Plan::xs, reinterpret_cast<int*>(fb), &bars->x_maxbits,
+                            &bars->x_scale);
         __syncthreads();
         tc_fence_after();
 
@@ -242,7 +247,10 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                             tc_fence_after();
                             issue_layer_part<TC_N, 5, 6, false>(tsv, wb + O_B1H, wb + O_B1L);
                         } else {
-                            issue_layer<TC_N, TC_K1 / 8>(tsv, wb + O_B1H, wb + O_B1L);
+                            // A straight from the tile's fp16 hi / lo arrays: M tile of this slot = team + 2 (slot in team)
+                            uint32_t xa = smem_u32(smem_tc + Plan::xs) + (uint32_t)(((slot >> 1) + 2 * (slot & 1)) * 4 * 2048);
+                            asm volatile("" : "+r"(xa));
+                            issue_layer1_f16<TC_N>(tsv, xa, xa + (uint32_t)XH_BYTES, wb + O_B1H, wb + O_B1L);
                         }
                     } else if (layer == 1)
                         issue_layer<TC_N, TC_K2 / 8>(tsv, wb + O_B2H, wb + O_B2L);
@@ -365,7 +373,14 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                         if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 2);
                         latent_to_fb(s);
                     }
-                    if (i < n_units) {
+                    if (i < n_units && !WIDE) {
+                        // layer 1 reads x from shared memory: all it needs from this warp is that the slot's accumulator is
+                        // free again (the previous unit's latent rows have been read out)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->a_ready[2 * team + s]);
+                    }
+                    if (i < n_units && WIDE) {
                         const int R = m * 128 + quad * 32 + lane;  // tile row of this thread (rows 500..511 of xs are zero)
                         uint32_t v[16];
 #pragma unroll
@@ -374,7 +389,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                             v[4 * g4] = a.x; v[4 * g4 + 1] = a.y; v[4 * g4 + 2] = a.z; v[4 * g4 + 3] = a.w;
                         }
                         split_store16<false>(v, nullptr, tl + TM_AHI + 16 * half, tl + TM_ALO + 16 * half);
-                        if (WIDE) {
+                        {
                             // live inputs 32..47 of this row from L2 (the x tile was just read by this CTA; they are the same
                             // for every unit, but 16 more columns of shared memory do not exist): half 0 puts 32..39 behind the
                             // 32 staged columns (first pass, K = 40); half 1 restages 40..47 into columns 0..7 once the first
@@ -416,9 +431,11 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                         uint32_t d0[16], d1[4];
                         tmem_ld16(tl + TM_D, d0);
                         tmem_ld4(tl + TM_D + 16, d1);
+                        const float sc = (!WIDE && layer == 0) ? bars->x_scale : 1.0f;   // undo the x tile's power-of-two down-scaling
+                        const u64 sc2 = pack2(sc, sc);
                         tc_wait_ld();
-                        split_store16<true>(d0, bl, tl + TM_AHI, tl + TM_ALO);
-                        split_store4<true>(d1, bl + 16, tl + TM_AHI + 16, tl + TM_ALO + 16);
+                        split_store16<true>(d0, bl, tl + TM_AHI, tl + TM_ALO, sc2);
+                        split_store4<true>(d1, bl + 16, tl + TM_AHI + 16, tl + TM_ALO + 16, sc2);
                         publish(s);
                         if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 10 * (layer + 1) + 3);
                     }

@@ -9,6 +9,8 @@
 // and SWAGModel.load (:748-761), which installs the flat vector into the module.
 //
 // HBM-bound: writes d floats per unit; pre_D rows are re-read from L2.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace bnn {
@@ -79,10 +81,11 @@ swag_sample_kernel(const float* __restrict__ w_avg, const float* __restrict__ w2
 }
 
 // Where packed float i of a unit comes from: index into the flat (flatten()-order) vector and how it is transformed.
-enum PackKind : int { PK_ZERO = 0, PK_COPY = 1, PK_TF32_HI = 2, PK_TF32_LO = 3 };
+enum PackKind : int { PK_ZERO = 0, PK_COPY = 1, PK_TF32_HI = 2, PK_TF32_LO = 3, PK_F16_HI = 4, PK_F16_LO = 5 };
 struct PackSrc {
     int src;
     int kind;
+    int src2;   // fp16 kinds: the word's second half (k + 1); -1 = zero
 };
 
 __device__ __forceinline__ PackSrc pack_source(int i, const FlatLayout& fl, const PackedLayout& pl, const LiveCols& lc) {
@@ -143,7 +146,19 @@ __device__ __forceinline__ PackSrc pack_source(int i, const FlatLayout& fl, cons
         // tensor-core B operands: element (n, k) of a [N][K] matrix sits at ((k/4)*N + n)*4 + k%4
         int r, N, nreal, wsrc, kreal, ld;
         bool lo;
-        if (i < pl.B2h) {
+        if (i < pl.B2h && pl.b1_f16) {
+            // fp16 hi / lo of W0: word r of [K1/8][48][4 words] holds the halves k = 8 chunk + 2 (r & 3) + {0, 1} of row n
+            r = i - pl.B1h;
+            const int b1 = pl.tc_k1 * TC_N / 2;
+            lo = r >= b1; r -= lo ? b1 : 0;
+            const int chunk = r / (TC_N * 4), n = (r / 4) % TC_N, k = chunk * 8 + 2 * (r & 3);
+            PackSrc ps{-1, lo ? PK_F16_LO : PK_F16_HI, -1};
+            if (n < H) {
+                if (k < pl.kin) ps.src = fl.W0 + n * fl.F + (int)lc.col[k];
+                if (k + 1 < pl.kin) ps.src2 = fl.W0 + n * fl.F + (int)lc.col[k + 1];
+            }
+            return ps;
+        } else if (i < pl.B2h) {
             r = i - pl.B1h; N = TC_N; lo = r >= pl.tc_k1 * TC_N; r -= lo ? pl.tc_k1 * TC_N : 0;
             nreal = H; kreal = pl.kin; wsrc = fl.W0; ld = fl.F;
         } else if (i < pl.B3h) {
@@ -155,14 +170,26 @@ __device__ __forceinline__ PackSrc pack_source(int i, const FlatLayout& fl, cons
         }
         const int chunk = r / (N * 4), n = (r / 4) % N, k = chunk * 4 + (r & 3);
         if (n < nreal && k < kreal)
-            return PackSrc{wsrc + n * ld + ((wsrc == fl.W0) ? (int)lc.col[k] : k), lo ? PK_TF32_LO : PK_TF32_HI};
-        return PackSrc{-1, PK_ZERO};
+            return PackSrc{wsrc + n * ld + ((wsrc == fl.W0) ? (int)lc.col[k] : k), lo ? PK_TF32_LO : PK_TF32_HI, -1};
+        return PackSrc{-1, PK_ZERO, -1};
     }
-    return PackSrc{src, src >= 0 ? PK_COPY : PK_ZERO};
+    return PackSrc{src, src >= 0 ? PK_COPY : PK_ZERO, -1};
+}
+
+// fp16 hi (round to nearest: 11 significant bits, like tf32) or lo = fp16(w - hi) of one weight, as 16 bits
+__device__ __forceinline__ uint32_t f16_part_bits(float w, bool lo) {
+    const __half h = __float2half_rn(w);
+    return (uint32_t)__half_as_ushort(lo ? __float2half_rn(w - __half2float(h)) : h);
 }
 
 __device__ __forceinline__ float pack_value(const float* th, PackSrc ps) {
     if (ps.kind == PK_ZERO) return 0.f;
+    if (ps.kind >= PK_F16_HI) {
+        const bool lo = ps.kind == PK_F16_LO;
+        const uint32_t a = ps.src >= 0 ? f16_part_bits(th[ps.src], lo) : 0u;
+        const uint32_t b = ps.src2 >= 0 ? f16_part_bits(th[ps.src2], lo) : 0u;
+        return __uint_as_float(a | (b << 16));
+    }
     const float w = th[ps.src];
     if (ps.kind == PK_COPY) return w;
     const float hi = tf32_rna(w);

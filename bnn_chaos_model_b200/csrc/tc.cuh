@@ -91,6 +91,15 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
            | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
+// Instruction descriptor for kind::f16 with fp16 A and B, fp32 accumulate, both K-major, dense (K = 16 per instruction).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4)                    // c_format  = F32
+           | (0u << 7)                  // a_format  = F16
+           | (0u << 10)                 // b_format  = F16
+           | ((uint32_t)(N >> 3) << 17) // n_dim
+           | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
 // One lane of a converged warp (uniform control flow around it keeps addresses/descriptors in uniform
 // registers, so that a tcgen05.mma costs a handful of issue slots instead of an R2UR/ELECT loop).
 __device__ __forceinline__ bool elect_one_sync() {
@@ -127,6 +136,19 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, one K = 16 step
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
