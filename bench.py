@@ -449,7 +449,7 @@ def run_ours(args):
             out = pend[0].result() if pend[0] is not None else None
             pend[0] = p
             return out
-        _, thp = ens.sample_thetas(n_samp, seed=i)  # K1 + pack (2 launches)
+        _, thp = ens.sample_thetas(n_samp, seed=i, want_flat=False)  # K1: sampler + packed layout, one fused launch
         if timed:
             a, b = ev(), ev()
             a.record(stream)
@@ -526,6 +526,33 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te[0])
 
+    # ---- the same through the C-ABI host entry a non-torch caller binds (bnn_multiswag_predict_host: pinned host x in,
+    # pinned [U, N, 2] predictions out, pipelined inside the library), rank 0 / N = 1 only
+    c_entry = None
+    if world == 1:
+        U = n_samp
+        out_c = torch.empty((U, n_sys, 2), dtype=torch.float32).pin_memory()
+        scratch = torch.empty(lib.bnn_multiswag_host_scratch_bytes(cfg, n_sys, U), dtype=torch.uint8, device=dev)
+
+        def c_step(i):
+            _lib.check(lib.bnn_multiswag_predict_host(cfg, xh.data_ptr(), n_sys, _lib.ptr(ens.w_avg), _lib.ptr(ens.w2_avg),
+                                                      _lib.ptr(ens.pre_D), 1, ens.K, n_samp, 0.5, i, out_c.data_ptr(),
+                                                      scratch.data_ptr(), _lib.current_stream_ptr()), "bnn_multiswag_predict_host")
+
+        c_step(0)
+        sync()
+        c0, c1 = ev(), ev()
+        c0.record(stream)
+        for i in range(n_e2e):
+            c_step(200 + i)
+        c1.record(stream)
+        sync()
+        c_ms = c0.elapsed_time(c1) / n_e2e
+        c_entry = {"value": n_sys * n_samp / (c_ms * 1e-3), "unit": "evals/s", "ms_per_step": c_ms,
+                   "entry": "bnn_multiswag_predict_host (include/bnnchaos.h), host buffers, [U, N, 2] out",
+                   "h2d_bytes_per_step": xh.numel() * 4, "d2h_bytes_per_step": out_c.numel() * 4}
+        del scratch, out_c
+
     # ---- measured FFMA peak (roofline denominator cross-check), rank 0
     ffma = {}
     sink = torch.zeros(4, device=dev)
@@ -591,10 +618,10 @@ def run_ours(args):
                 "l2": "inputs (164 MB x + 38 MB theta + 80 MB out per step) exceed the 126 MB L2; fresh theta every step",
             },
             "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": xh.numel() * 4,
-                    "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": e2e_ms},
-            "gpu_launches": 3 * args.steps,
+                    "d2h_bytes_per_step": out_h.numel() * 4, "ms_per_step": e2e_ms, "c_abi_host_entry": c_entry},
+            "gpu_launches": 2 * args.steps,
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "predict (K2, tcgen05 kind::tf32, 3xTF32)", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": "predict (K2, tcgen05: layer 1 kind::f16 on fp16 hi / lo, layers 2-3 kind::tf32, three split terms each)", "achieved": achieved,
                          "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                          "frac_tensor": achieved / tf32_peak, "frac_fp32": achieved / FP32_PEAK_NOMINAL,
                          "fp32_peak": FP32_PEAK_NOMINAL,

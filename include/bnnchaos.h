@@ -129,9 +129,12 @@ int bnn_add_input_noise(const bnn_model_config* cfg, const float* d_x, const flo
 int bnn_predict_instability(const bnn_model_config* cfg, const float* d_summary, int64_t B,
                             const float* d_theta_packed, float* d_out, void* stream);
 
-/* Host-buffer convenience entry (what a non-torch caller binds): h_x [N,T,F] and h_out
- * are HOST buffers; SWAG statistics are device-resident.  Copies x in, samples U =
- * n_models*samples_per_model units with Philox, predicts, copies out back, synchronises.
+/* Host-buffer convenience entry (what a non-torch caller binds): h_x [N,T,F] and h_out [U,N,2]
+ * are HOST buffers (pinned for real overlap); SWAG statistics are device-resident.  Samples U =
+ * n_models*samples_per_model units with Philox and predicts; the systems are cut into up to three
+ * chunks (at multiples of bnn_predict_system_granule) whose upload / prediction / download are
+ * pipelined over two internal side streams; synchronises before returning.  Bit-identical to one
+ * bnn_swag_sample + bnn_predict on device-resident data.
  * d_scratch must hold bnn_multiswag_host_scratch_bytes() bytes of device memory. */
 size_t bnn_multiswag_host_scratch_bytes(const bnn_model_config* cfg, int64_t n_systems, int64_t n_units);
 int bnn_multiswag_predict_host(const bnn_model_config* cfg, const float* h_x, int64_t n_systems,

@@ -178,21 +178,22 @@ def test_c_host_entry_with_plain_host_buffers(dev):
     lib = _lib.load()
     ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(17, dev)], device=dev)
     cfg = ens.config(100)
-    N, S_, seed = 57, 5, 21
-    xh = np.ascontiguousarray(synth.make_systems(N, seed=106))
-    U = ens.n_models * S_
-    out_h = np.full((U, N, 2), np.nan, np.float32)
-    nbytes = lib.bnn_multiswag_host_scratch_bytes(cfg, N, U)
-    assert nbytes > xh.nbytes
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        rc = lib.bnn_multiswag_predict_host(cfg, xh.ctypes.data_as(ctypes.c_void_p), N, _lib.ptr(ens.w_avg), _lib.ptr(ens.w2_avg),
-                                            _lib.ptr(ens.pre_D), ens.n_models, ens.K, S_, 0.5, seed,
-                                            out_h.ctypes.data_as(ctypes.c_void_p), scratch.data_ptr(),
-                                            _lib.current_stream_ptr())
-    _lib.check(rc, "bnn_multiswag_predict_host")
-    want = ens.predict(torch.from_numpy(xh).to(dev), S_, seed=seed).cpu().numpy()
-    assert np.array_equal(out_h, want)
+    S_, seed = 5, 21
+    for N in (57, 333, 1280):   # one chunk; three pipelined chunks with a ragged tail; three chunks, whole tiles
+        xh = np.ascontiguousarray(synth.make_systems(N, seed=106))
+        U = ens.n_models * S_
+        out_h = np.full((U, N, 2), np.nan, np.float32)
+        nbytes = lib.bnn_multiswag_host_scratch_bytes(cfg, N, U)
+        assert nbytes > xh.nbytes
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.bnn_multiswag_predict_host(cfg, xh.ctypes.data_as(ctypes.c_void_p), N, _lib.ptr(ens.w_avg),
+                                                _lib.ptr(ens.w2_avg), _lib.ptr(ens.pre_D), ens.n_models, ens.K, S_, 0.5, seed,
+                                                out_h.ctypes.data_as(ctypes.c_void_p), scratch.data_ptr(),
+                                                _lib.current_stream_ptr())
+        _lib.check(rc, "bnn_multiswag_predict_host")
+        want = ens.predict(torch.from_numpy(xh).to(dev), S_, seed=seed).cpu().numpy()
+        assert np.array_equal(out_h, want), N
     # argument errors come back as negative codes with a message, not as a crash
     rc = lib.bnn_multiswag_predict_host(cfg, None, N, _lib.ptr(ens.w_avg), _lib.ptr(ens.w2_avg), _lib.ptr(ens.pre_D),
                                         ens.n_models, ens.K, S_, 0.5, seed, out_h.ctypes.data_as(ctypes.c_void_p),
