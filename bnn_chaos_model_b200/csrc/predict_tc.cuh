@@ -153,6 +153,9 @@ constexpr int XH_BYTES = XS_ROWS * 32 * 2;   // bytes of the hi (and of the lo) 
 __device__ __forceinline__ int x16_offset(int row, int k) {   // byte offset of (row, k) inside the hi or lo array
     return ((((row >> 7) * 4 + (k >> 3)) * 128 + (row & 127)) << 4) + ((k & 7) << 1);
 }
+// One warp per time-step row, lane = input column (columns lane and lane + 32): coalesced row reads, the column -> live
+// index map is looked up once per lane.  (Element-indexed loops with a per-element lookup of the map in constant memory --
+// 32 different addresses per warp load, serialised -- made the tile load 8 % of the kernel's time: ncu source view.)
 __device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int64_t n0, int n_valid, int F,
                                                 const ColMap& cm, unsigned char* __restrict__ xs16,
                                                 int* __restrict__ poison, unsigned int* __restrict__ maxbits,
@@ -161,23 +164,28 @@ __device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) poison[r] = 0;
     if (threadIdx.x == 0) *maxbits = 0u;
     __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int c1 = lane + 32;
+    // role of this lane's two columns: live index k >= 0 (staged when k < 32), -1 = zeroed by the model's flags, -2 = none
+    const int k0 = lane < F ? (int)cm.inv[lane] : -2;
+    const int k1 = c1 < F ? (int)cm.inv[c1] : -2;
+    const bool live0 = k0 >= 0 && k0 < 32, live1 = k1 >= 0 && k1 < 32;
     const float* src = X + n0 * (int64_t)T_FIXED * F;
-    const int total = n_valid * T_FIXED * F;
+    const int rows = n_valid * T_FIXED;
     // pass 1 (L2 hits: the tile was bulk-prefetched while the previous item ran): largest finite |x| of the live columns,
     // non-finite values in zeroed columns
     unsigned int mx = 0u;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const float v = __ldg(src + idx);
-        const int row = idx / F, c = idx - row * F;
-        const int k = cm.inv[c];
-        if (k >= 0) {
-            if (k < 32 && isfinite(v)) mx = max(mx, __float_as_uint(fabsf(v)));
-        } else if (!isfinite(v)) {
-            poison[row] = 1;
-        }
+#pragma unroll 4
+    for (int row = warp; row < rows; row += n_warps) {
+        const float* p = src + (int64_t)row * F;
+        const float v0 = k0 != -2 ? __ldg(p + lane) : 0.f;
+        const float v1 = k1 != -2 ? __ldg(p + c1) : 0.f;
+        if (live0 && isfinite(v0)) mx = max(mx, __float_as_uint(fabsf(v0)));
+        if (live1 && isfinite(v1)) mx = max(mx, __float_as_uint(fabsf(v1)));
+        if ((k0 == -1 && !isfinite(v0)) || (k1 == -1 && !isfinite(v1))) poison[row] = 1;
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
-    if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxbits, mx);
+    if (lane == 0 && mx) atomicMax(maxbits, mx);
     __syncthreads();
     const int e = (int)(*maxbits >> 23) - 127;
     const int kk = e > 14 ? e - 14 : 0;                      // |x| 2^-kk < 2^15
@@ -185,16 +193,19 @@ __device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int
     if (threadIdx.x == 0) *scale_out = __uint_as_float((uint32_t)(127 + kk) << 23);
     unsigned char* xh = xs16;
     unsigned char* xl = xs16 + XH_BYTES;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const float v = __ldg(src + idx) * down;
-        const int row = idx / F, c = idx - row * F;
-        const int k = cm.inv[c];
-        if (k >= 0 && k < 32) {
-            const __half h = __float2half_rn(v);
-            const int off = x16_offset(row, k);
-            *reinterpret_cast<__half*>(xh + off) = h;
-            *reinterpret_cast<__half*>(xl + off) = __float2half_rn(v - __half2float(h));
-        }
+    auto put = [&](int row, int k, float v) {
+        const __half h = __float2half_rn(v);
+        const int off = x16_offset(row, k);
+        *reinterpret_cast<__half*>(xh + off) = h;
+        *reinterpret_cast<__half*>(xl + off) = __float2half_rn(v - __half2float(h));
+    };
+#pragma unroll 4
+    for (int row = warp; row < rows; row += n_warps) {
+        const float* p = src + (int64_t)row * F;
+        const float v0 = live0 ? __ldg(p + lane) * down : 0.f;
+        const float v1 = live1 ? __ldg(p + c1) * down : 0.f;
+        if (live0) put(row, k0, v0);
+        if (live1) put(row, k1, v1);
     }
     __syncthreads();
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
