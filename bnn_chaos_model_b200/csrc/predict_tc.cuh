@@ -57,8 +57,8 @@ struct Bars {
     uint64_t sum_full[2], sum_free[2];                 // tail pair j: summary statistics written by the stats warp / consumed
     uint32_t tmem_base;
     int next_item;                                     // dynamic work distribution: the item this CTA runs next
-    unsigned int x_maxbits;                            // fp16 x tile: bits of the largest finite |x| of the tile
-    float x_scale;                                     // ... and the power of two that undoes the tile's down-scaling
+    unsigned int x_maxbits[SYS];                       // fp16 x tile: bits of the largest finite |x| of each system
+    float x_scale[SYS];                                // ... and the power of two that undoes the system's down-scaling
 };
 
 // The 4 records of system p (T = 100, 5 systems per tile, 32-row blocks): record index (block*2 + segment) and
@@ -145,9 +145,10 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
 // x area), which the tensor core reads straight from shared memory: no per-unit staging through registers and tensor
 // memory (16 values split + two tcgen05.st per thread, unit and slot before), and K = 16 per instruction.
 // fp16 range: lo below 2^-14 loses bits to gradual underflow (absolute error <= 2^-25 per input, ~1e-8 of a
-// pre-activation); a tile whose largest finite |x| reaches 2^15 is scaled down by a power of two and the layer-1
-// epilogue scales the accumulator back (*x_scale; 1 for in-distribution inputs), so large inputs stay finite like in
-// the fp32 reference.  NaN / Inf propagate (Inf: hi = Inf, lo = NaN).
+// pre-activation); a SYSTEM whose largest finite |x| reaches 2^15 is scaled down by a power of two and the layer-1
+// epilogue scales its rows of the accumulator back (x_scale[system]; 1 for in-distribution inputs), so large inputs stay
+// finite like in the fp32 reference and cost precision only in their own system.  NaN / Inf propagate (Inf: hi = Inf,
+// lo = NaN).
 // ---------------------------------------------------------------------------------------
 constexpr int XH_BYTES = XS_ROWS * 32 * 2;   // bytes of the hi (and of the lo) array
 __device__ __forceinline__ int x16_offset(int row, int k) {   // byte offset of (row, k) inside the hi or lo array
@@ -162,7 +163,7 @@ __device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int
                                                 float* __restrict__ scale_out) {
     for (int i = threadIdx.x; i < 2 * XH_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(xs16)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) poison[r] = 0;
-    if (threadIdx.x == 0) *maxbits = 0u;
+    if (threadIdx.x < SYS) maxbits[threadIdx.x] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int c1 = lane + 32;
@@ -174,23 +175,27 @@ __device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int
     const int rows = n_valid * T_FIXED;
     // pass 1 (L2 hits: the tile was bulk-prefetched while the previous item ran): largest finite |x| of the live columns,
     // non-finite values in zeroed columns
-    unsigned int mx = 0u;
 #pragma unroll 4
     for (int row = warp; row < rows; row += n_warps) {
         const float* p = src + (int64_t)row * F;
         const float v0 = k0 != -2 ? __ldg(p + lane) : 0.f;
         const float v1 = k1 != -2 ? __ldg(p + c1) : 0.f;
-        if (live0 && isfinite(v0)) mx = max(mx, __float_as_uint(fabsf(v0)));
+        unsigned int mx = 0u;
+        if (live0 && isfinite(v0)) mx = __float_as_uint(fabsf(v0));
         if (live1 && isfinite(v1)) mx = max(mx, __float_as_uint(fabsf(v1)));
         if ((k0 == -1 && !isfinite(v0)) || (k1 == -1 && !isfinite(v1))) poison[row] = 1;
+        if (__any_sync(0xffffffffu, mx >= 0x47000000u)) {   // only |x| >= 2^15 matters (rare)
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0) atomicMax(maxbits + row / T_FIXED, mx);
+        }
     }
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if (lane == 0 && mx) atomicMax(maxbits, mx);
     __syncthreads();
-    const int e = (int)(*maxbits >> 23) - 127;
-    const int kk = e > 14 ? e - 14 : 0;                      // |x| 2^-kk < 2^15
-    const float down = __uint_as_float((uint32_t)(127 - kk) << 23);
-    if (threadIdx.x == 0) *scale_out = __uint_as_float((uint32_t)(127 + kk) << 23);
+    // per system: |x| 2^-kk < 2^15
+    auto shift_of = [&](int sys) {
+        const int e = (int)(maxbits[sys] >> 23) - 127;
+        return e > 14 ? e - 14 : 0;
+    };
+    if (threadIdx.x < SYS) scale_out[threadIdx.x] = __uint_as_float((uint32_t)(127 + shift_of(threadIdx.x)) << 23);
     unsigned char* xh = xs16;
     unsigned char* xl = xs16 + XH_BYTES;
     auto put = [&](int row, int k, float v) {
@@ -202,6 +207,7 @@ __device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int
 #pragma unroll 4
     for (int row = warp; row < rows; row += n_warps) {
         const float* p = src + (int64_t)row * F;
+        const float down = __uint_as_float((uint32_t)(127 - shift_of(row / T_FIXED)) << 23);
         const float v0 = live0 ? __ldg(p + lane) * down : 0.f;
         const float v1 = live1 ? __ldg(p + c1) * down : 0.f;
         if (live0) put(row, k0, v0);

@@ -145,8 +145,8 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
         if (WIDE)
             load_x_tile_tc(prm.X, n0, n_valid, prm.F, prm.kin, prm.cm, xs, reinterpret_cast<int*>(fb));
         else
-            load_x_tile_f16(prm.X, n0, n_valid, prm.F, prm.cm, smem_tc + Plan::xs, reinterpret_cast<int*>(fb), &bars->x_maxbits,
-                            &bars->x_scale);
+            load_x_tile_f16(prm.X, n0, n_valid, prm.F, prm.cm, smem_tc + Plan::xs, reinterpret_cast<int*>(fb), bars->x_maxbits,
+                            bars->x_scale);
         __syncthreads();
         tc_fence_after();
 
@@ -360,6 +360,16 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                 if (lane == 0) mbar_arrive(&bars->unit_done[rs]);
             };
 
+            // down-scaling exponents of this thread's rows in the team's two slots (0 unless the row's system holds |x| >= 2^15):
+            // the layer-1 epilogue multiplies the accumulator by 2^kk; one register for the whole item
+            int x_kk = 0;
+            if (!WIDE) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int sys = min(((team + 2 * s) * 128 + quad * 32 + lane) / T_FIXED, SYS - 1);
+                    x_kk |= (int)((__float_as_uint(bars->x_scale[sys]) >> 23) - 127u) << (8 * s);
+                }
+            }
 #pragma unroll 1
             for (int i = 0; i <= n_units; ++i) {
                 // ---- phase 0 of both slots: latent rows of the previous unit -> fb, x -> A (layer 1 starts), pooling ----
@@ -431,7 +441,8 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                         uint32_t d0[16], d1[4];
                         tmem_ld16(tl + TM_D, d0);
                         tmem_ld4(tl + TM_D + 16, d1);
-                        const float sc = (!WIDE && layer == 0) ? bars->x_scale : 1.0f;   // undo the x tile's power-of-two down-scaling
+                        // undo the power-of-two down-scaling of this row's system (1 unless the system holds |x| >= 2^15)
+                        const float sc = (!WIDE && layer == 0) ? __uint_as_float((127u + ((uint32_t)(x_kk >> (8 * s)) & 0xffu)) << 23) : 1.0f;
                         const u64 sc2 = pack2(sc, sc);
                         tc_wait_ld();
                         split_store16<true>(d0, bl, tl + TM_AHI, tl + TM_ALO, sc2);

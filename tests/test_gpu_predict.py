@@ -334,6 +334,30 @@ def test_edge_cases(dev):
         m.sample_weights(0.5)
 
 
+def test_fp16_layer1_input_range(dev, predict_variant):
+    """The tensor-core kernel stages x as fp16 hi / lo: a system with |x| >= 2^15 in a live column is scaled down by a
+    power of two (and its layer-1 accumulator scaled back), tiny inputs lose nothing that matters.  Both against the fp32
+    FFMA kernel (same Philox draws) at 1e-5; the out-of-range system must not change its tile neighbours by one bit."""
+    ens = MultiSWAG([make_swag_model(0, dev)], device=dev)
+    S_, N = 6, 20
+    base = synth.make_systems(N, seed=61)
+    live = [c for c in range(41) if c not in R.ModelSpec.from_hparams(swag_stats(0)["hparams"]).zero_cols]
+    big = base.copy()
+    big[7, :, live[3]] *= 3.0e5          # system 7 (tile 1) far out of distribution: |x| ~ 1e6
+    big[12, 40:60, live[10]] = -7.0e7    # system 12 (tile 2): a burst of huge values
+    tiny = base * 1.0e-6
+    outs = {}
+    for name in ("tc", "v2"):
+        predict_variant(name)
+        outs[name] = [ens.predict(torch.from_numpy(a).to(dev), S_, seed=4) for a in (base, big, tiny)]
+    for k, label in enumerate(("base", "big", "tiny")):
+        assert bool(torch.isfinite(outs["tc"][k]).all()), label
+        assert rel_err(outs["tc"][k].cpu(), outs["v2"][k].cpu()) < TOL, label
+    keep = [n for n in range(N) if n not in (7, 12)]
+    assert torch.equal(outs["tc"][1][:, keep], outs["tc"][0][:, keep])
+    assert not torch.equal(outs["tc"][1][:, 7], outs["tc"][0][:, 7])
+
+
 def test_full_size_properties(dev):
     """BASELINE config-2-sized run (10k systems x 1000 samples would take the oracle hours):
     check size-independent properties at a large size + spot checks against the oracle."""
