@@ -117,20 +117,23 @@ __device__ __forceinline__ void load_x_tile_tc(const float* __restrict__ X, int6
     for (int i = threadIdx.x; i < XS_ROWS * 32; i += blockDim.x) xs[i] = 0.f;
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) poison[r] = 0;
     __syncthreads();
+    // one warp per row, lane = column (columns lane and lane + 32): coalesced reads, the column map looked up once per lane
+    // (see load_x_tile_f16); live columns 32.. (wide variant) are read from L2 by the stage
     const float* src = X + n0 * (int64_t)T_FIXED * F;
-    const int total = n_valid * T_FIXED * F;
-    auto put = [&](int idx, float v) {
-        const int row = idx / F, c = idx - row * F;
-        const int k = cm.inv[c];
-        if (k >= 0) {
-            if (k < 32) xs[xs_index(row, k)] = v;   // live columns 32.. (wide variant) are read from L2 by the stage
-        } else if (!isfinite(v)) {
-            poison[row] = 1;
-        }
-    };
-    // (the tile was bulk-prefetched into L2 while the previous item ran, so these scalar rounds are L2 hits; a version with
-    // 16-byte loads and four scattered stores per thread measured 1.6 ms slower per 1e7-eval launch)
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) put(idx, __ldg(src + idx));
+    const int rows = n_valid * T_FIXED;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int c1 = lane + 32;
+    const int k0 = lane < F ? (int)cm.inv[lane] : -2;
+    const int k1 = c1 < F ? (int)cm.inv[c1] : -2;
+#pragma unroll 4
+    for (int row = warp; row < rows; row += n_warps) {
+        const float* p = src + (int64_t)row * F;
+        const float v0 = k0 != -2 ? __ldg(p + lane) : 0.f;
+        const float v1 = k1 != -2 ? __ldg(p + c1) : 0.f;
+        if (k0 >= 0 && k0 < 32) xs[xs_index(row, k0)] = v0;
+        if (k1 >= 0 && k1 < 32) xs[xs_index(row, k1)] = v1;
+        if ((k0 == -1 && !isfinite(v0)) || (k1 == -1 && !isfinite(v1))) poison[row] = 1;
+    }
     __syncthreads();
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
         if (poison[r]) xs[xs_index(r, 0)] = __int_as_float(0x7fc00000);  // x - mask keeps NaN/Inf as NaN (:452-478)
