@@ -160,7 +160,7 @@ __device__ __forceinline__ int x16_offset(int row, int k) {   // byte offset of 
 // One warp per time-step row, lane = input column (columns lane and lane + 32): coalesced row reads, the column -> live
 // index map is looked up once per lane.  (Element-indexed loops with a per-element lookup of the map in constant memory --
 // 32 different addresses per warp load, serialised -- made the tile load 8 % of the kernel's time: ncu source view.)
-__device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int64_t n0, int n_valid, int F,
+__device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int64_t n0, int n_valid, int F, int kin,
                                                 const ColMap& cm, unsigned char* __restrict__ xs16,
                                                 int* __restrict__ poison, unsigned int* __restrict__ maxbits,
                                                 float* __restrict__ scale_out) {
@@ -210,11 +210,17 @@ __device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int
 #pragma unroll 4
     for (int row = warp; row < rows; row += n_warps) {
         const float* p = src + (int64_t)row * F;
-        const float down = __uint_as_float((uint32_t)(127 - shift_of(row / T_FIXED)) << 23);
+        const int kk = shift_of(row / T_FIXED);
+        const float down = __uint_as_float((uint32_t)(127 - kk) << 23);
         const float v0 = live0 ? __ldg(p + lane) * down : 0.f;
         const float v1 = live1 ? __ldg(p + c1) * down : 0.f;
         if (live0) put(row, k0, v0);
         if (live1) put(row, k1, v1);
+        // a spare K column (at most 31 live inputs) carries 1.0 and W0's row there the layer-1 bias (hi + lo): the bias comes
+        // out of the MMA and the layer-1 epilogue has nothing to add -- for rows whose block holds no scaled-down system
+        // (decided per 32-row block = per epilogue warp, whose tcgen05.st must not diverge: no system touching the block is scaled)
+        if (lane == 0 && kin < TC_K1 && shift_of((row & ~31) / T_FIXED) == 0 && shift_of(min((row | 31) / T_FIXED, SYS - 1)) == 0)
+            *reinterpret_cast<unsigned short*>(xh + x16_offset(row, TC_K1 - 1)) = 0x3c00u;
     }
     __syncthreads();
     for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
@@ -231,16 +237,19 @@ __device__ __forceinline__ void load_x_tile_f16(const float* __restrict__ X, int
 //   lo = v - hi (exact).  Three instructions per PAIR of values.  The integer form ((bits + 0x1000) & ~0x1fff: IADD3 +
 // LOP3 per value) kept the half-rate ALU pipe at 62 % of its peak -- the busiest pipe of the kernel, `math pipe throttle`
 // the top stall of the epilogue.  Inf becomes NaN (Inf - Inf), as it did in lo = v - hi before.
-template <bool EPI>
+// EPI: 0 = plain split, 1 = (d * scale + bias) -> ReLU -> split, 2 = ReLU -> split (the bias is already in the accumulator)
+template <int EPI>
 __device__ __forceinline__ void split_group4(const uint32_t* __restrict__ d, const float* __restrict__ bias,
                                              uint32_t* __restrict__ h, uint32_t* __restrict__ l, u64 scale2 = 0x3f8000003f800000ull) {
     u64 v01 = pack2(__uint_as_float(d[0]), __uint_as_float(d[1]));
     u64 v23 = pack2(__uint_as_float(d[2]), __uint_as_float(d[3]));
     if (EPI) {
-        // d * scale + bias: scale = 1 (one rounding, the same value as d + bias) except in layer 1 of a down-scaled x tile
-        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bias);
-        v01 = fma2(v01, scale2, b.x);
-        v23 = fma2(v23, scale2, b.y);
+        if (EPI == 1) {
+            // d * scale + bias: scale = 1 (one rounding, the same value as d + bias) except in layer 1 of a down-scaled system
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bias);
+            v01 = fma2(v01, scale2, b.x);
+            v23 = fma2(v23, scale2, b.y);
+        }
         float v[4];
         unpack2(v01, v[0], v[1]);
         unpack2(v23, v[2], v[3]);
@@ -262,7 +271,7 @@ __device__ __forceinline__ void split_group4(const uint32_t* __restrict__ d, con
 #pragma unroll
     for (int u = 0; u < 4; ++u) l[u] = __float_as_uint(f[u]);
 }
-template <bool EPI>
+template <int EPI>
 __device__ __forceinline__ void split_store16(const uint32_t (&d)[16], const float* __restrict__ bias, uint32_t t_hi,
                                               uint32_t t_lo, u64 scale2 = 0x3f8000003f800000ull) {
     uint32_t h[16], l[16];
@@ -271,7 +280,7 @@ __device__ __forceinline__ void split_store16(const uint32_t (&d)[16], const flo
     tmem_st16(t_hi, h);
     tmem_st16(t_lo, l);
 }
-template <bool EPI>
+template <int EPI>
 __device__ __forceinline__ void split_store8(const uint32_t (&d)[8], const float* __restrict__ bias, uint32_t t_hi,
                                              uint32_t t_lo) {
     uint32_t h[8], l[8];
@@ -280,7 +289,7 @@ __device__ __forceinline__ void split_store8(const uint32_t (&d)[8], const float
     tmem_st8(t_hi, h);
     tmem_st8(t_lo, l);
 }
-template <bool EPI>
+template <int EPI>
 __device__ __forceinline__ void split_store4(const uint32_t (&d)[4], const float* __restrict__ bias, uint32_t t_hi,
                                              uint32_t t_lo, u64 scale2 = 0x3f8000003f800000ull) {
     uint32_t h[4], l[4];

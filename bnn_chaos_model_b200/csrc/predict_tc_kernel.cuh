@@ -145,7 +145,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
         if (WIDE)
             load_x_tile_tc(prm.X, n0, n_valid, prm.F, prm.kin, prm.cm, xs, reinterpret_cast<int*>(fb));
         else
-            load_x_tile_f16(prm.X, n0, n_valid, prm.F, prm.cm, smem_tc + Plan::xs, reinterpret_cast<int*>(fb), bars->x_maxbits,
+            load_x_tile_f16(prm.X, n0, n_valid, prm.F, prm.kin, prm.cm, smem_tc + Plan::xs, reinterpret_cast<int*>(fb), bars->x_maxbits,
                             bars->x_scale);
         __syncthreads();
         tc_fence_after();
@@ -367,7 +367,11 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     const int sys = min(((team + 2 * s) * 128 + quad * 32 + lane) / T_FIXED, SYS - 1);
-                    x_kk |= (int)((__float_as_uint(bars->x_scale[sys]) >> 23) - 127u) << (8 * s);
+                    const int kk = (int)((__float_as_uint(bars->x_scale[sys]) >> 23) - 127u);
+                    x_kk |= kk << (8 * s);
+                    // bit 16 + s: no row of this warp's 32-row block is scaled -> its layer-1 bias comes out of the MMA (warp-uniform:
+                    // the epilogue's tcgen05.ld / st are .sync.aligned)
+                    if (__all_sync(0xffffffffu, kk == 0)) x_kk |= 1 << (16 + s);
                 }
             }
 #pragma unroll 1
@@ -398,7 +402,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                             const uint4 a = *reinterpret_cast<const uint4*>(xs + R * 32 + (((4 * half + g4) ^ (lane & 7)) << 2));
                             v[4 * g4] = a.x; v[4 * g4 + 1] = a.y; v[4 * g4 + 2] = a.z; v[4 * g4 + 3] = a.w;
                         }
-                        split_store16<false>(v, nullptr, tl + TM_AHI + 16 * half, tl + TM_ALO + 16 * half);
+                        split_store16<0>(v, nullptr, tl + TM_AHI + 16 * half, tl + TM_ALO + 16 * half);
                         {
                             // live inputs 32..47 of this row from L2 (the x tile was just read by this CTA; they are the same
                             // for every unit, but 16 more columns of shared memory do not exist): half 0 puts 32..39 behind the
@@ -411,13 +415,13 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                                 w[j] = (c >= 0 && R < n_valid * T_FIXED) ? __float_as_uint(__ldg(prm.X + (n0 * T_FIXED + R) * (int64_t)prm.F + c)) : 0u;
                             }
                             if (half == 0) {
-                                split_store8<false>(w, nullptr, tl + TM_AHI + 32, tl + TM_ALO + 32);
+                                split_store8<0>(w, nullptr, tl + TM_AHI + 32, tl + TM_ALO + 32);
                                 publish(s);
                                 wait_d(s);
                             } else {
                                 publish(s);
                                 wait_d(s);
-                                split_store8<false>(w, nullptr, tl + TM_AHI, tl + TM_ALO);
+                                split_store8<0>(w, nullptr, tl + TM_AHI, tl + TM_ALO);
                             }
                         }
                         publish(s);
@@ -445,8 +449,14 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                         const float sc = (!WIDE && layer == 0) ? __uint_as_float((127u + ((uint32_t)(x_kk >> (8 * s)) & 0xffu)) << 23) : 1.0f;
                         const u64 sc2 = pack2(sc, sc);
                         tc_wait_ld();
-                        split_store16<true>(d0, bl, tl + TM_AHI, tl + TM_ALO, sc2);
-                        split_store4<true>(d1, bl + 16, tl + TM_AHI + 16, tl + TM_ALO + 16, sc2);
+                        if (!WIDE && layer == 0 && prm.kin < TC_K1 && ((x_kk >> (16 + s)) & 1)) {
+                            // the layer-1 bias came out of the MMA (ones column of x, see load_x_tile_f16)
+                            split_store16<2>(d0, nullptr, tl + TM_AHI, tl + TM_ALO);
+                            split_store4<2>(d1, nullptr, tl + TM_AHI + 16, tl + TM_ALO + 16);
+                        } else {
+                            split_store16<1>(d0, bl, tl + TM_AHI, tl + TM_ALO, sc2);
+                            split_store4<1>(d1, bl + 16, tl + TM_AHI + 16, tl + TM_ALO + 16, sc2);
+                        }
                         publish(s);
                         if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 10 * (layer + 1) + 3);
                     }

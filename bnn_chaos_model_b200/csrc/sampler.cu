@@ -156,6 +156,8 @@ __device__ __forceinline__ PackSrc pack_source(int i, const FlatLayout& fl, cons
             if (n < H) {
                 if (k < pl.kin) ps.src = fl.W0 + n * fl.F + (int)lc.col[k];
                 if (k + 1 < pl.kin) ps.src2 = fl.W0 + n * fl.F + (int)lc.col[k + 1];
+                // spare K column (at most 31 live inputs): the layer-1 bias, multiplied by the ones column of the x tile
+                if (k + 1 == TC_K1 - 1 && pl.kin < TC_K1) ps.src2 = fl.b0 + n;
             }
             return ps;
         } else if (i < pl.B2h) {
