@@ -214,7 +214,11 @@ def test_forward_noisy_and_split_api(dev):
     e1 = torch.randn((B, 20), device=dev).cpu(); e2 = torch.randn((B, 20), device=dev).cpu()
     p = R.unflatten(spec, theta)
     s_ref = R.compute_summary_stats(spec, p, x, e1, e2)
-    np.testing.assert_allclose(s.cpu().numpy(), s_ref.numpy(), rtol=2e-5, atol=2e-6)
+    # 1e-5 (north_star), relative to the magnitude of what is pooled: the sampled std half element-wise; the sampled mean half
+    # -- averages of latent series that may cancel to ~0 -- against |mean| + std of the same latent column
+    got, want = s.cpu().numpy(), s_ref.numpy()
+    np.testing.assert_allclose(got[:, 20:], want[:, 20:], rtol=1e-5, atol=0)
+    assert (np.abs(got[:, :20] - want[:, :20]) <= 1e-5 * (np.abs(want[:, :20]) + want[:, 20:])).all()
     mu, sd = m.predict_instability(s)
     mu_ref, sd_ref = R.predict_instability(spec, p, s.cpu())
     assert mu.shape == (B, 1) and rel_err(mu.cpu(), mu_ref) < TOL and rel_err(sd.cpu(), sd_ref) < TOL
@@ -235,7 +239,7 @@ def test_batched_philox_vs_oracle(dev):
     spec = R.ModelSpec.from_hparams(swag_stats(0)["hparams"])
     for u in units:
         th = R.sample_weights(*cpu_stats(SEEDS[u // S_]), 30, 0.5, z1[u], z2[u])
-        np.testing.assert_allclose(theta[u].cpu().numpy(), th.numpy(), rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(theta[u].cpu().numpy(), th.numpy(), rtol=1e-5, atol=1e-6)
         ref = R.forward_swag_fast(spec, theta[u].cpu(), x, eps[u, :, :20], eps[u, :, 20:])
         assert rel_err(got[u], ref) < TOL
 
