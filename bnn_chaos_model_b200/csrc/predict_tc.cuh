@@ -41,8 +41,8 @@ constexpr int XS_ROWS = MT * 128;   // rows of the shared-memory x tile: the 12 
 constexpr int TM_AHI = 0, TM_ALO = 40, TM_D = 80, TM_SLOT = 128;  // TMEM columns of one slot
 constexpr int N_BLOCKS = MT * 4;  // 32-row blocks per tile
 constexpr int REC_FLOATS = N_BLOCKS * 2 * L * 2;  // [block][segment][col][mean, M2]
-constexpr int FB_PITCH = 12;                     // latent rows staged for the pooling: 32 rows x 12 columns per epilogue warp
-constexpr int FB_FLOATS = 32 * FB_PITCH;
+constexpr int FB_PITCH = 36;                     // latent staging for the pooling, per epilogue warp: 10 columns x (32 rows + 4 pad) -- column-major, so that
+constexpr int FB_FLOATS = 10 * FB_PITCH;         // a 4-row granule of a column is one 16-byte load (pitch 36: the 8 lanes of a quarter warp hit 8 bank groups)
 constexpr int TAIL_SCRATCH = 4 * 208;            // per tail pair: eS[5*40] | sum[5*41] | sB[5*41] | sC[5*41] (208-float areas)
 constexpr int HEAD_FLOATS = S2 * HP + HP + H * HP + HP + 2 * H + 4 + S2;  // PackedLayout V0p .. lv_sum: one contiguous block
 constexpr int NREC = 4;                          // depth of the block-record ring (units the epilogue may run ahead of the tails; 2 in the wide variant)

@@ -281,18 +281,19 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->a_ready[2 * team + s]);
             };
-            // layer 3 of the slot's job: D -> this warp's latent columns [8 half, 8 half + 12) of its 32 rows (the bias is
-            // added to the pooled mean: the deviations do not see it)
+            // layer 3 of the slot's job: D -> this warp's 10 latent columns [10 half, 10 half + 10) of its 32 rows, column-major
+            // (the bias is added to the pooled mean: the deviations do not see it)
             auto latent_to_fb = [&](int s) {
                 const uint32_t tl = tq + s * TM_SLOT;
-                uint32_t d0[8], d1[4];
-                tmem_ld8(tl + TM_D + 8 * half, d0);
-                tmem_ld4(tl + TM_D + 8 * half + 8, d1);
+                uint32_t d0[8], d1[2];
+                tmem_ld8(tl + TM_D + 10 * half, d0);
+                tmem_ld2(tl + TM_D + 10 * half + 8, d1);
                 tc_wait_ld();
-                uint4* dst = reinterpret_cast<uint4*>(my_fb + lane * FB_PITCH);
-                dst[0] = make_uint4(d0[0], d0[1], d0[2], d0[3]);
-                dst[1] = make_uint4(d0[4], d0[5], d0[6], d0[7]);
-                dst[2] = make_uint4(d1[0], d1[1], d1[2], d1[3]);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(my_fb) + lane;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) dst[c * FB_PITCH] = d0[c];
+                dst[8 * FB_PITCH] = d1[0];
+                dst[9 * FB_PITCH] = d1[1];
                 __syncwarp();
             };
             // pooled (mean, M2) records of this warp's 10 latent columns of one 32-row block, two-pass per segment like
@@ -302,7 +303,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
             // meet through shuffles.  Runs in the shadow of the slot's layer-1 MMAs.  Lane constants (column pointer, first
             // granule row) live in two registers, the block's geometry comes from constant memory.
             const int pj3 = lane / 10, pc = lane - 10 * pj3;
-            const float* pool_col = my_fb + 2 * half + pc + 4 * min(pj3, 2) * FB_PITCH;
+            const float* pool_col = my_fb + pc * FB_PITCH + 4 * min(pj3, 2);   // granule i of this lane: 16 bytes at pool_col + 12 i
             const int pool_r0 = lane < 30 ? 4 * pj3 : 64;     // rows of granule i: pool_r0 + 12 i ...; lanes 30, 31 idle
             auto pool_block = [&](int pi, int m) {
                 static_assert(T_FIXED % 4 == 0 && ROWS % 4 == 0, "4-row granules must not straddle systems");
@@ -312,15 +313,16 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                 const int b = m * 4 + quad;
                 const PoolGeom pg = c_pool_geom[b];
                 const bool two = pg.nvalid > pg.e0;            // the block holds rows of two systems (warp-uniform)
-                float v[3][4];
+                u64 vlo[3], vhi[3];                            // rows (0, 1) and (2, 3) of granule i
                 bool in0[3], in1[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const int r0 = pool_r0 + 12 * i;           // r0 >= 32 is beyond nvalid: both predicates false (the loads
-                    in0[i] = r0 < pg.e0;                       // then touch the next warp's rows; their values are dropped)
+                    const int r0 = pool_r0 + 12 * i;           // r0 >= 32 is beyond nvalid: both predicates false (the load
+                    in0[i] = r0 < pg.e0;                       // then reads the column's pad; its values are dropped)
                     in1[i] = !in0[i] && r0 < pg.nvalid;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) v[i][r] = pool_col[(12 * i + r) * FB_PITCH];
+                    const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(pool_col + 12 * i);
+                    vlo[i] = g.x;
+                    vhi[i] = g.y;
                 }
                 auto gather3 = [&](float x) {
                     return __shfl_sync(0xffffffffu, x, pc) + __shfl_sync(0xffffffffu, x, pc + 10) + __shfl_sync(0xffffffffu, x, pc + 20);
@@ -328,7 +330,9 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const float pr = (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+                    float pa, pb;
+                    unpack2(add2(vlo[i], vhi[i]), pa, pb);     // packed fp32x2: (row 0 + row 2, row 1 + row 3)
+                    const float pr = pa + pb;
                     s0 += in0[i] ? pr : 0.f;
                     s1 += in1[i] ? pr : 0.f;
                 }
@@ -344,9 +348,11 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const float mu = in1[i] ? mean1 : mean0;
-                    float qp = 0.f;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { const float d = v[i][r] - mu; qp = fmaf(d, d, qp); }
+                    const u64 mu2 = pack2(mu, mu);
+                    const u64 dlo = sub2(vlo[i], mu2), dhi = sub2(vhi[i], mu2);
+                    float qa, qb;
+                    unpack2(fma2(dhi, dhi, mul2(dlo, dlo)), qa, qb);
+                    const float qp = qa + qb;
                     q0 += in0[i] ? qp : 0.f;
                     q1 += in1[i] ? qp : 0.f;
                 }
