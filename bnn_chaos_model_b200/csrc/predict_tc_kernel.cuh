@@ -333,8 +333,8 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                     float pa, pb;
                     unpack2(add2(vlo[i], vhi[i]), pa, pb);     // packed fp32x2: (row 0 + row 2, row 1 + row 3)
                     const float pr = pa + pb;
-                    s0 += in0[i] ? pr : 0.f;
-                    s1 += in1[i] ? pr : 0.f;
+                    if (in0[i]) s0 += pr;                      // (predicated adds: a granule belongs to at most one segment)
+                    if (in1[i]) s1 += pr;
                 }
                 // S / n as S r corrected by the residual (r = the rounded reciprocal from the table): the correctly rounded
                 // quotient without the ~60-cycle divide sequence on the warp's critical path (exact for power-of-two counts)
@@ -353,8 +353,8 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                     float qa, qb;
                     unpack2(fma2(dhi, dhi, mul2(dlo, dlo)), qa, qb);
                     const float qp = qa + qb;
-                    q0 += in0[i] ? qp : 0.f;
-                    q1 += in1[i] ? qp : 0.f;
+                    if (in0[i]) q0 += qp;
+                    if (in1[i]) q1 += qp;
                 }
                 q0 = gather3(q0);
                 if (two) q1 = gather3(q1);
