@@ -267,11 +267,16 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
             const int team = warp >> 3, half = (warp >> 2) & 1, quad = warp & 3;
             const uint32_t tq = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * team * TM_SLOT);  // slot s: + s * TM_SLOT
             float* my_fb = fb + warp * FB_FLOATS;
-            uint32_t pd = 0;  // bit s: parity of d_ready[2 * team + s]
+            uint32_t pd = 0;  // wide variant (an extra commit in layer 1): bit s = parity of d_ready[2 * team + s]
 
-            auto wait_d = [&](int s) {
-                mbar_wait(&bars->d_ready[2 * team + s], (pd >> s) & 1u);
-                pd ^= 1u << s;
+            // the slot's commit number c = 3 unit + layer completes phase c of d_ready: its parity follows from (unit, layer) --
+            // (i + layer) & 1 for the hidden-layer epilogues, (i + 1) & 1 for the read-out of unit i - 1 -- without per-slot state
+            auto wait_d = [&](int s, uint32_t par) {
+                if (WIDE) {
+                    par = (pd >> s) & 1u;
+                    pd ^= 1u << s;
+                }
+                mbar_wait(&bars->d_ready[2 * team + s], par);
                 tc_fence_after();
             };
             // A of the slot's next layer is written: TMEM stores complete, then one arrival per warp on the issuer's barrier
@@ -389,7 +394,7 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                     const uint32_t tl = tq + s * TM_SLOT;
                     if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 1);
                     if (i > 0) {
-                        wait_d(s);
+                        wait_d(s, (uint32_t)(i + 1) & 1u);
                         if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 2);
                         latent_to_fb(s);
                     }
@@ -423,10 +428,10 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                             if (half == 0) {
                                 split_store8<0>(w, nullptr, tl + TM_AHI + 32, tl + TM_ALO + 32);
                                 publish(s);
-                                wait_d(s);
+                                wait_d(s, 0u);
                             } else {
                                 publish(s);
-                                wait_d(s);
+                                wait_d(s, 0u);
                                 split_store8<0>(w, nullptr, tl + TM_AHI, tl + TM_ALO);
                             }
                         }
@@ -446,20 +451,20 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                         const uint32_t tl = tq + s * TM_SLOT + HC * half;
                         const float* bl = bias + layer * TC_N;
                         if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 10 * (layer + 1) + 1);
-                        wait_d(s);
+                        wait_d(s, (uint32_t)(i + layer) & 1u);
                         if ((warp & 7) == 0) TC_STAMP(team, 100 * s + 10 * (layer + 1) + 2);
                         uint32_t d0[16], d1[4];
                         tmem_ld16(tl + TM_D, d0);
                         tmem_ld4(tl + TM_D + 16, d1);
-                        // undo the power-of-two down-scaling of this row's system (1 unless the system holds |x| >= 2^15)
-                        const float sc = (!WIDE && layer == 0) ? __uint_as_float((127u + ((uint32_t)(x_kk >> (8 * s)) & 0xffu)) << 23) : 1.0f;
-                        const u64 sc2 = pack2(sc, sc);
                         tc_wait_ld();
                         if (!WIDE && layer == 0 && prm.kin < TC_K1 && ((x_kk >> (16 + s)) & 1)) {
                             // the layer-1 bias came out of the MMA (ones column of x, see load_x_tile_f16)
                             split_store16<2>(d0, nullptr, tl + TM_AHI, tl + TM_ALO);
                             split_store4<2>(d1, nullptr, tl + TM_AHI + 16, tl + TM_ALO + 16);
                         } else {
+                            // undo the power-of-two down-scaling of this row's system (1 unless the system holds |x| >= 2^15)
+                            const float sc = (!WIDE && layer == 0) ? __uint_as_float((127u + ((uint32_t)(x_kk >> (8 * s)) & 0xffu)) << 23) : 1.0f;
+                            const u64 sc2 = pack2(sc, sc);
                             split_store16<1>(d0, bl, tl + TM_AHI, tl + TM_ALO, sc2);
                             split_store4<1>(d1, bl + 16, tl + TM_AHI + 16, tl + TM_ALO + 16, sc2);
                         }
