@@ -69,7 +69,7 @@ struct SmemPlan {
 //                   two warps they were the kernel's critical path (ncu: 100 % busy at 0.14 IPC behind 16 epilogue warps)
 template <int NT, bool WIDE>
 __global__ void __launch_bounds__((EW + NISS + 2 * NT) * 32, 1)
-predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, unsigned int* __restrict__ item_counter) {
+predict_tc_kernel(const PredictParams prm, const int n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     static_assert(NT >= 1 && NT <= 2 && NT <= RingPlan<WIDE>::NREC && MT == 2 * N_TEAM && N_SLOT == 2 * N_TEAM && N_SLOT * TM_SLOT <= 512, "role layout");
     const PackedLayout pl(prm.kin, prm.F);
@@ -86,7 +86,6 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
     Bars* bars = reinterpret_cast<Bars*>(smem_tc + Plan::bars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = n_tiles * chunks;
     constexpr int W_ISS = EW, W_TAIL = EW + NISS;
 #ifdef BNN_TC_TIMELINE
     int dbg_n = 0;
@@ -102,23 +101,30 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    // items (system tile, unit chunk) are handed out dynamically: the first one is the CTA's index, the following come
-    // from a global counter
-    for (int item = blockIdx.x, first_item = 1; item < n_items; first_item = 0) {
-        const int tile = item / chunks, chunk = item % chunks;
+    // Static, exactly balanced partition: the launch's (system tile, unit) pairs in tile-major order are cut into gridDim.x
+    // equal contiguous ranges (every pair costs the same, so equal counts end together: no partial last wave whatever the
+    // shape of the launch, and a CTA loads ceil(range / U) + 1 x tiles at most).  An item = the part of one tile's units
+    // that lies in the CTA's range; only the first item of a CTA starts behind unit 0 of its tile.
+    int tile, u_first, rem;
+    {
+        const int64_t W = (int64_t)n_tiles * prm.U;
+        const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
+        tile = (int)(w0 / prm.U);
+        u_first = (int)(w0 - (int64_t)tile * prm.U);
+        rem = (int)(w1 - w0);
+    }
+    for (int first_item = 1; rem > 0; first_item = 0) {
         const int64_t n0 = (int64_t)tile * SYS;
         const int n_valid = (int)min((int64_t)SYS, prm.N - n0);
-        const int64_t u_begin = prm.U * chunk / chunks, u_end = prm.U * (chunk + 1) / chunks;
-        const int n_units = (int)(u_end - u_begin);
+        const int64_t u_begin = u_first;
+        const int n_units = (int)min((int64_t)rem, prm.U - u_begin);
 
         tc_fence_before();
         __syncthreads();  // previous item drained by every role
         if (threadIdx.x == 0) {
-            const int next = (int)(atomicAdd(item_counter, 1u) + gridDim.x);  // the item after this one
-            bars->next_item = next;
-            if (next < n_items && next / chunks != tile) {
-                // its x tile (82 kB of a 164 MB array, HBM-cold) starts moving to L2 now, a whole item ahead of its load
-                const int64_t n1 = (int64_t)(next / chunks) * SYS;
+            if (rem > n_units) {
+                // the next item's x tile (82 kB of a 164 MB array, HBM-cold) starts moving to L2 now, a whole item ahead of its load
+                const int64_t n1 = n0 + SYS;
                 const int64_t nv = min((int64_t)SYS, prm.N - n1);
                 const int64_t bytes = nv * T_FIXED * prm.F * 4;
                 const float* p1 = prm.X + n1 * (int64_t)T_FIXED * prm.F;
@@ -474,7 +480,9 @@ predict_tc_kernel(const PredictParams prm, const int n_tiles, const int chunks, 
                 }
             }
         }
-        item = bars->next_item;  // written by thread 0 before the barriers of the x-tile load: visible to every thread
+        rem -= n_units;
+        ++tile;
+        u_first = 0;
     }
 
     tc_fence_before();
@@ -496,32 +504,9 @@ static int launch_tc(const PredictParams& prm, cudaStream_t st) {
     BNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = (prm.N + SYS - 1) / SYS;
     BNN_REQUIRE(tiles < (1ll << 24), BNN_E_ARG, "too many system tiles for one launch (%lld)", (long long)tiles);
-    // Split each tile's units into `chunks` items so that the item count is close to a multiple of the SM count (items
-    // of one launch take the same time, so also a dynamic hand-out ends in a partial wave) while items stay long
-    // enough to amortise the x-tile load.
-    int64_t max_chunks = prm.U >= 64 ? prm.U / 32 : 1;
-    if (max_chunks > 64) max_chunks = 64;
-    int best = 1;
-    double best_eff = 0.0;
-    for (int c = 1; c <= max_chunks; ++c) {
-        const int64_t items = tiles * c;
-        const int64_t rounds = (items + n_sms - 1) / n_sms;
-        const double eff = (double)items / (double)(rounds * n_sms);
-        if (eff > best_eff + 0.005) { best_eff = eff; best = c; }
-    }
-    const int64_t items = tiles * best;
-    const int grid = (int)(items < n_sms ? items : n_sms);
-    unsigned int* counter = nullptr;
-    {   // a zeroed work counter per launch, from a small per-device pool used round-robin (launches in flight on
-        // different streams never share one unless more than 64 are outstanding on the device)
-        static unsigned int* pool[64] = {nullptr};
-        static unsigned long long next = 0;
-        const int d = dev & 63;
-        if (!pool[d]) BNN_CUDA(cudaMalloc(&pool[d], 64 * sizeof(unsigned int)));
-        counter = pool[d] + (__atomic_fetch_add(&next, 1ull, __ATOMIC_RELAXED) & 63);
-        BNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-    }
-    predict_tc_kernel<NT, WIDE><<<grid, threads, smem, st>>>(prm, (int)tiles, best, counter);
+    const int64_t pairs = tiles * prm.U;   // (tile, unit) pairs, cut into `grid` equal ranges by the kernel
+    const int grid = (int)(pairs < n_sms ? pairs : n_sms);
+    predict_tc_kernel<NT, WIDE><<<grid, threads, smem, st>>>(prm, (int)tiles);
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }
