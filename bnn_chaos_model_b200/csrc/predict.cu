@@ -371,6 +371,11 @@ int bnn_predict_strided(const bnn_model_config* cfg, const float* d_x, int64_t n
     // depend on the chunking (Philox is keyed on the global unit index).  bnn_set_predict_unit_chunk overrides (tests).
     int64_t unit_chunk = predict_unit_chunk() > 0 ? predict_unit_chunk() : 1024;
     if (unit_chunk < 1 || n_units <= unit_chunk + unit_chunk / 2) unit_chunk = n_units;
+    else if (predict_unit_chunk() <= 0) {
+        // equal launches (no short last one): ceil(n / 1024) launches of ceil(n / launches) units
+        const int64_t launches = (n_units + unit_chunk - 1) / unit_chunk;
+        unit_chunk = (n_units + launches - 1) / launches;
+    }
     const PredictParams prm_all = prm;
     const int L2_ = 2 * L;
     int n_sms = 148;

@@ -11,6 +11,9 @@
 // HBM-bound: writes d floats per unit; pre_D rows are re-read from L2.
 #include <cuda_fp16.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace bnn {
@@ -82,10 +85,11 @@ swag_sample_kernel(const float* __restrict__ w_avg, const float* __restrict__ w2
 
 // Where packed float i of a unit comes from: index into the flat (flatten()-order) vector and how it is transformed.
 enum PackKind : int { PK_ZERO = 0, PK_COPY = 1, PK_TF32_HI = 2, PK_TF32_LO = 3, PK_F16_HI = 4, PK_F16_LO = 5 };
-struct PackSrc {
+struct alignas(16) PackSrc {
     int src;
     int kind;
     int src2;   // fp16 kinds: the word's second half (k + 1); -1 = zero
+    int pad_ = 0;
 };
 
 __device__ __forceinline__ PackSrc pack_source(int i, const FlatLayout& fl, const PackedLayout& pl, const LiveCols& lc) {
@@ -240,7 +244,7 @@ swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict
                         int64_t unit_offset, int samples_per_model, int n_models, float c1, float scale, float c2div,
                         uint64_t seed, const float* __restrict__ z1, const float* __restrict__ z2, int64_t n_units,
                         float* __restrict__ theta, float* __restrict__ packed, FlatLayout fl, PackedLayout pl,
-                        LiveCols lc) {
+                        LiveCols lc, const PackSrc* __restrict__ pack_table) {
     typedef typename VecT<V>::type vec_t;
     extern __shared__ __align__(16) float sp_smem[];
     const int dpad = (d + 3) & ~3;
@@ -291,11 +295,30 @@ swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict
             // (mt d + jb) K floats from a 16-byte aligned base: V-float aligned because K is a multiple of V (jb K too)
             const vec_t* src = reinterpret_cast<const vec_t*>(pre_D + ((int64_t)mt * d + jb) * K);
             __syncthreads();                      // the previous chunk's readers are done with the tile
-            const int nv = rows * K / V;
-            for (int iv = tid; iv < nv; iv += SP_QUADS * G) {
-                const vec_t v = __ldg(src + iv);
-                const int qq = iv / qv, r = iv - qq * qv;
-                *reinterpret_cast<vec_t*>(tile + qq * pitch + r * V) = v;
+            // a warp per quad of rows (qv consecutive V-float words -> one padded tile row): no index division per word, and
+            // the loads of two quads are in flight before the first store
+            {
+                const int wp = tid >> 5, ln = tid & 31, nw = SP_QUADS * G / 32, nq = (rows + 3) >> 2;
+                for (int qq = wp; qq < nq; qq += 2 * nw) {
+                    const int qb = qq + nw;
+                    const int na = min(qv, (rows - 4 * qq) * K / V), nb = qb < nq ? min(qv, (rows - 4 * qb) * K / V) : 0;
+                    const vec_t* sa = src + (int64_t)qq * qv;
+                    const vec_t* sb = src + (int64_t)qb * qv;
+                    vec_t* da = reinterpret_cast<vec_t*>(tile + qq * pitch);
+                    vec_t* db = reinterpret_cast<vec_t*>(tile + qb * pitch);
+                    for (int r = ln; r < qv; r += 64) {
+                        vec_t a0, a1, b0, b1;
+                        const bool pa0 = r < na, pa1 = r + 32 < na, pb0 = r < nb, pb1 = r + 32 < nb;
+                        if (pa0) a0 = __ldg(sa + r);
+                        if (pa1) a1 = __ldg(sa + r + 32);
+                        if (pb0) b0 = __ldg(sb + r);
+                        if (pb1) b1 = __ldg(sb + r + 32);
+                        if (pa0) da[r] = a0;
+                        if (pa1) da[r + 32] = a1;
+                        if (pb0) db[r] = b0;
+                        if (pb1) db[r + 32] = b1;
+                    }
+                }
             }
             __syncthreads();
             const int j0 = jb + 4 * q;
@@ -309,25 +332,44 @@ swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict
                     zz[0] = n4.x; zz[1] = n4.y; zz[2] = n4.z; zz[3] = n4.w;
                 }
                 const float* zs = z2s + g * MAXK;
+                // the thread's four elements advance together through k (every element still sums k = 0 .. K-1 in order,
+                // like swag_sample_kernel): four independent FMA chains instead of one, z2 read once per k
+                float w[4], th[4], dot[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int j = j0 + i;
-                    if (j >= d) break;
-                    const float w = wa[j];
+                    const int j = min(j0 + i, d - 1);
+                    w[i] = wa[j];
                     // explicit _rn intrinsics: keep the reference's separate mul/sub/add roundings (no FMA contraction)
-                    const float sig = fabsf(__fsub_rn(w2a[j], __fmul_rn(w, w)));
-                    float th = __fadd_rn(w, __fmul_rn(__fmul_rn(c1, zz[i]), sqrtf(sig)));
-                    const float* row = tile + q * pitch + i * K;
-                    float dot = 0.f;   // k = 0 .. K-1 in order, like swag_sample_kernel
-                    for (int k = 0; k < K; k += V) {
-                        const vec_t rv = *reinterpret_cast<const vec_t*>(row + k);
-                        const float* r = reinterpret_cast<const float*>(&rv);
-#pragma unroll
-                        for (int e = 0; e < V; ++e) dot = fmaf(__fsub_rn(r[e], w), zs[k + e], dot);
-                    }
-                    th = __fadd_rn(th, __fdiv_rn(__fmul_rn(scale, dot), c2div));
-                    th_s[g * dpad + j] = th;
+                    const float sig = fabsf(__fsub_rn(w2a[j], __fmul_rn(w[i], w[i])));
+                    th[i] = __fadd_rn(w[i], __fmul_rn(__fmul_rn(c1, zz[i]), sqrtf(sig)));
+                    dot[i] = 0.f;
                 }
+                const float* rows4 = tile + q * pitch;
+                // software-pipelined: the shared-memory loads of step k + V are in flight while step k is summed
+                vec_t zc = *reinterpret_cast<const vec_t*>(zs), rc[4], zn = zc, rn[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rn[i] = rc[i] = *reinterpret_cast<const vec_t*>(rows4 + i * K);
+#pragma unroll 2
+                for (int k = 0; k < K; k += V) {
+                    if (k + V < K) {
+                        zn = *reinterpret_cast<const vec_t*>(zs + k + V);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) rn[i] = *reinterpret_cast<const vec_t*>(rows4 + i * K + k + V);
+                    }
+                    const float* z = reinterpret_cast<const float*>(&zc);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float* r = reinterpret_cast<const float*>(&rc[i]);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) dot[i] = fmaf(__fsub_rn(r[e], w[i]), z[e], dot[i]);
+                    }
+                    zc = zn;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rc[i] = rn[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (j0 + i < d) th_s[g * dpad + j0 + i] = __fadd_rn(th[i], __fdiv_rn(__fmul_rn(scale, dot[i]), c2div));
             }
         }
     }
@@ -339,7 +381,13 @@ swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict
     }
     if (packed) {
         for (int i = tid; i < pl.P; i += SP_QUADS * G) {
-            const PackSrc ps = pack_source(i, fl, pl, lc);
+            PackSrc ps;
+            if (pack_table) {
+                const int4 e = __ldg(reinterpret_cast<const int4*>(pack_table) + i);
+                ps.src = e.x; ps.kind = e.y; ps.src2 = e.z;
+            } else {
+                ps = pack_source(i, fl, pl, lc);
+            }
 #pragma unroll
             for (int gg = 0; gg < G; ++gg)
                 if (gg < n_live) packed[(u0 + gg) * (int64_t)pl.P + i] = pack_value(th_s + gg * dpad, ps);
@@ -372,7 +420,43 @@ struct SamplePackArgs {
     const float *z1, *z2;
     int64_t n_units;
     float *theta, *packed;
+    const PackSrc* pack_table;
 };
+
+// packed index -> flat source for one (n_features, zero_mask): the same for every unit, CTA and call, so it is built once
+// per device and configuration (a 16-byte entry per packed float, ~280 kB) and read by the fused sampler instead of being
+// recomputed by every CTA (pack_source is ~100 instructions of branches and divisions: a quarter of the kernel's
+// instructions in the ncu source view).  Entries are immutable once built; nullptr (allocation failed) = compute inline.
+__global__ void pack_table_kernel(FlatLayout fl, PackedLayout pl, LiveCols lc, PackSrc* __restrict__ table) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pl.P) table[i] = pack_source(i, fl, pl, lc);
+}
+
+static const PackSrc* pack_table_for(const bnn_model_config* cfg, const FlatLayout& fl, const PackedLayout& pl,
+                                     const LiveCols& lc, cudaStream_t st) {
+    struct Entry { int dev, F; unsigned long long mask; const PackSrc* table; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : cache)
+        if (e.dev == dev && e.F == cfg->n_features && e.mask == (unsigned long long)cfg->zero_mask) return e.table;
+    PackSrc* t = nullptr;
+    if (cache.size() >= 64 || cudaMalloc(&t, (size_t)pl.P * sizeof(PackSrc)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    pack_table_kernel<<<(pl.P + 255) / 256, 256, 0, st>>>(fl, pl, lc, t);
+    // one-time: later launches on other streams read the finished table
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(t);
+        return nullptr;
+    }
+    cache.push_back(Entry{dev, cfg->n_features, (unsigned long long)cfg->zero_mask, t});
+    return t;
+}
 
 template <int G, int V>
 static int launch_sample_pack(const SamplePackArgs& a, const FlatLayout& fl, const PackedLayout& pl, const LiveCols& lc,
@@ -385,7 +469,7 @@ static int launch_sample_pack(const SamplePackArgs& a, const FlatLayout& fl, con
     BNN_REQUIRE(blocks < (1ll << 31), BNN_E_ARG, "bnn_swag_sample: too many units for one launch");
     swag_sample_pack_kernel<G, V><<<(unsigned)blocks, SP_QUADS * G, smem, st>>>(
         a.w_avg, a.w2_avg, a.pre_D, a.d, a.K, a.unit_model, a.unit_offset, a.samples_per_model, a.n_models, a.c1, a.scale,
-        a.c2div, a.seed, a.z1, a.z2, a.n_units, a.theta, a.packed, fl, pl, lc);
+        a.c2div, a.seed, a.z1, a.z2, a.n_units, a.theta, a.packed, fl, pl, lc, a.pack_table);
     BNN_CUDA(cudaGetLastError());
     return BNN_OK;
 }
@@ -443,6 +527,7 @@ int bnn_swag_sample(const bnn_model_config* cfg, const float* d_w_avg, const flo
     a.c2div = (float)sqrt(2.0 * (K - 1));
     a.seed = seed; a.z1 = d_z1; a.z2 = d_z2; a.n_units = n_units; a.theta = d_theta; a.packed = d_theta_packed;
     cudaStream_t st = (cudaStream_t)stream;
+    a.pack_table = d_theta_packed ? pack_table_for(cfg, fl, pl, lc, st) : nullptr;
     // G units per CTA share the pre_D tiles and the packed-index arithmetic: 4 when there are enough units to fill the
     // GPU with such CTAs (and the tile fits), else one unit per CTA
     int n_sms = 148;

@@ -389,7 +389,7 @@ class MultiSWAG:
 
     def posterior_summary(self, x: torch.Tensor, samples_per_model: int, n_trios: int = 1, seed: int = 0,
                           scale: float = 0.5, system_offset: int = 0, max_block_bytes: int = 640 << 20,
-                          unit_chunk: int = 2048):
+                          unit_chunk: Optional[int] = None):
         """Predict + post-process on the device: x [N*n_trios, T, F] (rows = system*n_trios + trio, the
         reshape(-1, 100, 41) of multiswag_5_planet.py:287) -> [N, 8] per-system statistics
         (``posterior.STAT_NAMES``) of the sampled instability time, min over trios (figures/main_figures.py:
@@ -397,8 +397,9 @@ class MultiSWAG:
         prediction block (+ the [rows, U] sampled times) nor the weights of all U units ever exist as a whole: systems
         are walked in chunks of at most ``max_block_bytes`` of predictions (12 bytes per (row, unit)), cut at multiples
         of the kernel's system granule, and inside a system chunk the units in chunks of ``unit_chunk`` whose weights are
-        sampled on the spot (77 kB per unit; the sampler costs ~0.1 us per unit against ~6 us per unit and 1,000
-        systems of prediction).  Philox draws are keyed on global (unit, row) indices, so the result does not depend on
+        sampled on the spot (77 kB per unit; the sampler costs ~0.2 us per unit against ~5 us per unit and 1,000
+        systems of prediction; default chunk: 16 units per SM = whole waves of the sampler's 4-unit CTAs, 2368 on a
+        B200).  Philox draws are keyed on global (unit, row) indices, so the result does not depend on
         either chunking (BASELINE configs[2]: 12,500 systems x 60,000 units per GPU would be 9 GB of predictions and
         4.6 GB of packed weights in one piece; peak here < 1 GB)."""
         import math
@@ -410,6 +411,8 @@ class MultiSWAG:
             raise ValueError(f"{rows} rows are not a multiple of {n_trios} trios")
         N = rows // n_trios
         U = self.n_models * samples_per_model
+        if unit_chunk is None:
+            unit_chunk = 16 * torch.cuda.get_device_properties(self.device).multi_processor_count
         unit_chunk = max(1, int(unit_chunk))
         with torch.cuda.device(self.device):
             thp_all = None
