@@ -75,7 +75,7 @@ namespace {
 // two side streams + events of one host-entry call, released on every return path
 struct HostPipe {
     cudaStream_t in = nullptr, out = nullptr;
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ~HostPipe() {
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
@@ -85,10 +85,11 @@ struct HostPipe {
 };
 }  // namespace
 
-// Copies, sampling and prediction are pipelined over the systems: the batch is cut into up to three chunks at multiples of
-// the kernel's system granule (4 % / 48 % / 48 %: compute starts after a small first upload), the upload of chunk k + 1
-// and the download of chunk k - 1 run on two side streams under the predictive kernel of chunk k.  Philox draws are keyed
-// on global (unit, system) indices, so the result equals the one-launch result bit for bit.
+// Copies, sampling and prediction are pipelined over the systems: the batch is cut into up to four chunks at multiples of
+// the kernel's system granule (4 % / 47 % / 47 % / 2 %: the first upload runs under the weight sampler, only 2 % of the
+// download is left when the last kernel ends), the upload of chunk k + 1 and the download of chunk k - 1 run on two side
+// streams under the predictive kernel of chunk k.  Philox draws are keyed on global (unit, system) indices, so the result
+// equals the one-launch result bit for bit.
 int bnn_multiswag_predict_host(const bnn_model_config* cfg, const float* h_x, int64_t n_systems, const float* d_w_avg,
                                const float* d_w2_avg, const float* d_pre_D, int32_t n_models, int32_t K,
                                int32_t samples_per_model, float scale, uint64_t seed, float* h_out, void* d_scratch,
@@ -112,14 +113,17 @@ int bnn_multiswag_predict_host(const bnn_model_config* cfg, const float* h_x, in
 
     const int64_t g = bnn_predict_system_granule(cfg);
     BNN_REQUIRE(g >= 1, (int)g, "bnn_multiswag_predict_host: no kernel for this configuration");
-    int64_t cut[4] = {0, 0, 0, N};
+    int64_t cut[5] = {0, 0, 0, 0, N};
     int n_chunks = 1;
     if (N >= 64 * g) {   // worth pipelining
         cut[1] = (int64_t)(0.04 * N / g + 0.5) * g;
-        cut[2] = (int64_t)(0.52 * N / g + 0.5) * g;
+        cut[2] = (int64_t)(0.51 * N / g + 0.5) * g;
+        cut[3] = (int64_t)(0.98 * N / g + 0.5) * g;
         if (cut[1] < g) cut[1] = g;
         if (cut[2] <= cut[1]) cut[2] = cut[1] + g;
-        n_chunks = 3;
+        if (cut[3] <= cut[2]) cut[3] = cut[2] + g;
+        if (cut[3] >= N) cut[3] = N - g;     // N >= 64 g: still behind cut[2]
+        n_chunks = 4;
     } else {
         cut[1] = N;
     }
@@ -128,8 +132,8 @@ int bnn_multiswag_predict_host(const bnn_model_config* cfg, const float* h_x, in
     BNN_CUDA(cudaStreamCreateWithFlags(&hp.out, cudaStreamNonBlocking));
     for (auto& e : hp.ev) BNN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaEvent_t ev_start = hp.ev[0], ev_done = hp.ev[1];
-    cudaEvent_t* ev_in = &hp.ev[2];   // [3]
-    cudaEvent_t* ev_k = &hp.ev[5];    // [3]
+    cudaEvent_t* ev_in = &hp.ev[2];   // [4]
+    cudaEvent_t* ev_k = &hp.ev[6];    // [4]
     // work already queued on the caller's stream (it may still use the scratch) comes first
     BNN_CUDA(cudaEventRecord(ev_start, st));
     BNN_CUDA(cudaStreamWaitEvent(hp.in, ev_start, 0));

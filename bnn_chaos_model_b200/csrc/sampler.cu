@@ -295,34 +295,28 @@ swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict
             // (mt d + jb) K floats from a 16-byte aligned base: V-float aligned because K is a multiple of V (jb K too)
             const vec_t* src = reinterpret_cast<const vec_t*>(pre_D + ((int64_t)mt * d + jb) * K);
             __syncthreads();                      // the previous chunk's readers are done with the tile
-            // a warp per quad of rows (qv consecutive V-float words -> one padded tile row): no index division per word, and
-            // the loads of two quads are in flight before the first store
+            // a warp per quad of rows (qv consecutive V-float words -> one padded tile row), as asynchronous copies: all of a
+            // thread's words are in flight at once and land while it draws its normals (as register loads in rounds of
+            // four, the L2 round trips of this loop were 31 % of the kernel's warp samples)
             {
                 const int wp = tid >> 5, ln = tid & 31, nw = SP_QUADS * G / 32, nq = (rows + 3) >> 2;
-                for (int qq = wp; qq < nq; qq += 2 * nw) {
-                    const int qb = qq + nw;
-                    const int na = min(qv, (rows - 4 * qq) * K / V), nb = qb < nq ? min(qv, (rows - 4 * qb) * K / V) : 0;
+                for (int qq = wp; qq < nq; qq += nw) {
+                    const int na = min(qv, (rows - 4 * qq) * K / V);
                     const vec_t* sa = src + (int64_t)qq * qv;
-                    const vec_t* sb = src + (int64_t)qb * qv;
-                    vec_t* da = reinterpret_cast<vec_t*>(tile + qq * pitch);
-                    vec_t* db = reinterpret_cast<vec_t*>(tile + qb * pitch);
-                    for (int r = ln; r < qv; r += 64) {
-                        vec_t a0, a1, b0, b1;
-                        const bool pa0 = r < na, pa1 = r + 32 < na, pb0 = r < nb, pb1 = r + 32 < nb;
-                        if (pa0) a0 = __ldg(sa + r);
-                        if (pa1) a1 = __ldg(sa + r + 32);
-                        if (pb0) b0 = __ldg(sb + r);
-                        if (pb1) b1 = __ldg(sb + r + 32);
-                        if (pa0) da[r] = a0;
-                        if (pa1) da[r + 32] = a1;
-                        if (pb0) db[r] = b0;
-                        if (pb1) db[r + 32] = b1;
-                    }
+                    const uint32_t da = (uint32_t)__cvta_generic_to_shared(tile + qq * pitch);
+                    for (int r = ln; r < na; r += 32)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(da + (uint32_t)(r * V * 4)), "l"(sa + r),
+                                     "n"(V * 4)
+                                     : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
-            __syncthreads();
             const int j0 = jb + 4 * q;
-            if (live && j0 < d && (same || g == pass)) {
+            const bool mine = live && j0 < d && (same || g == pass);
+            // the thread's four elements advance together through k (every element still sums k = 0 .. K-1 in order,
+            // like swag_sample_kernel): four independent FMA chains instead of one, z2 read once per k
+            float w[4], th[4], dot[4];
+            if (mine) {
                 float zz[4];
                 if (z1) {
 #pragma unroll
@@ -331,10 +325,6 @@ swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict
                     float4 n4 = philox_normal4(seed, STREAM_Z1, (uint32_t)gu, 0u, (uint32_t)(j0 >> 2));
                     zz[0] = n4.x; zz[1] = n4.y; zz[2] = n4.z; zz[3] = n4.w;
                 }
-                const float* zs = z2s + g * MAXK;
-                // the thread's four elements advance together through k (every element still sums k = 0 .. K-1 in order,
-                // like swag_sample_kernel): four independent FMA chains instead of one, z2 read once per k
-                float w[4], th[4], dot[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int j = min(j0 + i, d - 1);
@@ -344,6 +334,11 @@ swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict
                     th[i] = __fadd_rn(w[i], __fmul_rn(__fmul_rn(c1, zz[i]), sqrtf(sig)));
                     dot[i] = 0.f;
                 }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (mine) {
+                const float* zs = z2s + g * MAXK;
                 const float* rows4 = tile + q * pitch;
                 // software-pipelined: the shared-memory loads of step k + V are in flight while step k is summed
                 vec_t zc = *reinterpret_cast<const vec_t*>(zs), rc[4], zn = zc, rn[4];
@@ -380,10 +375,14 @@ swag_sample_pack_kernel(const float* __restrict__ w_avg, const float* __restrict
             for (int j = tid; j < d; j += SP_QUADS * G) theta[(u0 + gg) * (int64_t)d + j] = th_s[gg * dpad + j];
     }
     if (packed) {
+        // the next index's table entry is in flight while this one's G values are gathered and stored
+        int4 e_next = make_int4(-1, PK_ZERO, -1, 0);
+        if (pack_table && tid < pl.P) e_next = __ldg(reinterpret_cast<const int4*>(pack_table) + tid);
         for (int i = tid; i < pl.P; i += SP_QUADS * G) {
             PackSrc ps;
             if (pack_table) {
-                const int4 e = __ldg(reinterpret_cast<const int4*>(pack_table) + i);
+                const int4 e = e_next;
+                if (i + SP_QUADS * G < pl.P) e_next = __ldg(reinterpret_cast<const int4*>(pack_table) + i + SP_QUADS * G);
                 ps.src = e.x; ps.kind = e.y; ps.src2 = e.z;
             } else {
                 ps = pack_source(i, fl, pl, lc);

@@ -311,17 +311,21 @@ class MultiSWAG:
             return pending if defer else pending.result()
 
     def predict_host(self, x_host: torch.Tensor, samples_per_model: int, seed: int = 0, scale: float = 0.5,
-                     out_host: Optional[torch.Tensor] = None, n_chunks=(0.04, 0.48, 0.48), system_offset: int = 0):
+                     out_host: Optional[torch.Tensor] = None, n_chunks=(0.04, 0.47, 0.47, 0.02), system_offset: int = 0):
         """Host-buffer entry: x_host [N, T, F] (pinned for real overlap) -> out_host [N, M*S, 2] (system-major).
         Systems are cut into chunks at multiples of the kernel's system granule (bit-identical to one launch: the
         Philox draws are keyed on global indices) and pipelined over three streams: the H2D copy of chunk k+1 and the
         D2H copy of chunk k-1 run under the predictive kernel of chunk k.  ``n_chunks``: a count of equal chunks or
-        a tuple of fractions of N; the default -- a small first chunk so that compute starts after 4 % of the upload,
-        then two large launches -- hides both copies at BASELINE config 2 (tools/e2e_sweep.py: 82.7 ms against 88.6 ms
-        for copy / compute / copy in sequence).  Returns out_host after synchronising."""
+        a tuple of fractions of N; the default -- a small first chunk whose upload runs under the weight sampler, two
+        large launches, and a small last chunk so that only 2 % of the download is left when the last kernel ends --
+        hides both copies at BASELINE config 2 (the kernel's exactly balanced partition makes short launches as
+        efficient as long ones).  Returns out_host after synchronising."""
         x_host = x_host.contiguous().float()
         N = x_host.shape[0]
         with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream()
+            ev_entry = torch.cuda.Event()
+            ev_entry.record(main)   # the copy streams start behind the caller's earlier work, not behind the sampler
             _, thp = self.sample_thetas(samples_per_model, seed, scale, want_flat=False)
             U = thp.shape[0]
             if out_host is None:
@@ -338,12 +342,11 @@ class MultiSWAG:
                 per = -(-N // max(1, n_chunks))
                 per = -(-per // g) * g
                 bounds = [(lo, min(lo + per, N)) for lo in range(0, N, per)]
-            main = torch.cuda.current_stream()
             if not hasattr(self, "_copy_streams"):
                 self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
             s_in, s_out = self._copy_streams
-            s_in.wait_stream(main)  # thp is ready before any chunk runs; x buffers of a previous call are released
-            s_out.wait_stream(main)
+            s_in.wait_event(ev_entry)   # the first upload runs under the sampler (the kernels wait for thp on `main`)
+            s_out.wait_event(ev_entry)
             xd = [None] * len(bounds)
             ev_in = [torch.cuda.Event() for _ in bounds]
             ev_k = [torch.cuda.Event() for _ in bounds]

@@ -506,7 +506,7 @@ def test_predict_host_pipelined_equals_single_launch(dev):
     N, S_ = 203, 6
     xh = torch.from_numpy(synth.make_systems(N, seed=31)).pin_memory()
     want = ens.predict(xh.to(dev), S_, seed=12, system_major=True).cpu()
-    for n_chunks in (1, 3, 8, 64):
+    for n_chunks in (1, 3, 8, 64, (0.04, 0.47, 0.47, 0.02), (0.5, 0.5)):
         got = ens.predict_host(xh, S_, seed=12, n_chunks=n_chunks)
         assert got.shape == (N, 2 * S_, 2) and torch.equal(got, want), n_chunks
     out = torch.empty((N, 2 * S_, 2)).pin_memory()

@@ -179,7 +179,7 @@ def test_c_host_entry_with_plain_host_buffers(dev):
     ens = MultiSWAG([make_swag_model(0, dev), make_swag_model(17, dev)], device=dev)
     cfg = ens.config(100)
     S_, seed = 5, 21
-    for N in (57, 333, 1280):   # one chunk; three pipelined chunks with a ragged tail; three chunks, whole tiles
+    for N in (57, 333, 1280):   # one chunk; four pipelined chunks with a ragged tail; four chunks, whole tiles
         xh = np.ascontiguousarray(synth.make_systems(N, seed=106))
         U = ens.n_models * S_
         out_h = np.full((U, N, 2), np.nan, np.float32)
