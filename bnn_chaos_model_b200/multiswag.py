@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import os
+
 import numpy as np
 import torch
 
@@ -92,10 +94,13 @@ class PeerPushGather:
     buffer), and ``add(part, a, b)`` copies the local systems [a, b) into slot [rank, a:b] of EVERY rank's buffer with
     plain device-to-device copies on a side stream.  Those run on the copy engines, so they overlap a persistent
     predictive kernel, which leaves no SM for an NCCL kernel to start on (one 768-thread CTA with 225 kB of shared
-    memory per SM).  ``finish()`` joins the side stream and runs the device-side barrier after which every peer's
-    writes into this rank's buffer are visible.  Two buffers alternate between gathers (``begin()`` picks the next one),
-    so a gather may be finished AFTER the next one has begun -- the previous batch's predictions travel under the next
-    batch's kernel -- and a returned tensor stays valid until the second ``begin()`` after its own."""
+    memory per SM).  ``seal()`` (after a gather's last ``add``) puts the device-side barrier, after which every peer's
+    writes into this rank's buffer are visible, on the SIDE stream behind the copies; ``finish()`` makes the caller's
+    stream wait for that point (and runs the barrier itself for a gather that was never sealed).  With the barrier on the
+    caller's stream -- queued behind the NEXT batch's kernel when the gather is deferred -- every rank waited for the
+    slowest GPU of the box at the end of every batch.  Two buffers alternate between gathers (``begin()`` picks the next
+    one), so a gather may be finished AFTER the next one has begun -- the previous batch's predictions travel under the
+    next batch's kernel -- and a returned tensor stays valid until the second ``begin()`` after its own."""
 
     _cache = {}
 
@@ -113,7 +118,8 @@ class PeerPushGather:
             self.hdls.append(hdl)
             self.peers.append([hdl.get_buffer(r, buf.shape, buf.dtype) for r in range(world)])
         self.stream = torch.cuda.Stream(device)
-        self.done = [None, None]   # per buffer: event after the last copy of its current gather
+        self.done = [None, None]   # per buffer: event after the last copy (sealed: after the barrier) of its current gather
+        self.sealed = [False, False]
         self.turn = 1
 
     @classmethod
@@ -125,6 +131,7 @@ class PeerPushGather:
 
     def begin(self) -> int:
         self.turn ^= 1
+        self.sealed[self.turn] = False
         return self.turn
 
     def add(self, part: torch.Tensor, a: int, b: int, turn: Optional[int] = None):
@@ -141,12 +148,25 @@ class PeerPushGather:
             self.done[turn] = torch.cuda.Event()
             self.done[turn].record(self.stream)
 
+    def seal(self, turn: Optional[int] = None):
+        """No more ``add`` for this gather: the barrier goes on the side stream, behind this gather's copies and ahead of
+        the next gather's (which wait for the next kernel)."""
+        turn = self.turn if turn is None else turn
+        if self.sealed[turn] or os.environ.get("BNN_GATHER_BARRIER", "side") == "main":   # "main": A/B switch (bench)
+            return
+        with torch.cuda.stream(self.stream):
+            self.hdls[turn].barrier()
+            self.done[turn] = torch.cuda.Event()
+            self.done[turn].record(self.stream)
+        self.sealed[turn] = True
+
     def finish(self, turn: Optional[int] = None) -> torch.Tensor:
         turn = self.turn if turn is None else turn
         cur = torch.cuda.current_stream(self.bufs[0].device)
         if self.done[turn] is not None:
             cur.wait_event(self.done[turn])   # THIS gather's copies only: a later gather's copies may still be in flight
-        self.hdls[turn].barrier()
+        if not self.sealed[turn]:
+            self.hdls[turn].barrier()
         out = self.bufs[turn]
         return out.view((out.shape[0] * out.shape[1],) + self.tail)
 
@@ -307,6 +327,8 @@ class MultiSWAG:
                     gather.add(part, a, b)
                 else:
                     gather.add(part, a, b, turn)
+            if turn is not None:
+                gather.seal(turn)
             pending = PendingGather((lambda: gather.finish()) if turn is None else (lambda: gather.finish(turn)))
             return pending if defer else pending.result()
 

@@ -144,6 +144,10 @@ def test_fast_truncnorm_oracle_vs_reference_golden():
     # the reference's 4*n-bin table inversion of the prior agrees with the closed-form CDF the kernel inverts
     r = np.random.default_rng(0).random(5000)
     assert np.abs(R.prior_cdf(R.prior_samples_table(r)) - r).max() < 3e-3
+    # ... and that 3e-3 is the TABLE's Riemann-sum error, first order in its bin width (4 bins per sample): it falls as
+    # 1 / n_samples towards the closed form (9.6e-6 at 1e6 samples; the evaluation scripts draw 1e7 and more)
+    errs = [np.abs(R.prior_cdf(R.prior_samples_table(r, n_samples=n)) - r).max() for n in (5000, 50000, 1000000)]
+    assert errs[2] < 1.2e-5 and 8.0 < errs[0] / errs[1] < 12.0 and 15.0 < errs[1] / errs[2] < 25.0
     assert R.prior_cdf(9.0) == 0.0 and abs(float(R.prior_cdf(100.0)) - 1.0) < 1e-12
 
 
