@@ -127,6 +127,7 @@ DIAG_SIGNATURES = {
          C.c_uint64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p],
     ),
     "bnn_set_train_variant": (C.c_int, [C.c_int32]),
+    "bnn_set_train_seed_groups": (C.c_int, [C.c_int32]),
     "bnn_set_summary_variant": (C.c_int, [C.c_int32]),
     "bnn_set_predict_variant": (C.c_int, [C.c_int32]),
     "bnn_set_predict_unit_chunk": (C.c_int, [C.c_int64]),

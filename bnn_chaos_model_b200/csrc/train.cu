@@ -51,6 +51,7 @@ struct Params {
     float* gx_out;             // [n_seeds, B, T, F] or null
     float* mu_out;             // [n_seeds, B]
     int B, T, F, FP, n_cta;
+    int seed0;                 // first seed of this launch: seed index = seed0 + blockIdx.y (seed groups, see pick_plan)
     uint64_t seed, step;
     uint64_t zero_mask;
     HeadConsts hc;
@@ -258,14 +259,32 @@ static int sm_count() {
 }
 
 // One CTA per SM, never more CTAs than SMs (a 149th CTA would run alone in a second wave); a seed's CTAs walk its
-// systems (tc: one per tile, v3: two per iteration).
-static int pick_n_cta(const bnn_model_config* cfg, int64_t B, int n_seeds) {
-    int64_t n = sm_count() / n_seeds;
+// systems (tc: one per tile, v3: two per iteration).  A CTA belongs to ONE seed (its weights live in shared memory, its
+// weight-gradient accumulators in tensor memory), so with n_seeds CTAs-per-seed = floor(SMs / n_seeds) can leave many SMs
+// idle: 30 seeds -> 4 CTAs each = 120 of 148 SMs, 500 systems per CTA.  The seeds are therefore run in `groups` launches of
+// `per` seeds each when that shortens the step: 3 launches of 10 seeds x 14 CTAs walk 143 systems per CTA each (429 in all).
+// Cost model: systems per CTA + ~4 systems' worth of fixed cost per launch (prologue, pipeline fill, partial write-out).
+struct SeedPlan { int n_cta, groups, per; };
+static int g_seed_groups = 0;   // bnn_set_train_seed_groups (diagnostic header): 0 = cost model, g = that many groups
+static SeedPlan pick_plan(const bnn_model_config* cfg, int64_t B, int n_seeds) {
+    const int64_t sms = sm_count();
     const int64_t cap = use_tc(cfg, B) ? B : (B + 1) / 2;
-    if (n > cap) n = cap;
-    if (n < 1) n = 1;
-    return (int)n;
+    SeedPlan best{1, 1, n_seeds};
+    double best_cost = 0.0;
+    const int g_lo = g_seed_groups > 0 ? (g_seed_groups < n_seeds ? g_seed_groups : n_seeds) : 1;
+    const int g_hi = g_seed_groups > 0 ? g_lo : 8;
+    for (int g = g_lo; g <= g_hi && g <= n_seeds; ++g) {
+        const int per = (n_seeds + g - 1) / g;
+        const int groups = (n_seeds + per - 1) / per;
+        int64_t n = sms / per;
+        if (n > cap) n = cap;
+        if (n < 1) n = 1;
+        const double cost = groups * ((double)((B + n - 1) / n) + 4.0);
+        if (g == g_lo || cost < 0.95 * best_cost) { best = SeedPlan{(int)n, groups, per}; best_cost = cost; }
+    }
+    return best;
 }
+static int pick_n_cta(const bnn_model_config* cfg, int64_t B, int n_seeds) { return pick_plan(cfg, B, n_seeds).n_cta; }
 
 }  // namespace train
 }  // namespace bnn
@@ -306,7 +325,8 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
                 "bnn_train_step: compiled for the reference's shape T=100, F=41 (got T=%d, F=%d)", T, F);
     const FlatLayout fl(F);
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_cta = train::pick_n_cta(cfg, B, n_seeds);
+    const train::SeedPlan plan = train::pick_plan(cfg, B, n_seeds);
+    const int n_cta = plan.n_cta;
     const int DP = fl.d + train::DPAD, nb = (DP + 255) / 256;
     float* partial = (float*)d_workspace;
     float* grad = partial + (size_t)n_seeds * n_cta * DP;
@@ -320,7 +340,7 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
     prm.partial = partial;
     prm.head_rec = head_rec;
     prm.xprod = head_rec + (size_t)n_seeds * B * train::REC;   // REC is a multiple of 4: stays 16-byte aligned
-    prm.B = (int)B; prm.T = T; prm.F = F; prm.FP = FP; prm.n_cta = n_cta;
+    prm.B = (int)B; prm.T = T; prm.F = F; prm.FP = FP; prm.n_cta = n_cta; prm.seed0 = 0;
     prm.seed = seed; prm.step = step; prm.zero_mask = cfg->zero_mask;
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
     prm.beta_out = hp->beta_out;
@@ -331,7 +351,11 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
         if (attr_tc_done.need()) {
             BNN_CUDA(cudaFuncSetAttribute(train::train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         }
-        train::train_tc_kernel<<<dim3(n_cta, n_seeds), train::tcx::NTHR_TC, smem_tc, st>>>(prm);
+        for (int s0 = 0; s0 < n_seeds; s0 += plan.per) {   // seed groups (pick_plan); every buffer is indexed by the global seed
+            prm.seed0 = s0;
+            train::train_tc_kernel<<<dim3(n_cta, n_seeds - s0 < plan.per ? n_seeds - s0 : plan.per), train::tcx::NTHR_TC, smem_tc,
+                                     st>>>(prm);
+        }
     } else {
         const size_t smem3 = (size_t)train::Smem3(T, F).total * sizeof(float);
         static PerDeviceOnce attr3_done;
@@ -339,7 +363,11 @@ int bnn_train_step(const bnn_model_config* cfg, const bnn_train_hparams* hp, int
             BNN_CUDA(cudaFuncSetAttribute(train::train_fwd_bwd3_kernel<100, 41>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           227 * 1024));
         }
-        train::train_fwd_bwd3_kernel<100, 41><<<dim3(n_cta, n_seeds), train::NTHR3, smem3, st>>>(prm);
+        for (int s0 = 0; s0 < n_seeds; s0 += plan.per) {
+            prm.seed0 = s0;
+            train::train_fwd_bwd3_kernel<100, 41><<<dim3(n_cta, n_seeds - s0 < plan.per ? n_seeds - s0 : plan.per), train::NTHR3,
+                                                   smem3, st>>>(prm);
+        }
     }
     BNN_CUDA(cudaGetLastError());
     train::train_reduce_kernel<<<dim3(nb, n_seeds), 256, 0, st>>>(partial, d_theta, n_cta, fl.d, F,
@@ -381,7 +409,7 @@ int bnn_saliency(const bnn_model_config* cfg, int32_t n_models, const float* d_t
     prm.theta = d_theta; prm.X = d_x; prm.Y = nullptr; prm.batch_index = nullptr;
     prm.eps_in = nullptr; prm.eps12 = d_eps12; prm.eps_sum = nullptr;
     prm.partial = partial; prm.head_rec = nullptr; prm.xprod = xprod;
-    prm.B = (int)B; prm.T = T; prm.F = F; prm.FP = (F + 3) & ~3; prm.n_cta = (int)n_cta;
+    prm.B = (int)B; prm.T = T; prm.F = F; prm.FP = (F + 3) & ~3; prm.n_cta = (int)n_cta; prm.seed0 = 0;
     prm.seed = seed; prm.step = 0; prm.zero_mask = cfg->zero_mask;
     prm.hc = HeadConsts{cfg->lo_mu, cfg->hi_mu, cfg->lo_sd, cfg->hi_sd};
     prm.beta_out = 0.f;
@@ -404,6 +432,13 @@ int bnn_set_train_variant(int32_t variant) {
     using namespace bnn;
     BNN_REQUIRE(variant >= 0 && variant <= 2, BNN_E_ARG, "bnn_set_train_variant: 0 = auto, 1 = tensor-core, 2 = FP32 FFMA (v3)");
     train::g_train_variant = variant;
+    return BNN_OK;
+}
+
+int bnn_set_train_seed_groups(int32_t groups) {
+    using namespace bnn;
+    BNN_REQUIRE(groups >= 0 && groups <= 64, BNN_E_ARG, "bnn_set_train_seed_groups: 0 = cost model, 1..64 = launches per step");
+    train::g_seed_groups = groups;
     return BNN_OK;
 }
 

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(tcx::NTHR_TC, 1) train_tc_kernel(const Params 
     const SmemTC L_(prm.zero_mask);
     const FlatLayout fl(F);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int sidx = blockIdx.y;
+    const int sidx = prm.seed0 + (int)blockIdx.y;
     const float* th = prm.theta + (int64_t)sidx * fl.d;
     Bars* bars = reinterpret_cast<Bars*>(sm + L_.bars);
     float* cst = sm + L_.consts;

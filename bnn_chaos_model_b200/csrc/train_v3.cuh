@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(NTHR3, 1) train_fwd_bwd3_kernel(const Params p
     const int tid = threadIdx.x;
     const int half = tid >= HALF3 ? 1 : 0, lt = tid - half * HALF3;
     const int lane = tid & 31;
-    const int sidx = blockIdx.y;
+    const int sidx = prm.seed0 + (int)blockIdx.y;
     const float* th = prm.theta + (int64_t)sidx * fl.d;
     float* xT = sm + L_.xT; float* h1T = sm + L_.h1T; float* h2T = sm + L_.h2T; float* fT = sm + L_.fT;
     float* g2T = sm + L_.g2T; float* g1T = sm + L_.g1T;

@@ -72,6 +72,12 @@ int bnn_set_summary_variant(int32_t variant);
  * read once from the environment variable BNN_TRAIN_VARIANT (tc | v3). */
 int bnn_set_train_variant(int32_t variant);
 
+/* Diagnostic: launches per training step.  A CTA of the training kernels belongs to one seed, so floor(SMs / n_seeds) CTAs
+ * per seed can leave SMs idle (30 seeds: 4 x 30 = 120 of 148); bnn_train_step then runs the seeds in groups, one launch
+ * per group, chosen by a cost model (0, the default).  1..64 forces that many groups.  A seed's gradient depends on the
+ * number of CTAs that summed it (rounding order), not on the grouping as such. */
+int bnn_set_train_seed_groups(int32_t groups);
+
 #ifdef __cplusplus
 }
 #endif

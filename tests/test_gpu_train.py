@@ -408,6 +408,53 @@ def test_repeated_steps_are_bit_identical(dev, train_variant):
         assert torch.equal(g, g0) and torch.equal(met, met0), (train_variant, rep)
 
 
+def test_seed_groups_do_not_change_a_seed(dev, train_variant):
+    """bnn_train_step runs many seeds in groups of launches when one launch would leave SMs idle (30 seeds: 4 CTAs each =
+    120 of 148 SMs).  Every buffer and Philox key is indexed by the global seed, so (a) with the CTA count per seed held
+    fixed (small batch: one CTA per system) any grouping, ragged ones included, gives bit-identical gradients, metrics,
+    weights and momenta; (b) at 30 seeds x batch 2000 the cost model's plan (more CTAs per seed) agrees with the
+    single-launch plan to rounding (a seed's gradient is summed over a different number of CTA partials)."""
+    lib = _lib.load()
+    m = make_swag_model(3, dev)
+    cfg = m.config(100)
+    try:
+        S, B, N = 7, 12, 40
+        x = torch.from_numpy(synth.make_systems(N, seed=77)).to(dev)
+        y = torch.from_numpy(synth.make_labels(N, seed=77)).to(dev)
+        gen = torch.Generator(device=dev); gen.manual_seed(5)
+        theta0 = (m.w_avg[None] + 1e-3 * torch.randn((S, m.w_avg.numel()), device=dev, generator=gen)).contiguous()
+        idx = torch.stack([torch.randperm(N, device=dev, generator=gen)[:B] for _ in range(S)]).to(torch.int32).contiguous()
+        hp = TrainHParams(lr=1e-4, momentum=0.9, weight_decay=1e-14, clip_norm=758.3, beta_in=1e-5, beta_out=1e-3,
+                          first_step=1, apply_update=1)
+        ref = None
+        for groups in (1, 2, 3, 7):
+            _lib.check(lib.bnn_set_train_seed_groups(groups))
+            th, mom = theta0.clone(), torch.zeros_like(theta0)
+            g, met = _step(lib, cfg, hp, S, th, mom, x, y, idx, B, None, 21, 4, dev)
+            if ref is None:
+                ref = (g, met, th, mom)
+                assert bool(torch.isfinite(g).all()) and not torch.equal(g[0], g[1])
+            else:
+                for a, b in zip(ref, (g, met, th, mom)):
+                    assert torch.equal(a, b), (train_variant, groups)
+        S, B, N = 30, 2000, 2000
+        x = torch.from_numpy(synth.make_systems(N, seed=78)).to(dev)
+        y = torch.from_numpy(synth.make_labels(N, seed=78)).to(dev)
+        theta0 = (m.w_avg[None] + 1e-3 * torch.randn((S, m.w_avg.numel()), device=dev, generator=gen)).contiguous()
+        hp = TrainHParams(lr=1e-4, momentum=0.9, weight_decay=1e-14, clip_norm=758.3, beta_in=1e-5, beta_out=1e-3,
+                          first_step=1, apply_update=0)
+        out = {}
+        for groups in (1, 0):
+            _lib.check(lib.bnn_set_train_seed_groups(groups))
+            out[groups] = _step(lib, cfg, hp, S, theta0.clone(), None, x, y, None, B, None, 22, 1, dev)
+        for s in range(S):
+            err = float((out[0][0][s] - out[1][0][s]).abs().max() / out[1][0][s].abs().max())
+            assert err <= 5e-5, (train_variant, s, err)   # the tolerance of the cross-kernel test above (measured: 2.2e-5 on tc)
+        np.testing.assert_allclose(out[0][1][:, :5].cpu().numpy(), out[1][1][:, :5].cpu().numpy(), rtol=2e-5)
+    finally:
+        _lib.check(lib.bnn_set_train_seed_groups(0))
+
+
 def test_trainer_noisy_validation_and_lr_milestone_vs_oracle(dev):
     """MultiSeedSWAGTrainer.validation_losses with the reference's default noisy_val=True (:787-799): loss at the current
     weights and at w_avg, / test_len, against the oracle's noisy forward fed the Philox draws of the launch; and the
