@@ -636,7 +636,7 @@ def run_ours(args):
                          "traffic_source": "profiles/r2_predict_tc_ncu.txt (ncu --set full, same workload, per launch); "
                                            "algorithmic HBM bytes per launch: 0.32e9",
                          "note": "north_star's roofline for this kernel is the FP32 CUDA-core FMA peak; the kernel runs the "
-                                 "feature MLP as three-term split GEMMs on tcgen05 (layer 1, 20 % of the MACs, as kind::f16; ncu: tensor pipe active 44 %, issue slots 69 %, profiles/r2_predict_tc_ncu.txt)"},
+                                 "feature MLP as three-term split GEMMs on tcgen05 (layer 1, 20 % of the MACs, as kind::f16; ncu: tensor pipe active 46 %, issue slots 70 %, profiles/r2_predict_tc_ncu.txt)"},
             "cpu_baseline": cb,
             "train": train,
             "train_30_seeds": train30,

@@ -131,7 +131,7 @@ int bnn_predict_instability(const bnn_model_config* cfg, const float* d_summary,
 
 /* Host-buffer convenience entry (what a non-torch caller binds): h_x [N,T,F] and h_out [U,N,2]
  * are HOST buffers (pinned for real overlap); SWAG statistics are device-resident.  Samples U =
- * n_models*samples_per_model units with Philox and predicts; the systems are cut into up to three
+ * n_models*samples_per_model units with Philox and predicts; the systems are cut into up to four
  * chunks (at multiples of bnn_predict_system_granule) whose upload / prediction / download are
  * pipelined over two internal side streams; synchronises before returning.  Bit-identical to one
  * bnn_swag_sample + bnn_predict on device-resident data.
