@@ -10,18 +10,23 @@
 //     (3 LDS.128 per 16 FFMA2 = 2.7 FMA per word) instead of 4 x 4 (2.0); thread = (column group, row quad) with the
 //     quad fastest, so a quarter warp reads 8 consecutive 16-byte chunks of activations and ONE weight address, and
 //     its epilogue STS.128 are conflict-free (quad-slowest ordering cost 2x on weight loads, 5x on the stores);
-//   * weight-gradient outer products: 8 x 8 blocks of dW per thread in plain FFMA (16 LDS.128 per 256 FFMA = 4.0 FMA
-//     per word) instead of 2 x 4 (1.3); the 2T rows are split over six row groups (five for dW2) so that 375 of the
-//     384 threads own a block of ONE matrix;
-//   * the Philox input noise of the NEXT pair of systems is drawn by the four warps that have no row-GEMM tile, while
-//     the other eight run the GEMMs, into an L2-resident scratch (x' and x' - mask(x), feature-major); the load phase
-//     is a float4 copy (it was 19 % of the kernel when every thread drew noise between two barriers);
+//   * weight-gradient outer products: warp-level tensor-core tiles (mma.sync.m16n8k8 tf32, 3xTF32 split in registers,
+//     two passes with <= 36 live accumulators per thread, the accumulators of the other pass stashed in TENSOR MEMORY --
+//     80 columns per thread, used as a register spill area, not as an MMA accumulator); 8 x 8 FFMA blocks per thread
+//     (16 LDS.128 per 256 FFMA) were the round-1 first version;
+//   * the Philox input noise of the next tiles is drawn by FOUR DEDICATED PRODUCER WARPS, up to two tiles ahead, into an
+//     L2-resident scratch (x' and x' - mask(x), feature-major; named barriers ready / free per scratch parity), so the
+//     twelve pipeline warps never wait for noise; the load phase is a float4 copy (it was 19 % of the kernel when every
+//     thread drew noise between two barriers);
 //   * regress_nn weights live in shared memory (six L2-latency-bound mat-vec phases per pair of systems before);
 //   * the head's weight gradients are rank-1 updates per system: the vectors they need go to a 1 kB record per
 //     system in the workspace and the outer products run once, at the end of the kernel, over the CTA's records --
 //     no head accumulators live through the main loop;
 //   * bias gradients and the 41st input column are row sums done by the two warps that have no g_x tile.
-// One CTA per SM, 384 threads (<= 168 registers), two systems (2T rows) per iteration.
+// One CTA per SM, 512 threads = 12 pipeline warps (NMAIN = 384) + 4 producer warps (NPROD = 128), 128 registers, 231.9 kB
+// of shared memory, two systems (2T rows) per iteration.  Since round 2 this is the FALLBACK of bnn_train_step (batches
+// below 256, flag sets whose input image does not fit the tensor-core kernel's plan) and the kernel behind bnn_saliency;
+// the default training kernel is train_tc.cuh (all eight GEMMs of a system on tcgen05).
 #pragma once
 #include "tc.cuh"
 
