@@ -56,7 +56,7 @@ struct Bars {
     uint64_t h_full[2];                                // head warp j: the head block of its next unit landed in its buffer
     uint64_t sum_full[2], sum_free[2];                 // tail pair j: summary statistics written by the stats warp / consumed
     uint32_t tmem_base;
-    int next_item;                                     // dynamic work distribution: the item this CTA runs next
+    int next_item;                                     // unused since the static partition (kept: the layout of Bars is measured)
     unsigned int x_maxbits[SYS];                       // fp16 x tile: bits of the largest finite |x| of each system
     float x_scale[SYS];                                // ... and the power of two that undoes the system's down-scaling
 };
