@@ -128,6 +128,7 @@ DIAG_SIGNATURES = {
     ),
     "bnn_set_train_variant": (C.c_int, [C.c_int32]),
     "bnn_set_train_seed_groups": (C.c_int, [C.c_int32]),
+    "bnn_train_seed_plan": (C.c_int, [_CFG, C.c_int64, C.c_int32, c_i32p, c_i32p, c_i32p]),
     "bnn_set_summary_variant": (C.c_int, [C.c_int32]),
     "bnn_set_predict_variant": (C.c_int, [C.c_int32]),
     "bnn_set_predict_unit_chunk": (C.c_int, [C.c_int64]),

@@ -252,9 +252,12 @@ static size_t scratch_floats_per_cta(const bnn_model_config* cfg) {
 }
 
 static int sm_count() {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms < 1) {
+        cudaGetLastError();   // no device (host-only plan queries): a B200's SM count
+        sms = 148;
+    }
     return sms;
 }
 
@@ -432,6 +435,17 @@ int bnn_set_train_variant(int32_t variant) {
     using namespace bnn;
     BNN_REQUIRE(variant >= 0 && variant <= 2, BNN_E_ARG, "bnn_set_train_variant: 0 = auto, 1 = tensor-core, 2 = FP32 FFMA (v3)");
     train::g_train_variant = variant;
+    return BNN_OK;
+}
+
+int bnn_train_seed_plan(const bnn_model_config* cfg, int64_t B, int32_t n_seeds, int32_t* n_cta, int32_t* groups,
+                        int32_t* seeds_per_group) {
+    using namespace bnn;
+    int rc = validate_config(cfg);
+    if (rc != BNN_OK) return rc;
+    BNN_REQUIRE(B >= 1 && n_seeds >= 1 && n_cta && groups && seeds_per_group, BNN_E_ARG, "bnn_train_seed_plan: bad arguments");
+    const train::SeedPlan p = train::pick_plan(cfg, B, n_seeds);
+    *n_cta = p.n_cta; *groups = p.groups; *seeds_per_group = p.per;
     return BNN_OK;
 }
 

@@ -77,6 +77,10 @@ int bnn_set_train_variant(int32_t variant);
  * per group, chosen by a cost model (0, the default).  1..64 forces that many groups.  A seed's gradient depends on the
  * number of CTAs that summed it (rounding order), not on the grouping as such. */
 int bnn_set_train_seed_groups(int32_t groups);
+/* The plan bnn_train_step uses for n_seeds seeds of batch B on the current device (148 SMs are assumed when no device is
+ * present): CTAs per seed, launches per step, seeds per launch.  Host-only query. */
+int bnn_train_seed_plan(const bnn_model_config* cfg, int64_t B, int32_t n_seeds, int32_t* n_cta, int32_t* groups,
+                        int32_t* seeds_per_group);
 
 #ifdef __cplusplus
 }

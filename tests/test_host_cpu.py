@@ -59,6 +59,34 @@ def test_layout_queries_and_config_errors():
     assert b"hidden" in lib.bnn_last_error_string()
 
 
+def test_training_seed_plan_host_query():
+    """A CTA of the training kernels belongs to one seed, so many seeds are run in groups of launches when one launch
+    would leave SMs idle (host-only query of the plan bnn_train_step uses; 148 SMs assumed without a device): the 3-4 seeds
+    per GPU of an 8-GPU run stay one launch, all 30 seeds on one GPU become two launches of 15 seeds x 9 CTAs."""
+    import ctypes as C
+
+    from bnn_chaos_model_b200 import _lib
+
+    lib = _lib.load()
+    cfg = _lib.ModelConfig(41, 40, 20, 1, 1, 100, 0x1C0000000FE, 4.0, 12.0, 0.5, 6.0)
+
+    def plan(B, S):
+        a, g, p = C.c_int32(), C.c_int32(), C.c_int32()
+        assert lib.bnn_train_seed_plan(cfg, B, S, C.byref(a), C.byref(g), C.byref(p)) == 0
+        return a.value, g.value, p.value
+
+    if torch.cuda.is_available() and torch.cuda.get_device_properties(0).multi_processor_count != 148:
+        pytest.skip("the expected plans are a B200's (148 SMs)")
+    assert plan(2000, 4) == (37, 1, 4) and plan(2000, 3) == (49, 1, 3) and plan(2000, 1) == (148, 1, 1)
+    assert plan(2000, 30) == (9, 2, 15)
+    assert plan(2000, 15) == (9, 1, 15) and plan(2000, 8) == (18, 1, 8)
+    assert plan(64, 30) == (4, 1, 30)                                 # short batches: the fixed cost per launch outweighs idle SMs
+    for S in range(1, 41):                                            # every seed is covered, never more CTAs than SMs
+        a, g, p = plan(2000, S)
+        assert (g - 1) * p < S <= g * p and a * min(p, S) <= 148 and a >= 1
+    assert lib.bnn_train_seed_plan(cfg, 0, 4, None, None, None) != 0
+
+
 def test_no_cpu_fallback():
     from bnn_chaos_model_b200 import spock_reg_model as S
     from bnn_chaos_model_b200._lib import BnnChaosError
