@@ -111,6 +111,24 @@ def test_fused_sampler_equals_unfused_bitwise(dev, n_units, unit_offset, S_):
     assert none is None and torch.equal(thp_only, thp_u)
 
 
+@pytest.mark.parametrize("K", [20, 7, 2])
+def test_fused_sampler_other_deviation_ranks(dev, K):
+    """The fused sampler moves the pre_D tiles in 16-, 8- or 4-byte words depending on K (K = 30 -> 8 bytes: every other
+    test); K = 20 takes the 16-byte path, odd K the 4-byte path, K = 2 is the smallest rank the reference's
+    sqrt(2 (K - 1)) allows.  Three models (an odd model index shifts the tile base by d K floats), bit-equal to the
+    unfused sampler + pack."""
+    models = [make_swag_model(s, dev) for s in SEEDS]
+    for m in models:
+        m.pre_D = m.pre_D[:, :K].contiguous()
+        m.K = K
+        m.swa_params["K"] = K
+    ens = MultiSWAG(models, device=dev)
+    assert ens.K == K and ens.pre_D.shape[2] == K
+    for n_units, S_ in ((601, 3), (9, 5)):
+        (th_f, thp_f), (th_u, thp_u) = _sample_both(ens, n_units, 2, S_, seed=23)
+        assert bool(torch.isfinite(th_u).all()) and torch.equal(th_f, th_u) and torch.equal(thp_f, thp_u), (K, n_units)
+
+
 def test_fused_sampler_explicit_draws_and_unit_model(dev):
     ens = MultiSWAG([make_swag_model(s, dev) for s in SEEDS], device=dev)
     g = torch.Generator(device="cpu").manual_seed(4)
